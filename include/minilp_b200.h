@@ -1,0 +1,250 @@
+/*
+ * minilp_b200 — C ABI of the B200-native revised-simplex pivot engine.
+ *
+ * This is the drop-in boundary for the hot path of ztlpn/minilp (pure Rust, commit b99146b).
+ * The reference has no FFI of its own: everything below `Problem`/`Solution` is private
+ * (lib.rs:52-59).  The seam is `BasisSolver` (solver.rs:1265-1339) widened to the O(m)/O(n)
+ * loops of `Solver` that consume its results, so that no m- or n-vector crosses the bus per
+ * pivot.  Each entry point names the reference item it replaces (file:line under
+ * /root/reference/src).  INTEGRATION.md shows the Rust `extern "C"` block a maintainer would add.
+ *
+ * Conventions
+ *  - plain C: opaque handles, pointers and sizes; no C++/torch types.
+ *  - every function returns an mlp_status; outputs go through out-pointers.
+ *  - one host thread per handle; calls are synchronous with respect to their outputs.
+ *  - "var" is a variable index in [0, n+m): structural j < n, slack of row i is n+i
+ *    (solver.rs:230-232).  "pos" is a non-basic position (index into nb_vars, solver.rs:44),
+ *    "row" a basis position / constraint row (index into basic_vars, solver.rs:37).
+ *  - the engine never falls back to the CPU: without a CUDA device every compute entry point
+ *    returns MLP_NO_DEVICE.
+ */
+#ifndef MINILP_B200_H
+#define MINILP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mlp_status {
+  MLP_OK = 0,
+  MLP_INFEASIBLE = 1, /* Error::Infeasible, lib.rs:175 */
+  MLP_UNBOUNDED = 2,  /* Error::Unbounded,  lib.rs:177 */
+  MLP_SINGULAR = 3,   /* Error::SingularMatrix (sparse.rs:335); the reference unwrap()s it: solver.rs:316,1301 */
+  MLP_NONFINITE = 4,  /* assert!(is_finite) solver.rs:1149,1172 */
+  MLP_INVALID = 5,    /* bad argument / call order */
+  MLP_CUDA_ERROR = 6,
+  MLP_NO_DEVICE = 7,
+  MLP_NOMEM = 8
+} mlp_status;
+
+const char* mlp_last_error(void);
+const char* mlp_version(void);
+/* number of visible CUDA devices (0 when there is none); never fails */
+int mlp_device_count(void);
+
+/* ===================================================================== engine (device state) */
+typedef struct mlp_engine mlp_engine;
+
+/* non-basic variable state bits: NonBasicVarState + nb_var_is_fixed (solver.rs:47-48, 66-70) */
+#define MLP_AT_MIN 1u
+#define MLP_AT_MAX 2u
+#define MLP_BASIC 4u
+#define MLP_FIXED 8u
+
+/* Allocate the device-resident state for an m x n dense constraint matrix A (row-major f64 in HBM).
+ * Replaces the storage half of Solver (solver.rs:15-58: orig_constraints / orig_constraints_csc). */
+mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out);
+void mlp_engine_destroy(mlp_engine* e);
+/* Stream `nrows` consecutive rows of A (row-major, n doubles each) from HOST memory, starting at row0. */
+mlp_status mlp_engine_upload_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host);
+
+/* State at the end of Solver::try_new (solver.rs:108-369).  Arrays are HOST pointers.
+ * Position-indexed arrays (nb_*) have n entries, row-indexed ones m, var-indexed ones n+m. */
+typedef struct mlp_init_state {
+  const double* orig_var_mins;        /* n+m  solver.rs:19,224 */
+  const double* orig_var_maxs;        /* n+m  solver.rs:20,225 */
+  const double* orig_obj_coeffs;      /* n+m  solver.rs:18,244-245 (internal sign: Maximize already negated) */
+  const double* orig_rhs;             /* m    solver.rs:23 */
+  const int64_t* nb_vars;             /* n    solver.rs:44 */
+  const double* nb_var_vals;          /* n    solver.rs:46 */
+  const double* nb_var_obj_coeffs;    /* n    solver.rs:45,279-295 */
+  const uint8_t* nb_var_states;       /* n    MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED */
+  const double* primal_edge_sq_norms; /* n or NULL: computed on device as |a_j|^2 + 1 (solver.rs:297-299) */
+  const int64_t* basic_vars;          /* m    solver.rs:37 */
+  const double* basic_var_vals;       /* m or NULL: computed on device as rhs - A x_N (solver.rs:234-238) */
+  const double* basic_var_mins;       /* m    solver.rs:39 */
+  const double* basic_var_maxs;       /* m    solver.rs:40 */
+  const double* dual_edge_sq_norms;   /* m or NULL: all 1.0 (solver.rs:264-268) */
+  int32_t enable_primal_steepest_edge; /* solver.rs:25,272 */
+  int32_t enable_dual_steepest_edge;   /* solver.rs:26,263 */
+} mlp_init_state;
+/* Uploads the state and factorizes the initial basis (lu_factorize at solver.rs:305-317). */
+mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st);
+/* solver.rs:482 clears the flag after the initial solve */
+mlp_status mlp_engine_set_primal_steepest_edge(mlp_engine* e, int32_t enable);
+
+/* BasisSolver::reset (solver.rs:1286-1303): refactorize the current basis, drop the eta file.
+ * Dense engine: the LU of the basis is computed on the device.  lu_nnz receives
+ * the value LUFactors::nnz (lu.rs:52-54) would report for the refactor rule at solver.rs:1096-1097. */
+mlp_status mlp_refactor(mlp_engine* e, int64_t* lu_nnz);
+
+/* choose_pivot's pricing scan (solver.rs:696-739). var = -1: no eligible column (optimal). */
+typedef struct mlp_entering {
+  int64_t var, pos;
+  double obj_coeff; /* nb_var_obj_coeffs[pos] */
+  double score;
+  double cur_val;   /* nb_var_vals[pos] */
+  double var_min, var_max;
+} mlp_entering;
+mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out);
+
+/* calc_col_coeffs (solver.rs:671-677) = BasisSolver::solve (FTRAN, 1305-1319) of the column of `var`.
+ * Result stays on the device as col_coeffs. */
+mlp_status mlp_ftran_col(mlp_engine* e, int64_t var);
+
+/* The two-pass Harris ratio test of choose_pivot (solver.rs:752-823) over col_coeffs.
+ * entering_diff_sign: solver.rs:743; max_step0 = |entering_other_val - entering_cur_val| (782).
+ * row = -1: no blocking row (bound flip or unbounded, 841-852). */
+typedef struct mlp_leaving {
+  int64_t row;
+  double coeff;           /* pivot_coeff */
+  double leaving_new_val; /* 813-819 */
+  double basic_val;       /* basic_var_vals[row] (828) */
+} mlp_leaving;
+mlp_status mlp_ratio_primal(mlp_engine* e, int32_t entering_diff_sign, double max_step0, mlp_leaving* out);
+
+/* calc_row_coeffs (solver.rs:680-693): BTRAN of e_row (BasisSolver::solve_transp, 1322-1338) followed
+ * by the price-out of the tableau row.  Results stay on the device (inv_basis_row_coeffs, row_coeffs). */
+mlp_status mlp_btran_unit(mlp_engine* e, int64_t row);
+mlp_status mlp_price_row(mlp_engine* e);
+mlp_status mlp_calc_row_coeffs(mlp_engine* e, int64_t row);
+
+/* choose_pivot_row_dual (solver.rs:855-917). row = -1: primal feasible. */
+typedef struct mlp_dual_row {
+  int64_t row;
+  double val, min, max;
+} mlp_dual_row;
+mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out);
+
+/* choose_entering_col_dual (solver.rs:919-1021) over row_coeffs. var = -1: Err(Infeasible) (1019). */
+typedef struct mlp_dual_entering {
+  int64_t var, pos;
+  double coeff;     /* pivot_coeff */
+  double obj_coeff; /* nb_var_obj_coeffs[pos] */
+  double cur_val;   /* nb_var_vals[pos] */
+} mlp_dual_entering;
+mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out);
+
+/* PivotInfo / PivotElem (solver.rs:1245-1261) plus the refactor decision of solver.rs:1096-1103,
+ * which the host takes from the running eta nnz and lu_nnz. */
+typedef struct mlp_pivot_info {
+  int64_t entering_var, col;
+  double entering_new_val, entering_diff;
+  int32_t has_elem;
+  int64_t row;
+  double coeff, leaving_new_val;
+  int32_t refactor; /* 1: BasisSolver::reset instead of push_eta_matrix */
+} mlp_pivot_info;
+typedef struct mlp_pivot_result {
+  int64_t leaving_var;   /* -1 on a bound flip */
+  int64_t col_nnz;       /* structural size of the pushed eta column (nnz of col_coeffs) */
+  int64_t eta_count;     /* eta_matrices.len() after the call */
+  int64_t lu_nnz;        /* valid after a refactor, else unchanged value */
+  int32_t refactored;    /* the engine may also force a refactor when its eta arena is full */
+} mlp_pivot_result;
+/* Solver::pivot (solver.rs:1023-1104) incl. update_dual_sq_norms (1153-1174), update_primal_sq_norms
+ * (1106-1151) and push_eta_matrix (1274-1284).  Returns MLP_NONFINITE where the reference asserts. */
+mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* info, mlp_pivot_result* out);
+
+/* recalc_obj_coeffs (solver.rs:1199-1231): y = B^-T c_B, d_N = c_N - N^T y, objective from scratch. */
+mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val);
+
+/* Downloads (device -> caller buffer).  Var-indexed arrays have n+m entries, row-indexed m. */
+typedef enum mlp_array {
+  MLP_ARR_OBJ_COEFFS = 0,   /* d, by var (valid where non-basic) */
+  MLP_ARR_PRIMAL_NORMS = 1, /* by var */
+  MLP_ARR_NB_VALS = 2,      /* by var */
+  MLP_ARR_BASIC_VALS = 3,   /* by row */
+  MLP_ARR_DUAL_NORMS = 4,   /* by row */
+  MLP_ARR_COL_COEFFS = 5,   /* by row: last FTRAN result */
+  MLP_ARR_INV_BASIS_ROW = 6,/* by row: last BTRAN result */
+  MLP_ARR_ROW_COEFFS = 7,   /* by var: last price-out */
+  MLP_ARR_BASIC_MINS = 8,
+  MLP_ARR_BASIC_MAXS = 9,
+  MLP_ARR_SE_HELPER = 10    /* by var: N^T v of the last primal steepest-edge update */
+} mlp_array;
+mlp_status mlp_download_f64(mlp_engine* e, int32_t which, double* out, int64_t count);
+mlp_status mlp_download_basic_vars(mlp_engine* e, int64_t* out /* m */);
+mlp_status mlp_download_var_state(mlp_engine* e, uint8_t* flags /* n+m */, int32_t* pos_or_row /* n+m */);
+
+/* Instrumentation. */
+typedef struct mlp_counters {
+  int64_t kernel_launches;
+  int64_t h2d_bytes, d2h_bytes;
+  int64_t refactors, etas_pushed;
+  int64_t k_structural; /* structural columns in the last factorized basis */
+  int64_t lu_nnz;       /* LUFactors::nnz of the current factors (lu.rs:52-54) */
+  int64_t eta_count;    /* eta_matrices.len() */
+} mlp_counters;
+mlp_status mlp_get_counters(mlp_engine* e, mlp_counters* out);
+/* cudaStream_t of the engine (as void*), for CUDA-event timing by the caller. */
+void* mlp_engine_stream(mlp_engine* e);
+mlp_status mlp_engine_sync(mlp_engine* e);
+
+/* Kernel-isolated bench hooks (bench.py roofline): run the price-out kernel `iters` times with a dense
+ * multiplier vector over all m rows; returns the mean device time of one launch pair in milliseconds. */
+mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_launch, int64_t* bytes_per_launch);
+
+/* ===================================================================== host control loop */
+/* C++ mirror of the reference's Solver control flow (try_new 108-369, initial_solve 470-485,
+ * optimize 487-511, restore_feasibility 513-547, choose_pivot 695-853, pivot's host half) written
+ * ONLY against the engine ABI above — it is what the Rust `Solver` would look like after the swap. */
+typedef struct mlp_solver mlp_solver;
+
+mlp_status mlp_solver_create_dense(int device, int64_t m, int64_t n, mlp_solver** out);
+void mlp_solver_destroy(mlp_solver* s);
+mlp_engine* mlp_solver_engine(mlp_solver* s);
+mlp_status mlp_solver_upload_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_host);
+/* Solver::try_new.  obj_coeffs are internal-sign (lib.rs:235-238 already applied); cmp_ops: 0 Eq, 1 Le, 2 Ge. */
+mlp_status mlp_solver_init(mlp_solver* s, const double* obj_coeffs, const double* var_mins, const double* var_maxs,
+                           const int32_t* cmp_ops, const double* rhs);
+/* Solver::initial_solve with a pivot budget (max_pivots < 0: to completion). *done = 1 when finished. */
+mlp_status mlp_solver_run(mlp_solver* s, int64_t max_pivots, int32_t* done);
+double mlp_solver_cur_obj_val(mlp_solver* s);
+int64_t mlp_solver_pivots_done(mlp_solver* s);
+int64_t mlp_solver_num_vars(mlp_solver* s);
+int64_t mlp_solver_num_constraints(mlp_solver* s);
+/* Solver::get_value for all structural variables (solver.rs:371-376). out: n doubles. */
+mlp_status mlp_solver_values(mlp_solver* s, double* out);
+/* Per-pivot trace, 13 doubles per record, same layout as the oracle's. */
+int64_t mlp_solver_trace_len(mlp_solver* s);
+int64_t mlp_solver_get_trace(mlp_solver* s, int64_t first, int64_t count, double* out);
+void mlp_solver_set_record_trace(mlp_solver* s, int32_t on);
+/* host mirrors of nb_vars (n) and basic_vars (m) */
+mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out);
+mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out);
+/* seconds of wall clock spent inside mlp_solver_run so far, and of that inside refactorizations */
+void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds);
+
+/* ===================================================================== sharding helpers (host, no GPU) */
+/* Column block [begin, end) of rank `rank` of `world` over n structural columns. */
+void mlp_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* begin, int64_t* end);
+/* Deterministic arg-reduce of per-rank pricing candidates (score, pos, var): highest score wins, ties go
+ * to the lowest position (solver.rs:719).  A candidate with var < 0 is "none".  Returns winner rank or -1. */
+int32_t mlp_reduce_candidates(const double* scores, const int64_t* pos, const int64_t* vars, int32_t world);
+
+/* ===================================================================== synthetic dense LPs (host) */
+/* Independent implementation of the generator the oracle defines in oracle/synth_lp.hpp. */
+void mlp_synth_rows(int32_t kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, int32_t threads,
+                    double* out_rows);
+/* obj (user sign), mins, maxs: n; ops, rhs: m. Returns the optimization direction (0 min, 1 max).
+ * Kind 3 needs A·x0 and therefore generates rows internally. */
+int32_t mlp_synth_vectors(int32_t kind, int64_t m, int64_t n, uint64_t seed, double* obj, double* mins, double* maxs,
+                          int32_t* ops, double* rhs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

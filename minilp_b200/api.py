@@ -1,0 +1,390 @@
+"""Host-side mirror of the reference's public API (lib.rs) and thin wrappers of the engine / solver handles."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (Counters, DualEntering, DualRow, Entering, InitState, Leaving, PivotInfo, PivotResult, pd, pi32, pi64,
+                   pu8)
+
+INF = float("inf")
+
+
+class Error(Exception):
+    """lib.rs:171-178"""
+
+
+class Infeasible(Error):
+    """Error::Infeasible"""
+
+
+class Unbounded(Error):
+    """Error::Unbounded"""
+
+
+class SingularBasis(Error):
+    """the reference panics here (solver.rs:316, 1301)"""
+
+
+class NonFinite(Error):
+    """the reference asserts here (solver.rs:1149, 1172)"""
+
+
+class NoDevice(RuntimeError):
+    pass
+
+
+_STATUS = {1: Infeasible, 2: Unbounded, 3: SingularBasis, 4: NonFinite, 5: ValueError, 6: RuntimeError, 7: NoDevice,
+           8: MemoryError}
+
+
+def _check(rc):
+    if rc != 0:
+        raise _STATUS.get(rc, RuntimeError)(_lib.lib().mlp_last_error().decode() or f"mlp_status {rc}")
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, t=pd):
+    return a.ctypes.data_as(t)
+
+
+class OptimizationDirection:
+    """lib.rs:61-68"""
+    Minimize = 0
+    Maximize = 1
+
+
+class ComparisonOp:
+    """lib.rs:160-169"""
+    Eq = 0
+    Le = 1
+    Ge = 2
+
+
+def device_count():
+    return int(_lib.lib().mlp_device_count())
+
+
+def shard_range(n, world, rank):
+    b, e = C.c_int64(), C.c_int64()
+    _lib.lib().mlp_shard_range(n, world, rank, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+def reduce_candidates(scores, pos, vars_):
+    scores = _f64(scores)
+    pos = np.ascontiguousarray(pos, dtype=np.int64)
+    vars_ = np.ascontiguousarray(vars_, dtype=np.int64)
+    return int(_lib.lib().mlp_reduce_candidates(_p(scores), _p(pos, pi64), _p(vars_, pi64), len(scores)))
+
+
+# ------------------------------------------------------------------------------------------------ synthetic LPs
+def synth_rows(kind, m, n, seed, row0, nrows, threads=1, out=None):
+    if out is None:
+        out = np.empty((nrows, n), dtype=np.float64)
+    _lib.lib().mlp_synth_rows(kind, m, n, seed, row0, nrows, threads, _p(out))
+    return out
+
+
+def synth_vectors(kind, m, n, seed):
+    obj, mins, maxs = np.empty(n), np.empty(n), np.empty(n)
+    ops, rhs = np.empty(m, dtype=np.int32), np.empty(m)
+    d = _lib.lib().mlp_synth_vectors(kind, m, n, seed, _p(obj), _p(mins), _p(maxs), _p(ops, pi32), _p(rhs))
+    return d, obj, mins, maxs, ops, rhs
+
+
+class DenseLP:
+    """A dense LP in host memory: direction, A (m x n), obj (user sign), bounds, row ops, rhs."""
+
+    def __init__(self, direction, a, obj, mins, maxs, ops, rhs):
+        self.direction = direction
+        self.a = _f64(a)
+        self.obj, self.mins, self.maxs, self.rhs = _f64(obj), _f64(mins), _f64(maxs), _f64(rhs)
+        self.ops = np.ascontiguousarray(ops, dtype=np.int32)
+        self.m, self.n = self.a.shape
+
+
+def synth_dense(kind, m, n, seed, threads=1):
+    d, obj, mins, maxs, ops, rhs = synth_vectors(kind, m, n, seed)
+    return DenseLP(d, synth_rows(kind, m, n, seed, 0, m, threads), obj, mins, maxs, ops, rhs)
+
+
+# ------------------------------------------------------------------------------------------------ engine
+class Engine:
+    """Borrowed view of an mlp_engine* (owned by a Solver) exposing the per-operation ABI for tests and benches."""
+
+    def __init__(self, handle, m, n):
+        self._e, self.m, self.n = handle, m, n
+
+    def select_entering_primal(self):
+        out = Entering()
+        _check(_lib.lib().mlp_select_entering_primal(self._e, C.byref(out)))
+        return out
+
+    def ftran_col(self, var):
+        _check(_lib.lib().mlp_ftran_col(self._e, var))
+
+    def ratio_primal(self, sign, max_step0):
+        out = Leaving()
+        _check(_lib.lib().mlp_ratio_primal(self._e, int(sign), max_step0, C.byref(out)))
+        return out
+
+    def btran_unit(self, row):
+        _check(_lib.lib().mlp_btran_unit(self._e, row))
+
+    def price_row(self):
+        _check(_lib.lib().mlp_price_row(self._e))
+
+    def calc_row_coeffs(self, row):
+        _check(_lib.lib().mlp_calc_row_coeffs(self._e, row))
+
+    def select_row_dual(self):
+        out = DualRow()
+        _check(_lib.lib().mlp_select_row_dual(self._e, C.byref(out)))
+        return out
+
+    def ratio_dual(self, row, leaving_new_val):
+        out = DualEntering()
+        _check(_lib.lib().mlp_ratio_dual(self._e, row, leaving_new_val, C.byref(out)))
+        return out
+
+    def refactor(self):
+        z = C.c_int64()
+        _check(_lib.lib().mlp_refactor(self._e, C.byref(z)))
+        return z.value
+
+    def download(self, which):
+        n = self.m if which in (3, 4, 5, 6, 8, 9) else self.n + self.m
+        out = np.empty(n)
+        _check(_lib.lib().mlp_download_f64(self._e, which, _p(out), n))
+        return out
+
+    def basic_vars(self):
+        out = np.empty(self.m, dtype=np.int64)
+        _check(_lib.lib().mlp_download_basic_vars(self._e, _p(out, pi64)))
+        return out
+
+    def var_state(self):
+        fl = np.empty(self.n + self.m, dtype=np.uint8)
+        pos = np.empty(self.n + self.m, dtype=np.int32)
+        _check(_lib.lib().mlp_download_var_state(self._e, _p(fl, pu8), _p(pos, pi32)))
+        return fl, pos
+
+    def counters(self):
+        c = Counters()
+        _check(_lib.lib().mlp_get_counters(self._e, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+    def sync(self):
+        _check(_lib.lib().mlp_engine_sync(self._e))
+
+    def bench_price_dense(self, iters):
+        ms, by = C.c_double(), C.c_int64()
+        _check(_lib.lib().mlp_bench_price_dense(self._e, iters, C.byref(ms), C.byref(by)))
+        return ms.value, by.value
+
+
+TRACE_FIELDS = ("phase", "entering_var", "entering_col", "leaving_row", "leaving_var", "pivot_coeff", "entering_diff",
+                "obj_after", "eta_count", "lu_nnz", "nnz_col", "nnz_rho", "refactored")
+
+
+class Solver:
+    """solver.rs `Solver` after the swap: host control loop (csrc/host_solver.cpp) + device engine."""
+
+    def __init__(self, m, n, device=0):
+        h = C.c_void_p()
+        _check(_lib.lib().mlp_solver_create_dense(device, m, n, C.byref(h)))
+        self._s, self.m, self.n = h, m, n
+        self.engine = Engine(C.c_void_p(_lib.lib().mlp_solver_engine(h)), m, n)
+
+    def close(self):
+        if getattr(self, "_s", None):
+            _lib.lib().mlp_solver_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        self.close()
+
+    def upload_rows(self, row0, rows):
+        rows = _f64(rows)
+        _check(_lib.lib().mlp_solver_upload_rows(self._s, row0, rows.shape[0], _p(rows)))
+
+    def init(self, obj_internal, mins, maxs, ops, rhs):
+        obj_internal, mins, maxs, rhs = _f64(obj_internal), _f64(mins), _f64(maxs), _f64(rhs)
+        ops = np.ascontiguousarray(ops, dtype=np.int32)
+        _check(_lib.lib().mlp_solver_init(self._s, _p(obj_internal), _p(mins), _p(maxs), _p(ops, pi32), _p(rhs)))
+
+    @classmethod
+    def from_dense(cls, lp, device=0, chunk_rows=None):
+        """Problem::solve's set-up half: stream A from host memory, then Solver::try_new."""
+        s = cls(lp.m, lp.n, device)
+        step = chunk_rows or max(1, (64 << 20) // (8 * lp.n))
+        for r0 in range(0, lp.m, step):
+            s.upload_rows(r0, lp.a[r0:r0 + step])
+        obj = -lp.obj if lp.direction == OptimizationDirection.Maximize else lp.obj  # lib.rs:235-238
+        s.init(obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
+        s.direction = lp.direction
+        return s
+
+    def run(self, max_pivots=-1):
+        done = C.c_int32(0)
+        _check(_lib.lib().mlp_solver_run(self._s, max_pivots, C.byref(done)))
+        return bool(done.value)
+
+    cur_obj_val = property(lambda s: float(_lib.lib().mlp_solver_cur_obj_val(s._s)))
+    pivots_done = property(lambda s: int(_lib.lib().mlp_solver_pivots_done(s._s)))
+
+    def values(self):
+        out = np.zeros(self.n)
+        _check(_lib.lib().mlp_solver_values(self._s, _p(out)))
+        return out
+
+    def trace(self):
+        k = int(_lib.lib().mlp_solver_trace_len(self._s))
+        out = np.empty((max(k, 1), 13))
+        got = _lib.lib().mlp_solver_get_trace(self._s, 0, k, _p(out))
+        return out[:got]
+
+    def set_record_trace(self, on):
+        _lib.lib().mlp_solver_set_record_trace(self._s, int(on))
+
+    def nb_vars(self):
+        out = np.empty(self.n, dtype=np.int64)
+        _check(_lib.lib().mlp_solver_get_nb_vars(self._s, _p(out, pi64)))
+        return out
+
+    def basic_vars(self):
+        out = np.empty(self.m, dtype=np.int64)
+        _check(_lib.lib().mlp_solver_get_basic_vars(self._s, _p(out, pi64)))
+        return out
+
+    def timers(self):
+        a, b = C.c_double(), C.c_double()
+        _lib.lib().mlp_solver_timers(self._s, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    # position-indexed views matching the reference's Solver fields (for parity tests)
+    def nb_var_obj_coeffs(self):
+        return self.engine.download(0)[self.nb_vars()]
+
+    def primal_edge_sq_norms(self):
+        return self.engine.download(1)[self.nb_vars()]
+
+    def nb_var_vals(self):
+        return self.engine.download(2)[self.nb_vars()]
+
+    def basic_var_vals(self):
+        return self.engine.download(3)
+
+    def dual_edge_sq_norms(self):
+        return self.engine.download(4)
+
+
+# ------------------------------------------------------------------------------------------------ public API mirror
+class Problem:
+    """lib.rs:192-305.  Constraints are collected on the host; solve() hands a dense A to the device engine."""
+
+    def __init__(self, direction):
+        self.direction = direction
+        self.obj_coeffs, self.var_mins, self.var_maxs = [], [], []
+        self.constraints = []
+
+    def add_var(self, obj_coeff, bounds):
+        v = len(self.obj_coeffs)
+        self.obj_coeffs.append(obj_coeff if self.direction == OptimizationDirection.Minimize else -obj_coeff)  # 235-238
+        self.var_mins.append(bounds[0])
+        self.var_maxs.append(bounds[1])
+        return v
+
+    def add_constraint(self, expr, cmp_op, rhs):
+        expr = [(int(v), float(c)) for v, c in expr]
+        vs = [v for v, _ in expr]
+        if len(set(vs)) != len(vs):
+            raise ValueError("variable added more than once to a constraint")  # lib.rs:247-249 panics
+        if any(v < 0 or v >= len(self.obj_coeffs) for v in vs):
+            raise ValueError("unknown variable")
+        self.constraints.append((sorted(expr), cmp_op, float(rhs)))  # CsVec::new sorts by index (lib.rs:279)
+
+    def solve(self, device=0, max_pivots=-1):
+        n = len(self.obj_coeffs)
+        for mn, mx in zip(self.var_mins, self.var_maxs):
+            if mn > mx:
+                raise Infeasible("min > max")  # solver.rs:138-140
+        kept = []
+        for expr, op, rhs in self.constraints:  # solver.rs:201-213
+            if not expr:
+                ok = (0.0 == rhs) if op == ComparisonOp.Eq else (0.0 <= rhs) if op == ComparisonOp.Le else (0.0 >= rhs)
+                if not ok:
+                    raise Infeasible("empty constraint cannot hold")
+                continue
+            kept.append((expr, op, rhs))
+        if n == 0 or not kept:
+            return _TrivialSolution(self, n)
+        m = len(kept)
+        a = np.zeros((m, n))
+        for i, (expr, _, _) in enumerate(kept):
+            for v, c in expr:
+                a[i, v] = c
+        s = Solver(m, n, device)
+        s.upload_rows(0, a)
+        s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs),
+               np.array([op for _, op, _ in kept], dtype=np.int32), np.array([r for _, _, r in kept]))
+        s.direction = self.direction
+        s.run(max_pivots)
+        return Solution(s, self.direction, n)
+
+
+class Solution:
+    """lib.rs:313-355 (objective, var_value, iteration).  The incremental methods (add_constraint, fix_var,
+    unfix_var, add_gomory_cut: lib.rs:368-423) are SURVEY.md §8 row f2 ("next") and are not built yet."""
+
+    def __init__(self, solver, direction, num_vars):
+        self.solver, self.direction, self.num_vars = solver, direction, num_vars
+        self._vals = solver.values()
+
+    def objective(self):
+        v = self.solver.cur_obj_val
+        return v if self.direction == OptimizationDirection.Minimize else -v  # lib.rs:334-339
+
+    def var_value(self, var):
+        assert var < self.num_vars
+        return float(self._vals[var])
+
+    __getitem__ = var_value
+
+    def __iter__(self):
+        return iter(enumerate(self._vals.tolist()))
+
+
+class _TrivialSolution:
+    """No constraints survive try_new (all tautological): the reference's loops make no pivot unless a variable
+    can improve without bound (solver.rs:841-844)."""
+
+    def __init__(self, p, n):
+        self.direction, self.num_vars = p.direction, n
+        vals, obj = [], 0.0
+        for c, mn, mx in zip(p.obj_coeffs, p.var_mins, p.var_maxs):
+            if mn == mx:
+                x = mn
+            elif c > 0:
+                x = mn
+            elif c < 0:
+                x = mx
+            else:
+                x = mn if np.isfinite(mn) else (mx if np.isfinite(mx) else 0.0)
+            if not np.isfinite(x):
+                raise Unbounded("problem is unbounded")
+            vals.append(x)
+            obj += c * x
+        self._vals, self._obj = np.array(vals), obj
+
+    def objective(self):
+        return self._obj if self.direction == OptimizationDirection.Minimize else -self._obj
+
+    def var_value(self, var):
+        return float(self._vals[var])
+
+    __getitem__ = var_value

@@ -1,0 +1,385 @@
+// Host control loop: the part of ztlpn/minilp's `Solver` that stays on the CPU after the swap —
+// problem set-up (Solver::try_new, solver.rs:108-369), phase logic (initial_solve 470-485), the two
+// iteration loops (optimize 487-511, restore_feasibility 513-547), the scalar glue of choose_pivot
+// (741-748, 825-852) and of pivot (1027, 1096-1103).  All bulk work goes through the engine's C ABI
+// (include/minilp_b200.h) and nothing else: this file is what the Rust `Solver` looks like once its
+// vector loops are replaced by `extern "C"` calls.
+#include "minilp_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+constexpr double kInf = std::numeric_limits<double>::infinity();
+using Clock = std::chrono::steady_clock;
+
+struct PivotRecord {
+  int32_t phase;
+  int64_t entering_var, entering_col, leaving_row, leaving_var;
+  double pivot_coeff, entering_diff, obj_after;
+  int64_t eta_count, lu_nnz, nnz_col, nnz_rho;
+  int32_t refactored;
+};
+}  // namespace
+
+struct mlp_solver {
+  mlp_engine* eng = nullptr;
+  int64_t m = 0, n = 0;
+  // host mirrors of the O(1)-per-pivot fields of Solver (solver.rs:15-58)
+  std::vector<double> orig_var_mins, orig_var_maxs, orig_obj_coeffs;
+  std::vector<int64_t> nb_vars, basic_vars;
+  std::vector<double> nb_var_vals;
+  bool is_primal_feasible = false, is_dual_feasible = false;
+  bool enable_primal_steepest_edge = false, enable_dual_steepest_edge = false;
+  double cur_obj_val = 0.0;
+  int64_t eta_nnz = 0, lu_nnz = 0;  // eta_matrices.coeff_cols.nnz(), lu_factors.nnz() (solver.rs:1096-1097)
+  int stage = 0;                    // initial_solve state machine: 0 start, 1 dual, 2 recalc, 3 primal, 4 done
+  int64_t pivots_done = 0;
+  bool record_trace = true;
+  std::vector<PivotRecord> trace;
+  double run_seconds = 0.0, refactor_seconds = 0.0;
+  bool initialized = false;
+};
+
+#define ST(x)                        \
+  do {                               \
+    mlp_status st__ = (x);           \
+    if (st__ != MLP_OK) return st__; \
+  } while (0)
+
+// Solver::pivot, host half (solver.rs:1023-1104): objective, mirrors, refactor rule, trace.
+static mlp_status do_pivot(mlp_solver* s, int phase, int64_t entering_var, int64_t col, double obj_coeff, double entering_new_val,
+                           double entering_diff, bool has_elem, int64_t row, double coeff, double leaving_new_val) {
+  s->cur_obj_val += obj_coeff * entering_diff;  // 1027
+  mlp_pivot_info pi;
+  std::memset(&pi, 0, sizeof(pi));
+  pi.entering_var = entering_var;
+  pi.col = col;
+  pi.entering_new_val = entering_new_val;
+  pi.entering_diff = entering_diff;
+  pi.has_elem = has_elem ? 1 : 0;
+  pi.row = row;
+  pi.coeff = coeff;
+  pi.leaving_new_val = leaving_new_val;
+  pi.refactor = (has_elem && !(s->eta_nnz < s->lu_nnz)) ? 1 : 0;  // 1096-1103
+  mlp_pivot_result pr;
+  auto t0 = Clock::now();
+  ST(mlp_pivot(s->eng, &pi, &pr));
+  if (!has_elem) {
+    s->nb_var_vals[col] = entering_new_val;  // 1034
+  } else {
+    s->nb_var_vals[col] = leaving_new_val;  // 1068
+    s->basic_vars[row] = entering_var;      // 1088-1091
+    s->nb_vars[col] = pr.leaving_var;
+    if (pr.refactored) {
+      s->eta_nnz = 0;
+      s->lu_nnz = pr.lu_nnz;
+      s->refactor_seconds += std::chrono::duration<double>(Clock::now() - t0).count();
+    } else {
+      s->eta_nnz += pr.col_nnz;
+    }
+  }
+  s->pivots_done += 1;
+  if (s->record_trace) {
+    PivotRecord r;
+    r.phase = phase;
+    r.entering_var = entering_var;
+    r.entering_col = col;
+    r.leaving_row = has_elem ? row : -1;
+    r.leaving_var = has_elem ? pr.leaving_var : -1;
+    r.pivot_coeff = has_elem ? coeff : 0.0;
+    r.entering_diff = entering_diff;
+    r.obj_after = s->cur_obj_val;
+    r.eta_count = pr.eta_count;
+    r.lu_nnz = s->lu_nnz;
+    r.nnz_col = pr.col_nnz;
+    r.nnz_rho = 0;
+    r.refactored = pr.refactored;
+    s->trace.push_back(r);
+  }
+  return MLP_OK;
+}
+
+// One iteration of optimize() (solver.rs:497-498): choose_pivot (695-853) + pivot. *moved = 0 at the optimum.
+static mlp_status primal_iteration(mlp_solver* s, int* moved) {
+  mlp_entering en;
+  ST(mlp_select_entering_primal(s->eng, &en));
+  if (en.var < 0) { *moved = 0; return MLP_OK; }  // 737
+  const double entering_cur_val = en.cur_val;                                          // 741
+  const bool entering_diff_sign = en.obj_coeff < 0.0;                                  // 743
+  const double entering_other_val = entering_diff_sign ? en.var_max : en.var_min;      // 744-748
+  ST(mlp_ftran_col(s->eng, en.var));                                                   // 750
+  mlp_leaving lv;
+  ST(mlp_ratio_primal(s->eng, entering_diff_sign ? 1 : 0, std::fabs(entering_other_val - entering_cur_val), &lv));  // 782-823
+  if (lv.row >= 0) {
+    ST(mlp_calc_row_coeffs(s->eng, lv.row));                                           // 826
+    const double entering_diff = (lv.basic_val - lv.leaving_new_val) / lv.coeff;       // 828
+    const double entering_new_val = entering_cur_val + entering_diff;                  // 829
+    ST(do_pivot(s, 1, en.var, en.pos, en.obj_coeff, entering_new_val, entering_diff, true, lv.row, lv.coeff, lv.leaving_new_val));
+  } else {
+    if (std::isinf(entering_other_val)) return MLP_UNBOUNDED;                          // 842-844
+    ST(do_pivot(s, 1, en.var, en.pos, en.obj_coeff, entering_other_val, entering_other_val - entering_cur_val, false, -1, 0.0, 0.0));
+  }
+  *moved = 1;
+  return MLP_OK;
+}
+
+// One iteration of restore_feasibility() (solver.rs:529-533).
+static mlp_status dual_iteration(mlp_solver* s, int* moved) {
+  mlp_dual_row dr;
+  ST(mlp_select_row_dual(s->eng, &dr));
+  if (dr.row < 0) { *moved = 0; return MLP_OK; }
+  double leaving_new_val;  // 908-915
+  if (dr.val < dr.min) leaving_new_val = dr.min;
+  else if (dr.val > dr.max) leaving_new_val = dr.max;
+  else return MLP_INVALID;  // unreachable!() in the reference
+  ST(mlp_calc_row_coeffs(s->eng, dr.row));  // 530
+  mlp_dual_entering de;
+  ST(mlp_ratio_dual(s->eng, dr.row, leaving_new_val, &de));  // 531
+  if (de.var < 0) return MLP_INFEASIBLE;                      // 1019
+  const double entering_diff = (dr.val - leaving_new_val) / de.coeff;  // 1005
+  const double entering_new_val = de.cur_val + entering_diff;          // 1006
+  ST(mlp_ftran_col(s->eng, de.var));                                   // 532
+  ST(do_pivot(s, 0, de.var, de.pos, de.obj_coeff, entering_new_val, entering_diff, true, dr.row, de.coeff, leaving_new_val));
+  *moved = 1;
+  return MLP_OK;
+}
+
+extern "C" {
+
+mlp_status mlp_solver_create_dense(int device, int64_t m, int64_t n, mlp_solver** out) {
+  *out = nullptr;
+  mlp_engine* e = nullptr;
+  ST(mlp_engine_create_dense(device, m, n, &e));
+  mlp_solver* s = new mlp_solver();
+  s->eng = e;
+  s->m = m;
+  s->n = n;
+  *out = s;
+  return MLP_OK;
+}
+void mlp_solver_destroy(mlp_solver* s) {
+  if (!s) return;
+  mlp_engine_destroy(s->eng);
+  delete s;
+}
+mlp_engine* mlp_solver_engine(mlp_solver* s) { return s ? s->eng : nullptr; }
+mlp_status mlp_solver_upload_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_host) {
+  return mlp_engine_upload_rows(s->eng, row0, nrows, rows_host);
+}
+
+// Solver::try_new, solver.rs:108-369.  (Dense rows are never empty, so the tautology branch 201-213 does not arise.)
+mlp_status mlp_solver_init(mlp_solver* s, const double* obj, const double* mins, const double* maxs, const int32_t* ops,
+                           const double* rhs) {
+  if (!s) return MLP_INVALID;
+  const int64_t n = s->n, m = s->m, nt = n + m;
+  s->orig_var_mins.assign(mins, mins + n);
+  s->orig_var_maxs.assign(maxs, maxs + n);
+  s->orig_obj_coeffs.assign(obj, obj + n);
+  s->orig_obj_coeffs.resize(nt, 0.0);  // 244-245
+  s->nb_vars.resize(n);
+  s->nb_var_vals.resize(n);
+  std::vector<uint8_t> nb_states(n);
+  double obj_val = 0.0;
+  bool is_dual_feasible = true;
+  for (int64_t v = 0; v < n; ++v) {  // 133-187
+    const double mn = mins[v], mx = maxs[v];
+    if (mn > mx) return MLP_INFEASIBLE;  // 138-140
+    s->nb_vars[v] = v;
+    double init_val;
+    if (mn == mx) init_val = mn;
+    else if (std::isinf(mn) && std::isinf(mx)) { if (obj[v] != 0.0) is_dual_feasible = false; init_val = 0.0; }
+    else if (obj[v] > 0.0) { if (std::isfinite(mn)) init_val = mn; else { is_dual_feasible = false; init_val = mx; } }
+    else if (obj[v] < 0.0) { if (std::isfinite(mx)) init_val = mx; else { is_dual_feasible = false; init_val = mn; } }
+    else if (std::isfinite(mn)) init_val = mn;
+    else init_val = mx;
+    s->nb_var_vals[v] = init_val;
+    obj_val += init_val * obj[v];
+    nb_states[v] = (uint8_t)((init_val == mn ? MLP_AT_MIN : 0u) | (init_val == mx ? MLP_AT_MAX : 0u));
+  }
+  std::vector<double> bmin(m), bmax(m);
+  s->basic_vars.resize(m);
+  for (int64_t i = 0; i < m; ++i) {  // 218-232
+    double smin, smax;
+    if (ops[i] == 1) { smin = 0.0; smax = kInf; }
+    else if (ops[i] == 2) { smin = -kInf; smax = 0.0; }
+    else { smin = 0.0; smax = 0.0; }
+    s->orig_var_mins.push_back(smin);
+    s->orig_var_maxs.push_back(smax);
+    bmin[i] = smin;
+    bmax[i] = smax;
+    s->basic_vars[i] = n + i;
+  }
+  // basic_var_vals = rhs - A x_N (234-238) is a pass over A: done on the device, then read back once
+  // to decide primal feasibility (255-259).
+  mlp_init_state st;
+  std::memset(&st, 0, sizeof(st));
+  std::vector<double> nb_obj(n, 0.0);
+  st.orig_var_mins = s->orig_var_mins.data();
+  st.orig_var_maxs = s->orig_var_maxs.data();
+  st.orig_obj_coeffs = s->orig_obj_coeffs.data();
+  st.orig_rhs = rhs;
+  st.nb_vars = s->nb_vars.data();
+  st.nb_var_vals = s->nb_var_vals.data();
+  st.nb_var_obj_coeffs = nb_obj.data();
+  st.nb_var_states = nb_states.data();
+  st.primal_edge_sq_norms = nullptr;
+  st.basic_vars = s->basic_vars.data();
+  st.basic_var_vals = nullptr;
+  st.basic_var_mins = bmin.data();
+  st.basic_var_maxs = bmax.data();
+  st.dual_edge_sq_norms = nullptr;
+  const bool enable_steepest_edge = true;  // 114
+  s->enable_dual_steepest_edge = enable_steepest_edge;
+  s->enable_primal_steepest_edge = enable_steepest_edge && !is_dual_feasible;  // 272
+  st.enable_primal_steepest_edge = s->enable_primal_steepest_edge;
+  st.enable_dual_steepest_edge = s->enable_dual_steepest_edge;
+  // First pass: upload with provisional reduced costs; need basic values to know whether the artificial
+  // objective is required (261), which only changes nb_var_obj_coeffs.
+  for (int64_t v = 0; v < n; ++v) nb_obj[v] = obj[v];
+  ST(mlp_engine_init_state(s->eng, &st));
+  std::vector<double> xb(m);
+  ST(mlp_download_f64(s->eng, MLP_ARR_BASIC_VALS, xb.data(), m));
+  bool is_primal_feasible = true;
+  for (int64_t i = 0; i < m; ++i)
+    if (!(xb[i] >= bmin[i] && xb[i] <= bmax[i])) is_primal_feasible = false;  // 255-259
+  const bool need_artificial_obj = !is_primal_feasible && !is_dual_feasible;   // 261
+  if (need_artificial_obj) {  // 284-292
+    for (int64_t v = 0; v < n; ++v) {
+      const bool at_min = nb_states[v] & MLP_AT_MIN, at_max = nb_states[v] & MLP_AT_MAX;
+      nb_obj[v] = (at_min && !at_max) ? 1.0 : (at_max && !at_min) ? -1.0 : 0.0;
+    }
+    st.basic_var_vals = xb.data();
+    ST(mlp_engine_init_state(s->eng, &st));
+  }
+  s->cur_obj_val = need_artificial_obj ? 0.0 : obj_val;  // 302
+  s->is_primal_feasible = is_primal_feasible;
+  s->is_dual_feasible = is_dual_feasible;
+  s->eta_nnz = 0;
+  ST(mlp_refactor(s->eng, &s->lu_nnz));  // value of lu_factors.nnz() for the slack basis
+  s->stage = 0;
+  s->pivots_done = 0;
+  s->trace.clear();
+  s->initialized = true;
+  return MLP_OK;
+}
+
+// Solver::initial_solve (solver.rs:470-485) as a resumable state machine with a pivot budget.
+mlp_status mlp_solver_run(mlp_solver* s, int64_t max_pivots, int32_t* done) {
+  if (!s || !s->initialized) return MLP_INVALID;
+  *done = 0;
+  const auto t0 = Clock::now();
+  const int64_t target = max_pivots < 0 ? -1 : s->pivots_done + max_pivots;
+  auto budget_left = [&] { return target < 0 || s->pivots_done < target; };
+  mlp_status rc = MLP_OK;
+  for (bool go = true; go && rc == MLP_OK;) {
+    switch (s->stage) {
+      case 0: s->stage = s->is_primal_feasible ? 2 : 1; break;
+      case 1: {
+        while (budget_left()) {
+          int moved = 0;
+          rc = dual_iteration(s, &moved);
+          if (rc != MLP_OK) break;
+          if (!moved) { s->is_primal_feasible = true; s->stage = 2; break; }
+        }
+        if (rc == MLP_OK && s->stage == 1) go = false;
+        break;
+      }
+      case 2:
+        if (!s->is_dual_feasible) {
+          rc = mlp_recalc_obj_coeffs(s->eng, &s->cur_obj_val);  // 476
+          if (rc == MLP_OK) {
+            mlp_counters c;
+            mlp_get_counters(s->eng, &c);
+            s->eta_nnz = 0;  // recalc_obj_coeffs refactors whenever etas exist (1200-1203)
+            s->lu_nnz = c.lu_nnz;
+            s->stage = 3;
+          }
+        } else s->stage = 4;
+        break;
+      case 3: {
+        while (budget_left()) {
+          int moved = 0;
+          rc = primal_iteration(s, &moved);
+          if (rc != MLP_OK) break;
+          if (!moved) { s->is_dual_feasible = true; s->stage = 4; break; }
+        }
+        if (rc == MLP_OK && s->stage == 3) go = false;
+        break;
+      }
+      default:
+        s->enable_primal_steepest_edge = false;  // 482
+        mlp_engine_set_primal_steepest_edge(s->eng, 0);
+        *done = 1;
+        go = false;
+        break;
+    }
+  }
+  s->run_seconds += std::chrono::duration<double>(Clock::now() - t0).count();
+  return rc;
+}
+
+double mlp_solver_cur_obj_val(mlp_solver* s) { return s->cur_obj_val; }
+int64_t mlp_solver_pivots_done(mlp_solver* s) { return s->pivots_done; }
+int64_t mlp_solver_num_vars(mlp_solver* s) { return s->n; }
+int64_t mlp_solver_num_constraints(mlp_solver* s) { return s->m; }
+
+mlp_status mlp_solver_values(mlp_solver* s, double* out) {  // Solver::get_value, 371-376
+  std::vector<double> xb(s->m);
+  ST(mlp_download_f64(s->eng, MLP_ARR_BASIC_VALS, xb.data(), s->m));
+  std::vector<int64_t> where(s->n, -1);
+  for (int64_t r = 0; r < s->m; ++r)
+    if (s->basic_vars[r] < s->n) out[s->basic_vars[r]] = xb[r];
+  for (int64_t c = 0; c < s->n; ++c)
+    if (s->nb_vars[c] < s->n) out[s->nb_vars[c]] = s->nb_var_vals[c];
+  return MLP_OK;
+}
+
+int64_t mlp_solver_trace_len(mlp_solver* s) { return (int64_t)s->trace.size(); }
+int64_t mlp_solver_get_trace(mlp_solver* s, int64_t first, int64_t count, double* out) {
+  int64_t k = 0;
+  for (int64_t i = first; i < first + count && i < (int64_t)s->trace.size(); ++i, ++k) {
+    const PivotRecord& r = s->trace[(size_t)i];
+    double* o = out + k * 13;
+    o[0] = r.phase; o[1] = (double)r.entering_var; o[2] = (double)r.entering_col; o[3] = (double)r.leaving_row;
+    o[4] = (double)r.leaving_var; o[5] = r.pivot_coeff; o[6] = r.entering_diff; o[7] = r.obj_after;
+    o[8] = (double)r.eta_count; o[9] = (double)r.lu_nnz; o[10] = (double)r.nnz_col; o[11] = (double)r.nnz_rho; o[12] = r.refactored;
+  }
+  return k;
+}
+void mlp_solver_set_record_trace(mlp_solver* s, int32_t on) { s->record_trace = on != 0; }
+mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out) {
+  std::memcpy(out, s->nb_vars.data(), s->n * sizeof(int64_t));
+  return MLP_OK;
+}
+mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out) {
+  std::memcpy(out, s->basic_vars.data(), s->m * sizeof(int64_t));
+  return MLP_OK;
+}
+void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds) {
+  *run_seconds = s->run_seconds;
+  *refactor_seconds = s->refactor_seconds;
+}
+
+// ---------------------------------------------------------------------------------- sharding helpers
+void mlp_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* begin, int64_t* end) {
+  // contiguous blocks, sizes differ by at most one, multiples of 16 columns where possible
+  const int64_t units = (n + 15) / 16;
+  const int64_t b = units * rank / world, e = units * (rank + 1) / world;
+  *begin = std::min<int64_t>(b * 16, n);
+  *end = std::min<int64_t>(e * 16, n);
+}
+int32_t mlp_reduce_candidates(const double* scores, const int64_t* pos, const int64_t* vars, int32_t world) {
+  int32_t best = -1;
+  for (int32_t r = 0; r < world; ++r) {
+    if (vars[r] < 0) continue;
+    if (best < 0 || scores[r] > scores[best] || (scores[r] == scores[best] && pos[r] < pos[best])) best = r;
+  }
+  return best;
+}
+
+}  // extern "C"
