@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — simplex pivots/sec on the 50k x 50k dense LP (BASELINE.json config 3), 1..8 B200.
+
+A "step" is one simplex pivot (one successful Solver::pivot, solver.rs:1023) of the full revised-simplex loop:
+pricing scan, FTRAN, Harris ratio test, BTRAN, price-out, x_B / reduced-cost / steepest-edge updates (second FTRAN,
+second BTRAN, second price-out) and the eta push or refactorization.  `value` is timed with CUDA events on the engine's
+stream, `e2e` with the host clock around the same host-driven loop through the C ABI (every per-pivot host<->device
+copy inside).  The matrix A is state, like weights: it is streamed from pinned HOST buffers before the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's engine
+  python bench.py --impl reference ...                         the reference's CPU algorithm (oracle port, 1 thread)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "simplex_pivots_per_sec"
+UNIT = "pivots/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--m", type=int, default=50000)
+    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--kind", type=int, default=0, help="synthetic LP family (0 = dense_pos, see DESIGN.md)")
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0,
+                    help="bounded CPU sample for the cpu_baseline object (0 disables)")
+    ap.add_argument("--ref-budget-seconds", type=float, default=150.0, help="time cap of the --impl reference arm")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    fam = {0: "dense_pos", 1: "dense_box", 2: "dense_cover", 3: "dense_mixed"}[a.kind]
+    return f"{fam} {a.m}x{a.n} seed {a.seed} (BASELINE config 3: full pivot loop with eta updates)"
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------- CPU arms
+def cpu_port_run(a, warmup, steps, budget_s, threads_for_gen):
+    """Times the oracle port (single thread: the reference has no threads anywhere) on the same LP.
+    Returns (pivots timed, seconds, note)."""
+    import oracle
+    m = a.m
+    note = ""
+    try:
+        s = oracle.DenseSolver.synth(a.kind, m, a.n, a.seed, threads=threads_for_gen)
+    except (MemoryError, RuntimeError) as exc:  # host RAM too small for the dense 8*m*n bytes
+        m = max(1000, a.m // 4)
+        note = f" (host could not hold {a.m}x{a.n}: {type(exc).__name__}; rows cut to {m})"
+        s = oracle.DenseSolver.synth(a.kind, m, a.n, a.seed, threads=threads_for_gen)
+    s.set_record_trace(False)
+    if warmup > 0:
+        s.continue_solve(warmup)
+    done_p, sec = 0, 0.0
+    while done_p < steps and sec < budget_s:
+        fin, dt = s.continue_timed(1)
+        sec += dt
+        done_p += 1
+        if fin:
+            break
+    return done_p, sec, m, note
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wu = min(a.warmup, 1)
+    piv, sec, m_used, note = cpu_port_run(a, wu, a.steps, a.ref_budget_seconds, cores)
+    val = piv / sec if sec > 0 else 0.0
+    sample = (f"{piv} consecutive pivots after {wu} warm-up pivot(s) from the slack basis of the same {m_used}x{a.n} LP, "
+              f"time-capped at {a.ref_budget_seconds:.0f}s{note}; matrix generation and try_new excluded")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": piv, "warmup": wu,
+        "ms_per_step": 1000.0 * sec / max(piv, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "m": m_used, "n": a.n, "l2": "inputs_exceed_l2",
+                   "note": "reference = C++ port of minilp's Rust solver (oracle/), no Rust toolchain in the image"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": cores},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def build_solver(a, device, col_range=None):
+    """Stream A from pinned host buffers (generated on the host cores) into the engine, then Solver::try_new."""
+    import torch
+
+    import minilp_b200 as mb
+    t0 = time.perf_counter()
+    d, obj, mins, maxs, ops, rhs = mb.synth_vectors(a.kind, a.m, a.n, a.seed)
+    s = mb.Solver(a.m, a.n, device)
+    rows_per_chunk = max(1, min(a.m, (256 << 20) // (8 * a.n)))
+    bufs = [torch.empty(rows_per_chunk * a.n, dtype=torch.float64).pin_memory().numpy().reshape(rows_per_chunk, a.n)
+            for _ in range(2)]
+    threads = os.cpu_count() or 1
+    gen_s = up_s = 0.0
+    for i, r0 in enumerate(range(0, a.m, rows_per_chunk)):
+        nr = min(rows_per_chunk, a.m - r0)
+        buf = bufs[i % 2]
+        t1 = time.perf_counter()
+        mb.synth_rows(a.kind, a.m, a.n, a.seed, r0, nr, threads, out=buf)
+        t2 = time.perf_counter()
+        s.upload_rows(r0, buf[:nr])
+        t3 = time.perf_counter()
+        gen_s += t2 - t1
+        up_s += t3 - t2
+    obj_int = -obj if d == mb.OptimizationDirection.Maximize else obj
+    t4 = time.perf_counter()
+    s.init(obj_int, mins, maxs, ops, rhs)
+    s.engine.sync()
+    t5 = time.perf_counter()
+    setup = {"generate_host_s": round(gen_s, 3), "h2d_upload_s": round(up_s, 3), "h2d_upload_bytes": 8 * a.m * a.n,
+             "try_new_s": round(t5 - t4, 3), "total_s": round(t5 - t0, 3)}
+    return s, setup
+
+
+def load_traffic(a):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "price_traffic.json")
+    try:
+        t = json.load(open(p))
+        if t.get("m") == a.m and t.get("n") == a.n:
+            return t.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    return None
+
+
+def run_ours(a):
+    import torch
+
+    import minilp_b200 as mb
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if mb.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: minilp_b200 has no CPU fallback")
+    if world > 1:
+        from minilp_b200 import dist_bench
+        return dist_bench.run(a, METRIC, UNIT, workload_name(a))
+
+    s, setup = build_solver(a, local)
+    e = s.engine
+    s.set_record_trace(True)
+    if a.warmup > 0:
+        s.run(a.warmup)
+    c0 = e.counters()
+    p0 = s.pivots_done
+    e.profile_enable(True)
+    sampler = ClockSampler(local)
+    time.sleep(0.3)
+    torch.cuda.synchronize()
+    e.sync()
+    t0 = time.perf_counter()
+    e.event_mark(0)
+    done = s.run(a.steps)
+    e.event_mark(1)
+    e.sync()
+    t1 = time.perf_counter()
+    dev_ms = e.event_elapsed_ms(0, 1)
+    clocks = sampler.stop()
+    e.profile_enable(False)
+    prof = e.profile()
+    c1 = e.counters()
+    steps = s.pivots_done - p0
+    if steps != a.steps:
+        print(f"# note: optimum reached after {steps} timed pivots (asked for {a.steps})", file=sys.stderr)
+    wall = t1 - t0
+    value = steps / (dev_ms / 1e3)
+    e2e = steps / wall
+    run_s, refac_s = s.timers()
+    tr = s.trace()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    nv = max(prof["price_v_launches"], 1)
+    ach = prof["price_v_bytes"] / nv / (prof["price_v_ms"] / nv * 1e-3) / 1e9 if prof["price_v_ms"] > 0 else 0.0
+    iso_ms, iso_bytes = e.bench_price_dense(5)
+    roofline = {
+        "bound": "hbm", "kernel": "k_price_partial<0> + k_price_finish (N^T v of update_primal_sq_norms, solver.rs:1117-1132)",
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(a),
+        "peak_source": peak_src, "launches_timed": prof["price_v_launches"],
+        "avg_launch_ms": prof["price_v_ms"] / nv, "algorithmic_bytes_per_launch": prof["price_v_bytes"] / nv,
+        "share_of_step_time": prof["price_v_ms"] / dev_ms,
+        "isolated_dense_GBps": iso_bytes / (iso_ms * 1e-3) / 1e9,
+        "price_rho": {"launches": prof["price_rho_launches"], "ms_total": prof["price_rho_ms"],
+                      "bytes_total": prof["price_rho_bytes"]},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "m": a.m, "n": a.n, "l2": "inputs_exceed_l2 (8*m*n bytes of A are read per pivot)",
+                   "pivots_before_timed_region": p0, "optimal_reached": bool(done),
+                   "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
+                   "refactors_in_region": c1["refactors"] - c0["refactors"], "setup": setup,
+                   "objective_after": s.cur_obj_val},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT,
+                "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),
+                "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(steps, 1),
+                "wall_s": wall, "refactor_wall_s": refac_s},
+        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "roofline": roofline,
+    }
+    if a.cpu_baseline_seconds > 0:
+        cores = os.cpu_count() or 1
+        piv, sec, m_used, note = cpu_port_run(a, 0, 1000, a.cpu_baseline_seconds, cores)
+        line["cpu_baseline"] = {
+            "value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": (f"first {piv} pivots of the same {m_used}x{a.n} LP ({sec:.1f}s of single-thread CPU work; the "
+                       f"reference is single-threaded){note}"), "host_cores_available": cores}
+    del tr
+    print(json.dumps(line), flush=True)
+    s.close()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

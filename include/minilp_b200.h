@@ -193,6 +193,23 @@ mlp_status mlp_get_counters(mlp_engine* e, mlp_counters* out);
 void* mlp_engine_stream(mlp_engine* e);
 mlp_status mlp_engine_sync(mlp_engine* e);
 
+/* CUDA-event marks on the engine's stream: mark(slot) records event `slot` (0..3); elapsed gives milliseconds
+ * between two recorded marks (synchronizes on the later one). */
+mlp_status mlp_event_mark(mlp_engine* e, int32_t slot);
+mlp_status mlp_event_elapsed_ms(mlp_engine* e, int32_t slot_a, int32_t slot_b, double* ms);
+
+/* Live per-launch timing of the price-out kernel pair (k_price_partial + k_price_finish) with CUDA events on
+ * the engine's stream, accumulated over the pivots made while enabled.  Slot "v" is the N^T v product of
+ * update_primal_sq_norms (solver.rs:1117-1132; v is dense), slot "rho" the tableau-row price-out (685-692).
+ * bytes are the ALGORITHMIC bytes 8 n s + 8 s + 8 n with s the actual support size of each launch. */
+typedef struct mlp_profile {
+  double price_v_ms, price_rho_ms;
+  int64_t price_v_launches, price_rho_launches;
+  int64_t price_v_bytes, price_rho_bytes;
+} mlp_profile;
+mlp_status mlp_profile_enable(mlp_engine* e, int32_t on);
+mlp_status mlp_profile_get(mlp_engine* e, mlp_profile* out);
+
 /* Kernel-isolated bench hooks (bench.py roofline): run the price-out kernel `iters` times with a dense
  * multiplier vector over all m rows; returns the mean device time of one launch pair in milliseconds. */
 mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_launch, int64_t* bytes_per_launch);

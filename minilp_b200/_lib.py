@@ -54,6 +54,11 @@ class Counters(C.Structure):
                 ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64)]
 
 
+class Profile(C.Structure):
+    _fields_ = [("price_v_ms", f64), ("price_rho_ms", f64), ("price_v_launches", i64), ("price_rho_launches", i64),
+                ("price_v_bytes", i64), ("price_rho_bytes", i64)]
+
+
 # every symbol include/minilp_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "mlp_last_error": (C.c_char_p, []),
@@ -82,6 +87,10 @@ SIGNATURES = {
     "mlp_engine_stream": (vp, [vp]),
     "mlp_engine_sync": (i32, [vp]),
     "mlp_bench_price_dense": (i32, [vp, i32, pd, pi64]),
+    "mlp_event_mark": (i32, [vp, i32]),
+    "mlp_event_elapsed_ms": (i32, [vp, i32, i32, pd]),
+    "mlp_profile_enable": (i32, [vp, i32]),
+    "mlp_profile_get": (i32, [vp, C.POINTER(Profile)]),
     "mlp_solver_create_dense": (i32, [C.c_int, i64, i64, C.POINTER(vp)]),
     "mlp_solver_destroy": (None, [vp]),
     "mlp_solver_engine": (vp, [vp]),

@@ -4,8 +4,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (Counters, DualEntering, DualRow, Entering, InitState, Leaving, PivotInfo, PivotResult, pd, pi32, pi64,
-                   pu8)
+from ._lib import (Counters, DualEntering, DualRow, Entering, InitState, Leaving, PivotInfo, PivotResult, Profile, pd, pi32,
+                   pi64, pu8)
 
 INF = float("inf")
 
@@ -181,6 +181,22 @@ class Engine:
     def sync(self):
         _check(_lib.lib().mlp_engine_sync(self._e))
 
+    def event_mark(self, slot):
+        _check(_lib.lib().mlp_event_mark(self._e, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        _check(_lib.lib().mlp_event_elapsed_ms(self._e, a, b, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        _check(_lib.lib().mlp_profile_enable(self._e, int(on)))
+
+    def profile(self):
+        p = Profile()
+        _check(_lib.lib().mlp_profile_get(self._e, C.byref(p)))
+        return {k: getattr(p, k) for k, _ in Profile._fields_}
+
     def bench_price_dense(self, iters):
         ms, by = C.c_double(), C.c_int64()
         _check(_lib.lib().mlp_bench_price_dense(self._e, iters, C.byref(ms), C.byref(by)))
@@ -201,7 +217,7 @@ class Solver:
         self.engine = Engine(C.c_void_p(_lib.lib().mlp_solver_engine(h)), m, n)
 
     def close(self):
-        if getattr(self, "_s", None):
+        if getattr(self, "_s", None) and _lib is not None and getattr(_lib, "lib", None) is not None:
             _lib.lib().mlp_solver_destroy(self._s)
             self._s = None
 

@@ -94,6 +94,12 @@ struct mlp_engine {
   double *tK = nullptr;               // Kcap
   int64_t lu_nnz = 0;
 
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t pev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][begin/end]; slot 0 rho, 1 v
+  bool ppending[2] = {false, false};
+  int prof_on = 0;
+  mlp_profile prof{};
+
   std::vector<int32_t> h_bvar;
   std::vector<int32_t> h_last_eta_of_row;  // m, -1 if none
   mlp_counters cnt{};
@@ -1014,11 +1020,31 @@ static int price_chunks(const mlp_engine* e) {
 
 // out (var-indexed) = N^T w over the listed rows (+ slack part), basic entries zeroed
 static mlp_status price_list(mlp_engine* e, const int32_t* rows, const double* wts, const int32_t* count_ptr, int fixed_count,
-                             const double* slack_vals, double* out) {
+                             const double* slack_vals, double* out, int prof_slot = -1) {
   const int C = price_chunks(e);
   dim3 grid(cdiv(e->lda, PR_TILE), C);
+  const bool prof = e->prof_on && prof_slot >= 0;
+  if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], e->stream));
   LAUNCH(e, k_price_partial<0>, grid, PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, e->partial);
   LAUNCH(e, k_price_finish, cdiv(e->nt, 256), 256, 0, e->partial, C, e->lda, e->n, e->m, slack_vals, e->vflag, out, 0);
+  if (prof) {
+    CU(cudaEventRecord(e->pev[prof_slot][1], e->stream));
+    e->ppending[prof_slot] = true;
+  }
+  return MLP_OK;
+}
+// after a stream sync: fold pending price-out timings into the profile. support sizes come from h_res->i[2..3].
+static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
+  for (int slot = 0; slot < 2; ++slot) {
+    if (!e->ppending[slot]) continue;
+    e->ppending[slot] = false;
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e->pev[slot][0], e->pev[slot][1]));
+    const int64_t sz = slot == 0 ? s_rho : s_v;
+    const int64_t bytes = 8 * e->n * sz + 8 * sz + 8 * e->n;
+    if (slot == 0) { e->prof.price_rho_ms += ms; e->prof.price_rho_launches += 1; e->prof.price_rho_bytes += bytes; }
+    else { e->prof.price_v_ms += ms; e->prof.price_v_launches += 1; e->prof.price_v_bytes += bytes; }
+  }
   return MLP_OK;
 }
 
@@ -1067,8 +1093,11 @@ static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
 
 static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
-  int64_t cap = std::max<int64_t>(32, e->kcap);
+  // first allocation is generous (up to ~1 GB for the basis columns): cudaFree/cudaMalloc of the big arenas
+  // costs tens of milliseconds, so capacity grows by doubling and rarely
+  int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->m)))));
   while (cap < k) cap *= 2;
+  cap = std::min<int64_t>(cap, e->m);
   dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
   e->kcap = cap;
   ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jvar, cap)); ST(dev_alloc(&e->Rp, cap));
@@ -1077,7 +1106,7 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
 }
 static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
   if (K <= e->Kcap && e->E) return MLP_OK;
-  int64_t cap = std::max<int64_t>(32, e->Kcap);
+  int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->m))));
   while (cap < K) cap *= 2;
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
   e->Kcap = cap;
@@ -1163,6 +1192,8 @@ mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine*
   A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16)); A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
   if (st != MLP_OK) { mlp_engine_destroy(e); return st; }
   CU(cudaHostAlloc((void**)&e->h_res, sizeof(DevRes), cudaHostAllocDefault));
+  for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) CU(cudaEventCreate(&e->pev[i][j]));
   CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->red_counter, 0, 4 * sizeof(unsigned), e->stream));
   CU(cudaMemsetAsync(e->d_res, 0, sizeof(DevRes), e->stream));
@@ -1188,6 +1219,8 @@ void mlp_engine_destroy(mlp_engine* e) {
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
   if (e->h_res) cudaFreeHost(e->h_res);
+  for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (e->pev[i][j]) cudaEventDestroy(e->pev[i][j]);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1328,7 +1361,7 @@ mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
 mlp_status mlp_price_row(mlp_engine* e) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  return price_list(e, e->list_idx, e->list_val, e->icnt, 0, e->rho, e->rc);
+  return price_list(e, e->list_idx, e->list_val, e->icnt, 0, e->rho, e->rc, 0);
 }
 
 mlp_status mlp_calc_row_coeffs(mlp_engine* e, int64_t row) {
@@ -1403,7 +1436,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     CU(cudaMemcpyAsync(e->work_m, e->alpha, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
     ST(btran(e, e->work_m, -1, e->vvec));
     LAUNCH(e, k_compact, 1, 1024, 0, e->vvec, m, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
-    ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));
+    ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
   }
   LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, q, pi->coeff, e->enable_pse,
          e->scal, e->d_res->flags);
@@ -1421,7 +1454,12 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   }
   // one device->host read per pivot: status flags, leaving var, nnz(alpha)
   CU(cudaMemcpyAsync(&e->d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+  if (e->prof_on) {
+    CU(cudaMemcpyAsync(&e->d_res->i[2], e->icnt + 0, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(&e->d_res->i[3], e->icnt + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+  }
   ST(fetch_res(e));
+  if (e->prof_on) ST(collect_profile(e, e->h_res->i[2] & 0xffffffffLL, e->h_res->i[3] & 0xffffffffLL));
   out->leaving_var = e->h_res->i[0];
   out->col_nnz = (int64_t)(int32_t)(e->h_res->i[1] & 0xffffffffLL);
   if (out->leaving_var != lv_host) { set_err("pivot: host/device basis mirrors diverged"); return MLP_INVALID; }
@@ -1500,6 +1538,34 @@ mlp_status mlp_engine_sync(mlp_engine* e) {
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
   CU(cudaGetLastError());
+  return MLP_OK;
+}
+
+mlp_status mlp_event_mark(mlp_engine* e, int32_t slot) {
+  if (!e || slot < 0 || slot > 3) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventRecord(e->ev[slot], e->stream));
+  return MLP_OK;
+}
+mlp_status mlp_event_elapsed_ms(mlp_engine* e, int32_t a, int32_t b, double* ms) {
+  if (!e || a < 0 || a > 3 || b < 0 || b > 3) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventSynchronize(e->ev[b]));
+  float f = 0.f;
+  CU(cudaEventElapsedTime(&f, e->ev[a], e->ev[b]));
+  *ms = f;
+  return MLP_OK;
+}
+mlp_status mlp_profile_enable(mlp_engine* e, int32_t on) {
+  if (!e) return MLP_INVALID;
+  e->prof_on = on;
+  e->ppending[0] = e->ppending[1] = false;
+  if (on) e->prof = mlp_profile{};
+  return MLP_OK;
+}
+mlp_status mlp_profile_get(mlp_engine* e, mlp_profile* out) {
+  if (!e || !out) return MLP_INVALID;
+  *out = e->prof;
   return MLP_OK;
 }
 

@@ -466,6 +466,11 @@ struct CsMatrix {  // faithful storage
     for (usize p = c_ptr[v]; p < c_ptr[v + 1]; ++p) f(c_idx[p], c_val[p]);
   }
   usize col_len(usize v) const { return c_ptr[v + 1] - c_ptr[v]; }
+  // sprs squared_l2_norm of every column: sum of squares in storage (ascending row) order
+  void col_sq_norms(usize nvars, std::vector<double>& out) const {
+    out.assign(nvars, 0.0);
+    for (usize v = 0; v < nvars; ++v) for_col(v, [&](usize, double x) { out[v] += x * x; });
+  }
 };
 
 // Memory-lean storage for fully dense A (every a_ij is a stored entry, exactly
@@ -489,6 +494,15 @@ struct DenseMatrix {
     else f(v - n_struct, 1.0);
   }
   usize col_len(usize v) const { return v < n_struct ? n_rows : 1; }
+  // same per-column accumulation order (rows ascending) as CsMatrix::col_sq_norms, swept row-major for locality
+  void col_sq_norms(usize nvars, std::vector<double>& out) const {
+    out.assign(nvars, 0.0);
+    for (usize r = 0; r < n_rows; ++r) {
+      const double* row = a + r * n_struct;
+      for (usize v = 0; v < n_struct && v < nvars; ++v) out[v] += row[v] * row[v];
+    }
+    for (usize v = n_struct; v < nvars; ++v) out[v] = 1.0;
+  }
 };
 
 enum class ComparisonOp { Eq = 0, Le = 1, Ge = 2 };  // lib.rs:160-169
@@ -696,6 +710,8 @@ struct Solver {  // solver.rs:14-58
     if (enable_dual_steepest_edge) dual_edge_sq_norms.assign(basic_vars.size(), 1.0);
     enable_primal_steepest_edge = enable_steepest_edge && !is_dual_feasible;  // 272
     if (enable_primal_steepest_edge) sq_norms_update_helper.assign(total - num_constraints_, 0.0);
+    std::vector<double> col_norms;
+    if (enable_primal_steepest_edge) mat.col_sq_norms(total, col_norms);
     for (usize k = 0; k < nb_vars.size(); ++k) {  // 281-300
       usize var = nb_vars[k];
       const NonBasicVarState& st = nb_var_states[k];
@@ -703,11 +719,7 @@ struct Solver {  // solver.rs:14-58
         double c = (st.at_min && !st.at_max) ? 1.0 : (st.at_max && !st.at_min) ? -1.0 : 0.0;
         nb_var_obj_coeffs.push_back(c);
       } else nb_var_obj_coeffs.push_back(orig_obj_coeffs[var]);
-      if (enable_primal_steepest_edge) {
-        double s = 0.0;  // sprs squared_l2_norm: sum of squares in storage order
-        mat.for_col(var, [&](usize, double v) { s += v * v; });
-        primal_edge_sq_norms.push_back(s + 1.0);
-      }
+      if (enable_primal_steepest_edge) primal_edge_sq_norms.push_back(col_norms[var] + 1.0);  // 297-299
     }
     cur_obj_val = need_artificial_obj ? 0.0 : iv.obj_val;
     basis_solver.scratch = ScratchSpace(num_constraints_);  // 304

@@ -2,6 +2,8 @@
 simplex path.  Each test names the reference test it restates (file:line under /root/reference/src).
 The reference is pure Rust and cannot be executed in this image; these vectors are the asserted values
 of its own #[test]s and doctests."""
+import os
+
 import numpy as np
 import pytest
 
@@ -306,32 +308,7 @@ def test_sparse_mat_transpose():
 
 
 # ----------------------------------------------------------------------------- mps.rs
-MPS_TEST_FILE = """\
-* test file
-NAME          TESTPROB
-ROWS
- N  COST
- L  LIM1
- G  LIM2
- E  MYEQN
-COLUMNS
-    XONE      COST                 1   LIM1                 1
-    XONE      LIM2                 1
-
-    YTWO      COST                 4   LIM1                 1
-    YTWO      MYEQN               -1
-
-    ZTHREE    COST                 9   LIM2                 1
-    ZTHREE    MYEQN                1
-RHS
-    RHS1      LIM1                 5   LIM2                10
-    RHS1      MYEQN                7
-BOUNDS
- UP BND1      XONE                 4
- LO BND1      YTWO                -1
- UP BND1      YTWO                 1
-ENDATA
-"""
+MPS_TEST_FILE = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testprob.mps")).read()
 
 
 def test_mps_parse_and_solve():

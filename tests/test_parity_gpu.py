@@ -215,7 +215,8 @@ def test_empty_constraints_and_unbounded_on_gpu():
 
 def test_mps_problem_on_gpu():
     """mps.rs:437-476: parse with the oracle's restated parser (host I/O), solve on the device."""
-    from tests.test_oracle_golden import MPS_TEST_FILE
+    import os
+    MPS_TEST_FILE = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testprob.mps")).read()
     f = oracle.MpsFile.parse(MPS_TEST_FILE, oracle.OptimizationDirection.Minimize)
     obj, mins, maxs, row_ptr, col_idx, vals, ops, rhs = f.problem.export()
     p = mb.Problem(mb.OptimizationDirection.Minimize)
