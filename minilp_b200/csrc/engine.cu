@@ -78,6 +78,9 @@ struct mlp_engine {
   unsigned* red_counter = nullptr;
   double* scal = nullptr;       // device scalars: [0] max_step [1] rho sumsq [2] alpha sumsq [3] v sumsq ...
   int32_t* icnt = nullptr;      // device ints: [0] rho nnz [1] alpha nnz [2] v nnz
+  int32_t* seg_cnt = nullptr;   // compaction: per-segment counts / sums of squares
+  double* seg_ss = nullptr;
+  double *gt_part_k = nullptr, *gt_part_K = nullptr;  // k_gemv_t partials: GT_MAXSPLIT x kcap / Kcap
   DevRes* d_res = nullptr;
   DevRes* h_res = nullptr;  // pinned
 
@@ -317,43 +320,61 @@ __global__ void k_price_finish(const double* __restrict__ partial, int C, int64_
 // ------------------------------------------------------------------------------------------------ compaction
 // ScatteredVec::to_sparse_vec (sparse.rs:115-121) for a device work vector: ordered list of the non-zero
 // entries (ascending index), their count, and the sum of squares (SparseVec::sq_norm, sparse.rs:32-34).
-__global__ void __launch_bounds__(1024) k_compact(const double* __restrict__ x, int m, int32_t* __restrict__ idx,
-                                                   double* __restrict__ val, int32_t* __restrict__ count,
-                                                   double* __restrict__ sumsq) {
+// Pass 1: every CTA counts the non-zeros and sums the squares of its 1024-entry segment; the last CTA to
+// finish adds the per-segment results in segment order (deterministic).  Pass 2 (only when the list is
+// needed): each CTA derives its output offset from the segment counts and writes its entries in order.
+constexpr int CP_SEG = 1024;
+__global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restrict__ x, int m, int32_t* __restrict__ seg_cnt,
+                                                           double* __restrict__ seg_ss, unsigned* counter,
+                                                           int32_t* __restrict__ count, double* __restrict__ sumsq) {
+  __shared__ double sm[32];
+  __shared__ int smi[32];
+  const int i = blockIdx.x * CP_SEG + threadIdx.x;
+  const double v = i < m ? x[i] : 0.0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(FULLMASK, v != 0.0);
+  if (lane == 0) smi[wid] = __popc(bal);
+  const double ss = block_sum(v * v, sm);  // has the barriers that publish smi
+  if (threadIdx.x == 0) {
+    int c = 0;
+    for (int w2 = 0; w2 < 32; ++w2) c += smi[w2];
+    seg_cnt[blockIdx.x] = c;
+    seg_ss[blockIdx.x] = ss;
+  }
+  if (!last_block(counter)) return;
+  if (threadIdx.x == 0) {
+    int c = 0;
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { c += __ldcg(seg_cnt + b); t += __ldcg(seg_ss + b); }
+    *count = c;
+    *sumsq = t;
+    *counter = 0;
+  }
+}
+__global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restrict__ x, int m, const int32_t* __restrict__ seg_cnt,
+                                                           int32_t* __restrict__ idx, double* __restrict__ val) {
   __shared__ int warp_cnt[32];
   __shared__ int base;
-  __shared__ double sm[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) base = 0;
-  double ss = 0.0;
+  if (wid == 0) {  // offset of this segment = sum of the counts of the segments before it
+    int acc = 0;
+    for (int b = lane; b < (int)blockIdx.x; b += 32) acc += seg_cnt[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULLMASK, acc, o);
+    if (lane == 0) base = acc;
+  }
+  const int i = blockIdx.x * CP_SEG + threadIdx.x;
+  const double v = i < m ? x[i] : 0.0;
+  const bool nz = v != 0.0;
+  const unsigned bal = __ballot_sync(FULLMASK, nz);
+  if (lane == 0) warp_cnt[wid] = __popc(bal);
   __syncthreads();
-  for (int i0 = 0; i0 < m; i0 += 1024) {
-    const int i = i0 + threadIdx.x;
-    const double v = i < m ? x[i] : 0.0;
-    const bool nz = v != 0.0;
-    ss += v * v;
-    const unsigned bal = __ballot_sync(FULLMASK, nz);
-    if (lane == 0) warp_cnt[wid] = __popc(bal);
-    __syncthreads();
+  if (nz) {
     int off = base;
     for (int w2 = 0; w2 < wid; ++w2) off += warp_cnt[w2];
-    if (nz && idx) {
-      const int p = off + __popc(bal & ((1u << lane) - 1u));
-      idx[p] = i;
-      val[p] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int tot = 0;
-      for (int w2 = 0; w2 < 32; ++w2) tot += warp_cnt[w2];
-      base += tot;
-    }
-    __syncthreads();
-  }
-  const double tot = block_sum(ss, sm);
-  if (threadIdx.x == 0) {
-    *count = base;
-    *sumsq = tot;
+    const int p = off + __popc(bal & ((1u << lane) - 1u));
+    idx[p] = i;
+    val[p] = v;
   }
 }
 
@@ -459,22 +480,30 @@ __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M
   if (i < rows) y[i] = acc;
 }
 
-// out[j] = base[j] - sum_i M[i + j*ld] * x[i]  (base may be null => 0; sign=+1 gives plain dot products)
-// One CTA per column. Used for BTRAN: u = E^T rhs (solver.rs:1326-1330) and the core right-hand side.
-__global__ void __launch_bounds__(256) k_gemv_t(const double* __restrict__ M, int64_t ld, int rows, int cols,
-                                                 const double* __restrict__ x, const double* __restrict__ base,
-                                                 const int32_t* __restrict__ base_idx, double* __restrict__ out, int negate) {
+// out[j] = base[idx[j]] - sum_i M[i + j*ld] * x[i]   (negate) or the plain dot products.
+// Grid (cols, S): CTA (j, s) reduces row slice s of column j; k_gemv_t_fin adds the S partials in order.
+// Used for BTRAN: u = E^T rhs (solver.rs:1326-1330) and the right-hand side of the core solve.
+constexpr int GT_MAXSPLIT = 16;
+__global__ void __launch_bounds__(256) k_gemv_t_part(const double* __restrict__ M, int64_t ld, int rows, int cols,
+                                                      const double* __restrict__ x, double* __restrict__ part) {
   __shared__ double sm[32];
-  const int j = blockIdx.x;
-  if (j >= cols) return;
+  const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
+  const int L = (rows + S - 1) / S;
+  const int r0 = sidx * L, r1 = min(rows, r0 + L);
   const double* p = M + (int64_t)j * ld;
   double acc = 0.0;
-  for (int i = threadIdx.x; i < rows; i += blockDim.x) acc += p[i] * x[i];
+  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
   const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) {
-    double b = base ? base[base_idx ? base_idx[j] : j] : 0.0;
-    out[j] = negate ? b - tot : tot;
-  }
+  if (threadIdx.x == 0) part[(int64_t)sidx * cols + j] = tot;
+}
+__global__ void k_gemv_t_fin(const double* __restrict__ part, int S, int cols, const double* __restrict__ base,
+                             const int32_t* __restrict__ base_idx, double* __restrict__ out, int negate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  double tot = 0.0;
+  for (int q = 0; q < S; ++q) tot += part[(int64_t)q * cols + j];
+  const double b = base ? base[base_idx ? base_idx[j] : j] : 0.0;
+  out[j] = negate ? b - tot : tot;
 }
 
 __global__ void k_gather_idx(const double* __restrict__ src, const int32_t* __restrict__ idx, int cnt, double* __restrict__ dst) {
@@ -1048,6 +1077,21 @@ static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
   return MLP_OK;
 }
 
+// list / stats of a dense m-vector (see k_compact_count). idx == nullptr: stats only.
+static void compact(mlp_engine* e, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq) {
+  const int m = (int)e->m, nseg = cdiv(m, CP_SEG);
+  LAUNCH(e, k_compact_count, nseg, CP_SEG, 0, x, m, e->seg_cnt, e->seg_ss, e->red_counter, count, sumsq);
+  if (idx) LAUNCH(e, k_compact_write, nseg, CP_SEG, 0, x, m, e->seg_cnt, idx, val);
+}
+static void gemv_t(mlp_engine* e, const double* M, int64_t ld, int rows, int cols, const double* x, double* part,
+                   const double* base, const int32_t* base_idx, double* out, int negate) {
+  if (cols <= 0) return;
+  int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(2 * (int64_t)e->sm_count, cols)));
+  S = std::min(S, std::max(1, rows / 2048));
+  LAUNCH(e, k_gemv_t_part, dim3((unsigned)cols, (unsigned)S), 256, 0, M, ld, rows, cols, x, part);
+  LAUNCH(e, k_gemv_t_fin, cdiv(cols, 256), 256, 0, part, S, cols, base, base_idx, out, negate);
+}
+
 template <bool FWD, bool AXPY, bool UNIT> static void trsv(mlp_engine* e, const double* M, int64_t ld, int n, double* x) {
   if (n <= 0) return;
   auto kern = k_trsv<FWD, AXPY, UNIT>;
@@ -1077,13 +1121,13 @@ static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   if (K > 0) {  // etas in reverse, 1325-1333
     if (unit_row >= 0) LAUNCH(e, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->m, unit_row, K, e->tK);
-    else LAUNCH(e, k_gemv_t, K, 256, 0, e->E, e->m, m, K, c, (const double*)nullptr, (const int32_t*)nullptr, e->tK, 0);
+    else gemv_t(e, e->E, e->m, m, K, c, e->gt_part_K, nullptr, nullptr, e->tK, 0);
     trsv<false, false, true>(e, e->G, e->Kcap, K, e->tK);
     LAUNCH(e, k_eta_scatter, cdiv(K, 256), 256, 0, e->tK, e->etaR, e->etaPrev, e->etaHead, K, c);
   }
   LAUNCH(e, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, e->work_m2);
   if (k > 0) {
-    LAUNCH(e, k_gemv_t, k, 256, 0, e->Bcols, e->m, m, k, e->work_m2, c, e->Jpos, e->xk, 1);
+    gemv_t(e, e->Bcols, e->m, m, k, e->work_m2, e->gt_part_k, c, e->Jpos, e->xk, 1);
     trsv<true, false, false>(e, e->LUc, e->kcap, k, e->xk);  // U^T z = rhs   (lu_factors_transp.lower = U^T, lu.rs:110)
     trsv<false, false, true>(e, e->LUc, e->kcap, k, e->xk);  // L^T y = z
     LAUNCH(e, k_scatter_idx, cdiv(k, 256), 256, 0, e->xk, e->Rp, k, out);
@@ -1099,7 +1143,9 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   while (cap < k) cap *= 2;
   cap = std::min<int64_t>(cap, e->m);
   dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
+  dev_free(e->gt_part_k);
   e->kcap = cap;
+  ST(dev_alloc(&e->gt_part_k, (size_t)GT_MAXSPLIT * cap));
   ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jvar, cap)); ST(dev_alloc(&e->Rp, cap));
   ST(dev_alloc(&e->Bcols, (size_t)e->m * cap)); ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->xk, cap));
   return MLP_OK;
@@ -1109,7 +1155,9 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
   int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->m))));
   while (cap < K) cap *= 2;
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
+  dev_free(e->gt_part_K);
   e->Kcap = cap;
+  ST(dev_alloc(&e->gt_part_K, (size_t)GT_MAXSPLIT * cap));
   ST(dev_alloc(&e->E, (size_t)e->m * cap)); ST(dev_alloc(&e->G, (size_t)cap * cap));
   ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap)); ST(dev_alloc(&e->tK, cap));
   return MLP_OK;
@@ -1189,7 +1237,8 @@ mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine*
   A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m));
   A(dev_alloc(&e->partial, (size_t)e->max_chunks * e->lda));
   A(dev_alloc(&e->red_f, 4096)); A(dev_alloc(&e->red_i, 4096)); A(dev_alloc(&e->red_counter, 4));
-  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16)); A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
+  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
+  A(dev_alloc(&e->seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->seg_ss, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
   if (st != MLP_OK) { mlp_engine_destroy(e); return st; }
   CU(cudaHostAlloc((void**)&e->h_res, sizeof(DevRes), cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
@@ -1218,6 +1267,7 @@ void mlp_engine_destroy(mlp_engine* e) {
   dev_free(e->red_f); dev_free(e->red_i); dev_free(e->red_counter); dev_free(e->scal); dev_free(e->icnt); dev_free(e->d_res);
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
+  dev_free(e->seg_cnt); dev_free(e->seg_ss); dev_free(e->gt_part_k); dev_free(e->gt_part_K);
   if (e->h_res) cudaFreeHost(e->h_res);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (e->pev[i][j]) cudaEventDestroy(e->pev[i][j]);
@@ -1328,7 +1378,7 @@ mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   LAUNCH(e, k_load_col, cdiv(e->m, 256), 256, 0, e->A, e->lda, e->n, (int)e->m, var, e->work_m);
   ST(ftran(e, e->work_m, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
-  LAUNCH(e, k_compact, 1, 1024, 0, e->alpha, (int)e->m, (int32_t*)nullptr, (double*)nullptr, e->icnt + 1, e->scal + 2);
+  compact(e, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
   return MLP_OK;
 }
 
@@ -1354,7 +1404,7 @@ mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
   LAUNCH(e, k_set_unit, cdiv(e->m, 256), 256, 0, e->work_m, e->m, row);
   ST(btran(e, e->work_m, (int)row, e->rho));
   // inv_basis_row_coeffs as a sparse list + |rho|^2 (solver.rs:683, 1160)
-  LAUNCH(e, k_compact, 1, 1024, 0, e->rho, (int)e->m, e->list_idx, e->list_val, e->icnt, e->scal + 1);
+  compact(e, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
   return MLP_OK;
 }
 
@@ -1435,7 +1485,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     // v = B^-T alpha_q (1114), helper = N^T v (1117-1132)
     CU(cudaMemcpyAsync(e->work_m, e->alpha, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
     ST(btran(e, e->work_m, -1, e->vvec));
-    LAUNCH(e, k_compact, 1, 1024, 0, e->vvec, m, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
+    compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
     ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
   }
   LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, q, pi->coeff, e->enable_pse,
@@ -1480,7 +1530,7 @@ mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {
   if (e->K > 0) ST(refactor_impl(e));  // solver.rs:1200-1203
   LAUNCH(e, k_gather_cB, cdiv(m, 256), 256, 0, e->cobj, e->bvar, m, e->work_m);
   ST(btran(e, e->work_m, -1, e->vvec));  // multipliers y (1205-1214)
-  LAUNCH(e, k_compact, 1, 1024, 0, e->vvec, m, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
+  compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
   ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));
   LAUNCH(e, k_recalc_d, cdiv(e->nt, 256), 256, 0, e->cobj, e->helper, e->vflag, e->nt, e->d);
   LAUNCH(e, k_recalc_obj, 1, 1024, 0, e->cobj, e->bvar, e->xB, m, e->xnb, e->vflag, e->nt, e->d_res);
@@ -1574,7 +1624,7 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
   LAUNCH(e, k_fill, cdiv(m, 256), 256, 0, e->vvec, (int64_t)m, 0.5);
-  LAUNCH(e, k_compact, 1, 1024, 0, e->vvec, m, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
+  compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a));
   CU(cudaEventCreate(&b));
