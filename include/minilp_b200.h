@@ -56,9 +56,28 @@ typedef struct mlp_engine mlp_engine;
 /* Allocate the device-resident state for an m x n dense constraint matrix A (row-major f64 in HBM).
  * Replaces the storage half of Solver (solver.rs:15-58: orig_constraints / orig_constraints_csc). */
 mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out);
+/* Column-sharded engine: rank `rank` of `world` owns the structural columns
+ * mlp_shard_range(n_global, world, rank) of A and all per-variable arrays of those columns; m-sized state and the
+ * basis factors are replicated and every rank runs the identical host control loop (SPMD).  All variable indices
+ * in this ABI stay GLOBAL.  The one exchange step per pivot — arg-reduce of the per-shard pricing candidates plus
+ * the winner's column — is a single all-gather inside mlp_select_entering_primal / mlp_ratio_dual.
+ *   comm_kind MLP_COMM_NCCL : comm_arg = 128-byte ncclUniqueId from mlp_nccl_get_unique_id (one process per GPU)
+ *   comm_kind MLP_COMM_LOCAL: comm_arg = handle from mlp_local_group_create (one host thread per shard, one process) */
+#define MLP_COMM_NONE 0
+#define MLP_COMM_NCCL 1
+#define MLP_COMM_LOCAL 2
+mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
+                                           int32_t comm_kind, const void* comm_arg, mlp_engine** out);
+mlp_status mlp_nccl_get_unique_id(void* out128);
+mlp_status mlp_local_group_create(int32_t world, void** out);
+void mlp_local_group_destroy(void* group);
+mlp_status mlp_engine_local_range(mlp_engine* e, int64_t* col_begin, int64_t* col_end);
 void mlp_engine_destroy(mlp_engine* e);
-/* Stream `nrows` consecutive rows of A (row-major, n doubles each) from HOST memory, starting at row0. */
+/* Stream `nrows` consecutive rows of A from HOST memory, starting at row0: full rows of n_global doubles (a sharded
+ * engine takes its own column slice) ... */
 mlp_status mlp_engine_upload_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host);
+/* ... or rows that hold only this shard's columns (col_end - col_begin doubles each). */
+mlp_status mlp_engine_upload_local_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_local);
 
 /* State at the end of Solver::try_new (solver.rs:108-369).  Arrays are HOST pointers.
  * Position-indexed arrays (nb_*) have n entries, row-indexed ones m, var-indexed ones n+m. */
@@ -67,7 +86,7 @@ typedef struct mlp_init_state {
   const double* orig_var_maxs;        /* n+m  solver.rs:20,225 */
   const double* orig_obj_coeffs;      /* n+m  solver.rs:18,244-245 (internal sign: Maximize already negated) */
   const double* orig_rhs;             /* m    solver.rs:23 */
-  const int64_t* nb_vars;             /* n    solver.rs:44 */
+  const int64_t* nb_vars;             /* n    solver.rs:44 (n = n_global on a sharded engine: every rank gets the full arrays) */
   const double* nb_var_vals;          /* n    solver.rs:46 */
   const double* nb_var_obj_coeffs;    /* n    solver.rs:45,279-295 */
   const uint8_t* nb_var_states;       /* n    MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED */
@@ -96,7 +115,7 @@ typedef struct mlp_entering {
   double obj_coeff; /* nb_var_obj_coeffs[pos] */
   double score;
   double cur_val;   /* nb_var_vals[pos] */
-  double var_min, var_max;
+  double var_min, var_max; /* unused (0): the host keeps orig_var_mins / orig_var_maxs, solver.rs:19-20 */
 } mlp_entering;
 mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out);
 
@@ -141,6 +160,7 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
  * which the host takes from the running eta nnz and lu_nnz. */
 typedef struct mlp_pivot_info {
   int64_t entering_var, col;
+  double entering_obj_coeff; /* nb_var_obj_coeffs[col] as returned by the selection (the column may live on another shard) */
   double entering_new_val, entering_diff;
   int32_t has_elem;
   int64_t row;
@@ -221,6 +241,9 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
 typedef struct mlp_solver mlp_solver;
 
 mlp_status mlp_solver_create_dense(int device, int64_t m, int64_t n, mlp_solver** out);
+mlp_status mlp_solver_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
+                                           int32_t comm_kind, const void* comm_arg, mlp_solver** out);
+mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local);
 void mlp_solver_destroy(mlp_solver* s);
 mlp_engine* mlp_solver_engine(mlp_solver* s);
 mlp_status mlp_solver_upload_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_host);
@@ -256,6 +279,9 @@ int32_t mlp_reduce_candidates(const double* scores, const int64_t* pos, const in
 /* Independent implementation of the generator the oracle defines in oracle/synth_lp.hpp. */
 void mlp_synth_rows(int32_t kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, int32_t threads,
                     double* out_rows);
+/* the column block [col0, col0+ncols) of those rows (nrows x ncols row-major): what one shard uploads */
+void mlp_synth_block(int32_t kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, int64_t col0,
+                     int64_t ncols, int32_t threads, double* out_block);
 /* obj (user sign), mins, maxs: n; ops, rhs: m. Returns the optimization direction (0 min, 1 max).
  * Kind 3 needs A·x0 and therefore generates rows internally. */
 int32_t mlp_synth_vectors(int32_t kind, int64_t m, int64_t n, uint64_t seed, double* obj, double* mins, double* maxs,

@@ -41,7 +41,7 @@ class DualEntering(C.Structure):
 
 
 class PivotInfo(C.Structure):
-    _fields_ = [("entering_var", i64), ("col", i64), ("entering_new_val", f64), ("entering_diff", f64), ("has_elem", i32),
+    _fields_ = [("entering_var", i64), ("col", i64), ("entering_obj_coeff", f64), ("entering_new_val", f64), ("entering_diff", f64), ("has_elem", i32),
                 ("row", i64), ("coeff", f64), ("leaving_new_val", f64), ("refactor", i32)]
 
 
@@ -66,6 +66,12 @@ SIGNATURES = {
     "mlp_device_count": (C.c_int, []),
     "mlp_engine_create_dense": (i32, [C.c_int, i64, i64, C.POINTER(vp)]),
     "mlp_engine_destroy": (None, [vp]),
+    "mlp_engine_create_dense_sharded": (i32, [C.c_int, i64, i64, i32, i32, i32, vp, C.POINTER(vp)]),
+    "mlp_nccl_get_unique_id": (i32, [vp]),
+    "mlp_local_group_create": (i32, [i32, C.POINTER(vp)]),
+    "mlp_local_group_destroy": (None, [vp]),
+    "mlp_engine_local_range": (i32, [vp, pi64, pi64]),
+    "mlp_engine_upload_local_rows": (i32, [vp, i64, i64, pd]),
     "mlp_engine_upload_rows": (i32, [vp, i64, i64, pd]),
     "mlp_engine_init_state": (i32, [vp, C.POINTER(InitState)]),
     "mlp_engine_set_primal_steepest_edge": (i32, [vp, i32]),
@@ -93,6 +99,8 @@ SIGNATURES = {
     "mlp_profile_get": (i32, [vp, C.POINTER(Profile)]),
     "mlp_solver_create_dense": (i32, [C.c_int, i64, i64, C.POINTER(vp)]),
     "mlp_solver_destroy": (None, [vp]),
+    "mlp_solver_create_dense_sharded": (i32, [C.c_int, i64, i64, i32, i32, i32, vp, C.POINTER(vp)]),
+    "mlp_solver_upload_local_rows": (i32, [vp, i64, i64, pd]),
     "mlp_solver_engine": (vp, [vp]),
     "mlp_solver_upload_rows": (i32, [vp, i64, i64, pd]),
     "mlp_solver_init": (i32, [vp, pd, pd, pd, pi32, pd]),
@@ -111,6 +119,7 @@ SIGNATURES = {
     "mlp_shard_range": (None, [i64, i32, i32, pi64, pi64]),
     "mlp_reduce_candidates": (i32, [pd, pi64, pi64, i32]),
     "mlp_synth_rows": (None, [i32, i64, i64, C.c_uint64, i64, i64, i32, pd]),
+    "mlp_synth_block": (None, [i32, i64, i64, C.c_uint64, i64, i64, i64, i64, i32, pd]),
     "mlp_synth_vectors": (i32, [i32, i64, i64, C.c_uint64, pd, pd, pd, pi32, pd]),
 }
 
@@ -118,7 +127,7 @@ SIGNATURES = {
 def build(force=False):
     """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("engine.cu", "host_solver.cpp", "synth.cpp", "Makefile")]
+    srcs = [os.path.join(csrc, f) for f in ("engine.cu", "kernels_common.cuh", "host_solver.cpp", "synth.cpp", "Makefile")]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "minilp_b200.h"))
     if (not force and os.path.exists(LIB_PATH)
             and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):

@@ -89,6 +89,13 @@ def synth_rows(kind, m, n, seed, row0, nrows, threads=1, out=None):
     return out
 
 
+def synth_block(kind, m, n, seed, row0, nrows, col0, ncols, threads=1, out=None):
+    if out is None:
+        out = np.empty((nrows, ncols), dtype=np.float64)
+    _lib.lib().mlp_synth_block(kind, m, n, seed, row0, nrows, col0, ncols, threads, _p(out))
+    return out
+
+
 def synth_vectors(kind, m, n, seed):
     obj, mins, maxs = np.empty(n), np.empty(n), np.empty(n)
     ops, rhs = np.empty(m, dtype=np.int32), np.empty(m)
@@ -113,11 +120,41 @@ def synth_dense(kind, m, n, seed, threads=1):
 
 
 # ------------------------------------------------------------------------------------------------ engine
-class Engine:
-    """Borrowed view of an mlp_engine* (owned by a Solver) exposing the per-operation ABI for tests and benches."""
+class LocalGroup:
+    """In-process rendezvous for `world` logical shards driven by one host thread each (MLP_COMM_LOCAL)."""
 
-    def __init__(self, handle, m, n):
-        self._e, self.m, self.n = handle, m, n
+    def __init__(self, world):
+        h = C.c_void_p()
+        _check(_lib.lib().mlp_local_group_create(world, C.byref(h)))
+        self._g, self.world = h, world
+
+    def __del__(self):
+        if getattr(self, "_g", None) and _lib is not None and getattr(_lib, "lib", None) is not None:
+            _lib.lib().mlp_local_group_destroy(self._g)
+            self._g = None
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(_lib.lib().mlp_nccl_get_unique_id(buf))
+    return buf.raw
+
+
+class Engine:
+    """Borrowed view of an mlp_engine* (owned by a Solver) exposing the per-operation ABI for tests and benches.
+    `n` is the number of structural columns THIS shard owns; var-indexed downloads have n + m entries in local order
+    (own structural columns, then the m slacks)."""
+
+    def __init__(self, handle, m, n_global):
+        self._e, self.m = handle, m
+        b, e = C.c_int64(), C.c_int64()
+        _check(_lib.lib().mlp_engine_local_range(handle, C.byref(b), C.byref(e)))
+        self.col_begin, self.col_end, self.n_global = b.value, e.value, n_global
+        self.n = e.value - b.value
+
+    def global_ids(self):
+        """GLOBAL variable index of every local variable slot."""
+        return np.concatenate([np.arange(self.col_begin, self.col_end), self.n_global + np.arange(self.m)])
 
     def select_entering_primal(self):
         out = Entering()
@@ -210,10 +247,18 @@ TRACE_FIELDS = ("phase", "entering_var", "entering_col", "leaving_row", "leaving
 class Solver:
     """solver.rs `Solver` after the swap: host control loop (csrc/host_solver.cpp) + device engine."""
 
-    def __init__(self, m, n, device=0):
+    def __init__(self, m, n, device=0, rank=0, world=1, comm=None):
+        """comm: None (single shard), a LocalGroup, or the 128-byte NCCL unique id shared by all ranks."""
         h = C.c_void_p()
-        _check(_lib.lib().mlp_solver_create_dense(device, m, n, C.byref(h)))
-        self._s, self.m, self.n = h, m, n
+        if world == 1:
+            _check(_lib.lib().mlp_solver_create_dense(device, m, n, C.byref(h)))
+        elif isinstance(comm, LocalGroup):
+            _check(_lib.lib().mlp_solver_create_dense_sharded(device, m, n, rank, world, 2, comm._g, C.byref(h)))
+        else:
+            buf = C.create_string_buffer(bytes(comm), 128)
+            _check(_lib.lib().mlp_solver_create_dense_sharded(device, m, n, rank, world, 1, C.cast(buf, C.c_void_p),
+                                                              C.byref(h)))
+        self._s, self.m, self.n, self.rank, self.world = h, m, n, rank, world
         self.engine = Engine(C.c_void_p(_lib.lib().mlp_solver_engine(h)), m, n)
 
     def close(self):
@@ -228,15 +273,20 @@ class Solver:
         rows = _f64(rows)
         _check(_lib.lib().mlp_solver_upload_rows(self._s, row0, rows.shape[0], _p(rows)))
 
+    def upload_local_rows(self, row0, rows):
+        rows = _f64(rows)
+        assert rows.shape[1] == self.engine.n
+        _check(_lib.lib().mlp_solver_upload_local_rows(self._s, row0, rows.shape[0], _p(rows)))
+
     def init(self, obj_internal, mins, maxs, ops, rhs):
         obj_internal, mins, maxs, rhs = _f64(obj_internal), _f64(mins), _f64(maxs), _f64(rhs)
         ops = np.ascontiguousarray(ops, dtype=np.int32)
         _check(_lib.lib().mlp_solver_init(self._s, _p(obj_internal), _p(mins), _p(maxs), _p(ops, pi32), _p(rhs)))
 
     @classmethod
-    def from_dense(cls, lp, device=0, chunk_rows=None):
+    def from_dense(cls, lp, device=0, chunk_rows=None, rank=0, world=1, comm=None):
         """Problem::solve's set-up half: stream A from host memory, then Solver::try_new."""
-        s = cls(lp.m, lp.n, device)
+        s = cls(lp.m, lp.n, device, rank, world, comm)
         step = chunk_rows or max(1, (64 << 20) // (8 * lp.n))
         for r0 in range(0, lp.m, step):
             s.upload_rows(r0, lp.a[r0:r0 + step])
@@ -282,7 +332,7 @@ class Solver:
         _lib.lib().mlp_solver_timers(self._s, C.byref(a), C.byref(b))
         return a.value, b.value
 
-    # position-indexed views matching the reference's Solver fields (for parity tests)
+    # position-indexed views matching the reference's Solver fields (for parity tests; single-shard engines)
     def nb_var_obj_coeffs(self):
         return self.engine.download(0)[self.nb_vars()]
 

@@ -6,12 +6,16 @@
 #include "minilp_b200.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -19,7 +23,7 @@
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
 extern "C" const char* mlp_last_error(void) { return g_err.c_str(); }
-extern "C" const char* mlp_version(void) { return "minilp_b200 0.1 (sm_100a)"; }
+extern "C" const char* mlp_version(void) { return "minilp_b200 0.2 (sm_100a)"; }
 extern "C" int mlp_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -43,58 +47,194 @@ extern "C" int mlp_device_count(void) {
 static constexpr double EPS = 1e-8;  // solver.rs:12
 #define FULLMASK 0xffffffffu
 
-// ------------------------------------------------------------------------------------------------ engine
 struct DevRes {  // small result block, mirrored in pinned host memory
   double f[8];
   long long i[6];
   int flags[4];  // [0] nonfinite, [1] singular
 };
+// Selection candidate exchanged between column shards: 64-byte header, followed in the exchange buffer by the
+// candidate's column of [A|I] (m doubles).  Ordering: larger key wins, ties go to the smaller `tie`.
+struct Cand {
+  double key;
+  long long tie;
+  long long var;  // GLOBAL variable index, -1: none
+  double f[5];    // primal: d, x_N, -, -, err   dual: coeff, d, x_N, pos, err
+};
+static_assert(sizeof(Cand) == 64, "Cand must be 64 bytes");
 
+#include "kernels_common.cuh"
+
+// ------------------------------------------------------------------------------------------------ communicators
+// The pivot path has ONE real exchange step per pivot: the arg-reduce of the per-shard pricing
+// candidates, fused here with the distribution of the winner's column (one all-gather of 64 + 8m bytes per rank).
+struct Comm {
+  int rank = 0, world = 1;
+  virtual ~Comm() {}
+  virtual mlp_status allgather(const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st) = 0;
+  virtual mlp_status broadcast(void* buf, size_t bytes, int root, cudaStream_t st) = 0;
+};
+
+// NCCL, loaded lazily so that single-GPU use has no dependency on libnccl.
+namespace ncclapi {
+typedef ncclResult_t (*GetUniqueId_t)(ncclUniqueId*);
+typedef ncclResult_t (*CommInitRank_t)(ncclComm_t*, int, ncclUniqueId, int);
+typedef ncclResult_t (*AllGather_t)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*Broadcast_t)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+typedef ncclResult_t (*CommDestroy_t)(ncclComm_t);
+typedef const char* (*GetErrorString_t)(ncclResult_t);
+static void* handle = nullptr;
+static GetUniqueId_t GetUniqueId;
+static CommInitRank_t CommInitRank;
+static AllGather_t AllGather;
+static Broadcast_t Broadcast;
+static CommDestroy_t CommDestroy;
+static GetErrorString_t GetErrorString;
+static bool load() {
+  if (handle) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { set_err(std::string("dlopen libnccl.so.2: ") + dlerror()); return false; }
+  GetUniqueId = (GetUniqueId_t)dlsym(h, "ncclGetUniqueId");
+  CommInitRank = (CommInitRank_t)dlsym(h, "ncclCommInitRank");
+  AllGather = (AllGather_t)dlsym(h, "ncclAllGather");
+  Broadcast = (Broadcast_t)dlsym(h, "ncclBroadcast");
+  CommDestroy = (CommDestroy_t)dlsym(h, "ncclCommDestroy");
+  GetErrorString = (GetErrorString_t)dlsym(h, "ncclGetErrorString");
+  if (!GetUniqueId || !CommInitRank || !AllGather || !Broadcast || !CommDestroy || !GetErrorString) {
+    set_err("libnccl is missing a required symbol");
+    return false;
+  }
+  handle = h;
+  return true;
+}
+}  // namespace ncclapi
+#define NC(x)                                                                       \
+  do {                                                                              \
+    ncclResult_t r__ = (x);                                                         \
+    if (r__ != ncclSuccess) {                                                       \
+      set_err(std::string(#x) + ": " + ncclapi::GetErrorString(r__));               \
+      return MLP_CUDA_ERROR;                                                        \
+    }                                                                               \
+  } while (0)
+
+struct NcclComm : Comm {
+  ncclComm_t comm = nullptr;
+  ~NcclComm() override { if (comm) ncclapi::CommDestroy(comm); }
+  mlp_status init(const void* id128, int rank_, int world_) {
+    if (!ncclapi::load()) return MLP_INVALID;
+    rank = rank_;
+    world = world_;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    NC(ncclapi::CommInitRank(&comm, world, id, rank));
+    return MLP_OK;
+  }
+  mlp_status allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
+    NC(ncclapi::AllGather(send, recv, bytes, ncclChar, comm, st));
+    return MLP_OK;
+  }
+  mlp_status broadcast(void* buf, size_t bytes, int root, cudaStream_t st) override {
+    NC(ncclapi::Broadcast(buf, buf, bytes, ncclChar, root, comm, st));
+    return MLP_OK;
+  }
+};
+
+// In-process group of logical shards driven by one host thread each (tests on a single GPU, or several GPUs of one
+// process): rendezvous on a host barrier, data moves with cudaMemcpyAsync between the shards' device buffers.
+struct LocalGroup {
+  int world;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  long gen = 0;
+  std::vector<const void*> ptrs;
+  explicit LocalGroup(int w) : world(w), ptrs(w, nullptr) {}
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const long g = gen;
+    if (++arrived == world) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+struct LocalComm : Comm {
+  LocalGroup* g = nullptr;
+  mlp_status allgather(const void* send, void* recv, size_t bytes, cudaStream_t st) override {
+    CU(cudaStreamSynchronize(st));
+    g->ptrs[rank] = send;
+    g->barrier();
+    for (int r = 0; r < world; ++r)
+      CU(cudaMemcpyAsync((char*)recv + (size_t)r * bytes, g->ptrs[r], bytes, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    g->barrier();
+    return MLP_OK;
+  }
+  mlp_status broadcast(void* buf, size_t bytes, int root, cudaStream_t st) override {
+    CU(cudaStreamSynchronize(st));
+    g->ptrs[rank] = buf;
+    g->barrier();
+    if (rank != root) CU(cudaMemcpyAsync(buf, g->ptrs[root], bytes, cudaMemcpyDefault, st));
+    CU(cudaStreamSynchronize(st));
+    g->barrier();
+    return MLP_OK;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ engine
 struct mlp_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
-  int64_t m = 0, n = 0, nt = 0, lda = 0, ldv = 0;  // ldv: padded length of var-indexed work arrays
+  // Column sharding: this engine owns structural columns [c0, c0+n) of the ng global ones; the m slack
+  // variables are replicated on every shard.  LOCAL variable index: structural g -> g-c0, slack ng+i -> n+i.
+  // Everything the ABI shows is GLOBAL.  world == 1: c0 = 0, n = ng.
+  int64_t m = 0, n = 0, nt = 0, lda = 0, ng = 0, c0 = 0;
+  Comm* comm = nullptr;
+  int rank = 0, world = 1;
   int sm_count = 148;
   bool initialized = false;
   int enable_pse = 0, enable_dse = 0;
 
-  double* A = nullptr;                                    // m x lda row-major
-  double *lo = nullptr, *hi = nullptr, *cobj = nullptr;  // n+m
-  double *d = nullptr, *gam = nullptr, *xnb = nullptr;   // n+m
+  double* A = nullptr;                                    // m x lda row-major, local column block
+  double *lo = nullptr, *hi = nullptr, *cobj = nullptr;  // ng+m, GLOBAL index, replicated
+  double *d = nullptr, *gam = nullptr, *xnb = nullptr;   // n+m, local index
   uint8_t* vflag = nullptr;                               // n+m
   int32_t* vpos = nullptr;                                // n+m
-  int32_t* bvar = nullptr;                                // m
+  int32_t* bvar = nullptr;                                // m, GLOBAL variable ids
   double *xB = nullptr, *loB = nullptr, *hiB = nullptr, *w = nullptr, *rhs = nullptr;  // m
   double *alpha = nullptr, *rho = nullptr, *tau = nullptr, *vvec = nullptr;             // m
   double *work_m = nullptr, *work_m2 = nullptr;                                          // m
-  double *rc = nullptr, *helper = nullptr;                                               // ldv (n+m padded)
-  int32_t* list_idx = nullptr;  // m
-  double* list_val = nullptr;   // m
-  double* partial = nullptr;    // price partial sums: max_chunks x lda
-  int max_chunks = 64;
-  // reduction scratch
-  double* red_f = nullptr;      // 4096 doubles
-  long long* red_i = nullptr;   // 4096
+  double* colq = nullptr;  // m: column of the entering variable; stored in the column cache by the pivot
+  int64_t colq_var = -1;
+  double *rc = nullptr, *helper = nullptr;  // n+m
+  int32_t* list_idx = nullptr;              // m
+  double* list_val = nullptr;               // m
+  double* partial = nullptr;                // price partial sums: PR_MAXC x lda
+  double* red_f = nullptr;                  // 4096
+  long long* red_i = nullptr;               // 4096
   unsigned* red_counter = nullptr;
-  double* scal = nullptr;       // device scalars: [0] max_step [1] rho sumsq [2] alpha sumsq [3] v sumsq ...
-  int32_t* icnt = nullptr;      // device ints: [0] rho nnz [1] alpha nnz [2] v nnz
-  int32_t* seg_cnt = nullptr;   // compaction: per-segment counts / sums of squares
+  double* scal = nullptr;   // device scalars: [0] max_step [1] |rho|^2 [2] |alpha|^2 [3] |v|^2 [4..6] objective parts
+  int32_t* icnt = nullptr;  // device ints: [0] nnz rho [1] nnz alpha [2] nnz v
+  int32_t* seg_cnt = nullptr;
   double* seg_ss = nullptr;
-  double *gt_part_k = nullptr, *gt_part_K = nullptr;  // k_gemv_t partials: GT_MAXSPLIT x kcap / Kcap
+  double *gt_part_k = nullptr, *gt_part_K = nullptr;
   DevRes* d_res = nullptr;
   DevRes* h_res = nullptr;  // pinned
+  // candidate exchange
+  char *xsend = nullptr, *xrecv = nullptr;
+  size_t xbytes = 0;
+  Cand* h_cands = nullptr;  // pinned, world entries
+  double* xred = nullptr;   // world * m doubles (vector sums across shards) / world scalars
 
-  // dense LU of the basis (see DESIGN.md §basis)
+  // dense LU of the basis (DESIGN.md §4)
   int64_t k = 0, kcap = 0;
-  int32_t *Jpos = nullptr, *Jvar = nullptr, *Rp = nullptr;  // kcap
-  int32_t* rowcover = nullptr;                                // m
-  double *Bcols = nullptr, *LUc = nullptr;                    // m x kcap, kcap x kcap
-  double *xk = nullptr;                                       // kcap
+  int32_t *Jpos = nullptr, *Jslot = nullptr, *Rp = nullptr;  // kcap
+  int32_t* rowcover = nullptr;                                 // m
+  double *Bcols = nullptr, *LUc = nullptr;                     // column cache m x kcap (slot-indexed), kcap x kcap
+  double* xk = nullptr;
   // eta file
   int64_t K = 0, Kcap = 0;
-  double *E = nullptr, *G = nullptr;  // m x Kcap, Kcap x Kcap (col-major, unit lower coupling matrix)
-  int32_t *etaR = nullptr, *etaPrev = nullptr, *etaHead = nullptr;  // Kcap
-  double *tK = nullptr;               // Kcap
+  double *E = nullptr, *G = nullptr;
+  int32_t *etaR = nullptr, *etaPrev = nullptr, *etaHead = nullptr;
+  double* tK = nullptr;
   int64_t lu_nnz = 0;
 
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -103,15 +243,17 @@ struct mlp_engine {
   int prof_on = 0;
   mlp_profile prof{};
 
-  std::vector<int32_t> h_bvar;
-  std::vector<int32_t> h_last_eta_of_row;  // m, -1 if none
+  std::vector<int64_t> h_bvar;           // GLOBAL ids
+  std::vector<int32_t> h_slot_of_row;    // cache slot of the structural basic variable at row r, or -1
+  std::vector<int32_t> h_free_slots;
+  std::vector<int32_t> h_last_eta_of_row;
   mlp_counters cnt{};
 };
 
-#define LAUNCH(e, kern, grid, block, smem, ...)              \
-  do {                                                       \
+#define LAUNCH(e, kern, grid, block, smem, ...)                  \
+  do {                                                           \
     kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__); \
-    (e)->cnt.kernel_launches += 1;                           \
+    (e)->cnt.kernel_launches += 1;                               \
   } while (0)
 
 template <class T> static mlp_status dev_alloc(T** p, size_t count) {
@@ -140,98 +282,39 @@ static mlp_status d2h(mlp_engine* e, void* dst, const void* src, size_t bytes) {
   return MLP_OK;
 }
 static mlp_status fetch_res(mlp_engine* e) { return d2h(e, e->h_res, e->d_res, sizeof(DevRes)); }
-
-// ------------------------------------------------------------------------------------------------ device helpers
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
-  return v;
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+// local index of a GLOBAL variable, -1 if the structural column lives on another shard
+static inline int64_t to_local(const mlp_engine* e, int64_t g) {
+  if (g >= e->ng) return e->n + (g - e->ng);
+  return (g >= e->c0 && g < e->c0 + e->n) ? g - e->c0 : -1;
 }
-// Deterministic block sum (result valid in thread 0). sm: >= 32 doubles.
-__device__ __forceinline__ double block_sum(double v, double* sm) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) sm[wid] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (wid == 0) {
-    r = lane < nw ? sm[lane] : 0.0;
-    r = warp_sum(r);
+static inline int owner_of(const mlp_engine* e, int64_t g) {
+  if (g >= e->ng) return e->rank;  // slack: replicated
+  for (int r = 0; r < e->world; ++r) {
+    int64_t b, en;
+    mlp_shard_range(e->ng, e->world, r, &b, &en);
+    if (g >= b && g < en) return r;
   }
-  return r;
-}
-struct KeyIdx {
-  double key;
-  long long idx;
-};
-// "better" orderings: max key then min idx / min key then min idx
-__device__ __forceinline__ bool better_max(double k, long long i, double bk, long long bi) { return k > bk || (k == bk && i < bi); }
-__device__ __forceinline__ KeyIdx warp_argmax(KeyIdx v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    double k = __shfl_down_sync(FULLMASK, v.key, o);
-    long long i = __shfl_down_sync(FULLMASK, v.idx, o);
-    if (better_max(k, i, v.key, v.idx)) { v.key = k; v.idx = i; }
-  }
-  return v;
-}
-__device__ __forceinline__ KeyIdx block_argmax(KeyIdx v, double* smk, long long* smi) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_argmax(v);
-  __syncthreads();
-  if (lane == 0) { smk[wid] = v.key; smi[wid] = v.idx; }
-  __syncthreads();
-  KeyIdx r{-INFINITY, LLONG_MAX};
-  if (wid == 0) {
-    if (lane < nw) { r.key = smk[lane]; r.idx = smi[lane]; }
-    r = warp_argmax(r);
-  }
-  return r;
-}
-__device__ __forceinline__ double warp_min(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(FULLMASK, v, o));
-  return v;
-}
-__device__ __forceinline__ double block_min(double v, double* sm) {
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  v = warp_min(v);
-  __syncthreads();
-  if (lane == 0) sm[wid] = v;
-  __syncthreads();
-  double r = INFINITY;
-  if (wid == 0) {
-    r = lane < nw ? sm[lane] : INFINITY;
-    r = warp_min(r);
-  }
-  return r;
-}
-// Grid-level "last block finishes" rendezvous. Returns true in every thread of the last-arriving block.
-__device__ __forceinline__ bool last_block(unsigned* counter) {
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned t = atomicAdd(counter, 1u);
-    is_last = (t == gridDim.x * gridDim.y - 1);
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last;
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------------ K5 price-out
-// calc_row_coeffs price-out (solver.rs:685-692), the N^T v product of update_primal_sq_norms (1117-1132)
-// and the column norms of try_new (297-299).  Row-gather GEMV^T over row-major A: a CTA owns a 512-column
-// tile and one chunk of the multiplier's support; each thread accumulates two adjacent columns with
-// 128-bit loads, rows of the chunk are taken in list order (the reference's order of accumulation within
-// the chunk); (row, weight) pairs are staged through shared memory.  Partial sums per chunk are reduced
-// in chunk order by k_price_finish — no atomics, bitwise reproducible.
+// calc_row_coeffs price-out (solver.rs:685-692), the N^T v product of update_primal_sq_norms (1117-1132), the full
+// c_N - N^T y of recalc_obj_coeffs (1216-1222) and the column norms of try_new (297-299).  Row-gather GEMV^T over
+// row-major A: a CTA owns a 512-column tile and one chunk of the multiplier's support; each thread accumulates two
+// adjacent columns with 128-bit streaming loads, 8 rows in flight; rows of a chunk are taken in list order;
+// (row, weight) pairs are staged through shared memory.  The chunking depends ONLY on the support size s
+// (C = clamp(ceil(s/128), 1, 64)), never on the grid or the shard width, so a column's sum is bit-identical however
+// the columns are sharded.  Chunk partials are reduced in chunk order by k_price_finish — no atomics.
 constexpr int PR_THREADS = 256;
 constexpr int PR_TILE = PR_THREADS * 2;
 constexpr int PR_BATCH = 256;
 constexpr int PR_UNROLL = 8;
+constexpr int PR_MAXC = 64;
+__host__ __device__ __forceinline__ int price_chunks_for(int s) {
+  int c = (s + 127) / 128;
+  return c < 1 ? 1 : (c > PR_MAXC ? PR_MAXC : c);
+}
 
 template <int MODE>  // 0: sum_r w_r * A[r,j]   1: sum_r A[r,j]^2
 __global__ void __launch_bounds__(PR_THREADS)
@@ -241,7 +324,8 @@ k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __rest
   __shared__ int32_t srow[PR_BATCH];
   __shared__ double sw[PR_BATCH];
   const int s = count_ptr ? *count_ptr : fixed_count;
-  const int C = gridDim.y;
+  const int C = price_chunks_for(s);
+  if ((int)blockIdx.y >= C) return;
   const int L = (s + C - 1) / C;
   const int k0 = blockIdx.y * L;
   const int k1 = min(s, k0 + L);
@@ -297,14 +381,15 @@ k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __rest
   }
 }
 
-// Reduce chunk partials in chunk order; slack columns of [A|I] contribute rho_i (the `I` part of the CSR
-// row, solver.rs:250); basic variables are not part of row_coeffs (solver.rs:688).
+// Reduce chunk partials in chunk order; slack columns of [A|I] contribute rho_i (the `I` part of the CSR row,
+// solver.rs:250); basic variables are not part of row_coeffs (solver.rs:688).
 // mode 0: out = sum   mode 1: out = sum + 1 (primal edge norms, solver.rs:298)
-__global__ void k_price_finish(const double* __restrict__ partial, int C, int64_t lda, int64_t n, int64_t m,
-                               const double* __restrict__ slack_vals, const uint8_t* __restrict__ vflag,
-                               double* __restrict__ out, int mode) {
+__global__ void k_price_finish(const double* __restrict__ partial, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
+                               int64_t lda, int64_t n, int64_t m, const double* __restrict__ slack_vals,
+                               const uint8_t* __restrict__ vflag, double* __restrict__ out, int mode) {
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n + m) return;
+  const int C = price_chunks_for(count_ptr ? *count_ptr : fixed_count);
   double r;
   if (v < n) {
     r = 0.0;
@@ -317,354 +402,88 @@ __global__ void k_price_finish(const double* __restrict__ partial, int C, int64_
   out[v] = r;
 }
 
-// ------------------------------------------------------------------------------------------------ compaction
-// ScatteredVec::to_sparse_vec (sparse.rs:115-121) for a device work vector: ordered list of the non-zero
-// entries (ascending index), their count, and the sum of squares (SparseVec::sq_norm, sparse.rs:32-34).
-// Pass 1: every CTA counts the non-zeros and sums the squares of its 1024-entry segment; the last CTA to
-// finish adds the per-segment results in segment order (deterministic).  Pass 2 (only when the list is
-// needed): each CTA derives its output offset from the segment counts and writes its entries in order.
-constexpr int CP_SEG = 1024;
-__global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restrict__ x, int m, int32_t* __restrict__ seg_cnt,
-                                                           double* __restrict__ seg_ss, unsigned* counter,
-                                                           int32_t* __restrict__ count, double* __restrict__ sumsq) {
-  __shared__ double sm[32];
-  __shared__ int smi[32];
-  const int i = blockIdx.x * CP_SEG + threadIdx.x;
-  const double v = i < m ? x[i] : 0.0;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(FULLMASK, v != 0.0);
-  if (lane == 0) smi[wid] = __popc(bal);
-  const double ss = block_sum(v * v, sm);  // has the barriers that publish smi
-  if (threadIdx.x == 0) {
-    int c = 0;
-    for (int w2 = 0; w2 < 32; ++w2) c += smi[w2];
-    seg_cnt[blockIdx.x] = c;
-    seg_ss[blockIdx.x] = ss;
-  }
-  if (!last_block(counter)) return;
-  if (threadIdx.x == 0) {
-    int c = 0;
-    double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { c += __ldcg(seg_cnt + b); t += __ldcg(seg_ss + b); }
-    *count = c;
-    *sumsq = t;
-    *counter = 0;
-  }
-}
-__global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restrict__ x, int m, const int32_t* __restrict__ seg_cnt,
-                                                           int32_t* __restrict__ idx, double* __restrict__ val) {
-  __shared__ int warp_cnt[32];
-  __shared__ int base;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (wid == 0) {  // offset of this segment = sum of the counts of the segments before it
-    int acc = 0;
-    for (int b = lane; b < (int)blockIdx.x; b += 32) acc += seg_cnt[b];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(FULLMASK, acc, o);
-    if (lane == 0) base = acc;
-  }
-  const int i = blockIdx.x * CP_SEG + threadIdx.x;
-  const double v = i < m ? x[i] : 0.0;
-  const bool nz = v != 0.0;
-  const unsigned bal = __ballot_sync(FULLMASK, nz);
-  if (lane == 0) warp_cnt[wid] = __popc(bal);
-  __syncthreads();
-  if (nz) {
-    int off = base;
-    for (int w2 = 0; w2 < wid; ++w2) off += warp_cnt[w2];
-    const int p = off + __popc(bal & ((1u << lane) - 1u));
-    idx[p] = i;
-    val[p] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ dense triangular solves
-// Blocked (32-wide) triangular solve on a column-major matrix by ONE CTA of 1024 threads; used for the
-// L/U factors of the basis core (LUFactors::solve lu.rs:79-106 / tri_solve_process_col 450-463) and for
-// the eta-file coupling matrix G (see k_gemv_* below).
-//   AXPY form (op(M) = M):   after a 32-block of unknowns is solved, every remaining row is updated
-//                            (the reference's column-oriented substitution).
-//   DOT form  (op(M) = M^T): before a 32-block is solved, each of its unknowns takes the dot product of
-//                            its (contiguous) column with the already-solved part.
-// FWD: unknowns 0..n-1, else n-1..0.  UNIT: unit diagonal.
-template <bool FWD, bool AXPY, bool UNIT>
-__global__ void __launch_bounds__(1024) k_trsv(const double* __restrict__ M, int64_t ld, int n, double* __restrict__ x) {
-  __shared__ double xs[32];
-  __shared__ double dots[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nblk = (n + 31) / 32;
-  for (int bi = 0; bi < nblk; ++bi) {
-    const int b = FWD ? bi * 32 : (nblk - 1 - bi) * 32;
-    const int nb = min(32, n - b);
-    if (!AXPY) {
-      // dot products with the solved part, one warp per unknown of the block
-      if (wid < nb) {
-        const double* colp = M + (int64_t)(b + wid) * ld;
-        double acc = 0.0;
-        if (FWD) { for (int j = lane; j < b; j += 32) acc += colp[j] * x[j]; }
-        else { for (int j = b + nb + lane; j < n; j += 32) acc += colp[j] * x[j]; }
-        acc = warp_sum(acc);
-        if (lane == 0) dots[wid] = acc;
-      }
-      __syncthreads();
-    }
-    if (wid == 0) {
-      double v = 0.0, dg = 1.0;
-      double coef[32];
-      if (lane < nb) {
-        v = x[b + lane];
-        if (!AXPY) v -= dots[lane];
-        if (!UNIT) dg = M[(int64_t)(b + lane) * ld + (b + lane)];
-      }
-#pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        // coefficient of unknown jj in equation `lane` of the diagonal block
-        const bool need = lane < nb && jj < nb && (FWD ? (jj < lane) : (jj > lane));
-        coef[jj] = need ? (AXPY ? M[(int64_t)(b + jj) * ld + (b + lane)] : M[(int64_t)(b + lane) * ld + (b + jj)]) : 0.0;
-      }
-#pragma unroll
-      for (int s = 0; s < 32; ++s) {
-        const int jj = FWD ? s : 31 - s;
-        if (!UNIT && lane == jj) v = v / dg;
-        const double xj = __shfl_sync(FULLMASK, v, jj);
-        const bool upd = FWD ? (lane > jj) : (lane < jj);
-        if (upd && jj < nb) v -= xj * coef[jj];
-      }
-      if (lane < nb) {
-        x[b + lane] = v;
-        xs[lane] = v;
-      }
-    }
-    __syncthreads();
-    if (AXPY) {
-      // rhs[r] -= x_val * coeff for every remaining row (lu.rs:460-462)
-      const int lo_i = FWD ? b + nb : 0;
-      const int hi_i = FWD ? n : b;
-      for (int i = lo_i + threadIdx.x; i < hi_i; i += 1024) {
-        double acc = x[i];
-        if (FWD) { for (int jj = 0; jj < nb; ++jj) acc -= xs[jj] * M[(int64_t)(b + jj) * ld + i]; }
-        else { for (int jj = nb - 1; jj >= 0; --jj) acc -= xs[jj] * M[(int64_t)(b + jj) * ld + i]; }
-        x[i] = acc;
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// y[i] = base[i] - sum_j M[i + j*ld] * t[j]   (column-major M: rows x cols; thread per row)
-// Used for: FTRAN eta application rhs -= E t (solver.rs:1310-1316 in closed form) and the slack rows of
-// the basis solve alpha_S = a_S - D1 x.
-__global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M, int64_t ld, int rows, int cols,
-                                                     const double* __restrict__ t, double* __restrict__ y) {
-  __shared__ double ts[512];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc = i < rows ? y[i] : 0.0;
-  for (int j0 = 0; j0 < cols; j0 += 512) {
-    const int nj = min(512, cols - j0);
-    __syncthreads();
-    for (int q = threadIdx.x; q < nj; q += blockDim.x) ts[q] = t[j0 + q];
-    __syncthreads();
-    if (i < rows) {
-      const double* p = M + (int64_t)j0 * ld + i;
-      int j = 0;
-      for (; j + 8 <= nj; j += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j + u) * ld];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) acc -= ts[j + u] * v[u];
-      }
-      for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)j * ld];
-    }
-  }
-  if (i < rows) y[i] = acc;
-}
-
-// out[j] = base[idx[j]] - sum_i M[i + j*ld] * x[i]   (negate) or the plain dot products.
-// Grid (cols, S): CTA (j, s) reduces row slice s of column j; k_gemv_t_fin adds the S partials in order.
-// Used for BTRAN: u = E^T rhs (solver.rs:1326-1330) and the right-hand side of the core solve.
-constexpr int GT_MAXSPLIT = 16;
-__global__ void __launch_bounds__(256) k_gemv_t_part(const double* __restrict__ M, int64_t ld, int rows, int cols,
-                                                      const double* __restrict__ x, double* __restrict__ part) {
-  __shared__ double sm[32];
-  const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
-  const int L = (rows + S - 1) / S;
-  const int r0 = sidx * L, r1 = min(rows, r0 + L);
-  const double* p = M + (int64_t)j * ld;
-  double acc = 0.0;
-  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
-  const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) part[(int64_t)sidx * cols + j] = tot;
-}
-__global__ void k_gemv_t_fin(const double* __restrict__ part, int S, int cols, const double* __restrict__ base,
-                             const int32_t* __restrict__ base_idx, double* __restrict__ out, int negate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
-  double tot = 0.0;
-  for (int q = 0; q < S; ++q) tot += part[(int64_t)q * cols + j];
-  const double b = base ? base[base_idx ? base_idx[j] : j] : 0.0;
-  out[j] = negate ? b - tot : tot;
-}
-
-__global__ void k_gather_idx(const double* __restrict__ src, const int32_t* __restrict__ idx, int cnt, double* __restrict__ dst) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) dst[t] = src[idx[t]];
-}
-__global__ void k_scatter_idx(const double* __restrict__ src, const int32_t* __restrict__ idx, int cnt, double* __restrict__ dst) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) dst[idx[t]] = src[t];
-}
-// strided gather of one row of a column-major matrix: dst[j] = M[row + j*ld]
-__global__ void k_gather_row(const double* __restrict__ M, int64_t ld, int row, int cnt, double* __restrict__ dst) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) dst[t] = M[(int64_t)t * ld + row];
-}
-__global__ void k_fill(double* p, int64_t cnt, double v) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) p[t] = v;
-}
-__global__ void k_set_unit(double* p, int64_t cnt, int64_t at) {
-  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) p[t] = (t == at) ? 1.0 : 0.0;
-}
-// rhs.set(column of var) (solver.rs:672-675, sparse.rs:103): column of [A|I] into a dense m-vector
-__global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int m, int64_t var, double* __restrict__ dst) {
+// ------------------------------------------------------------------------------------------------ columns
+// rhs.set(column of var) (solver.rs:672-675, sparse.rs:103): column of [A|I] of LOCAL variable lv as a dense m-vector
+__global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int m, int64_t lv, double* __restrict__ dst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
-  dst[i] = var < n ? A[(int64_t)i * lda + var] : ((int64_t)i == var - n ? 1.0 : 0.0);
+  dst[i] = lv < n ? A[(int64_t)i * lda + lv] : ((int64_t)i == lv - n ? 1.0 : 0.0);
+}
+// same, for the variable named by a candidate header that is still on the device (no host round trip)
+__global__ void k_cand_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int64_t c0, int64_t ng, int m,
+                                const Cand* __restrict__ cand, double* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const long long g = cand->var;
+  if (g < 0) { dst[i] = 0.0; return; }
+  const int64_t lv = g >= ng ? n + (g - ng) : g - c0;
+  dst[i] = lv < n ? A[(int64_t)i * lda + lv] : ((int64_t)i == lv - n ? 1.0 : 0.0);
 }
 
-// BTRAN through the eta file, last step (solver.rs:1331-1332): rhs[r_leaving(idx)] -= coeff(idx), idx = K-1..0.
-// Several etas may share a leaving row; thread j owns the chain headed by the LAST eta of a row and walks it in
-// the reference's order (descending idx), so the subtraction order is the reference's.
-__global__ void k_eta_scatter(const double* __restrict__ s, const int32_t* __restrict__ etaR,
-                              const int32_t* __restrict__ etaPrev, const int32_t* __restrict__ etaHead, int K,
-                              double* __restrict__ rhs) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= K || !etaHead[j]) return;
-  double v = rhs[etaR[j]];
-  for (int q = j; q >= 0; q = etaPrev[q]) v -= s[q];
-  rhs[etaR[j]] = v;
-}
-
-// ------------------------------------------------------------------------------------------------ basis solve pieces
 // FTRAN tail: alpha[pos] for slack positions = a_i - (D1 x)_i ; alpha[Jpos[t]] = x[t]   (U-solve of the
-// identity-bordered basis, lu.rs:93 with B = [D | E_S]).
+// identity-bordered basis, lu.rs:93 with B = [D | E_S]).  The t-th dense column lives in cache slot Jslot[t].
 __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__ Bcols, int64_t ldb, int m, int k,
                                                        const double* __restrict__ xk, const double* __restrict__ rhs0,
                                                        const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                                       double* __restrict__ out) {
+                                                       const int32_t* __restrict__ Jslot, double* __restrict__ out) {
   __shared__ double ts[512];
+  __shared__ int32_t sl[512];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc = i < m ? rhs0[i] : 0.0;
   const int cov = i < m ? rowcover[i] : -1;
   for (int j0 = 0; j0 < k; j0 += 512) {
     const int nj = min(512, k - j0);
     __syncthreads();
-    for (int q = threadIdx.x; q < nj; q += blockDim.x) ts[q] = xk[j0 + q];
+    for (int q = threadIdx.x; q < nj; q += blockDim.x) { ts[q] = xk[j0 + q]; sl[q] = Jslot[j0 + q]; }
     __syncthreads();
     if (cov >= 0) {
-      const double* p = Bcols + (int64_t)j0 * ldb + i;
+      const double* p = Bcols + i;
       int j = 0;
       for (; j + 8 <= nj; j += 8) {
         double v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j + u) * ldb];
+        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc -= ts[j + u] * v[u];
       }
-      for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)j * ldb];
+      for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)sl[j] * ldb];
     }
   }
   if (cov >= 0) out[cov] = acc;
   if (i < k) out[Jpos[i]] = xk[i];
 }
-// BTRAN head: rho_i = c[pos of slack i] on covered rows (U^T solve over the identity block); cov copy with zeros elsewhere
-__global__ void k_btran_start(const double* __restrict__ c, const int32_t* __restrict__ rowcover, int m,
-                              double* __restrict__ out, double* __restrict__ cov) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const int p = rowcover[i];
-  const double v = p >= 0 ? c[p] : 0.0;
-  out[i] = v;
-  cov[i] = v;
-}
-
-// ------------------------------------------------------------------------------------------------ dense LU of the core
-// lu_factorize (lu.rs:118-304) specialised to B = [D | E_S]: the unit columns come first in order_simple
-// (ordering.rs:4-21) and pivot on their own rows; what remains is the k x k core C = D[R,:] whose columns
-// are taken in basis-position order and whose pivots follow the reference's threshold rule:
-// among rows with |x| >= 0.1 max|x| (lu.rs:224) — all have the same original-row count, lu.rs:225-229 —
-// the first in list order, i.e. the lowest original row index.
-__global__ void __launch_bounds__(1024) k_lu_pivot(double* __restrict__ C, int64_t ld, int k, int t,
-                                                    int32_t* __restrict__ Rp, int* __restrict__ flags) {
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  __shared__ double s_max;
-  __shared__ int s_piv;
-  if (flags[1]) return;
-  double* col = C + (int64_t)t * ld;
-  double mx = 0.0;
-  for (int i = t + threadIdx.x; i < k; i += blockDim.x) mx = fmax(mx, fabs(col[i]));
-  KeyIdx r = block_argmax(KeyIdx{mx, 0}, smk, smi);
-  if (threadIdx.x == 0) s_max = r.key;
-  __syncthreads();
-  const double max_abs = s_max;
-  if (!(max_abs >= 1e-8) || isinf(max_abs)) {  // lu.rs:207-211
-    if (threadIdx.x == 0) flags[1] = 1;
-    return;
-  }
-  // lowest original row among eligible: maximise -Rp
-  KeyIdx c{-INFINITY, LLONG_MAX};
-  for (int i = t + threadIdx.x; i < k; i += blockDim.x)
-    if (fabs(col[i]) >= 0.1 * max_abs) {
-      const double key = -(double)Rp[i];
-      if (better_max(key, i, c.key, c.idx)) { c.key = key; c.idx = i; }
-    }
-  c = block_argmax(c, smk, smi);
-  if (threadIdx.x == 0) s_piv = (int)c.idx;
-  __syncthreads();
-  const int p = s_piv;
-  if (p != t) {
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const double a = C[(int64_t)j * ld + t], b = C[(int64_t)j * ld + p];
-      C[(int64_t)j * ld + t] = b;
-      C[(int64_t)j * ld + p] = a;
-    }
-    if (threadIdx.x == 0) { const int a = Rp[t]; Rp[t] = Rp[p]; Rp[p] = a; }
-  }
-  __syncthreads();
-  const double pv = col[t];
-  for (int i = t + 1 + threadIdx.x; i < k; i += blockDim.x) col[i] = col[i] / pv;  // lu.rs:261
-}
-__global__ void k_lu_update(double* __restrict__ C, int64_t ld, int k, int t, const int* __restrict__ flags) {
-  if (flags[1]) return;
-  const int i = t + 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = t + 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  if (i < k && j < k) C[(int64_t)j * ld + i] -= C[(int64_t)t * ld + i] * C[(int64_t)j * ld + t];
-}
-__global__ void k_gather_bcols(const double* __restrict__ A, int64_t lda, int m, int k, const int32_t* __restrict__ Jvar,
-                               double* __restrict__ Bcols, int64_t ldb) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (i < m && t < k) Bcols[(int64_t)t * ldb + i] = A[(int64_t)i * lda + Jvar[t]];
-}
+// core C = D[R,:] (k x k, column-major) from the column cache
 __global__ void k_extract_core(const double* __restrict__ Bcols, int64_t ldb, int k, const int32_t* __restrict__ Rp,
-                               double* __restrict__ C, int64_t ld) {
+                               const int32_t* __restrict__ Jslot, double* __restrict__ C, int64_t ld) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
-  if (i < k && t < k) C[(int64_t)t * ld + i] = Bcols[(int64_t)t * ldb + Rp[i]];
+  if (i < k && t < k) C[(int64_t)t * ld + i] = Bcols[(int64_t)Jslot[t] * ldb + Rp[i]];
+}
+// BTRAN: right-hand side of the core solve, rhs_t = c[Jpos[t]] - sum_i Bcols[i, slot_t] cov_i; CTA (t, s) reduces a row
+// slice, k_gemv_t_fin adds the slices in order.
+__global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict__ Bcols, int64_t ldb, int rows, int k,
+                                                        const int32_t* __restrict__ Jslot, const double* __restrict__ x,
+                                                        double* __restrict__ part) {
+  __shared__ double sm[32];
+  const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
+  const int L = (rows + S - 1) / S;
+  const int r0 = sidx * L, r1 = min(rows, r0 + L);
+  const double* p = Bcols + (int64_t)Jslot[j] * ldb;
+  double acc = 0.0;
+  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
+  const double tot = block_sum(acc, sm);
+  if (threadIdx.x == 0) part[(int64_t)sidx * k + j] = tot;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 pricing scan
-// choose_pivot, solver.rs:696-739: arg-max of d^2/gamma (or |d|) over eligible non-basic variables,
-// strict '>' in ascending position order => lowest position wins ties.
+// choose_pivot, solver.rs:696-739: arg-max of d^2/gamma (or |d|) over eligible non-basic variables, strict '>' in
+// ascending position order => lowest position wins ties.  Writes this shard's candidate header.
 __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict__ d, const double* __restrict__ gam,
                                                         const uint8_t* __restrict__ vflag, const int32_t* __restrict__ vpos,
-                                                        int64_t nt, int use_se, double* __restrict__ red_f,
-                                                        long long* __restrict__ red_i, unsigned* counter,
-                                                        const double* __restrict__ xnb, const double* __restrict__ lo,
-                                                        const double* __restrict__ hi, DevRes* res) {
+                                                        int64_t nt, int64_t n, int64_t c0, int64_t ng, int use_se,
+                                                        double* __restrict__ red_f, long long* __restrict__ red_i,
+                                                        unsigned* counter, const double* __restrict__ xnb,
+                                                        const int* __restrict__ flags, Cand* out) {
   __shared__ double smk[32];
   __shared__ long long smi[32];
   KeyIdx best{-INFINITY, LLONG_MAX};
@@ -674,8 +493,7 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
     const double dv = d[v];
     if (((f & MLP_AT_MIN) && dv > -EPS) || ((f & MLP_AT_MAX) && dv < EPS)) continue;  // 705-708
     const double score = use_se ? dv * dv / gam[v] : fabs(dv);
-    // idx packs (pos, var): pos decides ties
-    const long long key2 = ((long long)vpos[v] << 32) | (long long)v;
+    const long long key2 = ((long long)vpos[v] << 32) | (long long)v;  // position decides ties
     if (better_max(score, key2, best.key, best.idx)) { best.key = score; best.idx = key2; }
   }
   best = block_argmax(best, smk, smi);
@@ -690,138 +508,20 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
   b = block_argmax(b, smk, smi);
   if (threadIdx.x == 0) {
     *counter = 0;
-    if (b.idx == LLONG_MAX) { res->i[0] = -1; res->i[1] = -1; }
+    out->f[4] = (double)flags[0];
+    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
     else {
       const long long v = b.idx & 0xffffffffLL;
-      res->i[0] = v;
-      res->i[1] = b.idx >> 32;
-      res->f[0] = d[v];
-      res->f[1] = b.key;
-      res->f[2] = xnb[v];
-      res->f[3] = lo[v];
-      res->f[4] = hi[v];
+      out->key = b.key;
+      out->tie = b.idx >> 32;
+      out->var = v < n ? c0 + v : ng + (v - n);
+      out->f[0] = d[v];
+      out->f[1] = xnb[v];
     }
   }
 }
 
-// ------------------------------------------------------------------------------------------------ K3 primal ratio test
-// Harris pass 1 (solver.rs:782-795): max_step = min(max_step0, min_r (slack_r + EPS)/|alpha_r|)
-__device__ __forceinline__ double leaving_step(double a, int sign, double val, double lo, double hi, bool& toward_max) {
-  toward_max = (sign && a < 0.0) || (!sign && a > 0.0);  // 756
-  if (toward_max) return val < hi ? hi - val : 0.0;
-  return val > lo ? val - lo : 0.0;
-}
-__global__ void __launch_bounds__(256) k_ratio_primal_1(const double* __restrict__ alpha, const double* __restrict__ xB,
-                                                         const double* __restrict__ loB, const double* __restrict__ hiB, int m,
-                                                         int sign, double max_step0, double* __restrict__ red_f,
-                                                         unsigned* counter, double* __restrict__ scal) {
-  __shared__ double sm[32];
-  double best = INFINITY;
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
-    const double a = alpha[r], aa = fabs(a);
-    if (aa < EPS) continue;
-    bool tm;
-    const double st = leaving_step(a, sign, xB[r], loB[r], hiB[r], tm);
-    const double cur = (st + EPS) / aa;  // 791
-    if (cur < best) best = cur;
-  }
-  best = block_min(best, sm);
-  if (threadIdx.x == 0) red_f[blockIdx.x] = best;
-  if (!last_block(counter)) return;
-  double b = INFINITY;
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) b = fmin(b, __ldcg(red_f + q));
-  b = block_min(b, sm);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    scal[0] = b < max_step0 ? b : max_step0;
-  }
-}
-// Harris pass 2 (solver.rs:800-823): among rows with slack/|alpha| <= max_step the largest |alpha|;
-// exact ties go to the lowest row (the reference: first in col_coeffs list order).
-__global__ void __launch_bounds__(256) k_ratio_primal_2(const double* __restrict__ alpha, const double* __restrict__ xB,
-                                                         const double* __restrict__ loB, const double* __restrict__ hiB, int m,
-                                                         int sign, const double* __restrict__ scal, double* __restrict__ red_f,
-                                                         long long* __restrict__ red_i, unsigned* counter, DevRes* res) {
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  const double max_step = scal[0];
-  KeyIdx best{-INFINITY, LLONG_MAX};
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
-    const double a = alpha[r], aa = fabs(a);
-    if (aa < EPS) continue;
-    bool tm;
-    const double st = leaving_step(a, sign, xB[r], loB[r], hiB[r], tm);
-    const double cur = st / aa;  // 810
-    if (cur <= max_step && better_max(aa, r, best.key, best.idx)) { best.key = aa; best.idx = r; }
-  }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
-  if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
-    const double k = __ldcg(red_f + q);
-    const long long i = __ldcg(red_i + q);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
-  }
-  b = block_argmax(b, smk, smi);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    if (b.idx == LLONG_MAX) res->i[0] = -1;
-    else {
-      const int r = (int)b.idx;
-      const double a = alpha[r];
-      bool tm;
-      leaving_step(a, sign, xB[r], loB[r], hiB[r], tm);
-      res->i[0] = r;
-      res->f[0] = a;
-      res->f[1] = tm ? hiB[r] : loB[r];  // 813-819
-      res->f[2] = xB[r];
-      res->f[3] = max_step;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ K11 dual selection
-// choose_pivot_row_dual, solver.rs:855-917
-__global__ void __launch_bounds__(256) k_select_row_dual(const double* __restrict__ xB, const double* __restrict__ loB,
-                                                          const double* __restrict__ hiB, const double* __restrict__ w, int m,
-                                                          int use_se, double* __restrict__ red_f, long long* __restrict__ red_i,
-                                                          unsigned* counter, DevRes* res) {
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  KeyIdx best{-INFINITY, LLONG_MAX};
-  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
-    const double val = xB[r], mn = loB[r], mx = hiB[r];
-    double infeas;
-    if (val < mn - EPS) infeas = mn - val;
-    else if (val > mx + EPS) infeas = val - mx;
-    else continue;
-    const double score = use_se ? infeas * infeas / w[r] : infeas;
-    if (better_max(score, r, best.key, best.idx)) { best.key = score; best.idx = r; }
-  }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
-  if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
-    const double k = __ldcg(red_f + q);
-    const long long i = __ldcg(red_i + q);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
-  }
-  b = block_argmax(b, smk, smi);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    if (b.idx == LLONG_MAX) res->i[0] = -1;
-    else {
-      const int r = (int)b.idx;
-      res->i[0] = r;
-      res->f[0] = xB[r];
-      res->f[1] = loB[r];
-      res->f[2] = hiB[r];
-    }
-  }
-}
-
+// ------------------------------------------------------------------------------------------------ K11 dual column
 // choose_entering_col_dual, solver.rs:919-1021
 __device__ __forceinline__ bool dual_eligible(double coeff, unsigned f, int leaving_diff_sign) {
   bool entering_diff_sign;
@@ -860,11 +560,18 @@ __global__ void __launch_bounds__(256) k_ratio_dual_1(const double* __restrict__
     scal[0] = b;
   }
 }
+__global__ void k_min_small(const double* __restrict__ vals, int cnt, double* __restrict__ out) {
+  double b = INFINITY;
+  for (int q = 0; q < cnt; ++q) b = fmin(b, vals[q]);
+  *out = b;
+}
+// pass 2: exact ties in |coeff| go to the lowest GLOBAL variable index (the reference: first-touch order)
 __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__ rc, const double* __restrict__ d,
                                                        const uint8_t* __restrict__ vflag, const int32_t* __restrict__ vpos,
-                                                       const double* __restrict__ xnb, int64_t nt, int lds,
-                                                       const double* __restrict__ scal, double* __restrict__ red_f,
-                                                       long long* __restrict__ red_i, unsigned* counter, DevRes* res) {
+                                                       const double* __restrict__ xnb, int64_t nt, int64_t n, int64_t c0,
+                                                       int64_t ng, int lds, const double* __restrict__ scal,
+                                                       double* __restrict__ red_f, long long* __restrict__ red_i,
+                                                       unsigned* counter, const int* __restrict__ flags, Cand* out) {
   __shared__ double smk[32];
   __shared__ long long smi[32];
   const double max_step = scal[0];
@@ -876,7 +583,8 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
     if (!dual_eligible(coeff, f, lds)) continue;
     const double oc = clamp_obj(d[v], f);
     const double cur = fabs(oc) / fabs(coeff);  // 993
-    if (cur <= max_step && better_max(fabs(coeff), v, best.key, best.idx)) { best.key = fabs(coeff); best.idx = v; }
+    const long long g = v < n ? c0 + v : ng + (v - n);
+    if (cur <= max_step && better_max(fabs(coeff), g, best.key, best.idx)) { best.key = fabs(coeff); best.idx = g; }
   }
   best = block_argmax(best, smk, smi);
   if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
@@ -890,21 +598,25 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
   b = block_argmax(b, smk, smi);
   if (threadIdx.x == 0) {
     *counter = 0;
-    if (b.idx == LLONG_MAX) res->i[0] = -1;
+    out->f[4] = (double)flags[0];
+    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
     else {
-      const long long v = b.idx;
-      res->i[0] = v;
-      res->i[1] = vpos[v];
-      res->f[0] = rc[v];
-      res->f[1] = d[v];
-      res->f[2] = xnb[v];
+      const long long g = b.idx;
+      const long long v = g >= ng ? n + (g - ng) : g - c0;
+      out->key = b.key;
+      out->tie = g;
+      out->var = g;
+      out->f[0] = rc[v];
+      out->f[1] = d[v];
+      out->f[2] = xnb[v];
+      out->f[3] = (double)vpos[v];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ pivot updates
-// Row half of Solver::pivot: basic values (solver.rs:1049-1055), dual steepest-edge norms
-// (update_dual_sq_norms 1163-1173) and the new eta column (push_eta_matrix 1274-1284).
+// Row half of Solver::pivot: basic values (solver.rs:1049-1055), dual steepest-edge norms (update_dual_sq_norms
+// 1163-1173) and the new eta column (push_eta_matrix 1274-1284).  Replicated on every shard.
 __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ alpha, const double* __restrict__ tau,
                                                      double* __restrict__ xB, double* __restrict__ w, int m, int row,
                                                      double entering_new_val, double entering_diff, double coeff, int has_elem,
@@ -933,17 +645,18 @@ __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ a
   }
   if (eta_col) eta_col[r] = (r == row) ? 1.0 - 1.0 / coeff : a / coeff;  // 1276-1280
 }
-// Variable half: reduced costs (solver.rs:1073-1080) and primal steepest-edge norms (1139-1150).
+// Variable half over this shard's variables: reduced costs (solver.rs:1073-1080) and primal steepest-edge norms
+// (1139-1150).  pivot_obj = d_q / coeff comes from the host (the entering column may live on another shard).
 __global__ void __launch_bounds__(256) k_pivot_vars(double* __restrict__ d, double* __restrict__ gam,
                                                      const double* __restrict__ rc, const double* __restrict__ helper,
-                                                     const uint8_t* __restrict__ vflag, int64_t nt, int64_t q, double coeff,
-                                                     int pse, const double* __restrict__ scal, int* __restrict__ flags) {
+                                                     const uint8_t* __restrict__ vflag, int64_t nt, int64_t q_local,
+                                                     double pivot_obj, double coeff, int pse, const double* __restrict__ scal,
+                                                     int* __restrict__ flags) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nt || v == q) return;
+  if (v >= nt || v == q_local) return;
   if (vflag[v] & MLP_BASIC) return;
   const double c = rc[v];
   if (c == 0.0) return;
-  const double pivot_obj = d[q] / coeff;  // 1073
   d[v] -= pivot_obj * c;
   if (pse) {
     const double psn = scal[2] + 1.0;  // 1136
@@ -954,84 +667,91 @@ __global__ void __launch_bounds__(256) k_pivot_vars(double* __restrict__ d, doub
   }
 }
 // Bookkeeping of Solver::pivot done by one thread: 1057-1058, 1066-1071, 1076, 1142, 1088-1091.
+// q / lv are GLOBAL ids; ql / lvl their local indices on this shard or -1.
 __global__ void k_pivot_swap(double* d, double* gam, double* xnb, uint8_t* vflag, int32_t* vpos, int32_t* bvar, double* loB,
-                             double* hiB, const double* lo, const double* hi, int64_t q, int col, int row, double coeff,
-                             double leaving_new_val, int pse, const double* scal, int* flags, DevRes* res) {
+                             double* hiB, const double* lo, const double* hi, int64_t q, int64_t ql, int64_t lvl, int col, int row,
+                             double pivot_obj, double coeff, double leaving_new_val, int pse, const double* scal, int* flags,
+                             DevRes* res) {
   const int lv = bvar[row];
-  const double pivot_obj = d[q] / coeff;
   loB[row] = lo[q];
   hiB[row] = hi[q];
-  xnb[lv] = leaving_new_val;
-  unsigned f = 0;  // nb_var_is_fixed stays with the non-basic position in the reference and is false on this path
-  if (leaving_new_val == lo[lv]) f |= MLP_AT_MIN;
-  if (leaving_new_val == hi[lv]) f |= MLP_AT_MAX;
-  vflag[lv] = (uint8_t)f;
-  vpos[lv] = col;
-  d[lv] = -pivot_obj;
-  if (pse) {
-    const double g = (scal[2] + 1.0) / (coeff * coeff);
-    gam[lv] = g;
-    if (!isfinite(g)) flags[0] = 1;
+  if (lvl >= 0) {
+    xnb[lvl] = leaving_new_val;
+    unsigned f = 0;  // nb_var_is_fixed stays with the non-basic position in the reference and is false on this path
+    if (leaving_new_val == lo[lv]) f |= MLP_AT_MIN;
+    if (leaving_new_val == hi[lv]) f |= MLP_AT_MAX;
+    vflag[lvl] = (uint8_t)f;
+    vpos[lvl] = col;
+    d[lvl] = -pivot_obj;
+    if (pse) {
+      const double g = (scal[2] + 1.0) / (coeff * coeff);
+      gam[lvl] = g;
+      if (!isfinite(g)) flags[0] = 1;
+    }
   }
   bvar[row] = (int32_t)q;
-  vflag[q] = MLP_BASIC;
-  vpos[q] = row;
+  if (ql >= 0) {
+    vflag[ql] = MLP_BASIC;
+    vpos[ql] = row;
+  }
   res->i[0] = lv;
   res->flags[0] = flags[0];
   res->flags[1] = flags[1];
 }
-__global__ void k_flip_var(double* xnb, uint8_t* vflag, const double* lo, const double* hi, int64_t q, double new_val) {
-  xnb[q] = new_val;
-  unsigned f = vflag[q] & MLP_FIXED;
+__global__ void k_flip_var(double* xnb, uint8_t* vflag, const double* lo, const double* hi, int64_t q, int64_t ql, double new_val) {
+  xnb[ql] = new_val;
+  unsigned f = vflag[ql] & MLP_FIXED;
   if (new_val == lo[q]) f |= MLP_AT_MIN;
   if (new_val == hi[q]) f |= MLP_AT_MAX;
-  vflag[q] = (uint8_t)f;  // solver.rs:1038-1040
-}
-// Coupling matrix of the eta file: G[i][j] = E_j[r_i] (j < i).  New eta K adds row K (a strided gather of row
-// r_K of E) — see DESIGN.md "eta chain in closed form".
-__global__ void k_eta_grow(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ G, int64_t ldg,
-                           int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int prev) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < K) G[(int64_t)j * ldg + K] = E[(int64_t)j * lde + rK];
-  if (j == 0) {
-    etaR[K] = rK;
-    etaPrev[K] = prev;
-    etaHead[K] = 1;
-    if (prev >= 0) etaHead[prev] = 0;
-  }
+  vflag[ql] = (uint8_t)f;  // solver.rs:1038-1040
 }
 
 // ------------------------------------------------------------------------------------------------ init kernels
-// basic_var_vals = rhs - A x_N at the initial point (solver.rs:234-238). One CTA per row.
-__global__ void __launch_bounds__(256) k_init_basic_vals(const double* __restrict__ A, int64_t lda, int64_t n,
-                                                          const double* __restrict__ xnb, const double* __restrict__ rhs,
-                                                          double* __restrict__ xB) {
+// partial of A x_N over this shard's columns (solver.rs:234-238). One CTA per row.
+__global__ void __launch_bounds__(256) k_row_dot(const double* __restrict__ A, int64_t lda, int64_t n,
+                                                  const double* __restrict__ xnb, double* __restrict__ out) {
   __shared__ double sm[32];
   const int r = blockIdx.x;
   const double* row = A + (int64_t)r * lda;
   double acc = 0.0;
   for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += row[j] * xnb[j];
   const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) xB[r] = rhs[r] - tot;
+  if (threadIdx.x == 0) out[r] = tot;
+}
+// basic_var_vals = rhs - sum over shards (in rank order) of the partial products
+__global__ void k_init_basic_vals(const double* __restrict__ parts, int world, int m, const double* __restrict__ rhs,
+                                  double* __restrict__ xB) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  double tot = 0.0;
+  for (int g = 0; g < world; ++g) tot += parts[(int64_t)g * m + r];
+  xB[r] = rhs[r] - tot;
 }
 // d_N = c_N - N^T y (recalc_obj_coeffs, solver.rs:1216-1222)
 __global__ void k_recalc_d(const double* __restrict__ cobj, const double* __restrict__ rc, const uint8_t* __restrict__ vflag,
-                           int64_t nt, double* __restrict__ d) {
+                           int64_t nt, int64_t n, int64_t c0, int64_t ng, double* __restrict__ d) {
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nt || (vflag[v] & MLP_BASIC)) return;
-  d[v] = cobj[v] - rc[v];
+  const int64_t g = v < n ? c0 + v : ng + (v - n);
+  d[v] = cobj[g] - rc[v];
 }
-// objective from scratch (solver.rs:1224-1230): basic part in row order, then non-basic part; single CTA
+// objective from scratch (solver.rs:1224-1230) in three parts: basic rows, non-basic slacks (both replicated),
+// non-basic structurals of this shard.  Single CTA, deterministic.
 __global__ void __launch_bounds__(1024) k_recalc_obj(const double* __restrict__ cobj, const int32_t* __restrict__ bvar,
                                                       const double* __restrict__ xB, int m, const double* __restrict__ xnb,
-                                                      const uint8_t* __restrict__ vflag, int64_t nt, DevRes* res) {
+                                                      const uint8_t* __restrict__ vflag, int64_t n, int64_t c0, int64_t ng,
+                                                      double* __restrict__ out3) {
   __shared__ double sm[32];
-  double acc = 0.0;
-  for (int r = threadIdx.x; r < m; r += blockDim.x) acc += cobj[bvar[r]] * xB[r];
-  for (int64_t v = threadIdx.x; v < nt; v += blockDim.x)
-    if (!(vflag[v] & MLP_BASIC)) acc += cobj[v] * xnb[v];
-  const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) res->f[0] = tot;
+  double a = 0.0, b = 0.0, c = 0.0;
+  for (int r = threadIdx.x; r < m; r += blockDim.x) a += cobj[bvar[r]] * xB[r];
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x)
+    if (!(vflag[n + i] & MLP_BASIC)) b += cobj[ng + i] * xnb[n + i];
+  for (int64_t v = threadIdx.x; v < n; v += blockDim.x)
+    if (!(vflag[v] & MLP_BASIC)) c += cobj[c0 + v] * xnb[v];
+  const double ta = block_sum(a, sm);
+  const double tb = block_sum(b, sm);
+  const double tc = block_sum(c, sm);
+  if (threadIdx.x == 0) { out3[0] = ta; out3[1] = tb; out3[2] = tc; }
 }
 __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __restrict__ bvar, int m, double* __restrict__ out) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1039,30 +759,22 @@ __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __re
 }
 
 // ================================================================================================ host side
-static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
-
-static int price_chunks(const mlp_engine* e) {
-  const int tiles = cdiv(e->lda, PR_TILE);
-  int c = cdiv((int64_t)e->sm_count * 8, tiles);
-  return std::max(1, std::min(c, e->max_chunks));
-}
-
-// out (var-indexed) = N^T w over the listed rows (+ slack part), basic entries zeroed
+// out (local variable index) = N^T w over the listed rows (+ slack part), basic entries zeroed
 static mlp_status price_list(mlp_engine* e, const int32_t* rows, const double* wts, const int32_t* count_ptr, int fixed_count,
                              const double* slack_vals, double* out, int prof_slot = -1) {
-  const int C = price_chunks(e);
-  dim3 grid(cdiv(e->lda, PR_TILE), C);
+  dim3 grid(cdiv(e->lda, PR_TILE), PR_MAXC);
   const bool prof = e->prof_on && prof_slot >= 0;
   if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], e->stream));
   LAUNCH(e, k_price_partial<0>, grid, PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, e->partial);
-  LAUNCH(e, k_price_finish, cdiv(e->nt, 256), 256, 0, e->partial, C, e->lda, e->n, e->m, slack_vals, e->vflag, out, 0);
+  LAUNCH(e, k_price_finish, cdiv(e->nt, 256), 256, 0, e->partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
+         e->vflag, out, 0);
   if (prof) {
     CU(cudaEventRecord(e->pev[prof_slot][1], e->stream));
     e->ppending[prof_slot] = true;
   }
   return MLP_OK;
 }
-// after a stream sync: fold pending price-out timings into the profile. support sizes come from h_res->i[2..3].
+// after a stream sync: fold pending price-out timings into the profile
 static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
   for (int slot = 0; slot < 2; ++slot) {
     if (!e->ppending[slot]) continue;
@@ -1083,15 +795,17 @@ static void compact(mlp_engine* e, const double* x, int32_t* idx, double* val, i
   LAUNCH(e, k_compact_count, nseg, CP_SEG, 0, x, m, e->seg_cnt, e->seg_ss, e->red_counter, count, sumsq);
   if (idx) LAUNCH(e, k_compact_write, nseg, CP_SEG, 0, x, m, e->seg_cnt, idx, val);
 }
+static int gemv_split(const mlp_engine* e, int rows, int cols) {
+  int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(2 * (int64_t)e->sm_count, cols)));
+  return std::min(S, std::max(1, rows / 2048));
+}
 static void gemv_t(mlp_engine* e, const double* M, int64_t ld, int rows, int cols, const double* x, double* part,
                    const double* base, const int32_t* base_idx, double* out, int negate) {
   if (cols <= 0) return;
-  int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(2 * (int64_t)e->sm_count, cols)));
-  S = std::min(S, std::max(1, rows / 2048));
+  const int S = gemv_split(e, rows, cols);
   LAUNCH(e, k_gemv_t_part, dim3((unsigned)cols, (unsigned)S), 256, 0, M, ld, rows, cols, x, part);
   LAUNCH(e, k_gemv_t_fin, cdiv(cols, 256), 256, 0, part, S, cols, base, base_idx, out, negate);
 }
-
 template <bool FWD, bool AXPY, bool UNIT> static void trsv(mlp_engine* e, const double* M, int64_t ld, int n, double* x) {
   if (n <= 0) return;
   auto kern = k_trsv<FWD, AXPY, UNIT>;
@@ -1106,7 +820,7 @@ static mlp_status ftran(mlp_engine* e, const double* rhs0, double* out) {
     trsv<true, true, true>(e, e->LUc, e->kcap, k, e->xk);    // L y = P a_R   (lu.rs:92)
     trsv<false, true, false>(e, e->LUc, e->kcap, k, e->xk);  // U x = y      (lu.rs:93)
   }
-  LAUNCH(e, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->m, m, k, e->xk, rhs0, e->rowcover, e->Jpos, out);
+  LAUNCH(e, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->m, m, k, e->xk, rhs0, e->rowcover, e->Jpos, e->Jslot, out);
   if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form
     LAUNCH(e, k_gather_idx, cdiv(K, 256), 256, 0, out, e->etaR, K, e->tK);
     trsv<true, true, true>(e, e->G, e->Kcap, K, e->tK);
@@ -1127,7 +841,9 @@ static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
   }
   LAUNCH(e, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, e->work_m2);
   if (k > 0) {
-    gemv_t(e, e->Bcols, e->m, m, k, e->work_m2, e->gt_part_k, c, e->Jpos, e->xk, 1);
+    const int S = gemv_split(e, m, k);
+    LAUNCH(e, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->m, m, k, e->Jslot, e->work_m2, e->gt_part_k);
+    LAUNCH(e, k_gemv_t_fin, cdiv(k, 256), 256, 0, e->gt_part_k, S, k, c, e->Jpos, e->xk, 1);
     trsv<true, false, false>(e, e->LUc, e->kcap, k, e->xk);  // U^T z = rhs   (lu_factors_transp.lower = U^T, lu.rs:110)
     trsv<false, false, true>(e, e->LUc, e->kcap, k, e->xk);  // L^T y = z
     LAUNCH(e, k_scatter_idx, cdiv(k, 256), 256, 0, e->xk, e->Rp, k, out);
@@ -1135,19 +851,27 @@ static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
   return MLP_OK;
 }
 
+// Column cache / LU arenas.  First allocation is generous (~1 GB of basis columns): cudaFree/cudaMalloc of the big
+// arenas costs tens of milliseconds, so capacity grows by doubling and rarely; the cache content survives growth.
 static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
-  // first allocation is generous (up to ~1 GB for the basis columns): cudaFree/cudaMalloc of the big arenas
-  // costs tens of milliseconds, so capacity grows by doubling and rarely
   int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->m)))));
   while (cap < k) cap *= 2;
   cap = std::min<int64_t>(cap, e->m);
-  dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
+  double* nb = nullptr;
+  ST(dev_alloc(&nb, (size_t)e->m * cap));
+  if (e->Bcols && e->kcap > 0) {
+    CU(cudaMemcpyAsync(nb, e->Bcols, (size_t)e->m * e->kcap * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
+  dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
   dev_free(e->gt_part_k);
+  e->Bcols = nb;
   e->kcap = cap;
+  ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jslot, cap)); ST(dev_alloc(&e->Rp, cap));
+  ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->xk, cap));
   ST(dev_alloc(&e->gt_part_k, (size_t)GT_MAXSPLIT * cap));
-  ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jvar, cap)); ST(dev_alloc(&e->Rp, cap));
-  ST(dev_alloc(&e->Bcols, (size_t)e->m * cap)); ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->xk, cap));
   return MLP_OK;
 }
 static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
@@ -1157,19 +881,23 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
   dev_free(e->gt_part_K);
   e->Kcap = cap;
-  ST(dev_alloc(&e->gt_part_K, (size_t)GT_MAXSPLIT * cap));
   ST(dev_alloc(&e->E, (size_t)e->m * cap)); ST(dev_alloc(&e->G, (size_t)cap * cap));
   ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap)); ST(dev_alloc(&e->tK, cap));
+  ST(dev_alloc(&e->gt_part_K, (size_t)GT_MAXSPLIT * cap));
   return MLP_OK;
 }
 
+// BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.
 static mlp_status refactor_impl(mlp_engine* e) {
-  const int64_t m = e->m, n = e->n;
-  std::vector<int32_t> jpos, jvar, rowcover(m, -1), R;
+  const int64_t m = e->m, ng = e->ng;
+  std::vector<int32_t> jpos, jslot, rowcover(m, -1), R;
   for (int64_t p = 0; p < m; ++p) {
-    const int32_t v = e->h_bvar[p];
-    if (v < n) { jpos.push_back((int32_t)p); jvar.push_back(v); }
-    else rowcover[v - n] = (int32_t)p;
+    const int64_t v = e->h_bvar[p];
+    if (v < ng) {
+      jpos.push_back((int32_t)p);
+      if (e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
+      jslot.push_back(e->h_slot_of_row[p]);
+    } else rowcover[v - ng] = (int32_t)p;
   }
   for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
   const int64_t k = (int64_t)jpos.size();
@@ -1179,16 +907,15 @@ static mlp_status refactor_impl(mlp_engine* e) {
   ST(ensure_eta_capacity(e, 2 * k + 32));
   e->k = k;
   e->K = 0;
-  CU(cudaMemsetAsync(e->d_res->flags, 0, 4 * sizeof(int), e->stream));
+  CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
   std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
   ST(h2d(e, e->rowcover, rowcover.data(), m * sizeof(int32_t)));
   if (k > 0) {
     ST(h2d(e, e->Jpos, jpos.data(), k * sizeof(int32_t)));
-    ST(h2d(e, e->Jvar, jvar.data(), k * sizeof(int32_t)));
+    ST(h2d(e, e->Jslot, jslot.data(), k * sizeof(int32_t)));
     ST(h2d(e, e->Rp, R.data(), k * sizeof(int32_t)));
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
-    LAUNCH(e, k_gather_bcols, dim3(cdiv(m, 256), (unsigned)k), 256, 0, e->A, e->lda, (int)m, (int)k, e->Jvar, e->Bcols, e->m);
-    LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->m, (int)k, e->Rp, e->LUc, e->kcap);
+    LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->m, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
     int* flags = e->d_res->flags;
     for (int t = 0; t < (int)k; ++t) {
       LAUNCH(e, k_lu_pivot, 1, 1024, 0, e->LUc, e->kcap, (int)k, t, e->Rp, flags);
@@ -1208,111 +935,255 @@ static mlp_status refactor_impl(mlp_engine* e) {
   return MLP_OK;
 }
 
-extern "C" {
-
-mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out) {
-  *out = nullptr;
-  if (m <= 0 || n <= 0 || m > 0x7fffffff || n + m > 0x7fffffff) { set_err("bad dimensions"); return MLP_INVALID; }
-  if (mlp_device_count() <= device) { set_err("no CUDA device: the engine has no CPU fallback"); return MLP_NO_DEVICE; }
-  CU(cudaSetDevice(device));
-  mlp_engine* e = new mlp_engine();
-  e->device = device;
-  e->m = m; e->n = n; e->nt = n + m;
-  e->lda = (n + 15) / 16 * 16;
-  e->ldv = e->nt;
-  cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, device));
-  e->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  mlp_status st = MLP_OK;
-  auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
-  A(dev_alloc(&e->A, (size_t)m * e->lda));
-  A(dev_alloc(&e->lo, e->nt)); A(dev_alloc(&e->hi, e->nt)); A(dev_alloc(&e->cobj, e->nt));
-  A(dev_alloc(&e->d, e->nt)); A(dev_alloc(&e->gam, e->nt)); A(dev_alloc(&e->xnb, e->nt));
-  A(dev_alloc(&e->vflag, e->nt)); A(dev_alloc(&e->vpos, e->nt)); A(dev_alloc(&e->bvar, m));
-  A(dev_alloc(&e->xB, m)); A(dev_alloc(&e->loB, m)); A(dev_alloc(&e->hiB, m)); A(dev_alloc(&e->w, m)); A(dev_alloc(&e->rhs, m));
-  A(dev_alloc(&e->alpha, m)); A(dev_alloc(&e->rho, m)); A(dev_alloc(&e->tau, m)); A(dev_alloc(&e->vvec, m));
-  A(dev_alloc(&e->work_m, m)); A(dev_alloc(&e->work_m2, m));
-  A(dev_alloc(&e->rc, e->nt)); A(dev_alloc(&e->helper, e->nt));
-  A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m));
-  A(dev_alloc(&e->partial, (size_t)e->max_chunks * e->lda));
-  A(dev_alloc(&e->red_f, 4096)); A(dev_alloc(&e->red_i, 4096)); A(dev_alloc(&e->red_counter, 4));
-  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
-  A(dev_alloc(&e->seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->seg_ss, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
-  if (st != MLP_OK) { mlp_engine_destroy(e); return st; }
-  CU(cudaHostAlloc((void**)&e->h_res, sizeof(DevRes), cudaHostAllocDefault));
-  for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) CU(cudaEventCreate(&e->pev[i][j]));
-  CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->red_counter, 0, 4 * sizeof(unsigned), e->stream));
-  CU(cudaMemsetAsync(e->d_res, 0, sizeof(DevRes), e->stream));
-  CU(cudaMemsetAsync(e->gam, 0, e->nt * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->helper, 0, e->nt * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->rc, 0, e->nt * sizeof(double), e->stream));
+// The exchange step: every shard's candidate header + candidate column are all-gathered, the winner is chosen with the
+// reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
+static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
+  const int m = (int)e->m;
+  LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend,
+         (double*)(e->xsend + sizeof(Cand)));
+  char* recv = e->xsend;
+  if (e->world > 1) {
+    ST(e->comm->allgather(e->xsend, e->xrecv, e->xbytes, e->stream));
+    recv = e->xrecv;
+  }
+  CU(cudaMemcpy2DAsync(e->h_cands, sizeof(Cand), recv, e->xbytes, sizeof(Cand), (size_t)e->world, cudaMemcpyDeviceToHost,
+                       e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  e->h_bvar.assign(m, 0);
-  e->h_last_eta_of_row.assign(m, -1);
-  *out = e;
+  e->cnt.d2h_bytes += (int64_t)sizeof(Cand) * e->world;
+  int best = -1;
+  bool err = false;
+  for (int r = 0; r < e->world; ++r) {
+    const Cand& c = e->h_cands[r];
+    if (c.f[4] != 0.0) err = true;
+    if (c.var < 0) continue;
+    if (best < 0 || c.key > e->h_cands[best].key || (c.key == e->h_cands[best].key && c.tie < e->h_cands[best].tie)) best = r;
+  }
+  if (err) { set_err("non-finite steepest-edge norm on a shard"); return MLP_NONFINITE; }
+  if (best < 0) { winner->var = -1; e->colq_var = -1; return MLP_OK; }
+  *winner = e->h_cands[best];
+  CU(cudaMemcpyAsync(e->colq, recv + (size_t)best * e->xbytes + sizeof(Cand), (size_t)m * sizeof(double),
+                     cudaMemcpyDeviceToDevice, e->stream));
+  e->colq_var = winner->var;
   return MLP_OK;
 }
 
-void mlp_engine_destroy(mlp_engine* e) {
+// make colq hold the column of GLOBAL variable var on every shard
+static mlp_status fetch_column(mlp_engine* e, int64_t var) {
+  if (e->colq_var == var) return MLP_OK;
+  const int m = (int)e->m;
+  const int64_t lv = to_local(e, var);
+  if (lv >= 0) LAUNCH(e, k_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, m, lv, e->colq);
+  if (e->world > 1 && var < e->ng) ST(e->comm->broadcast(e->colq, (size_t)m * sizeof(double), owner_of(e, var), e->stream));
+  e->colq_var = var;
+  return MLP_OK;
+}
+
+static void destroy_engine(mlp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
   dev_free(e->rhs); dev_free(e->alpha); dev_free(e->rho); dev_free(e->tau); dev_free(e->vvec); dev_free(e->work_m);
-  dev_free(e->work_m2); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val); dev_free(e->partial);
-  dev_free(e->red_f); dev_free(e->red_i); dev_free(e->red_counter); dev_free(e->scal); dev_free(e->icnt); dev_free(e->d_res);
-  dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jvar); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
+  dev_free(e->work_m2); dev_free(e->colq); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val);
+  dev_free(e->partial); dev_free(e->red_f); dev_free(e->red_i); dev_free(e->red_counter); dev_free(e->scal); dev_free(e->icnt);
+  dev_free(e->seg_cnt); dev_free(e->seg_ss); dev_free(e->gt_part_k); dev_free(e->gt_part_K); dev_free(e->d_res);
+  dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred);
+  dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
   dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
-  dev_free(e->seg_cnt); dev_free(e->seg_ss); dev_free(e->gt_part_k); dev_free(e->gt_part_K);
   if (e->h_res) cudaFreeHost(e->h_res);
+  if (e->h_cands) cudaFreeHost(e->h_cands);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (e->pev[i][j]) cudaEventDestroy(e->pev[i][j]);
+  delete e->comm;
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
 
-mlp_status mlp_engine_upload_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host) {
+static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out) {
+  *out = nullptr;
+  if (m <= 0 || ng <= 0 || m > 0x7fffffff || ng + m > 0x7fffffff || world < 1 || rank < 0 || rank >= world) {
+    set_err("bad dimensions");
+    delete comm;
+    return MLP_INVALID;
+  }
+  if (mlp_device_count() <= device) {
+    set_err("no CUDA device: the engine has no CPU fallback");
+    delete comm;
+    return MLP_NO_DEVICE;
+  }
+  CU(cudaSetDevice(device));
+  mlp_engine* e = new mlp_engine();
+  e->device = device;
+  e->comm = comm;
+  e->rank = rank;
+  e->world = world;
+  int64_t c0, c1;
+  mlp_shard_range(ng, world, rank, &c0, &c1);
+  e->m = m; e->ng = ng; e->c0 = c0; e->n = c1 - c0; e->nt = e->n + m;
+  e->lda = std::max<int64_t>(16, (e->n + 15) / 16 * 16);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  e->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  mlp_status st = MLP_OK;
+  auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
+  const int64_t nt = e->nt, gt = ng + m;
+  A(dev_alloc(&e->A, (size_t)m * e->lda));
+  A(dev_alloc(&e->lo, gt)); A(dev_alloc(&e->hi, gt)); A(dev_alloc(&e->cobj, gt));
+  A(dev_alloc(&e->d, nt)); A(dev_alloc(&e->gam, nt)); A(dev_alloc(&e->xnb, nt));
+  A(dev_alloc(&e->vflag, nt)); A(dev_alloc(&e->vpos, nt)); A(dev_alloc(&e->bvar, m));
+  A(dev_alloc(&e->xB, m)); A(dev_alloc(&e->loB, m)); A(dev_alloc(&e->hiB, m)); A(dev_alloc(&e->w, m)); A(dev_alloc(&e->rhs, m));
+  A(dev_alloc(&e->alpha, m)); A(dev_alloc(&e->rho, m)); A(dev_alloc(&e->tau, m)); A(dev_alloc(&e->vvec, m));
+  A(dev_alloc(&e->work_m, m)); A(dev_alloc(&e->work_m2, m)); A(dev_alloc(&e->colq, m));
+  A(dev_alloc(&e->rc, nt)); A(dev_alloc(&e->helper, nt));
+  A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m));
+  A(dev_alloc(&e->partial, (size_t)PR_MAXC * e->lda));
+  A(dev_alloc(&e->red_f, 4096)); A(dev_alloc(&e->red_i, 4096)); A(dev_alloc(&e->red_counter, 4));
+  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
+  A(dev_alloc(&e->seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->seg_ss, (size_t)cdiv(m, CP_SEG) + 1));
+  A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
+  e->xbytes = sizeof(Cand) + (size_t)m * sizeof(double);
+  A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * m + 64));
+  if (st != MLP_OK) { destroy_engine(e); return st; }
+  CU(cudaHostAlloc((void**)&e->h_res, sizeof(DevRes), cudaHostAllocDefault));
+  CU(cudaHostAlloc((void**)&e->h_cands, sizeof(Cand) * world, cudaHostAllocDefault));
+  for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) CU(cudaEventCreate(&e->pev[i][j]));
+  CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->red_counter, 0, 4 * sizeof(unsigned), e->stream));
+  CU(cudaMemsetAsync(e->d_res, 0, sizeof(DevRes), e->stream));
+  CU(cudaMemsetAsync(e->gam, 0, nt * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->helper, 0, nt * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->rc, 0, nt * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->xsend, 0, e->xbytes, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  e->h_bvar.assign(m, 0);
+  e->h_slot_of_row.assign(m, -1);
+  e->h_last_eta_of_row.assign(m, -1);
+  *out = e;
+  return MLP_OK;
+}
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------- sharding helpers (host only)
+void mlp_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* begin, int64_t* end) {
+  // contiguous blocks of whole 16-column units (128-byte row segments), sizes differ by at most one unit
+  const int64_t units = (n + 15) / 16;
+  const int64_t b = units * rank / world, e = units * (rank + 1) / world;
+  *begin = std::min<int64_t>(b * 16, n);
+  *end = std::min<int64_t>(e * 16, n);
+}
+int32_t mlp_reduce_candidates(const double* scores, const int64_t* pos, const int64_t* vars, int32_t world) {
+  int32_t best = -1;
+  for (int32_t r = 0; r < world; ++r) {
+    if (vars[r] < 0) continue;
+    if (best < 0 || scores[r] > scores[best] || (scores[r] == scores[best] && pos[r] < pos[best])) best = r;
+  }
+  return best;
+}
+mlp_status mlp_local_group_create(int32_t world, void** out) {
+  if (world < 1) return MLP_INVALID;
+  *out = new LocalGroup(world);
+  return MLP_OK;
+}
+void mlp_local_group_destroy(void* g) { delete (LocalGroup*)g; }
+mlp_status mlp_nccl_get_unique_id(void* out128) {
+  if (!ncclapi::load()) return MLP_INVALID;
+  ncclUniqueId id;
+  NC(ncclapi::GetUniqueId(&id));
+  std::memcpy(out128, &id, sizeof(id));
+  return MLP_OK;
+}
+
+mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out) {
+  return create_engine(device, m, n, 0, 1, nullptr, out);
+}
+mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
+                                           int32_t comm_kind, const void* comm_arg, mlp_engine** out) {
+  *out = nullptr;
+  Comm* comm = nullptr;
+  if (world > 1) {
+    if (mlp_device_count() <= device) { set_err("no CUDA device: the engine has no CPU fallback"); return MLP_NO_DEVICE; }
+    CU(cudaSetDevice(device));
+    if (comm_kind == MLP_COMM_NCCL) {
+      NcclComm* c = new NcclComm();
+      mlp_status st = c->init(comm_arg, rank, world);
+      if (st != MLP_OK) { delete c; return st; }
+      comm = c;
+    } else if (comm_kind == MLP_COMM_LOCAL) {
+      LocalComm* c = new LocalComm();
+      c->g = (LocalGroup*)comm_arg;
+      c->rank = rank;
+      c->world = world;
+      if (!c->g || c->g->world != world) { delete c; set_err("local group size mismatch"); return MLP_INVALID; }
+      comm = c;
+    } else { set_err("unknown comm kind"); return MLP_INVALID; }
+  }
+  return create_engine(device, m, n_global, rank, world, comm, out);
+}
+void mlp_engine_destroy(mlp_engine* e) { destroy_engine(e); }
+mlp_status mlp_engine_local_range(mlp_engine* e, int64_t* begin, int64_t* end) {
+  if (!e) return MLP_INVALID;
+  *begin = e->c0;
+  *end = e->c0 + e->n;
+  return MLP_OK;
+}
+
+// rows_host: nrows x src_cols row-major; src_cols == n_global (full rows: this shard's slice is taken) or == local width
+static mlp_status upload_rows_impl(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host, bool local) {
   if (!e || row0 < 0 || nrows < 0 || row0 + nrows > e->m) { set_err("upload_rows: range"); return MLP_INVALID; }
   CU(cudaSetDevice(e->device));
-  CU(cudaMemcpy2DAsync(e->A + row0 * e->lda, e->lda * sizeof(double), rows_host, e->n * sizeof(double), e->n * sizeof(double),
-                       (size_t)nrows, cudaMemcpyHostToDevice, e->stream));
+  if (e->n == 0 || nrows == 0) return MLP_OK;
+  const double* src = local ? rows_host : rows_host + e->c0;
+  const size_t spitch = (local ? e->n : e->ng) * sizeof(double);
+  CU(cudaMemcpy2DAsync(e->A + row0 * e->lda, e->lda * sizeof(double), src, spitch, e->n * sizeof(double), (size_t)nrows,
+                       cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   e->cnt.h2d_bytes += nrows * e->n * (int64_t)sizeof(double);
   return MLP_OK;
+}
+mlp_status mlp_engine_upload_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host) {
+  return upload_rows_impl(e, row0, nrows, rows_host, false);
+}
+mlp_status mlp_engine_upload_local_rows(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_local) {
+  return upload_rows_impl(e, row0, nrows, rows_local, true);
 }
 
 mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (!e || !st) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  const int64_t m = e->m, n = e->n, nt = e->nt;
-  ST(h2d(e, e->lo, st->orig_var_mins, nt * 8));
-  ST(h2d(e, e->hi, st->orig_var_maxs, nt * 8));
-  ST(h2d(e, e->cobj, st->orig_obj_coeffs, nt * 8));
+  const int64_t m = e->m, n = e->n, nt = e->nt, ng = e->ng, gt = ng + m;
+  ST(h2d(e, e->lo, st->orig_var_mins, gt * 8));
+  ST(h2d(e, e->hi, st->orig_var_maxs, gt * 8));
+  ST(h2d(e, e->cobj, st->orig_obj_coeffs, gt * 8));
   ST(h2d(e, e->rhs, st->orig_rhs, m * 8));
   std::vector<double> d(nt, 0.0), xnb(nt, 0.0), gam(nt, 0.0);
   std::vector<uint8_t> fl(nt, 0);
   std::vector<int32_t> pos(nt, 0), bvar(m);
-  for (int64_t c = 0; c < n; ++c) {
-    const int64_t v = st->nb_vars[c];
-    if (v < 0 || v >= nt) { set_err("init_state: nb_vars"); return MLP_INVALID; }
+  e->h_bvar.assign(m, 0);
+  for (int64_t c = 0; c < ng; ++c) {  // nb_vars has one entry per structural column count (global)
+    const int64_t g = st->nb_vars[c];
+    if (g < 0 || g >= gt) { set_err("init_state: nb_vars"); return MLP_INVALID; }
+    const int64_t v = to_local(e, g);
+    if (v < 0) continue;
     d[v] = st->nb_var_obj_coeffs[c];
     xnb[v] = st->nb_var_vals[c];
     fl[v] = st->nb_var_states[c] & (MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED);
     pos[v] = (int32_t)c;
     if (st->primal_edge_sq_norms) gam[v] = st->primal_edge_sq_norms[c];
   }
+  bool any_structural_basic = false;
   for (int64_t r = 0; r < m; ++r) {
-    const int64_t v = st->basic_vars[r];
-    if (v < 0 || v >= nt) { set_err("init_state: basic_vars"); return MLP_INVALID; }
-    fl[v] = MLP_BASIC;
-    pos[v] = (int32_t)r;
-    bvar[r] = (int32_t)v;
+    const int64_t g = st->basic_vars[r];
+    if (g < 0 || g >= gt) { set_err("init_state: basic_vars"); return MLP_INVALID; }
+    if (g < ng) any_structural_basic = true;
+    const int64_t v = to_local(e, g);
+    if (v >= 0) { fl[v] = MLP_BASIC; pos[v] = (int32_t)r; }
+    bvar[r] = (int32_t)g;
+    e->h_bvar[r] = g;
   }
-  e->h_bvar = bvar;
   e->enable_pse = st->enable_primal_steepest_edge;
   e->enable_dse = st->enable_dual_steepest_edge;
   ST(h2d(e, e->d, d.data(), nt * 8));
@@ -1326,15 +1197,38 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (st->basic_var_vals) ST(h2d(e, e->xB, st->basic_var_vals, m * 8));
   if (st->dual_edge_sq_norms) ST(h2d(e, e->w, st->dual_edge_sq_norms, m * 8));
   CU(cudaStreamSynchronize(e->stream));
-  if (!st->basic_var_vals) LAUNCH(e, k_init_basic_vals, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, e->rhs, e->xB);
+  if (!st->basic_var_vals) {
+    double* part = e->world > 1 ? e->work_m : e->xred;
+    LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, part);
+    if (e->world > 1) ST(e->comm->allgather(part, e->xred, (size_t)m * sizeof(double), e->stream));
+    LAUNCH(e, k_init_basic_vals, cdiv(m, 256), 256, 0, e->xred, e->world, (int)m, e->rhs, e->xB);
+  }
   if (!st->dual_edge_sq_norms) LAUNCH(e, k_fill, cdiv(m, 256), 256, 0, e->w, m, 1.0);
   if (e->enable_pse && !st->primal_edge_sq_norms) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
-    const int C = price_chunks(e);
-    dim3 grid(cdiv(e->lda, PR_TILE), C);
+    dim3 grid(cdiv(e->lda, PR_TILE), PR_MAXC);
     LAUNCH(e, k_price_partial<1>, grid, PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
            (const int32_t*)nullptr, (int32_t)m, e->partial);
-    LAUNCH(e, k_price_finish, cdiv(nt, 256), 256, 0, e->partial, C, e->lda, n, m, (const double*)nullptr, e->vflag, e->gam, 1);
+    LAUNCH(e, k_price_finish, cdiv(nt, 256), 256, 0, e->partial, (const int32_t*)nullptr, (int32_t)m, e->lda, n, m,
+           (const double*)nullptr, e->vflag, e->gam, 1);
+  }
+  // column cache: an initial basis with structural columns (warm start) fetches them one by one
+  e->h_slot_of_row.assign(m, -1);
+  e->h_free_slots.clear();
+  for (int64_t s = e->kcap - 1; s >= 0; --s) e->h_free_slots.push_back((int32_t)s);
+  e->colq_var = -1;
+  if (any_structural_basic) {
+    int64_t cnt = 0;
+    for (int64_t r = 0; r < m; ++r) if (e->h_bvar[r] < ng) ++cnt;
+    ST(ensure_lu_capacity(e, cnt));
+    for (int64_t r = 0; r < m; ++r) {
+      if (e->h_bvar[r] >= ng) continue;
+      ST(fetch_column(e, e->h_bvar[r]));
+      const int32_t slot = e->h_free_slots.back();
+      e->h_free_slots.pop_back();
+      CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * m, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+      e->h_slot_of_row[r] = slot;
+    }
   }
   e->initialized = true;
   ST(refactor_impl(e));
@@ -1359,24 +1253,26 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int grid = std::min(cdiv(e->nt, 256), 1024);
-  LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->enable_pse, e->red_f, e->red_i,
-         e->red_counter, e->xnb, e->lo, e->hi, e->d_res);
-  ST(fetch_res(e));
-  out->var = e->h_res->i[0];
-  out->pos = e->h_res->i[1];
-  out->obj_coeff = e->h_res->f[0];
-  out->score = e->h_res->f[1];
-  out->cur_val = e->h_res->f[2];
-  out->var_min = e->h_res->f[3];
-  out->var_max = e->h_res->f[4];
+  LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->n, e->c0, e->ng, e->enable_pse, e->red_f,
+         e->red_i, e->red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
+  Cand w;
+  w.var = -1;
+  ST(exchange_candidates(e, &w));
+  out->var = w.var;
+  if (w.var < 0) { out->pos = -1; return MLP_OK; }
+  out->pos = w.tie;
+  out->score = w.key;
+  out->obj_coeff = w.f[0];
+  out->cur_val = w.f[1];
+  out->var_min = out->var_max = 0.0;  // the host keeps orig_var_mins / orig_var_maxs (solver.rs:19-20)
   return MLP_OK;
 }
 
 mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
-  if (!e || !e->initialized || var < 0 || var >= e->nt) return MLP_INVALID;
+  if (!e || !e->initialized || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  LAUNCH(e, k_load_col, cdiv(e->m, 256), 256, 0, e->A, e->lda, e->n, (int)e->m, var, e->work_m);
-  ST(ftran(e, e->work_m, e->alpha));
+  ST(fetch_column(e, var));
+  ST(ftran(e, e->colq, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
   compact(e, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
   return MLP_OK;
@@ -1436,21 +1332,27 @@ mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
 mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out) {
   if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925): the host knows basic_val from
-  // select_row_dual, but fix_var-style callers may not; read it back (8 bytes).
+  // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925)
   double bv = 0.0;
   ST(d2h(e, &bv, e->xB + row, sizeof(double)));
   const int lds = leaving_new_val > bv ? 1 : 0;
   const int grid = std::min(cdiv(e->nt, 256), 1024);
   LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, e->red_f, e->red_counter, e->scal);
-  LAUNCH(e, k_ratio_dual_2, grid, 256, 0, e->rc, e->d, e->vflag, e->vpos, e->xnb, e->nt, lds, e->scal, e->red_f, e->red_i,
-         e->red_counter, e->d_res);
-  ST(fetch_res(e));
-  out->var = e->h_res->i[0];
-  out->pos = e->h_res->i[1];
-  out->coeff = e->h_res->f[0];
-  out->obj_coeff = e->h_res->f[1];
-  out->cur_val = e->h_res->f[2];
+  if (e->world > 1) {  // Harris pass 1 is a min over ALL variables: all-gather the shard minima
+    ST(e->comm->allgather(e->scal, e->xred, sizeof(double), e->stream));
+    LAUNCH(e, k_min_small, 1, 1, 0, e->xred, e->world, e->scal);
+  }
+  LAUNCH(e, k_ratio_dual_2, grid, 256, 0, e->rc, e->d, e->vflag, e->vpos, e->xnb, e->nt, e->n, e->c0, e->ng, lds, e->scal,
+         e->red_f, e->red_i, e->red_counter, e->d_res->flags, (Cand*)e->xsend);
+  Cand w;
+  w.var = -1;
+  ST(exchange_candidates(e, &w));
+  out->var = w.var;
+  if (w.var < 0) { out->pos = -1; return MLP_OK; }
+  out->coeff = w.f[0];
+  out->obj_coeff = w.f[1];
+  out->cur_val = w.f[2];
+  out->pos = (int64_t)w.f[3];
   return MLP_OK;
 }
 
@@ -1459,25 +1361,26 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
   const int64_t q = pi->entering_var;
+  const int64_t ql = to_local(e, q);
   out->leaving_var = -1;
   out->col_nnz = 0;
   out->refactored = 0;
   out->lu_nnz = e->lu_nnz;
-  CU(cudaMemsetAsync(e->d_res->flags, 0, 4 * sizeof(int), e->stream));
   if (!pi->has_elem) {  // solver.rs:1031-1042
     LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, -1, pi->entering_new_val, pi->entering_diff,
            1.0, 0, 0, e->scal, (double*)nullptr, e->d_res->flags);
-    LAUNCH(e, k_flip_var, 1, 1, 0, e->xnb, e->vflag, e->lo, e->hi, q, pi->entering_new_val);
+    if (ql >= 0) LAUNCH(e, k_flip_var, 1, 1, 0, e->xnb, e->vflag, e->lo, e->hi, q, ql, pi->entering_new_val);
     out->eta_count = e->K;
     return MLP_OK;
   }
+  if (e->colq_var != q) { set_err("pivot: mlp_ftran_col(entering_var) must precede mlp_pivot"); return MLP_INVALID; }
   const int row = (int)pi->row;
+  const int64_t lv = e->h_bvar[row];
+  const int64_t lvl = to_local(e, lv);
+  const double pivot_obj = pi->entering_obj_coeff / pi->coeff;  // solver.rs:1073
   bool do_refactor = pi->refactor != 0;
   if (!do_refactor && e->K >= e->Kcap) do_refactor = true;  // arena full
-  if (e->enable_dse) {
-    // tau = B^-1 rho (solver.rs:1157). rho is by constraint row = the layout FTRAN takes.
-    ST(ftran(e, e->rho, e->tau));
-  }
+  if (e->enable_dse) ST(ftran(e, e->rho, e->tau));  // tau = B^-1 rho (solver.rs:1157)
   double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->m;
   LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val, pi->entering_diff,
          pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags);
@@ -1488,12 +1391,24 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
     ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
   }
-  LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, q, pi->coeff, e->enable_pse,
-         e->scal, e->d_res->flags);
-  LAUNCH(e, k_pivot_swap, 1, 1, 0, e->d, e->gam, e->xnb, e->vflag, e->vpos, e->bvar, e->loB, e->hiB, e->lo, e->hi, q, (int)pi->col,
-         row, pi->coeff, pi->leaving_new_val, e->enable_pse, e->scal, e->d_res->flags, e->d_res);
-  const int32_t lv_host = e->h_bvar[row];
-  e->h_bvar[row] = (int32_t)q;
+  LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, ql, pivot_obj, pi->coeff,
+         e->enable_pse, e->scal, e->d_res->flags);
+  LAUNCH(e, k_pivot_swap, 1, 1, 0, e->d, e->gam, e->xnb, e->vflag, e->vpos, e->bvar, e->loB, e->hiB, e->lo, e->hi, q, ql, lvl,
+         (int)pi->col, row, pivot_obj, pi->coeff, pi->leaving_new_val, e->enable_pse, e->scal, e->d_res->flags, e->d_res);
+  // column cache: the leaving structural column frees its slot, the entering one takes a slot
+  if (e->h_slot_of_row[row] >= 0) { e->h_free_slots.push_back(e->h_slot_of_row[row]); e->h_slot_of_row[row] = -1; }
+  if (q < e->ng) {
+    if (e->h_free_slots.empty()) {
+      int64_t used = 0;
+      for (int32_t s : e->h_slot_of_row) if (s >= 0) ++used;
+      ST(ensure_lu_capacity(e, std::max<int64_t>(used + 1, e->kcap + 1)));
+    }
+    const int32_t slot = e->h_free_slots.back();
+    e->h_free_slots.pop_back();
+    CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->m, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+    e->h_slot_of_row[row] = slot;
+  }
+  e->h_bvar[row] = q;
   if (!do_refactor) {
     const int prev = e->h_last_eta_of_row[row];
     LAUNCH(e, k_eta_grow, cdiv(std::max<int64_t>(e->K, 1), 256), 256, 0, e->E, e->m, (int)e->K, row, e->G, e->Kcap, e->etaR,
@@ -1512,8 +1427,8 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (e->prof_on) ST(collect_profile(e, e->h_res->i[2] & 0xffffffffLL, e->h_res->i[3] & 0xffffffffLL));
   out->leaving_var = e->h_res->i[0];
   out->col_nnz = (int64_t)(int32_t)(e->h_res->i[1] & 0xffffffffLL);
-  if (out->leaving_var != lv_host) { set_err("pivot: host/device basis mirrors diverged"); return MLP_INVALID; }
-  if (e->h_res->flags[0]) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
+  if (out->leaving_var != lv) { set_err("pivot: host/device basis mirrors diverged"); return MLP_INVALID; }
+  if (e->h_res->flags[0] && e->world == 1) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   if (do_refactor) {
     ST(refactor_impl(e));
     out->refactored = 1;
@@ -1532,10 +1447,20 @@ mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {
   ST(btran(e, e->work_m, -1, e->vvec));  // multipliers y (1205-1214)
   compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
   ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));
-  LAUNCH(e, k_recalc_d, cdiv(e->nt, 256), 256, 0, e->cobj, e->helper, e->vflag, e->nt, e->d);
-  LAUNCH(e, k_recalc_obj, 1, 1024, 0, e->cobj, e->bvar, e->xB, m, e->xnb, e->vflag, e->nt, e->d_res);
-  ST(fetch_res(e));
-  *cur_obj_val = e->h_res->f[0];
+  LAUNCH(e, k_recalc_d, cdiv(e->nt, 256), 256, 0, e->cobj, e->helper, e->vflag, e->nt, e->n, e->c0, e->ng, e->d);
+  LAUNCH(e, k_recalc_obj, 1, 1024, 0, e->cobj, e->bvar, e->xB, m, e->xnb, e->vflag, e->n, e->c0, e->ng, e->scal + 4);
+  std::vector<double> parts((size_t)e->world, 0.0);
+  double three[3];
+  if (e->world > 1) {
+    ST(e->comm->allgather(e->scal + 6, e->xred, sizeof(double), e->stream));
+    ST(d2h(e, parts.data(), e->xred, sizeof(double) * e->world));
+  }
+  ST(d2h(e, three, e->scal + 4, sizeof(three)));
+  if (e->world == 1) parts[0] = three[2];
+  double tot = three[0];  // basic rows first (1225-1227), then the non-basic variables (1228-1230)
+  tot += three[1];
+  for (int r = 0; r < e->world; ++r) tot += parts[r];
+  *cur_obj_val = tot;
   return MLP_OK;
 }
 
@@ -1590,7 +1515,6 @@ mlp_status mlp_engine_sync(mlp_engine* e) {
   CU(cudaGetLastError());
   return MLP_OK;
 }
-
 mlp_status mlp_event_mark(mlp_engine* e, int32_t slot) {
   if (!e || slot < 0 || slot > 3) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
@@ -1638,7 +1562,7 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
   cudaEventDestroy(a);
   cudaEventDestroy(b);
   *ms_per_launch = (double)ms / iters;
-  // algorithmic bytes: 8 n s + 8 s + 8 n  with s = m
+  // algorithmic bytes: 8 n s + 8 s + 8 n  with s = m, n = this shard's columns
   *bytes_per_launch = 8 * e->n * (int64_t)m + 8 * (int64_t)m + 8 * e->n;
   return MLP_OK;
 }

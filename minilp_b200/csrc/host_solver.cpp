@@ -59,6 +59,7 @@ static mlp_status do_pivot(mlp_solver* s, int phase, int64_t entering_var, int64
   std::memset(&pi, 0, sizeof(pi));
   pi.entering_var = entering_var;
   pi.col = col;
+  pi.entering_obj_coeff = obj_coeff;
   pi.entering_new_val = entering_new_val;
   pi.entering_diff = entering_diff;
   pi.has_elem = has_elem ? 1 : 0;
@@ -111,7 +112,7 @@ static mlp_status primal_iteration(mlp_solver* s, int* moved) {
   if (en.var < 0) { *moved = 0; return MLP_OK; }  // 737
   const double entering_cur_val = en.cur_val;                                          // 741
   const bool entering_diff_sign = en.obj_coeff < 0.0;                                  // 743
-  const double entering_other_val = entering_diff_sign ? en.var_max : en.var_min;      // 744-748
+  const double entering_other_val = entering_diff_sign ? s->orig_var_maxs[en.var] : s->orig_var_mins[en.var];  // 744-748
   ST(mlp_ftran_col(s->eng, en.var));                                                   // 750
   mlp_leaving lv;
   ST(mlp_ratio_primal(s->eng, entering_diff_sign ? 1 : 0, std::fabs(entering_other_val - entering_cur_val), &lv));  // 782-823
@@ -161,6 +162,21 @@ mlp_status mlp_solver_create_dense(int device, int64_t m, int64_t n, mlp_solver*
   s->n = n;
   *out = s;
   return MLP_OK;
+}
+mlp_status mlp_solver_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
+                                           int32_t comm_kind, const void* comm_arg, mlp_solver** out) {
+  *out = nullptr;
+  mlp_engine* e = nullptr;
+  ST(mlp_engine_create_dense_sharded(device, m, n_global, rank, world, comm_kind, comm_arg, &e));
+  mlp_solver* s = new mlp_solver();
+  s->eng = e;
+  s->m = m;
+  s->n = n_global;  // the control loop works on GLOBAL indices; sharding is an engine-internal property
+  *out = s;
+  return MLP_OK;
+}
+mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local) {
+  return mlp_engine_upload_local_rows(s->eng, row0, nrows, rows_local);
 }
 void mlp_solver_destroy(mlp_solver* s) {
   if (!s) return;
@@ -363,23 +379,6 @@ mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out) {
 void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds) {
   *run_seconds = s->run_seconds;
   *refactor_seconds = s->refactor_seconds;
-}
-
-// ---------------------------------------------------------------------------------- sharding helpers
-void mlp_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* begin, int64_t* end) {
-  // contiguous blocks, sizes differ by at most one, multiples of 16 columns where possible
-  const int64_t units = (n + 15) / 16;
-  const int64_t b = units * rank / world, e = units * (rank + 1) / world;
-  *begin = std::min<int64_t>(b * 16, n);
-  *end = std::min<int64_t>(e * 16, n);
-}
-int32_t mlp_reduce_candidates(const double* scores, const int64_t* pos, const int64_t* vars, int32_t world) {
-  int32_t best = -1;
-  for (int32_t r = 0; r < world; ++r) {
-    if (vars[r] < 0) continue;
-    if (best < 0 || scores[r] > scores[best] || (scores[r] == scores[best] && pos[r] < pos[best])) best = r;
-  }
-  return best;
 }
 
 }  // extern "C"

@@ -25,22 +25,27 @@ struct Rng {
 };
 bool signed_kind(int kind) { return kind == 1 || kind == 3; }
 
-void fill_rows(int kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, double* out) {
+// rows [row0, row0+nrows) x columns [col0, col0+ncols) of A, written row-major with ncols per row
+void fill_block(int kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, int64_t col0, int64_t ncols,
+                double* out) {
   const Rng ra(seed, 0);
   const bool sg = signed_kind(kind);
   for (int64_t i = 0; i < nrows; ++i) {
     const int64_t r = row0 + i;
-    double* dst = out + i * n;
+    double* dst = out + i * ncols;
     if (kind == 3 && r == m - 1) {
-      for (int64_t j = 0; j < n; ++j) dst[j] = 1.0;
+      for (int64_t j = 0; j < ncols; ++j) dst[j] = 1.0;
       continue;
     }
-    const uint64_t base = (uint64_t)r * (uint64_t)n;
-    for (int64_t j = 0; j < n; ++j) {
+    const uint64_t base = (uint64_t)r * (uint64_t)n + (uint64_t)col0;
+    for (int64_t j = 0; j < ncols; ++j) {
       const double u = ra(base + (uint64_t)j);
       dst[j] = sg ? 2.0 * u - 1.0 : u;
     }
   }
+}
+void fill_rows(int kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, double* out) {
+  fill_block(kind, m, n, seed, row0, nrows, 0, n, out);
 }
 }  // namespace
 
@@ -53,6 +58,17 @@ void mlp_synth_rows(int32_t kind, int64_t m, int64_t n, uint64_t seed, int64_t r
   for (int t = 0; t < threads; ++t) {
     const int64_t a = nrows * t / threads, b = nrows * (t + 1) / threads;
     th.emplace_back(fill_rows, kind, m, n, seed, row0 + a, b - a, out_rows + a * n);
+  }
+  for (auto& x : th) x.join();
+}
+
+void mlp_synth_block(int32_t kind, int64_t m, int64_t n, uint64_t seed, int64_t row0, int64_t nrows, int64_t col0,
+                     int64_t ncols, int32_t threads, double* out_block) {
+  if (threads < 2 || nrows < 2 * threads) { fill_block(kind, m, n, seed, row0, nrows, col0, ncols, out_block); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < threads; ++t) {
+    const int64_t a = nrows * t / threads, b = nrows * (t + 1) / threads;
+    th.emplace_back(fill_block, kind, m, n, seed, row0 + a, b - a, col0, ncols, out_block + a * ncols);
   }
   for (auto& x : th) x.join();
 }

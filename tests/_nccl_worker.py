@@ -1,0 +1,43 @@
+"""torchrun worker: the column-sharded solve over NCCL (one process per GPU) against the oracle.
+   torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/_nccl_worker.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import minilp_b200 as mb  # noqa: E402
+import oracle  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, 0)
+    uid = bytes(idt.cpu().tolist())
+    for kind, m, n, seed in ((0, 200, 300, 1), (3, 97, 131, 9), (1, 64, 96, 2)):
+        lp = mb.synth_dense(kind, m, n, seed)
+        s = mb.Solver.from_dense(lp, device=local, rank=rank, world=world, comm=uid)
+        assert s.run()
+        ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+        assert ref.continue_solve()
+        tg, tr = s.trace(), ref.trace()
+        assert tg.shape == tr.shape and np.array_equal(tg[:, :5], tr[:, :5]), "basis sequence differs from the oracle"
+        assert abs(s.cur_obj_val - ref.cur_obj_val) <= 1e-8 * max(1.0, abs(ref.cur_obj_val))
+        objs = [None] * world
+        dist.all_gather_object(objs, s.cur_obj_val)
+        assert all(o == objs[0] for o in objs), objs
+        print(f"NCCL_OK rank {rank}/{world} kind {kind}: {s.pivots_done} pivots obj {s.cur_obj_val:.12g}", flush=True)
+        s.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

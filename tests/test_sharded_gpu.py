@@ -1,0 +1,83 @@
+"""Column-sharded pricing on ONE GPU: G logical shards, one host thread each, exchanging candidates through
+the in-process communicator (MLP_COMM_LOCAL).  Every shard must take the single-shard pivot sequence — and the oracle's."""
+import threading
+
+import numpy as np
+import pytest
+
+import minilp_b200 as mb
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sharded(lp, world, max_pivots=-1):
+    group = mb.LocalGroup(world)
+    out = [None] * world
+    errs = []
+
+    def work(rank):
+        try:
+            s = mb.Solver.from_dense(lp, rank=rank, world=world, comm=group)
+            done = s.run(max_pivots)
+            e = s.engine
+            out[rank] = dict(done=done, trace=s.trace(), obj=s.cur_obj_val, values=s.values(), basic=s.basic_vars(),
+                             nb=s.nb_vars(), d=e.download(0), gam=e.download(1), xb=e.download(3), w=e.download(4),
+                             ids=e.global_ids(), flags=e.var_state()[0], counters=e.counters())
+            s.close()
+        except Exception as exc:  # noqa: BLE001
+            errs.append((rank, repr(exc)))
+            raise
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    assert all(o is not None for o in out), "a shard thread did not finish"
+    return out
+
+
+@pytest.mark.parametrize("kind,m,n,seed,world", [
+    (0, 60, 80, 3, 2), (3, 60, 80, 3, 2), (1, 48, 64, 2, 4), (2, 50, 70, 1, 3), (3, 97, 131, 9, 4), (0, 200, 300, 1, 8),
+    (3, 24, 30, 7, 2),
+])
+def test_sharded_matches_single_and_oracle(kind, m, n, seed, world):
+    lp = mb.synth_dense(kind, m, n, seed)
+    single = mb.Solver.from_dense(lp)
+    assert single.run()
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    assert ref.continue_solve()
+    shards = run_sharded(lp, world)
+    t1 = single.trace()
+    tr = ref.trace()
+    assert np.array_equal(t1[:, :5], tr[:, :5])
+    for o in shards:
+        assert o["done"]
+        assert np.array_equal(o["trace"][:, :5], t1[:, :5]), "sharded basis sequence differs from the single-shard one"
+        # the price-out chunking is shard-independent, so the floating-point trace is bit-identical too
+        assert np.array_equal(o["trace"][:, 5:8], t1[:, 5:8])
+        assert o["obj"] == single.cur_obj_val
+        assert np.array_equal(o["values"], single.values())
+        assert np.array_equal(o["basic"], single.basic_vars())
+        assert np.array_equal(o["xb"], single.basic_var_vals())
+        assert np.array_equal(o["w"], single.dual_edge_sq_norms())
+    # per-variable state: every shard's slice equals the single-shard arrays
+    d1, g1 = single.engine.download(0), single.engine.download(1)
+    f1 = single.engine.var_state()[0]
+    for o in shards:
+        nb = (o["flags"] & 4) == 0
+        assert np.array_equal(o["flags"], f1[o["ids"]])
+        assert np.array_equal(o["d"][nb], d1[o["ids"]][nb])
+        assert np.array_equal(o["gam"][nb], g1[o["ids"]][nb])
+    assert abs(single.cur_obj_val - ref.cur_obj_val) <= 1e-8 * max(1.0, abs(ref.cur_obj_val))
+    single.close()
+
+
+def test_sharded_budgeted_run_stays_in_lockstep():
+    lp = mb.synth_dense(3, 80, 120, 5)
+    shards = run_sharded(lp, 2, max_pivots=25)
+    assert not shards[0]["done"]
+    assert np.array_equal(shards[0]["trace"], shards[1]["trace"])
+    assert shards[0]["trace"].shape[0] == 25
