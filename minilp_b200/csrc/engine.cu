@@ -246,6 +246,8 @@ struct mlp_engine {
   std::vector<int64_t> h_bvar;           // GLOBAL ids
   std::vector<int32_t> h_slot_of_row;    // cache slot of the structural basic variable at row r, or -1
   std::vector<int32_t> h_free_slots;
+  std::vector<int32_t> h_pending_free;   // slots of columns that left the basis since the last refactor: the factors of
+                                         // the refactor-time basis still read them (U = [D1; U2]), so they are recycled only then
   std::vector<int32_t> h_last_eta_of_row;
   mlp_counters cnt{};
 };
@@ -856,8 +858,7 @@ static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
 static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->m)))));
-  while (cap < k) cap *= 2;
-  cap = std::min<int64_t>(cap, e->m);
+  while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
   double* nb = nullptr;
   ST(dev_alloc(&nb, (size_t)e->m * cap));
   if (e->Bcols && e->kcap > 0) {
@@ -902,6 +903,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
   for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
   const int64_t k = (int64_t)jpos.size();
   if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
+  for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
+  e->h_pending_free.clear();
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
   ST(ensure_eta_capacity(e, 2 * k + 32));
@@ -1215,6 +1218,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   // column cache: an initial basis with structural columns (warm start) fetches them one by one
   e->h_slot_of_row.assign(m, -1);
   e->h_free_slots.clear();
+  e->h_pending_free.clear();
   for (int64_t s = e->kcap - 1; s >= 0; --s) e->h_free_slots.push_back((int32_t)s);
   e->colq_var = -1;
   if (any_structural_basic) {
@@ -1396,12 +1400,12 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   LAUNCH(e, k_pivot_swap, 1, 1, 0, e->d, e->gam, e->xnb, e->vflag, e->vpos, e->bvar, e->loB, e->hiB, e->lo, e->hi, q, ql, lvl,
          (int)pi->col, row, pivot_obj, pi->coeff, pi->leaving_new_val, e->enable_pse, e->scal, e->d_res->flags, e->d_res);
   // column cache: the leaving structural column frees its slot, the entering one takes a slot
-  if (e->h_slot_of_row[row] >= 0) { e->h_free_slots.push_back(e->h_slot_of_row[row]); e->h_slot_of_row[row] = -1; }
+  if (e->h_slot_of_row[row] >= 0) { e->h_pending_free.push_back(e->h_slot_of_row[row]); e->h_slot_of_row[row] = -1; }
   if (q < e->ng) {
     if (e->h_free_slots.empty()) {
-      int64_t used = 0;
-      for (int32_t s : e->h_slot_of_row) if (s >= 0) ++used;
-      ST(ensure_lu_capacity(e, std::max<int64_t>(used + 1, e->kcap + 1)));
+      // doubles the cache; its content and slot numbers survive, the LU arrays do not: refactor in this pivot
+      ST(ensure_lu_capacity(e, e->kcap + 1));
+      do_refactor = true;
     }
     const int32_t slot = e->h_free_slots.back();
     e->h_free_slots.pop_back();
