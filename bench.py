@@ -145,26 +145,29 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
-def build_solver(a, device, col_range=None):
-    """Stream A from pinned host buffers (generated on the host cores) into the engine, then Solver::try_new."""
+def build_solver(a, device, rank=0, world=1, comm=None):
+    """Stream this shard's column block of A from pinned host buffers (generated on the host cores) into the engine, then
+    Solver::try_new.  world == 1: the block is all of A."""
     import torch
 
     import minilp_b200 as mb
     t0 = time.perf_counter()
     d, obj, mins, maxs, ops, rhs = mb.synth_vectors(a.kind, a.m, a.n, a.seed)
-    s = mb.Solver(a.m, a.n, device)
-    rows_per_chunk = max(1, min(a.m, (256 << 20) // (8 * a.n)))
-    bufs = [torch.empty(rows_per_chunk * a.n, dtype=torch.float64).pin_memory().numpy().reshape(rows_per_chunk, a.n)
+    s = mb.Solver(a.m, a.n, device, rank, world, comm)
+    c0, c1 = s.engine.col_begin, s.engine.col_end
+    nloc = c1 - c0
+    rows_per_chunk = max(1, min(a.m, (256 << 20) // (8 * nloc)))
+    bufs = [torch.empty(rows_per_chunk * nloc, dtype=torch.float64).pin_memory().numpy().reshape(rows_per_chunk, nloc)
             for _ in range(2)]
-    threads = os.cpu_count() or 1
+    threads = max(1, (os.cpu_count() or 1) // world)
     gen_s = up_s = 0.0
     for i, r0 in enumerate(range(0, a.m, rows_per_chunk)):
         nr = min(rows_per_chunk, a.m - r0)
         buf = bufs[i % 2]
         t1 = time.perf_counter()
-        mb.synth_rows(a.kind, a.m, a.n, a.seed, r0, nr, threads, out=buf)
+        mb.synth_block(a.kind, a.m, a.n, a.seed, r0, nr, c0, nloc, threads, out=buf)
         t2 = time.perf_counter()
-        s.upload_rows(r0, buf[:nr])
+        s.upload_local_rows(r0, buf[:nr])
         t3 = time.perf_counter()
         gen_s += t2 - t1
         up_s += t3 - t2
@@ -173,17 +176,17 @@ def build_solver(a, device, col_range=None):
     s.init(obj_int, mins, maxs, ops, rhs)
     s.engine.sync()
     t5 = time.perf_counter()
-    setup = {"generate_host_s": round(gen_s, 3), "h2d_upload_s": round(up_s, 3), "h2d_upload_bytes": 8 * a.m * a.n,
+    setup = {"generate_host_s": round(gen_s, 3), "h2d_upload_s": round(up_s, 3), "h2d_upload_bytes": 8 * a.m * nloc,
              "try_new_s": round(t5 - t4, 3), "total_s": round(t5 - t0, 3)}
     return s, setup
 
 
-def load_traffic(a):
+def load_traffic(a, nloc):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
     p = os.path.join(ROOT, "profiles", "price_traffic.json")
     try:
         t = json.load(open(p))
-        if t.get("m") == a.m and t.get("n") == a.n:
+        if t.get("m") == a.m and t.get("n") == nloc:
             return t.get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -191,6 +194,8 @@ def load_traffic(a):
 
 
 def run_ours(a):
+    """One process per GPU.  world > 1 (torchrun): the SAME LP is column-sharded over the ranks (strong scaling); every rank
+    runs the identical host control loop, the one exchange step per pivot goes over NCCL inside the engine."""
     import torch
 
     import minilp_b200 as mb
@@ -199,41 +204,63 @@ def run_ours(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if mb.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: minilp_b200 has no CPU fallback")
+    dist = None
+    comm = None
     if world > 1:
-        from minilp_b200 import dist_bench
-        return dist_bench.run(a, METRIC, UNIT, workload_name(a))
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        comm = bytes(idt.cpu().tolist())
 
-    s, setup = build_solver(a, local)
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    s, setup = build_solver(a, local, rank, world, comm)
     e = s.engine
+    nloc = e.n
     s.set_record_trace(True)
     if a.warmup > 0:
         s.run(a.warmup)
     c0 = e.counters()
     p0 = s.pivots_done
     e.profile_enable(True)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
-    torch.cuda.synchronize()
     e.sync()
+    barrier()
     t0 = time.perf_counter()
     e.event_mark(0)
     done = s.run(a.steps)
     e.event_mark(1)
     e.sync()
+    barrier()
     t1 = time.perf_counter()
-    dev_ms = e.event_elapsed_ms(0, 1)
-    clocks = sampler.stop()
+    dev_ms = max_over_ranks(e.event_elapsed_ms(0, 1))
+    wall = max_over_ranks(t1 - t0)
+    clocks = sampler.stop() if sampler else None
     e.profile_enable(False)
     prof = e.profile()
     c1 = e.counters()
     steps = s.pivots_done - p0
-    if steps != a.steps:
+    if steps != a.steps and rank == 0:
         print(f"# note: optimum reached after {steps} timed pivots (asked for {a.steps})", file=sys.stderr)
-    wall = t1 - t0
     value = steps / (dev_ms / 1e3)
     e2e = steps / wall
     run_s, refac_s = s.timers()
-    tr = s.trace()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -244,9 +271,14 @@ def run_ours(a):
     nv = max(prof["price_v_launches"], 1)
     ach = prof["price_v_bytes"] / nv / (prof["price_v_ms"] / nv * 1e-3) / 1e9 if prof["price_v_ms"] > 0 else 0.0
     iso_ms, iso_bytes = e.bench_price_dense(5)
+    barrier()
+    if rank != 0:
+        s.close()
+        dist.destroy_process_group()
+        return
     roofline = {
         "bound": "hbm", "kernel": "k_price_partial<0> + k_price_finish (N^T v of update_primal_sq_norms, solver.rs:1117-1132)",
-        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(a),
+        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(a, nloc),
         "peak_source": peak_src, "launches_timed": prof["price_v_launches"],
         "avg_launch_ms": prof["price_v_ms"] / nv, "algorithmic_bytes_per_launch": prof["price_v_bytes"] / nv,
         "share_of_step_time": prof["price_v_ms"] / dev_ms,
@@ -254,11 +286,16 @@ def run_ours(a):
         "price_rho": {"launches": prof["price_rho_launches"], "ms_total": prof["price_rho_ms"],
                       "bytes_total": prof["price_rho_bytes"]},
     }
+    if world > 1:
+        roofline["note"] = f"per GPU (rank 0): its {a.m} x {nloc} column block"
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": a.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "m": a.m, "n": a.n, "l2": "inputs_exceed_l2 (8*m*n bytes of A are read per pivot)",
+        "config": {"workload": workload_name(a), "m": a.m, "n": a.n,
+                   "l2": f"inputs_exceed_l2 (8*m*n/N = {8 * a.m * nloc / 1e9:.1f} GB of A are read per GPU per pivot)",
+                   "parallelism": (f"columns sharded over {world} GPUs ({nloc} each), basis replicated, one NCCL all-gather "
+                                   "(candidate + entering column) per pivot") if world > 1 else "single GPU",
                    "pivots_before_timed_region": p0, "optimal_reached": bool(done),
                    "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
                    "refactors_in_region": c1["refactors"] - c0["refactors"], "setup": setup,
@@ -268,19 +305,20 @@ def run_ours(a):
                 "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),
                 "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(steps, 1),
                 "wall_s": wall, "refactor_wall_s": refac_s},
-        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "gpu_launches": (c1["kernel_launches"] - c0["kernel_launches"]) * world,
         "roofline": roofline,
     }
-    if a.cpu_baseline_seconds > 0:
+    if a.cpu_baseline_seconds > 0 and world == 1:
         cores = os.cpu_count() or 1
         piv, sec, m_used, note = cpu_port_run(a, 0, 1000, a.cpu_baseline_seconds, cores)
         line["cpu_baseline"] = {
             "value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"first {piv} pivots of the same {m_used}x{a.n} LP ({sec:.1f}s of single-thread CPU work; the "
                        f"reference is single-threaded){note}"), "host_cores_available": cores}
-    del tr
     print(json.dumps(line), flush=True)
     s.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():

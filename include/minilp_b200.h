@@ -61,7 +61,8 @@ mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine*
  * basis factors are replicated and every rank runs the identical host control loop (SPMD).  All variable indices
  * in this ABI stay GLOBAL.  The one exchange step per pivot — arg-reduce of the per-shard pricing candidates plus
  * the winner's column — is a single all-gather inside mlp_select_entering_primal / mlp_ratio_dual.
- *   comm_kind MLP_COMM_NCCL : comm_arg = 128-byte ncclUniqueId from mlp_nccl_get_unique_id (one process per GPU)
+ *   comm_kind MLP_COMM_NCCL : comm_arg = 128-byte ncclUniqueId from mlp_nccl_get_unique_id (one process per GPU;
+ *                             an id serves one engine: fetch a fresh one per create call)
  *   comm_kind MLP_COMM_LOCAL: comm_arg = handle from mlp_local_group_create (one host thread per shard, one process) */
 #define MLP_COMM_NONE 0
 #define MLP_COMM_NCCL 1

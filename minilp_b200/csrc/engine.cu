@@ -14,6 +14,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -180,9 +181,29 @@ struct LocalComm : Comm {
 };
 
 // ------------------------------------------------------------------------------------------------ engine
+// Per-stream scratch.  The pivot runs two chains concurrently: lane 0 carries the critical path
+// (FTRAN of the entering column, BTRAN of alpha_q, the dense N^T v price-out, the reduced-cost update), lane 1 the
+// latency-bound rest (ratio test, BTRAN of e_r, tableau-row price-out, FTRAN of rho, row updates, eta push).
+struct Lane {
+  cudaStream_t st = nullptr;
+  double *xk = nullptr, *xk2 = nullptr;  // kcap: core right-hand side / solution
+  double *tK = nullptr, *tK2 = nullptr;  // Kcap: eta scalars
+  double* wm = nullptr;                   // m
+  double *gt_part_k = nullptr, *gt_part_K = nullptr;
+  int32_t* seg_cnt = nullptr;
+  double* seg_ss = nullptr;
+  double* red_f = nullptr;      // 4096
+  long long* red_i = nullptr;   // 4096
+  unsigned* red_counter = nullptr;
+  double* partial = nullptr;    // price partial sums: PR_MAXC x lda
+  DevRes* d_res = nullptr;
+  DevRes* h_res = nullptr;      // pinned
+};
+
 struct mlp_engine {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // == lane[0].st
+  Lane lane[2];
   // Column sharding: this engine owns structural columns [c0, c0+n) of the ng global ones; the m slack
   // variables are replicated on every shard.  LOCAL variable index: structural g -> g-c0, slack ng+i -> n+i.
   // Everything the ABI shows is GLOBAL.  world == 1: c0 = 0, n = ng.
@@ -201,23 +222,16 @@ struct mlp_engine {
   int32_t* bvar = nullptr;                                // m, GLOBAL variable ids
   double *xB = nullptr, *loB = nullptr, *hiB = nullptr, *w = nullptr, *rhs = nullptr;  // m
   double *alpha = nullptr, *rho = nullptr, *tau = nullptr, *vvec = nullptr;             // m
-  double *work_m = nullptr, *work_m2 = nullptr;                                          // m
+  double *work_m = nullptr, *work_mb = nullptr;                                          // m: BTRAN inputs of lane 0 / lane 1
   double* colq = nullptr;  // m: column of the entering variable; stored in the column cache by the pivot
   int64_t colq_var = -1;
   double *rc = nullptr, *helper = nullptr;  // n+m
-  int32_t* list_idx = nullptr;              // m
-  double* list_val = nullptr;               // m
-  double* partial = nullptr;                // price partial sums: PR_MAXC x lda
-  double* red_f = nullptr;                  // 4096
-  long long* red_i = nullptr;               // 4096
-  unsigned* red_counter = nullptr;
+  int32_t *list_idx = nullptr, *vlist_idx = nullptr;  // m: support of rho / of v = B^-T alpha_q
+  double *list_val = nullptr, *vlist_val = nullptr;    // m
   double* scal = nullptr;   // device scalars: [0] max_step [1] |rho|^2 [2] |alpha|^2 [3] |v|^2 [4..6] objective parts
   int32_t* icnt = nullptr;  // device ints: [0] nnz rho [1] nnz alpha [2] nnz v
-  int32_t* seg_cnt = nullptr;
-  double* seg_ss = nullptr;
-  double *gt_part_k = nullptr, *gt_part_K = nullptr;
-  DevRes* d_res = nullptr;
-  DevRes* h_res = nullptr;  // pinned
+  DevRes* d_res = nullptr;  // == lane[0].d_res
+  DevRes* h_res = nullptr;  // pinned, == lane[0].h_res
   // candidate exchange
   char *xsend = nullptr, *xrecv = nullptr;
   size_t xbytes = 0;
@@ -228,14 +242,20 @@ struct mlp_engine {
   int64_t k = 0, kcap = 0;
   int32_t *Jpos = nullptr, *Jslot = nullptr, *Rp = nullptr;  // kcap
   int32_t* rowcover = nullptr;                                 // m
-  double *Bcols = nullptr, *LUc = nullptr;                     // column cache m x kcap (slot-indexed), kcap x kcap
-  double* xk = nullptr;
+  double *Bcols = nullptr, *LUc = nullptr, *Cinv = nullptr;   // column cache m x kcap (slot-indexed); LU factors and (LU)^-1, kcap x kcap
   // eta file
   int64_t K = 0, Kcap = 0;
-  double *E = nullptr, *G = nullptr;
+  double *E = nullptr, *Ginv = nullptr, *gK = nullptr;  // eta columns m x Kcap; (I+G)^-1 Kcap x Kcap; coupling row of the newest eta
   int32_t *etaR = nullptr, *etaPrev = nullptr, *etaHead = nullptr;
-  double* tK = nullptr;
   int64_t lu_nnz = 0;
+
+  // lane synchronisation (see "host side")
+  int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
+  int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
+                        // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
+  cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr;
+  int64_t spec_var = -1;  // variable whose v = B^-T alpha_q / N^T v were computed ahead by mlp_ftran_col
+  size_t smem_optin = 48 << 10;
 
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t pev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][begin/end]; slot 0 rho, 1 v
@@ -252,11 +272,12 @@ struct mlp_engine {
   mlp_counters cnt{};
 };
 
-#define LAUNCH(e, kern, grid, block, smem, ...)                  \
-  do {                                                           \
-    kern<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__); \
-    (e)->cnt.kernel_launches += 1;                               \
+#define LAUNCHS(e, st, kern, grid, block, smem, ...)        \
+  do {                                                      \
+    kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);   \
+    (e)->cnt.kernel_launches += 1;                          \
   } while (0)
+#define LAUNCH(e, kern, grid, block, smem, ...) LAUNCHS(e, (e)->stream, kern, grid, block, smem, __VA_ARGS__)
 
 template <class T> static mlp_status dev_alloc(T** p, size_t count) {
   *p = nullptr;
@@ -283,7 +304,6 @@ static mlp_status d2h(mlp_engine* e, void* dst, const void* src, size_t bytes) {
   e->cnt.d2h_bytes += (int64_t)bytes;
   return MLP_OK;
 }
-static mlp_status fetch_res(mlp_engine* e) { return d2h(e, e->h_res, e->d_res, sizeof(DevRes)); }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // local index of a GLOBAL variable, -1 if the structural column lives on another shard
 static inline int64_t to_local(const mlp_engine* e, int64_t g) {
@@ -327,59 +347,64 @@ k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __rest
   __shared__ double sw[PR_BATCH];
   const int s = count_ptr ? *count_ptr : fixed_count;
   const int C = price_chunks_for(s);
-  if ((int)blockIdx.y >= C) return;
   const int L = (s + C - 1) / C;
-  const int k0 = blockIdx.y * L;
-  const int k1 = min(s, k0 + L);
-  const int64_t col = ((int64_t)blockIdx.x * PR_THREADS + threadIdx.x) * 2;
-  const bool active = col < lda;
-  double acc0 = 0.0, acc1 = 0.0;
-  const double* base = A + col;
-  for (int kb = k0; kb < k1; kb += PR_BATCH) {
-    const int nb = min(PR_BATCH, k1 - kb);
-    __syncthreads();
-    for (int t = threadIdx.x; t < nb; t += PR_THREADS) {
-      srow[t] = rows ? rows[kb + t] : kb + t;
-      sw[t] = (MODE == 0) ? wts[kb + t] : 1.0;
-    }
-    __syncthreads();
-    if (active) {
-      int i = 0;
-      for (; i + PR_UNROLL <= nb; i += PR_UNROLL) {
-        double2 v[PR_UNROLL];
+  const int tiles = (int)((lda + PR_TILE - 1) / PR_TILE);
+  // Persistent CTAs: the grid is sized to a fixed number of CTAs per SM (not to the work), so that the rest of each SM stays
+  // free for the latency-bound kernels of the other lane; work item = (column tile, support chunk).
+  for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
+    const int tile = item % tiles, chunk = item / tiles;
+    const int k0 = chunk * L;
+    const int k1 = min(s, k0 + L);
+    const int64_t col = ((int64_t)tile * PR_THREADS + threadIdx.x) * 2;
+    const bool active = col < lda;
+    double acc0 = 0.0, acc1 = 0.0;
+    const double* base = A + col;
+    for (int kb = k0; kb < k1; kb += PR_BATCH) {
+      const int nb = min(PR_BATCH, k1 - kb);
+      __syncthreads();
+      for (int t = threadIdx.x; t < nb; t += PR_THREADS) {
+        srow[t] = rows ? rows[kb + t] : kb + t;
+        sw[t] = (MODE == 0) ? wts[kb + t] : 1.0;
+      }
+      __syncthreads();
+      if (active) {
+        int i = 0;
+        for (; i + PR_UNROLL <= nb; i += PR_UNROLL) {
+          double2 v[PR_UNROLL];
 #pragma unroll
-        for (int u = 0; u < PR_UNROLL; ++u)
-          v[u] = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i + u] * lda));
+          for (int u = 0; u < PR_UNROLL; ++u)
+            v[u] = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i + u] * lda));
 #pragma unroll
-        for (int u = 0; u < PR_UNROLL; ++u) {
+          for (int u = 0; u < PR_UNROLL; ++u) {
+            if (MODE == 0) {
+              const double wv = sw[i + u];
+              acc0 += wv * v[u].x;
+              acc1 += wv * v[u].y;
+            } else {
+              acc0 += v[u].x * v[u].x;
+              acc1 += v[u].y * v[u].y;
+            }
+          }
+        }
+        for (; i < nb; ++i) {
+          const double2 v = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i] * lda));
           if (MODE == 0) {
-            const double wv = sw[i + u];
-            acc0 += wv * v[u].x;
-            acc1 += wv * v[u].y;
+            const double wv = sw[i];
+            acc0 += wv * v.x;
+            acc1 += wv * v.y;
           } else {
-            acc0 += v[u].x * v[u].x;
-            acc1 += v[u].y * v[u].y;
+            acc0 += v.x * v.x;
+            acc1 += v.y * v.y;
           }
         }
       }
-      for (; i < nb; ++i) {
-        const double2 v = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i] * lda));
-        if (MODE == 0) {
-          const double wv = sw[i];
-          acc0 += wv * v.x;
-          acc1 += wv * v.y;
-        } else {
-          acc0 += v.x * v.x;
-          acc1 += v.y * v.y;
-        }
-      }
     }
-  }
-  if (active) {
-    double2 o;
-    o.x = acc0;
-    o.y = acc1;
-    *reinterpret_cast<double2*>(partial + (int64_t)blockIdx.y * lda + col) = o;
+    if (active) {
+      double2 o;
+      o.x = acc0;
+      o.y = acc1;
+      *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col) = o;
+    }
   }
 }
 
@@ -761,27 +786,44 @@ __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __re
 }
 
 // ================================================================================================ host side
+// Two lanes (streams).  API calls keep sequential semantics through two marks: s0_mark is recorded on lane 0 at the end of
+// the non-speculative part of every lane-0 call, s1_mark on lane 1 at the end of every lane-1 call; a call on one lane
+// first waits for the other lane's mark.  The only work that runs AHEAD of the marks is the speculative tail of
+// mlp_ftran_col (v = B^-T alpha_q and the dense N^T v price-out), which touches nothing the lane-1 calls write except
+// the eta file (guarded by ev_vbtran).
+static mlp_status mark0(mlp_engine* e) { CU(cudaEventRecord(e->s0_mark, e->lane[0].st)); return MLP_OK; }
+static mlp_status mark1(mlp_engine* e) { if (e->overlap) CU(cudaEventRecord(e->s1_mark, e->lane[1].st)); return MLP_OK; }
+static mlp_status begin0(mlp_engine* e) { if (e->overlap) CU(cudaStreamWaitEvent(e->lane[0].st, e->s1_mark, 0)); return MLP_OK; }
+static mlp_status begin1(mlp_engine* e) { if (e->overlap) CU(cudaStreamWaitEvent(e->lane[1].st, e->s0_mark, 0)); return MLP_OK; }
+static mlp_status fetch_res(mlp_engine* e, Lane& ln) {
+  CU(cudaMemcpyAsync(ln.h_res, ln.d_res, sizeof(DevRes), cudaMemcpyDeviceToHost, ln.st));
+  CU(cudaStreamSynchronize(ln.st));
+  e->cnt.d2h_bytes += (int64_t)sizeof(DevRes);
+  return MLP_OK;
+}
+static int price_grid(const mlp_engine* e) { return e->sm_count * e->price_ctas; }
+
 // out (local variable index) = N^T w over the listed rows (+ slack part), basic entries zeroed
-static mlp_status price_list(mlp_engine* e, const int32_t* rows, const double* wts, const int32_t* count_ptr, int fixed_count,
-                             const double* slack_vals, double* out, int prof_slot = -1) {
-  dim3 grid(cdiv(e->lda, PR_TILE), PR_MAXC);
+static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const double* wts, const int32_t* count_ptr,
+                             int fixed_count, const double* slack_vals, double* out, int prof_slot = -1) {
   const bool prof = e->prof_on && prof_slot >= 0;
-  if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], e->stream));
-  LAUNCH(e, k_price_partial<0>, grid, PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, e->partial);
-  LAUNCH(e, k_price_finish, cdiv(e->nt, 256), 256, 0, e->partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
-         e->vflag, out, 0);
+  if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], ln.st));
+  LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
+  LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
+          e->vflag, out, 0);
   if (prof) {
-    CU(cudaEventRecord(e->pev[prof_slot][1], e->stream));
+    CU(cudaEventRecord(e->pev[prof_slot][1], ln.st));
     e->ppending[prof_slot] = true;
   }
   return MLP_OK;
 }
-// after a stream sync: fold pending price-out timings into the profile
+// after both lanes are idle: fold pending price-out timings into the profile
 static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
   for (int slot = 0; slot < 2; ++slot) {
     if (!e->ppending[slot]) continue;
     e->ppending[slot] = false;
     float ms = 0.f;
+    CU(cudaEventSynchronize(e->pev[slot][1]));
     CU(cudaEventElapsedTime(&ms, e->pev[slot][0], e->pev[slot][1]));
     const int64_t sz = slot == 0 ? s_rho : s_v;
     const int64_t bytes = 8 * e->n * sz + 8 * sz + 8 * e->n;
@@ -792,63 +834,54 @@ static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
 }
 
 // list / stats of a dense m-vector (see k_compact_count). idx == nullptr: stats only.
-static void compact(mlp_engine* e, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq) {
+static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq) {
   const int m = (int)e->m, nseg = cdiv(m, CP_SEG);
-  LAUNCH(e, k_compact_count, nseg, CP_SEG, 0, x, m, e->seg_cnt, e->seg_ss, e->red_counter, count, sumsq);
-  if (idx) LAUNCH(e, k_compact_write, nseg, CP_SEG, 0, x, m, e->seg_cnt, idx, val);
+  LAUNCHS(e, ln.st, k_compact_count, nseg, CP_SEG, 0, x, m, ln.seg_cnt, ln.seg_ss, ln.red_counter, count, sumsq);
+  if (idx) LAUNCHS(e, ln.st, k_compact_write, nseg, CP_SEG, 0, x, m, ln.seg_cnt, idx, val);
 }
 static int gemv_split(const mlp_engine* e, int rows, int cols) {
   int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(2 * (int64_t)e->sm_count, cols)));
   return std::min(S, std::max(1, rows / 2048));
 }
-static void gemv_t(mlp_engine* e, const double* M, int64_t ld, int rows, int cols, const double* x, double* part,
+static void gemv_t(mlp_engine* e, Lane& ln, const double* M, int64_t ld, int rows, int cols, const double* x, double* part,
                    const double* base, const int32_t* base_idx, double* out, int negate) {
   if (cols <= 0) return;
   const int S = gemv_split(e, rows, cols);
-  LAUNCH(e, k_gemv_t_part, dim3((unsigned)cols, (unsigned)S), 256, 0, M, ld, rows, cols, x, part);
-  LAUNCH(e, k_gemv_t_fin, cdiv(cols, 256), 256, 0, part, S, cols, base, base_idx, out, negate);
-}
-template <bool FWD, bool AXPY, bool UNIT> static void trsv(mlp_engine* e, const double* M, int64_t ld, int n, double* x) {
-  if (n <= 0) return;
-  auto kern = k_trsv<FWD, AXPY, UNIT>;
-  LAUNCH(e, kern, 1, 1024, 0, M, ld, n, x);
+  LAUNCHS(e, ln.st, k_gemv_t_part, dim3((unsigned)cols, (unsigned)S), 256, 0, M, ld, rows, cols, x, part);
+  LAUNCHS(e, ln.st, k_gemv_t_fin, cdiv(cols, 256), 256, 0, part, S, cols, base, base_idx, out, negate);
 }
 
 // BasisSolver::solve (solver.rs:1305-1319). rhs0: dense m-vector by constraint row (device). out: by basis position.
-static mlp_status ftran(mlp_engine* e, const double* rhs0, double* out) {
+static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
-  if (k > 0) {
-    LAUNCH(e, k_gather_idx, cdiv(k, 256), 256, 0, rhs0, e->Rp, k, e->xk);
-    trsv<true, true, true>(e, e->LUc, e->kcap, k, e->xk);    // L y = P a_R   (lu.rs:92)
-    trsv<false, true, false>(e, e->LUc, e->kcap, k, e->xk);  // U x = y      (lu.rs:93)
-  }
-  LAUNCH(e, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->m, m, k, e->xk, rhs0, e->rowcover, e->Jpos, e->Jslot, out);
-  if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form
-    LAUNCH(e, k_gather_idx, cdiv(K, 256), 256, 0, out, e->etaR, K, e->tK);
-    trsv<true, true, true>(e, e->G, e->Kcap, K, e->tK);
-    LAUNCH(e, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->m, m, K, e->tK, out);
+  // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
+  if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
+  LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->m, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
+          e->Jslot, out);
+  if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
+    LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
+    LAUNCHS(e, ln.st, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->m, m, K, ln.tK, out);
   }
   return MLP_OK;
 }
 
 // BasisSolver::solve_transp (solver.rs:1322-1338). c: dense m-vector by basis position (device, DESTROYED).
 // unit_row >= 0 tells that c == e_unit_row (the eta dot products degenerate to a row gather). out: by constraint row.
-static mlp_status btran(mlp_engine* e, double* c, int unit_row, double* out) {
+static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
-  if (K > 0) {  // etas in reverse, 1325-1333
-    if (unit_row >= 0) LAUNCH(e, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->m, unit_row, K, e->tK);
-    else gemv_t(e, e->E, e->m, m, K, c, e->gt_part_K, nullptr, nullptr, e->tK, 0);
-    trsv<false, false, true>(e, e->G, e->Kcap, K, e->tK);
-    LAUNCH(e, k_eta_scatter, cdiv(K, 256), 256, 0, e->tK, e->etaR, e->etaPrev, e->etaHead, K, c);
+  if (K > 0) {  // etas in reverse, 1325-1333: u = E^T c, s = (I+G)^-T u, c[r_j] -= s_j
+    if (unit_row >= 0) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->m, unit_row, K, ln.tK);
+    else gemv_t(e, ln, e->E, e->m, m, K, c, ln.gt_part_K, nullptr, nullptr, ln.tK, 0);
+    LAUNCHS(e, ln.st, k_mv_t<true>, cdiv(K, 8), 256, 0, e->Ginv, e->Kcap, K, ln.tK, (const int32_t*)nullptr, ln.tK2);
+    LAUNCHS(e, ln.st, k_eta_scatter, cdiv(K, 256), 256, 0, ln.tK2, e->etaR, e->etaPrev, e->etaHead, K, c);
   }
-  LAUNCH(e, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, e->work_m2);
+  LAUNCHS(e, ln.st, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, ln.wm);
   if (k > 0) {
     const int S = gemv_split(e, m, k);
-    LAUNCH(e, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->m, m, k, e->Jslot, e->work_m2, e->gt_part_k);
-    LAUNCH(e, k_gemv_t_fin, cdiv(k, 256), 256, 0, e->gt_part_k, S, k, c, e->Jpos, e->xk, 1);
-    trsv<true, false, false>(e, e->LUc, e->kcap, k, e->xk);  // U^T z = rhs   (lu_factors_transp.lower = U^T, lu.rs:110)
-    trsv<false, false, true>(e, e->LUc, e->kcap, k, e->xk);  // L^T y = z
-    LAUNCH(e, k_scatter_idx, cdiv(k, 256), 256, 0, e->xk, e->Rp, k, out);
+    LAUNCHS(e, ln.st, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->m, m, k, e->Jslot, ln.wm, ln.gt_part_k);
+    LAUNCHS(e, ln.st, k_gemv_t_fin, cdiv(k, 256), 256, 0, ln.gt_part_k, S, k, c, e->Jpos, ln.xk, 1);
+    // y = L^-T U^-T rhs (lu_factors_transp, lu.rs:108-115) = (C^-1)^T rhs, scattered to the core's constraint rows
+    LAUNCHS(e, ln.st, k_mv_t<false>, cdiv(k, 8), 256, 0, e->Cinv, e->kcap, k, ln.xk, e->Rp, out);
   }
   return MLP_OK;
 }
@@ -859,6 +892,7 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->m)))));
   while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   double* nb = nullptr;
   ST(dev_alloc(&nb, (size_t)e->m * cap));
   if (e->Bcols && e->kcap > 0) {
@@ -866,25 +900,32 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
     CU(cudaStreamSynchronize(e->stream));
   }
   for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
-  dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
-  dev_free(e->gt_part_k);
+  dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   e->Bcols = nb;
   e->kcap = cap;
   ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jslot, cap)); ST(dev_alloc(&e->Rp, cap));
-  ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->xk, cap));
-  ST(dev_alloc(&e->gt_part_k, (size_t)GT_MAXSPLIT * cap));
+  ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->Cinv, (size_t)cap * cap));
+  for (int l = 0; l < 2; ++l) {
+    Lane& ln = e->lane[l];
+    dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.gt_part_k);
+    ST(dev_alloc(&ln.xk, cap)); ST(dev_alloc(&ln.xk2, cap)); ST(dev_alloc(&ln.gt_part_k, (size_t)GT_MAXSPLIT * cap));
+  }
   return MLP_OK;
 }
 static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
   if (K <= e->Kcap && e->E) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->m))));
   while (cap < K) cap *= 2;
-  dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
-  dev_free(e->gt_part_K);
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   e->Kcap = cap;
-  ST(dev_alloc(&e->E, (size_t)e->m * cap)); ST(dev_alloc(&e->G, (size_t)cap * cap));
-  ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap)); ST(dev_alloc(&e->tK, cap));
-  ST(dev_alloc(&e->gt_part_K, (size_t)GT_MAXSPLIT * cap));
+  ST(dev_alloc(&e->E, (size_t)e->m * cap)); ST(dev_alloc(&e->Ginv, (size_t)cap * cap)); ST(dev_alloc(&e->gK, cap));
+  ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap));
+  for (int l = 0; l < 2; ++l) {
+    Lane& ln = e->lane[l];
+    dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.gt_part_K);
+    ST(dev_alloc(&ln.tK, cap)); ST(dev_alloc(&ln.tK2, cap)); ST(dev_alloc(&ln.gt_part_K, (size_t)GT_MAXSPLIT * cap));
+  }
   return MLP_OK;
 }
 
@@ -905,6 +946,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
   if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
   for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
   e->h_pending_free.clear();
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  e->spec_var = -1;
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
   ST(ensure_eta_capacity(e, 2 * k + 32));
@@ -925,7 +968,12 @@ static mlp_status refactor_impl(mlp_engine* e) {
       const int rem = (int)k - t - 1;
       if (rem > 0) LAUNCH(e, k_lu_update, dim3(cdiv(rem, 32), cdiv(rem, 8)), dim3(32, 8), 0, e->LUc, e->kcap, (int)k, t, flags);
     }
-    ST(fetch_res(e));
+    {  // (L U)^-1, one CTA per column
+      const size_t need = (size_t)k * sizeof(double);
+      const int use_smem = need <= e->smem_optin ? 1 : 0;
+      LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
+    }
+    ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
   } else {
     CU(cudaStreamSynchronize(e->stream));
@@ -981,25 +1029,47 @@ static mlp_status fetch_column(mlp_engine* e, int64_t var) {
   return MLP_OK;
 }
 
+// update_primal_sq_norms' bulk part on lane 0: v = B^-T alpha_q (solver.rs:1114), helper = N^T v (1117-1132).
+// Depends only on alpha_q, so mlp_ftran_col starts it ahead of the ratio test; the eta file may change only after ev_vbtran.
+static mlp_status se_helper(mlp_engine* e, int64_t var) {
+  Lane& l0 = e->lane[0];
+  CU(cudaMemcpyAsync(e->work_m, e->alpha, (size_t)e->m * 8, cudaMemcpyDeviceToDevice, l0.st));
+  ST(btran(e, l0, e->work_m, -1, e->vvec));
+  CU(cudaEventRecord(e->ev_vbtran, l0.st));
+  compact(e, l0, e->vvec, e->vlist_idx, e->vlist_val, e->icnt + 2, e->scal + 3);
+  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
+  e->spec_var = var;
+  return MLP_OK;
+}
+
 static void destroy_engine(mlp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
-  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int l = 0; l < 2; ++l) if (e->lane[l].st) cudaStreamSynchronize(e->lane[l].st);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
   dev_free(e->rhs); dev_free(e->alpha); dev_free(e->rho); dev_free(e->tau); dev_free(e->vvec); dev_free(e->work_m);
-  dev_free(e->work_m2); dev_free(e->colq); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val);
-  dev_free(e->partial); dev_free(e->red_f); dev_free(e->red_i); dev_free(e->red_counter); dev_free(e->scal); dev_free(e->icnt);
-  dev_free(e->seg_cnt); dev_free(e->seg_ss); dev_free(e->gt_part_k); dev_free(e->gt_part_K); dev_free(e->d_res);
+  dev_free(e->work_mb); dev_free(e->colq); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val);
+  dev_free(e->vlist_idx); dev_free(e->vlist_val); dev_free(e->scal); dev_free(e->icnt);
   dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred);
-  dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->xk);
-  dev_free(e->E); dev_free(e->G); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead); dev_free(e->tK);
-  if (e->h_res) cudaFreeHost(e->h_res);
+  dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
+  dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
+  for (int l = 0; l < 2; ++l) {
+    Lane& ln = e->lane[l];
+    dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.wm); dev_free(ln.gt_part_k);
+    dev_free(ln.gt_part_K); dev_free(ln.seg_cnt); dev_free(ln.seg_ss); dev_free(ln.red_f); dev_free(ln.red_i);
+    dev_free(ln.red_counter); dev_free(ln.partial); dev_free(ln.d_res);
+    if (ln.h_res) cudaFreeHost(ln.h_res);
+  }
   if (e->h_cands) cudaFreeHost(e->h_cands);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (e->pev[i][j]) cudaEventDestroy(e->pev[i][j]);
+  if (e->s0_mark) cudaEventDestroy(e->s0_mark);
+  if (e->s1_mark) cudaEventDestroy(e->s1_mark);
+  if (e->ev_vbtran) cudaEventDestroy(e->ev_vbtran);
   delete e->comm;
-  if (e->stream) cudaStreamDestroy(e->stream);
+  if (e->lane[1].st && e->lane[1].st != e->lane[0].st) cudaStreamDestroy(e->lane[1].st);
+  if (e->lane[0].st) cudaStreamDestroy(e->lane[0].st);
   delete e;
 }
 
@@ -1028,7 +1098,18 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
+  if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
+  {  // lane 1 carries short latency-bound kernels that must slip in beside the price-out: highest priority
+    int lo_p = 0, hi_p = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+    CU(cudaStreamCreateWithPriority(&e->lane[0].st, cudaStreamNonBlocking, lo_p));
+    if (e->overlap) CU(cudaStreamCreateWithPriority(&e->lane[1].st, cudaStreamNonBlocking, hi_p));
+    else e->lane[1].st = e->lane[0].st;
+    e->stream = e->lane[0].st;
+  }
+  e->smem_optin = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 << 10);
+  CU(cudaFuncSetAttribute(k_core_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin));
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
   const int64_t nt = e->nt, gt = ng + m;
@@ -1038,24 +1119,36 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   A(dev_alloc(&e->vflag, nt)); A(dev_alloc(&e->vpos, nt)); A(dev_alloc(&e->bvar, m));
   A(dev_alloc(&e->xB, m)); A(dev_alloc(&e->loB, m)); A(dev_alloc(&e->hiB, m)); A(dev_alloc(&e->w, m)); A(dev_alloc(&e->rhs, m));
   A(dev_alloc(&e->alpha, m)); A(dev_alloc(&e->rho, m)); A(dev_alloc(&e->tau, m)); A(dev_alloc(&e->vvec, m));
-  A(dev_alloc(&e->work_m, m)); A(dev_alloc(&e->work_m2, m)); A(dev_alloc(&e->colq, m));
+  A(dev_alloc(&e->work_m, m)); A(dev_alloc(&e->work_mb, m)); A(dev_alloc(&e->colq, m));
   A(dev_alloc(&e->rc, nt)); A(dev_alloc(&e->helper, nt));
-  A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m));
-  A(dev_alloc(&e->partial, (size_t)PR_MAXC * e->lda));
-  A(dev_alloc(&e->red_f, 4096)); A(dev_alloc(&e->red_i, 4096)); A(dev_alloc(&e->red_counter, 4));
+  A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m)); A(dev_alloc(&e->vlist_idx, m)); A(dev_alloc(&e->vlist_val, m));
   A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
-  A(dev_alloc(&e->seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&e->seg_ss, (size_t)cdiv(m, CP_SEG) + 1));
-  A(dev_alloc(&e->d_res, 1)); A(dev_alloc(&e->rowcover, m));
+  for (int l = 0; l < 2; ++l) {
+    Lane& ln = e->lane[l];
+    A(dev_alloc(&ln.wm, m));
+    A(dev_alloc(&ln.partial, (size_t)PR_MAXC * e->lda));
+    A(dev_alloc(&ln.red_f, 4096)); A(dev_alloc(&ln.red_i, 4096)); A(dev_alloc(&ln.red_counter, 4));
+    A(dev_alloc(&ln.seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&ln.seg_ss, (size_t)cdiv(m, CP_SEG) + 1));
+    A(dev_alloc(&ln.d_res, 1));
+  }
+  e->d_res = e->lane[0].d_res;
+  A(dev_alloc(&e->rowcover, m));
   e->xbytes = sizeof(Cand) + (size_t)m * sizeof(double);
   A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * m + 64));
   if (st != MLP_OK) { destroy_engine(e); return st; }
-  CU(cudaHostAlloc((void**)&e->h_res, sizeof(DevRes), cudaHostAllocDefault));
+  for (int l = 0; l < 2; ++l) CU(cudaHostAlloc((void**)&e->lane[l].h_res, sizeof(DevRes), cudaHostAllocDefault));
+  e->h_res = e->lane[0].h_res;
   CU(cudaHostAlloc((void**)&e->h_cands, sizeof(Cand) * world, cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
   for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) CU(cudaEventCreate(&e->pev[i][j]));
+  CU(cudaEventCreateWithFlags(&e->s0_mark, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->s1_mark, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_vbtran, cudaEventDisableTiming));
   CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->red_counter, 0, 4 * sizeof(unsigned), e->stream));
-  CU(cudaMemsetAsync(e->d_res, 0, sizeof(DevRes), e->stream));
+  for (int l = 0; l < 2; ++l) {
+    CU(cudaMemsetAsync(e->lane[l].red_counter, 0, 4 * sizeof(unsigned), e->stream));
+    CU(cudaMemsetAsync(e->lane[l].d_res, 0, sizeof(DevRes), e->stream));
+  }
   CU(cudaMemsetAsync(e->gam, 0, nt * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->helper, 0, nt * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->rc, 0, nt * sizeof(double), e->stream));
@@ -1200,6 +1293,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (st->basic_var_vals) ST(h2d(e, e->xB, st->basic_var_vals, m * 8));
   if (st->dual_edge_sq_norms) ST(h2d(e, e->w, st->dual_edge_sq_norms, m * 8));
   CU(cudaStreamSynchronize(e->stream));
+  e->spec_var = -1;
   if (!st->basic_var_vals) {
     double* part = e->world > 1 ? e->work_m : e->xred;
     LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, part);
@@ -1209,10 +1303,9 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (!st->dual_edge_sq_norms) LAUNCH(e, k_fill, cdiv(m, 256), 256, 0, e->w, m, 1.0);
   if (e->enable_pse && !st->primal_edge_sq_norms) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
-    dim3 grid(cdiv(e->lda, PR_TILE), PR_MAXC);
-    LAUNCH(e, k_price_partial<1>, grid, PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
-           (const int32_t*)nullptr, (int32_t)m, e->partial);
-    LAUNCH(e, k_price_finish, cdiv(nt, 256), 256, 0, e->partial, (const int32_t*)nullptr, (int32_t)m, e->lda, n, m,
+    LAUNCH(e, k_price_partial<1>, price_grid(e), PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
+           (const int32_t*)nullptr, (int32_t)m, e->lane[0].partial);
+    LAUNCH(e, k_price_finish, cdiv(nt, 256), 256, 0, e->lane[0].partial, (const int32_t*)nullptr, (int32_t)m, e->lda, n, m,
            (const double*)nullptr, e->vflag, e->gam, 1);
   }
   // column cache: an initial basis with structural columns (warm start) fetches them one by one
@@ -1236,6 +1329,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   }
   e->initialized = true;
   ST(refactor_impl(e));
+  ST(mark0(e));
   return MLP_OK;
 }
 
@@ -1249,6 +1343,7 @@ mlp_status mlp_refactor(mlp_engine* e, int64_t* lu_nnz) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   ST(refactor_impl(e));
+  ST(mark0(e));
   if (lu_nnz) *lu_nnz = e->lu_nnz;
   return MLP_OK;
 }
@@ -1257,11 +1352,14 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int grid = std::min(cdiv(e->nt, 256), 1024);
-  LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->n, e->c0, e->ng, e->enable_pse, e->red_f,
-         e->red_i, e->red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
+  LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->n, e->c0, e->ng, e->enable_pse, l0.red_f,
+         l0.red_i, l0.red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w));
+  ST(mark0(e));
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
   out->pos = w.tie;
@@ -1275,10 +1373,15 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
 mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   if (!e || !e->initialized || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
   ST(fetch_column(e, var));
-  ST(ftran(e, e->colq, e->alpha));
+  ST(ftran(e, l0, e->colq, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
-  compact(e, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+  compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+  ST(mark0(e));
+  e->spec_var = -1;
+  if (e->enable_pse && e->overlap) ST(se_helper(e, var));  // runs ahead of the ratio test on lane 0
   return MLP_OK;
 }
 
@@ -1286,32 +1389,40 @@ mlp_status mlp_ratio_primal(mlp_engine* e, int32_t sign, double max_step0, mlp_l
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int grid = std::min(cdiv(e->m, 256), 1024);
-  LAUNCH(e, k_ratio_primal_1, grid, 256, 0, e->alpha, e->xB, e->loB, e->hiB, (int)e->m, sign, max_step0, e->red_f,
-         e->red_counter, e->scal);
-  LAUNCH(e, k_ratio_primal_2, grid, 256, 0, e->alpha, e->xB, e->loB, e->hiB, (int)e->m, sign, e->scal, e->red_f, e->red_i,
-         e->red_counter, e->d_res);
-  ST(fetch_res(e));
-  out->row = e->h_res->i[0];
-  out->coeff = e->h_res->f[0];
-  out->leaving_new_val = e->h_res->f[1];
-  out->basic_val = e->h_res->f[2];
+  Lane& l1 = e->lane[1];
+  ST(begin1(e));
+  LAUNCHS(e, l1.st, k_ratio_primal_1, grid, 256, 0, e->alpha, e->xB, e->loB, e->hiB, (int)e->m, sign, max_step0, l1.red_f,
+          l1.red_counter, e->scal);
+  LAUNCHS(e, l1.st, k_ratio_primal_2, grid, 256, 0, e->alpha, e->xB, e->loB, e->hiB, (int)e->m, sign, e->scal, l1.red_f, l1.red_i,
+          l1.red_counter, l1.d_res);
+  ST(mark1(e));
+  ST(fetch_res(e, l1));
+  out->row = l1.h_res->i[0];
+  out->coeff = l1.h_res->f[0];
+  out->leaving_new_val = l1.h_res->f[1];
+  out->basic_val = l1.h_res->f[2];
   return MLP_OK;
 }
 
 mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
   if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  LAUNCH(e, k_set_unit, cdiv(e->m, 256), 256, 0, e->work_m, e->m, row);
-  ST(btran(e, e->work_m, (int)row, e->rho));
+  Lane& l1 = e->lane[1];
+  ST(begin1(e));
+  LAUNCHS(e, l1.st, k_set_unit, cdiv(e->m, 256), 256, 0, e->work_mb, e->m, row);
+  ST(btran(e, l1, e->work_mb, (int)row, e->rho));
   // inv_basis_row_coeffs as a sparse list + |rho|^2 (solver.rs:683, 1160)
-  compact(e, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
+  compact(e, l1, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
+  ST(mark1(e));
   return MLP_OK;
 }
 
 mlp_status mlp_price_row(mlp_engine* e) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  return price_list(e, e->list_idx, e->list_val, e->icnt, 0, e->rho, e->rc, 0);
+  ST(begin1(e));
+  ST(price_list(e, e->lane[1], e->list_idx, e->list_val, e->icnt, 0, e->rho, e->rc, 0));
+  return mark1(e);
 }
 
 mlp_status mlp_calc_row_coeffs(mlp_engine* e, int64_t row) {
@@ -1323,9 +1434,12 @@ mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int grid = std::min(cdiv(e->m, 256), 1024);
-  LAUNCH(e, k_select_row_dual, grid, 256, 0, e->xB, e->loB, e->hiB, e->w, (int)e->m, e->enable_dse, e->red_f, e->red_i,
-         e->red_counter, e->d_res);
-  ST(fetch_res(e));
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
+  LAUNCH(e, k_select_row_dual, grid, 256, 0, e->xB, e->loB, e->hiB, e->w, (int)e->m, e->enable_dse, l0.red_f, l0.red_i,
+         l0.red_counter, e->d_res);
+  ST(mark0(e));
+  ST(fetch_res(e, l0));
   out->row = e->h_res->i[0];
   out->val = e->h_res->f[0];
   out->min = e->h_res->f[1];
@@ -1337,20 +1451,23 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925)
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
   double bv = 0.0;
   ST(d2h(e, &bv, e->xB + row, sizeof(double)));
   const int lds = leaving_new_val > bv ? 1 : 0;
   const int grid = std::min(cdiv(e->nt, 256), 1024);
-  LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, e->red_f, e->red_counter, e->scal);
+  LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, l0.red_f, l0.red_counter, e->scal);
   if (e->world > 1) {  // Harris pass 1 is a min over ALL variables: all-gather the shard minima
     ST(e->comm->allgather(e->scal, e->xred, sizeof(double), e->stream));
     LAUNCH(e, k_min_small, 1, 1, 0, e->xred, e->world, e->scal);
   }
   LAUNCH(e, k_ratio_dual_2, grid, 256, 0, e->rc, e->d, e->vflag, e->vpos, e->xnb, e->nt, e->n, e->c0, e->ng, lds, e->scal,
-         e->red_f, e->red_i, e->red_counter, e->d_res->flags, (Cand*)e->xsend);
+         l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend);
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w));
+  ST(mark0(e));
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
   out->coeff = w.f[0];
@@ -1364,6 +1481,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (!e || !e->initialized || !pi || !out) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
+  Lane &l0 = e->lane[0], &l1 = e->lane[1];
   const int64_t q = pi->entering_var;
   const int64_t ql = to_local(e, q);
   out->leaving_var = -1;
@@ -1371,9 +1489,11 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   out->refactored = 0;
   out->lu_nnz = e->lu_nnz;
   if (!pi->has_elem) {  // solver.rs:1031-1042
+    ST(begin0(e));
     LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, -1, pi->entering_new_val, pi->entering_diff,
            1.0, 0, 0, e->scal, (double*)nullptr, e->d_res->flags);
     if (ql >= 0) LAUNCH(e, k_flip_var, 1, 1, 0, e->xnb, e->vflag, e->lo, e->hi, q, ql, pi->entering_new_val);
+    ST(mark0(e));
     out->eta_count = e->K;
     return MLP_OK;
   }
@@ -1384,17 +1504,31 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   const double pivot_obj = pi->entering_obj_coeff / pi->coeff;  // solver.rs:1073
   bool do_refactor = pi->refactor != 0;
   if (!do_refactor && e->K >= e->Kcap) do_refactor = true;  // arena full
-  if (e->enable_dse) ST(ftran(e, e->rho, e->tau));  // tau = B^-1 rho (solver.rs:1157)
-  double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->m;
-  LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val, pi->entering_diff,
-         pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags);
+  // lane 1: tau = B^-1 rho (solver.rs:1157)
+  ST(begin1(e));
+  if (e->enable_dse) ST(ftran(e, l1, e->rho, e->tau));
+  // lane 0: v = B^-T alpha_q and helper = N^T v, unless mlp_ftran_col already started them
   if (e->enable_pse) {
-    // v = B^-T alpha_q (1114), helper = N^T v (1117-1132)
-    CU(cudaMemcpyAsync(e->work_m, e->alpha, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
-    ST(btran(e, e->work_m, -1, e->vvec));
-    compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
-    ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
+    if (e->spec_var != q) { ST(begin0(e)); ST(se_helper(e, q)); }
+    if (e->overlap) CU(cudaStreamWaitEvent(l1.st, e->ev_vbtran, 0));  // the eta file is about to change
   }
+  e->spec_var = -1;
+  // lane 1: row half of the pivot, eta push
+  double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->m;
+  LAUNCHS(e, l1.st, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val,
+          pi->entering_diff, pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags);
+  if (!do_refactor) {
+    const int prev = e->h_last_eta_of_row[row];
+    const int K = (int)e->K;
+    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->m, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, prev);
+    LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
+    e->h_last_eta_of_row[row] = K;
+    e->K += 1;
+    e->cnt.etas_pushed += 1;
+  }
+  ST(mark1(e));
+  // lane 0: variable half
+  ST(begin0(e));
   LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, ql, pivot_obj, pi->coeff,
          e->enable_pse, e->scal, e->d_res->flags);
   LAUNCH(e, k_pivot_swap, 1, 1, 0, e->d, e->gam, e->xnb, e->vflag, e->vpos, e->bvar, e->loB, e->hiB, e->lo, e->hi, q, ql, lvl,
@@ -1413,21 +1547,14 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     e->h_slot_of_row[row] = slot;
   }
   e->h_bvar[row] = q;
-  if (!do_refactor) {
-    const int prev = e->h_last_eta_of_row[row];
-    LAUNCH(e, k_eta_grow, cdiv(std::max<int64_t>(e->K, 1), 256), 256, 0, e->E, e->m, (int)e->K, row, e->G, e->Kcap, e->etaR,
-           e->etaPrev, e->etaHead, prev);
-    e->h_last_eta_of_row[row] = (int)e->K;
-    e->K += 1;
-    e->cnt.etas_pushed += 1;
-  }
   // one device->host read per pivot: status flags, leaving var, nnz(alpha)
   CU(cudaMemcpyAsync(&e->d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
   if (e->prof_on) {
     CU(cudaMemcpyAsync(&e->d_res->i[2], e->icnt + 0, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaMemcpyAsync(&e->d_res->i[3], e->icnt + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
   }
-  ST(fetch_res(e));
+  ST(mark0(e));
+  ST(fetch_res(e, l0));
   if (e->prof_on) ST(collect_profile(e, e->h_res->i[2] & 0xffffffffLL, e->h_res->i[3] & 0xffffffffLL));
   out->leaving_var = e->h_res->i[0];
   out->col_nnz = (int64_t)(int32_t)(e->h_res->i[1] & 0xffffffffLL);
@@ -1435,6 +1562,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (e->h_res->flags[0] && e->world == 1) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   if (do_refactor) {
     ST(refactor_impl(e));
+    ST(mark0(e));
     out->refactored = 1;
     out->lu_nnz = e->lu_nnz;
   }
@@ -1446,11 +1574,14 @@ mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {
   if (!e || !e->initialized) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
+  e->spec_var = -1;
   if (e->K > 0) ST(refactor_impl(e));  // solver.rs:1200-1203
   LAUNCH(e, k_gather_cB, cdiv(m, 256), 256, 0, e->cobj, e->bvar, m, e->work_m);
-  ST(btran(e, e->work_m, -1, e->vvec));  // multipliers y (1205-1214)
-  compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
-  ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));
+  ST(btran(e, l0, e->work_m, -1, e->vvec));  // multipliers y (1205-1214)
+  compact(e, l0, e->vvec, e->vlist_idx, e->vlist_val, e->icnt + 2, e->scal + 3);
+  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper));
   LAUNCH(e, k_recalc_d, cdiv(e->nt, 256), 256, 0, e->cobj, e->helper, e->vflag, e->nt, e->n, e->c0, e->ng, e->d);
   LAUNCH(e, k_recalc_obj, 1, 1024, 0, e->cobj, e->bvar, e->xB, m, e->xnb, e->vflag, e->n, e->c0, e->ng, e->scal + 4);
   std::vector<double> parts((size_t)e->world, 0.0);
@@ -1465,7 +1596,7 @@ mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {
   tot += three[1];
   for (int r = 0; r < e->world; ++r) tot += parts[r];
   *cur_obj_val = tot;
-  return MLP_OK;
+  return mark0(e);
 }
 
 mlp_status mlp_download_f64(mlp_engine* e, int32_t which, double* out, int64_t count) {
@@ -1488,12 +1619,14 @@ mlp_status mlp_download_f64(mlp_engine* e, int32_t which, double* out, int64_t c
     default: return MLP_INVALID;
   }
   if (count != len) { set_err("download: count mismatch"); return MLP_INVALID; }
+  ST(begin0(e));
   return d2h(e, out, src, len * 8);
 }
 mlp_status mlp_download_basic_vars(mlp_engine* e, int64_t* out) {
   if (!e) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   std::vector<int32_t> tmp(e->m);
+  ST(begin0(e));
   ST(d2h(e, tmp.data(), e->bvar, e->m * 4));
   for (int64_t i = 0; i < e->m; ++i) out[i] = tmp[i];
   return MLP_OK;
@@ -1501,6 +1634,7 @@ mlp_status mlp_download_basic_vars(mlp_engine* e, int64_t* out) {
 mlp_status mlp_download_var_state(mlp_engine* e, uint8_t* flags, int32_t* pos) {
   if (!e) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
+  ST(begin0(e));
   ST(d2h(e, flags, e->vflag, e->nt));
   return d2h(e, pos, e->vpos, e->nt * 4);
 }
@@ -1515,13 +1649,14 @@ void* mlp_engine_stream(mlp_engine* e) { return e ? (void*)e->stream : nullptr; 
 mlp_status mlp_engine_sync(mlp_engine* e) {
   if (!e) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
-  CU(cudaStreamSynchronize(e->stream));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   CU(cudaGetLastError());
   return MLP_OK;
 }
 mlp_status mlp_event_mark(mlp_engine* e, int32_t slot) {
   if (!e || slot < 0 || slot > 3) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
+  ST(begin0(e));
   CU(cudaEventRecord(e->ev[slot], e->stream));
   return MLP_OK;
 }
@@ -1551,14 +1686,17 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
   if (!e || iters <= 0) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
+  e->spec_var = -1;
   LAUNCH(e, k_fill, cdiv(m, 256), 256, 0, e->vvec, (int64_t)m, 0.5);
-  compact(e, e->vvec, e->list_idx, e->list_val, e->icnt + 2, e->scal + 3);
+  compact(e, l0, e->vvec, e->vlist_idx, e->vlist_val, e->icnt + 2, e->scal + 3);
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a));
   CU(cudaEventCreate(&b));
-  ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));  // warm-up
+  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper));  // warm-up
   CU(cudaEventRecord(a, e->stream));
-  for (int i = 0; i < iters; ++i) ST(price_list(e, e->list_idx, e->list_val, e->icnt + 2, 0, e->vvec, e->helper));
+  for (int i = 0; i < iters; ++i) ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper));
   CU(cudaEventRecord(b, e->stream));
   CU(cudaEventSynchronize(b));
   float ms = 0.f;

@@ -141,77 +141,96 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restri
   }
 }
 
-// ------------------------------------------------------------------------------------------------ dense triangular solves
-// Blocked (32-wide) triangular solve on a column-major matrix by ONE CTA of 1024 threads; used for the
-// L/U factors of the basis core (LUFactors::solve lu.rs:79-106 / tri_solve_process_col 450-463) and for
-// the eta-file coupling matrix G (see k_gemv_* below).
-//   AXPY form (op(M) = M):   after a 32-block of unknowns is solved, every remaining row is updated
-//                            (the reference's column-oriented substitution).
-//   DOT form  (op(M) = M^T): before a 32-block is solved, each of its unknowns takes the dot product of
-//                            its (contiguous) column with the already-solved part.
-// FWD: unknowns 0..n-1, else n-1..0.  UNIT: unit diagonal.
-template <bool FWD, bool AXPY, bool UNIT>
-__global__ void __launch_bounds__(1024) k_trsv(const double* __restrict__ M, int64_t ld, int n, double* __restrict__ x) {
-  __shared__ double xs[32];
-  __shared__ double dots[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nblk = (n + 31) / 32;
-  for (int bi = 0; bi < nblk; ++bi) {
-    const int b = FWD ? bi * 32 : (nblk - 1 - bi) * 32;
-    const int nb = min(32, n - b);
-    if (!AXPY) {
-      // dot products with the solved part, one warp per unknown of the block
-      if (wid < nb) {
-        const double* colp = M + (int64_t)(b + wid) * ld;
-        double acc = 0.0;
-        if (FWD) { for (int j = lane; j < b; j += 32) acc += colp[j] * x[j]; }
-        else { for (int j = b + nb + lane; j < n; j += 32) acc += colp[j] * x[j]; }
-        acc = warp_sum(acc);
-        if (lane == 0) dots[wid] = acc;
+// ------------------------------------------------------------------------------------------------ explicit inverses
+// The two small triangular systems of every FTRAN/BTRAN — the k x k core of the basis (L U = P C) and the K x K eta
+// coupling matrix I+G — are latency-bound as substitutions (k/32 dependent steps on one CTA).  Their INVERSES are kept
+// instead (C^-1 rebuilt at every refactorization, (I+G)^-1 extended by one row per eta), so that each solve becomes
+// one grid-parallel matrix-vector product.
+//   k_mv_n: y[i]        = sum_j M[i + j ld] x[gidx ? gidx[j] : j]     (TRI: j <= i)   CTA = 32 rows x 8 column groups
+//   k_mv_t: y[sidx?[j]] = sum_i M[i + j ld] x[i]                      (TRI: i >= j)   one warp per column
+template <bool TRI>
+__global__ void __launch_bounds__(256) k_mv_n(const double* __restrict__ M, int64_t ld, int n, const double* __restrict__ xin,
+                                              const int32_t* __restrict__ gidx, double* __restrict__ y) {
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  double acc = 0.0;
+  if (i < n) {
+    const int jend = TRI ? i + 1 : n;
+    const double* p = M + i;
+    int j = g;
+    for (; j + 24 < jend; j += 32) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a[u] = p[(int64_t)(j + 8 * u) * ld];
+        b[u] = xin[gidx ? gidx[j + 8 * u] : j + 8 * u];
       }
-      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += a[u] * b[u];
     }
-    if (wid == 0) {
-      double v = 0.0, dg = 1.0;
-      double coef[32];
-      if (lane < nb) {
-        v = x[b + lane];
-        if (!AXPY) v -= dots[lane];
-        if (!UNIT) dg = M[(int64_t)(b + lane) * ld + (b + lane)];
-      }
+    for (; j < jend; j += 8) acc += p[(int64_t)j * ld] * xin[gidx ? gidx[j] : j];
+  }
+  part[g][lane] = acc;
+  __syncthreads();
+  if (g == 0 && i < n) {
+    double t = 0.0;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        // coefficient of unknown jj in equation `lane` of the diagonal block
-        const bool need = lane < nb && jj < nb && (FWD ? (jj < lane) : (jj > lane));
-        coef[jj] = need ? (AXPY ? M[(int64_t)(b + jj) * ld + (b + lane)] : M[(int64_t)(b + lane) * ld + (b + jj)]) : 0.0;
-      }
-#pragma unroll
-      for (int s = 0; s < 32; ++s) {
-        const int jj = FWD ? s : 31 - s;
-        if (!UNIT && lane == jj) v = v / dg;
-        const double xj = __shfl_sync(FULLMASK, v, jj);
-        const bool upd = FWD ? (lane > jj) : (lane < jj);
-        if (upd && jj < nb) v -= xj * coef[jj];
-      }
-      if (lane < nb) {
-        x[b + lane] = v;
-        xs[lane] = v;
-      }
+    for (int q = 0; q < 8; ++q) t += part[q][lane];
+    y[i] = t;
+  }
+}
+template <bool TRI>
+__global__ void __launch_bounds__(256) k_mv_t(const double* __restrict__ M, int64_t ld, int n, const double* __restrict__ xin,
+                                              const int32_t* __restrict__ sidx, double* __restrict__ y) {
+  const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= n) return;
+  const double* col = M + (int64_t)j * ld;
+  double acc = 0.0;
+  for (int i = (TRI ? j : 0) + lane; i < n; i += 32) acc += col[i] * xin[i];
+  acc = warp_sum(acc);
+  if (lane == 0) y[sidx ? sidx[j] : j] = acc;
+}
+// Column j of (L U)^-1 by substitution on e_j (the reference's column-oriented solves, lu.rs:450-463), one CTA per
+// column; the work vector lives in shared memory when it fits (use_smem), else in the output column itself.
+__global__ void __launch_bounds__(256) k_core_inverse(const double* __restrict__ LU, int64_t ld, int k, double* __restrict__ Cinv,
+                                                       const int* __restrict__ flags, int use_smem) {
+  extern __shared__ double smem_v[];
+  if (flags[1]) return;
+  const int j = blockIdx.x, tid = threadIdx.x;
+  double* out = Cinv + (int64_t)j * ld;
+  double* v = use_smem ? smem_v : out;
+  for (int i = tid; i < k; i += 256) v[i] = (i == j) ? 1.0 : 0.0;
+  __syncthreads();
+  for (int t = j; t < k - 1; ++t) {  // L y = e_j (unit diagonal; y_i = 0 for i < j)
+    const double vt = v[t];
+    if (vt != 0.0) {
+      const double* c = LU + (int64_t)t * ld;
+      for (int i = t + 1 + tid; i < k; i += 256) v[i] -= c[i] * vt;
     }
     __syncthreads();
-    if (AXPY) {
-      // rhs[r] -= x_val * coeff for every remaining row (lu.rs:460-462)
-      const int lo_i = FWD ? b + nb : 0;
-      const int hi_i = FWD ? n : b;
-      for (int i = lo_i + threadIdx.x; i < hi_i; i += 1024) {
-        double acc = x[i];
-        if (FWD) { for (int jj = 0; jj < nb; ++jj) acc -= xs[jj] * M[(int64_t)(b + jj) * ld + i]; }
-        else { for (int jj = nb - 1; jj >= 0; --jj) acc -= xs[jj] * M[(int64_t)(b + jj) * ld + i]; }
-        x[i] = acc;
-      }
-      __syncthreads();
-    }
   }
+  for (int t = k - 1; t >= 0; --t) {  // U x = y
+    const double* c = LU + (int64_t)t * ld;
+    const double vt = v[t] / c[t];
+    if (!use_smem) __syncthreads();  // out aliases v: every thread must have read v[t] before thread 0 overwrites it
+    if (vt != 0.0)
+      for (int i = tid; i < t; i += 256) v[i] -= c[i] * vt;
+    if (tid == 0) out[t] = vt;
+    __syncthreads();
+  }
+}
+// New row K of (I+G)^-1 when eta K with coupling row g (g[i] = E_i[r_K], i < K) is appended:
+// [[T,0],[g^T,1]]^-1 = [[T^-1,0],[-g^T T^-1,1]].  One warp per column.
+__global__ void __launch_bounds__(256) k_eta_inv_row(const double* __restrict__ g, double* __restrict__ Ginv, int64_t ld, int K) {
+  const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j > K) return;
+  double* col = Ginv + (int64_t)j * ld;
+  if (j == K) { if (lane == 0) col[K] = 1.0; return; }
+  double acc = 0.0;
+  for (int i = j + lane; i < K; i += 32) acc += g[i] * col[i];
+  acc = warp_sum(acc);
+  if (lane == 0) col[K] = -acc;
 }
 
 // y[i] = base[i] - sum_j M[i + j*ld] * t[j]   (column-major M: rows x cols; thread per row)
@@ -485,12 +504,12 @@ __global__ void __launch_bounds__(256) k_select_row_dual(const double* __restric
   }
 }
 
-// Coupling matrix of the eta file: G[i][j] = E_j[r_i] (j < i).  New eta K adds row K (a strided gather of row
-// r_K of E) — see DESIGN.md "eta chain in closed form".
-__global__ void k_eta_grow(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ G, int64_t ldg,
+// Coupling row of a new eta K: g[j] = E_j[r_K] (j < K), a strided gather of row r_K of E, plus the per-row chains used by
+// k_eta_scatter — see DESIGN.md "eta chain in closed form".
+__global__ void k_eta_grow(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ g,
                            int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int prev) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < K) G[(int64_t)j * ldg + K] = E[(int64_t)j * lde + rK];
+  if (j < K) g[j] = E[(int64_t)j * lde + rK];
   if (j == 0) {
     etaR[K] = rK;
     etaPrev[K] = prev;

@@ -16,13 +16,17 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt = torch.tensor(list(mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-    dist.broadcast(idt, 0)
-    uid = bytes(idt.cpu().tolist())
+
+    def fresh_uid():  # an ncclUniqueId serves ONE ncclCommInitRank round: every engine gets its own
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
+
     for kind, m, n, seed in ((0, 200, 300, 1), (3, 97, 131, 9), (1, 64, 96, 2)):
         lp = mb.synth_dense(kind, m, n, seed)
+        uid = fresh_uid()
         s = mb.Solver.from_dense(lp, device=local, rank=rank, world=world, comm=uid)
         assert s.run()
         ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)

@@ -93,3 +93,18 @@ def test_sharded_budgeted_run_stays_in_lockstep():
     assert not shards[0]["done"]
     assert np.array_equal(shards[0]["trace"], shards[1]["trace"])
     assert shards[0]["trace"].shape[0] == 25
+
+
+def test_nccl_two_processes_match_oracle():
+    """One process per GPU over NCCL (the deployment shape); needs two devices."""
+    import os
+    import subprocess
+    import sys
+    if mb.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "_nccl_worker.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("NCCL_OK") == 6, out.stdout[-3000:] + out.stderr[-3000:]
