@@ -56,6 +56,12 @@ typedef struct mlp_engine mlp_engine;
 /* Allocate the device-resident state for an m x n dense constraint matrix A (row-major f64 in HBM).
  * Replaces the storage half of Solver (solver.rs:15-58: orig_constraints / orig_constraints_csc). */
 mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out);
+/* Sparse storage (BASELINE config 4): A as CSR — row_ptr (m+1), col_idx / vals (nnz), columns ascending within a row, the
+ * order CsVec::new gives every constraint (lib.rs:279) — copied to the device together with the CSC copy the engine
+ * derives (CsMat::to_csc, solver.rs:253).  Replaces orig_constraints / orig_constraints_csc (solver.rs:21-22) with 32-bit
+ * indices.  Every other entry point is storage-agnostic; mlp_engine_upload_rows is rejected. */
+mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                    const int32_t* col_idx, const double* vals, mlp_engine** out);
 /* Column-sharded engine: rank `rank` of `world` owns the structural columns
  * mlp_shard_range(n_global, world, rank) of A and all per-variable arrays of those columns; m-sized state and the
  * basis factors are replicated and every rank runs the identical host control loop (SPMD).  All variable indices
@@ -244,6 +250,8 @@ typedef struct mlp_solver mlp_solver;
 mlp_status mlp_solver_create_dense(int device, int64_t m, int64_t n, mlp_solver** out);
 mlp_status mlp_solver_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
                                            int32_t comm_kind, const void* comm_arg, mlp_solver** out);
+mlp_status mlp_solver_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                    const int32_t* col_idx, const double* vals, mlp_solver** out);
 mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local);
 void mlp_solver_destroy(mlp_solver* s);
 mlp_engine* mlp_solver_engine(mlp_solver* s);

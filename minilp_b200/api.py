@@ -247,10 +247,19 @@ TRACE_FIELDS = ("phase", "entering_var", "entering_col", "leaving_row", "leaving
 class Solver:
     """solver.rs `Solver` after the swap: host control loop (csrc/host_solver.cpp) + device engine."""
 
-    def __init__(self, m, n, device=0, rank=0, world=1, comm=None):
-        """comm: None (single shard), a LocalGroup, or the 128-byte NCCL unique id shared by all ranks."""
+    def __init__(self, m, n, device=0, rank=0, world=1, comm=None, csr=None):
+        """comm: None (single shard), a LocalGroup, or the 128-byte NCCL unique id shared by all ranks.
+        csr: (row_ptr int64[m+1], col_idx int32[nnz], vals f64[nnz]) selects the sparse-storage engine."""
         h = C.c_void_p()
-        if world == 1:
+        if csr is not None:
+            assert world == 1, "the sparse engine is single-shard"
+            rp = np.ascontiguousarray(csr[0], dtype=np.int64)
+            ci = np.ascontiguousarray(csr[1], dtype=np.int32)
+            va = _f64(csr[2])
+            assert rp.shape[0] == m + 1 and ci.shape == va.shape
+            _check(_lib.lib().mlp_solver_create_sparse(device, m, n, int(va.shape[0]), _p(rp, pi64), _p(ci, pi32), _p(va),
+                                                       C.byref(h)))
+        elif world == 1:
             _check(_lib.lib().mlp_solver_create_dense(device, m, n, C.byref(h)))
         elif isinstance(comm, LocalGroup):
             _check(_lib.lib().mlp_solver_create_dense_sharded(device, m, n, rank, world, 2, comm._g, C.byref(h)))
@@ -293,6 +302,15 @@ class Solver:
         obj = -lp.obj if lp.direction == OptimizationDirection.Maximize else lp.obj  # lib.rs:235-238
         s.init(obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
         s.direction = lp.direction
+        return s
+
+    @classmethod
+    def from_csr(cls, direction, m, n, row_ptr, col_idx, vals, obj, mins, maxs, ops, rhs, device=0):
+        """Sparse storage (BASELINE config 4).  obj in user sign."""
+        s = cls(m, n, device, csr=(row_ptr, col_idx, vals))
+        obj = _f64(obj)
+        s.init(-obj if direction == OptimizationDirection.Maximize else obj, mins, maxs, ops, rhs)
+        s.direction = direction
         return s
 
     def run(self, max_pivots=-1):
@@ -374,7 +392,21 @@ class Problem:
             raise ValueError("unknown variable")
         self.constraints.append((sorted(expr), cmp_op, float(rhs)))  # CsVec::new sorts by index (lib.rs:279)
 
-    def solve(self, device=0, max_pivots=-1):
+    def to_csr(self):
+        """The constraint rows that survive Solver::try_new's empty-row filter (solver.rs:201-213) as CSR, plus ops / rhs."""
+        kept = [(e, op, r) for e, op, r in self.constraints if e]
+        row_ptr = np.zeros(len(kept) + 1, dtype=np.int64)
+        for i, (e, _, _) in enumerate(kept):
+            row_ptr[i + 1] = row_ptr[i] + len(e)
+        col_idx = np.fromiter((v for e, _, _ in kept for v, _ in e), dtype=np.int32, count=int(row_ptr[-1]))
+        vals = np.fromiter((c for e, _, _ in kept for _, c in e), dtype=np.float64, count=int(row_ptr[-1]))
+        ops = np.array([op for _, op, _ in kept], dtype=np.int32)
+        rhs = np.array([r for _, _, r in kept], dtype=np.float64)
+        return row_ptr, col_idx, vals, ops, rhs
+
+    def solve(self, device=0, max_pivots=-1, storage="auto"):
+        """storage: "dense" (row-major f64 A in HBM), "sparse" (CSR + CSC), or "auto" (sparse below 10 % density once A
+        has more than 2^20 entries)."""
         n = len(self.obj_coeffs)
         for mn, mx in zip(self.var_mins, self.var_maxs):
             if mn > mx:
@@ -390,14 +422,22 @@ class Problem:
         if n == 0 or not kept:
             return _TrivialSolution(self, n)
         m = len(kept)
-        a = np.zeros((m, n))
-        for i, (expr, _, _) in enumerate(kept):
-            for v, c in expr:
-                a[i, v] = c
-        s = Solver(m, n, device)
-        s.upload_rows(0, a)
-        s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs),
-               np.array([op for _, op, _ in kept], dtype=np.int32), np.array([r for _, _, r in kept]))
+        nnz = sum(len(e) for e, _, _ in kept)
+        if storage == "auto":
+            storage = "sparse" if (m * n > (1 << 20) and nnz < 0.1 * m * n) else "dense"
+        if storage == "sparse":
+            row_ptr, col_idx, vals, ops, rhs = self.to_csr()
+            s = Solver(m, n, device, csr=(row_ptr, col_idx, vals))
+            s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs), ops, rhs)
+        else:
+            a = np.zeros((m, n))
+            for i, (expr, _, _) in enumerate(kept):
+                for v, c in expr:
+                    a[i, v] = c
+            s = Solver(m, n, device)
+            s.upload_rows(0, a)
+            s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs),
+                   np.array([op for _, op, _ in kept], dtype=np.int32), np.array([r for _, _, r in kept]))
         s.direction = self.direction
         s.run(max_pivots)
         return Solution(s, self.direction, n)

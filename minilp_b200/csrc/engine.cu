@@ -214,7 +214,14 @@ struct mlp_engine {
   bool initialized = false;
   int enable_pse = 0, enable_dse = 0;
 
-  double* A = nullptr;                                    // m x lda row-major, local column block
+  double* A = nullptr;                                    // m x lda row-major, local column block (dense storage)
+  // sparse storage (BASELINE config 4): CSR + CSC copies of A with 32-bit indices, as solver.rs:21-22 keeps both
+  bool sparse = false;
+  int64_t nnz = 0;
+  int64_t *csr_ptr = nullptr, *csc_ptr = nullptr;         // m+1, n+1
+  int32_t *csr_idx = nullptr, *csc_idx = nullptr;         // nnz
+  double *csr_val = nullptr, *csc_val = nullptr;          // nnz
+  std::vector<int64_t> h_csc_ptr;                         // host copy: column counts for LUFactors::nnz
   double *lo = nullptr, *hi = nullptr, *cobj = nullptr;  // ng+m, GLOBAL index, replicated
   double *d = nullptr, *gam = nullptr, *xnb = nullptr;   // n+m, local index
   uint8_t* vflag = nullptr;                               // n+m
@@ -500,6 +507,63 @@ __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict_
   for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
   const double tot = block_sum(acc, sm);
   if (threadIdx.x == 0) part[(int64_t)sidx * k + j] = tot;
+}
+
+// ------------------------------------------------------------------------------------------------ sparse storage
+// Sparse A (CSR + CSC, u32 indices).  The basis-inverse machinery is shared with the dense engine: basis columns are
+// expanded into the dense column cache when they enter, so only three things read the sparse matrix — the column
+// load, the price-out and the set-up passes.
+// rhs.set(column) (solver.rs:672-675): dst is zero-filled by the caller; var < 0 comes from a candidate header.
+__global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                               int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst) {
+  int64_t lv = lv_arg;
+  if (cand) {
+    if (cand->var < 0) return;
+    lv = cand->var;  // single shard: local == global
+  }
+  if (lv >= n) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[lv - n] = 1.0;
+    return;
+  }
+  const int64_t b = ptr[lv], e = ptr[lv + 1];
+  for (int64_t t = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < e; t += (int64_t)gridDim.x * blockDim.x) dst[idx[t]] = val[t];
+}
+// Price-out over the CSC copy (calc_row_coeffs 685-692, update_primal_sq_norms 1117-1132, recalc_obj_coeffs 1216-1222,
+// column norms 297-299): one warp per column gathers the DENSE multiplier vector w at the column's row indices —
+// 12 bytes per stored entry, rows ascending within a column, fixed shuffle tree: bit-reproducible, no atomics.
+// MODE 0: out[v] = sum_i A[i,v] w[i] (slack v: w[v-n]; basic v: 0)     MODE 1: out[v] = |a_v|^2 + 1
+template <int MODE>
+__global__ void __launch_bounds__(256) k_price_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                   const double* __restrict__ val, int64_t n, int64_t m,
+                                                   const double* __restrict__ w, const uint8_t* __restrict__ vflag,
+                                                   double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t v = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); v < n; v += warps) {
+    if (MODE == 0 && (vflag[v] & MLP_BASIC)) { if (lane == 0) out[v] = 0.0; continue; }
+    const int64_t b = ptr[v], e = ptr[v + 1];
+    double acc = 0.0;
+    for (int64_t t = b + lane; t < e; t += 32) {
+      const double a = __ldcs(val + t);
+      acc += (MODE == 0) ? a * w[__ldcs(idx + t)] : a * a;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[v] = (MODE == 1) ? acc + 1.0 : acc;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
+    out[n + i] = (MODE == 1) ? 2.0 : ((vflag[n + i] & MLP_BASIC) ? 0.0 : w[i]);
+}
+// rows of A x_N over the CSR copy (solver.rs:234-238): one warp per row
+__global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                     const double* __restrict__ val, int64_t m, const double* __restrict__ xnb,
+                                                     double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= m) return;
+  double acc = 0.0;
+  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) acc += val[t] * xnb[idx[t]];
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 pricing scan
@@ -808,9 +872,15 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
                              int fixed_count, const double* slack_vals, double* out, int prof_slot = -1) {
   const bool prof = e->prof_on && prof_slot >= 0;
   if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], ln.st));
-  LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
-  LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
-          e->vflag, out, 0);
+  if (e->sparse) {
+    // slack_vals is the dense multiplier vector the list was compacted from
+    LAUNCHS(e, ln.st, k_price_csc<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, e->m, slack_vals,
+            e->vflag, out);
+  } else {
+    LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
+    LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
+            e->vflag, out, 0);
+  }
   if (prof) {
     CU(cudaEventRecord(e->pev[prof_slot][1], ln.st));
     e->ppending[prof_slot] = true;
@@ -826,7 +896,7 @@ static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
     CU(cudaEventSynchronize(e->pev[slot][1]));
     CU(cudaEventElapsedTime(&ms, e->pev[slot][0], e->pev[slot][1]));
     const int64_t sz = slot == 0 ? s_rho : s_v;
-    const int64_t bytes = 8 * e->n * sz + 8 * sz + 8 * e->n;
+    const int64_t bytes = e->sparse ? 12 * e->nnz + 8 * e->m + 8 * e->nt : 8 * e->n * sz + 8 * sz + 8 * e->n;
     if (slot == 0) { e->prof.price_rho_ms += ms; e->prof.price_rho_launches += 1; e->prof.price_rho_bytes += bytes; }
     else { e->prof.price_v_ms += ms; e->prof.price_v_launches += 1; e->prof.price_v_bytes += bytes; }
   }
@@ -978,9 +1048,18 @@ static mlp_status refactor_impl(mlp_engine* e) {
   } else {
     CU(cudaStreamSynchronize(e->stream));
   }
-  // LUFactors::nnz (lu.rs:52-54) of the reference's factors of this basis when A is fully dense:
-  // L: k(k-1)/2, U: (m-k)k + k(k-1)/2, plus m.
-  e->lu_nnz = k * (k - 1) + (m - k) * k + m;
+  // LUFactors::nnz (lu.rs:52-54) of the reference's factors of this basis: every stored entry of the k structural basic
+  // columns lands in L or U except the k pivots, plus the m diagonal entries — nnz(D) - k + m.  Exact when A is fully
+  // dense (L: k(k-1)/2, U: (m-k)k + k(k-1)/2); for a sparse A it leaves out the fill-in of the core (a lower bound: the
+  // engine then refactorizes no later than the reference would).
+  if (e->sparse) {
+    int64_t nz = 0;
+    for (int64_t p = 0; p < m; ++p) {
+      const int64_t v = e->h_bvar[p];
+      if (v < ng) nz += e->h_csc_ptr[v + 1] - e->h_csc_ptr[v];
+    }
+    e->lu_nnz = nz - k + m;
+  } else e->lu_nnz = k * (k - 1) + (m - k) * k + m;
   e->cnt.refactors += 1;
   e->cnt.k_structural = k;
   return MLP_OK;
@@ -990,8 +1069,14 @@ static mlp_status refactor_impl(mlp_engine* e) {
 // reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
 static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   const int m = (int)e->m;
-  LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend,
-         (double*)(e->xsend + sizeof(Cand)));
+  if (e->sparse) {
+    CU(cudaMemsetAsync(e->xsend + sizeof(Cand), 0, (size_t)m * sizeof(double), e->stream));
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, (int64_t)-1, (const Cand*)e->xsend,
+           (double*)(e->xsend + sizeof(Cand)));
+  } else {
+    LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend,
+           (double*)(e->xsend + sizeof(Cand)));
+  }
   char* recv = e->xsend;
   if (e->world > 1) {
     ST(e->comm->allgather(e->xsend, e->xrecv, e->xbytes, e->stream));
@@ -1023,7 +1108,10 @@ static mlp_status fetch_column(mlp_engine* e, int64_t var) {
   if (e->colq_var == var) return MLP_OK;
   const int m = (int)e->m;
   const int64_t lv = to_local(e, var);
-  if (lv >= 0) LAUNCH(e, k_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, m, lv, e->colq);
+  if (e->sparse) {
+    CU(cudaMemsetAsync(e->colq, 0, (size_t)m * sizeof(double), e->stream));
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, lv, (const Cand*)nullptr, e->colq);
+  } else if (lv >= 0) LAUNCH(e, k_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, m, lv, e->colq);
   if (e->world > 1 && var < e->ng) ST(e->comm->broadcast(e->colq, (size_t)m * sizeof(double), owner_of(e, var), e->stream));
   e->colq_var = var;
   return MLP_OK;
@@ -1046,6 +1134,7 @@ static void destroy_engine(mlp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (int l = 0; l < 2; ++l) if (e->lane[l].st) cudaStreamSynchronize(e->lane[l].st);
+  dev_free(e->csr_ptr); dev_free(e->csc_ptr); dev_free(e->csr_idx); dev_free(e->csc_idx); dev_free(e->csr_val); dev_free(e->csc_val);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
   dev_free(e->rhs); dev_free(e->alpha); dev_free(e->rho); dev_free(e->tau); dev_free(e->vvec); dev_free(e->work_m);
@@ -1073,7 +1162,8 @@ static void destroy_engine(mlp_engine* e) {
   delete e;
 }
 
-static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out) {
+static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out,
+                                bool sparse = false) {
   *out = nullptr;
   if (m <= 0 || ng <= 0 || m > 0x7fffffff || ng + m > 0x7fffffff || world < 1 || rank < 0 || rank >= world) {
     set_err("bad dimensions");
@@ -1088,6 +1178,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaSetDevice(device));
   mlp_engine* e = new mlp_engine();
   e->device = device;
+  e->sparse = sparse;
   e->comm = comm;
   e->rank = rank;
   e->world = world;
@@ -1113,7 +1204,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
   const int64_t nt = e->nt, gt = ng + m;
-  A(dev_alloc(&e->A, (size_t)m * e->lda));
+  if (!sparse) A(dev_alloc(&e->A, (size_t)m * e->lda));
   A(dev_alloc(&e->lo, gt)); A(dev_alloc(&e->hi, gt)); A(dev_alloc(&e->cobj, gt));
   A(dev_alloc(&e->d, nt)); A(dev_alloc(&e->gam, nt)); A(dev_alloc(&e->xnb, nt));
   A(dev_alloc(&e->vflag, nt)); A(dev_alloc(&e->vpos, nt)); A(dev_alloc(&e->bvar, m));
@@ -1144,7 +1235,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaEventCreateWithFlags(&e->s0_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->s1_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_vbtran, cudaEventDisableTiming));
-  CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
+  if (!sparse) CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
   for (int l = 0; l < 2; ++l) {
     CU(cudaMemsetAsync(e->lane[l].red_counter, 0, 4 * sizeof(unsigned), e->stream));
     CU(cudaMemsetAsync(e->lane[l].d_res, 0, sizeof(DevRes), e->stream));
@@ -1196,6 +1287,54 @@ mlp_status mlp_nccl_get_unique_id(void* out128) {
 mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out) {
   return create_engine(device, m, n, 0, 1, nullptr, out);
 }
+mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
+                                    const double* vals, mlp_engine** out) {
+  *out = nullptr;
+  if (!row_ptr || !col_idx || !vals || nnz < 0 || m <= 0 || n <= 0 || row_ptr[0] != 0 || row_ptr[m] != nnz) {
+    set_err("create_sparse: bad CSR");
+    return MLP_INVALID;
+  }
+  // CsMat::to_csc (solver.rs:253): counting transpose, rows ascending within a column (sparse.rs:230-269 does the same)
+  std::vector<int64_t> cptr((size_t)n + 1, 0);
+  for (int64_t t = 0; t < nnz; ++t) {
+    if (col_idx[t] < 0 || col_idx[t] >= n) { set_err("create_sparse: column index out of range"); return MLP_INVALID; }
+    cptr[(size_t)col_idx[t] + 1] += 1;
+  }
+  for (int64_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+  std::vector<int32_t> cidx((size_t)nnz);
+  std::vector<double> cval((size_t)nnz);
+  {
+    std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int64_t i = 0; i < m; ++i) {
+      if (row_ptr[i + 1] < row_ptr[i]) { set_err("create_sparse: row_ptr not monotone"); return MLP_INVALID; }
+      for (int64_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
+        const int64_t d = fill[col_idx[t]]++;
+        cidx[d] = (int32_t)i;
+        cval[d] = vals[t];
+      }
+    }
+  }
+  mlp_engine* e = nullptr;
+  ST(create_engine(device, m, n, 0, 1, nullptr, &e, true));
+  e->nnz = nnz;
+  e->h_csc_ptr = cptr;
+  mlp_status st = MLP_OK;
+  auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
+  A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
+  A(dev_alloc(&e->csc_ptr, n + 1)); A(dev_alloc(&e->csc_idx, nnz)); A(dev_alloc(&e->csc_val, nnz));
+  if (st == MLP_OK) {
+    A(h2d(e, e->csr_ptr, row_ptr, (m + 1) * sizeof(int64_t)));
+    A(h2d(e, e->csr_idx, col_idx, nnz * sizeof(int32_t)));
+    A(h2d(e, e->csr_val, vals, nnz * sizeof(double)));
+    A(h2d(e, e->csc_ptr, cptr.data(), (n + 1) * sizeof(int64_t)));
+    A(h2d(e, e->csc_idx, cidx.data(), nnz * sizeof(int32_t)));
+    A(h2d(e, e->csc_val, cval.data(), nnz * sizeof(double)));
+  }
+  if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("create_sparse: upload failed"); st = MLP_CUDA_ERROR; }
+  if (st != MLP_OK) { destroy_engine(e); return st; }
+  *out = e;
+  return MLP_OK;
+}
 mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
                                            int32_t comm_kind, const void* comm_arg, mlp_engine** out) {
   *out = nullptr;
@@ -1230,6 +1369,7 @@ mlp_status mlp_engine_local_range(mlp_engine* e, int64_t* begin, int64_t* end) {
 // rows_host: nrows x src_cols row-major; src_cols == n_global (full rows: this shard's slice is taken) or == local width
 static mlp_status upload_rows_impl(mlp_engine* e, int64_t row0, int64_t nrows, const double* rows_host, bool local) {
   if (!e || row0 < 0 || nrows < 0 || row0 + nrows > e->m) { set_err("upload_rows: range"); return MLP_INVALID; }
+  if (e->sparse) { set_err("upload_rows: the engine holds a sparse matrix (given at creation)"); return MLP_INVALID; }
   CU(cudaSetDevice(e->device));
   if (e->n == 0 || nrows == 0) return MLP_OK;
   const double* src = local ? rows_host : rows_host + e->c0;
@@ -1296,17 +1436,23 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   e->spec_var = -1;
   if (!st->basic_var_vals) {
     double* part = e->world > 1 ? e->work_m : e->xred;
-    LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, part);
+    if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->xnb, part);
+    else LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, part);
     if (e->world > 1) ST(e->comm->allgather(part, e->xred, (size_t)m * sizeof(double), e->stream));
     LAUNCH(e, k_init_basic_vals, cdiv(m, 256), 256, 0, e->xred, e->world, (int)m, e->rhs, e->xB);
   }
   if (!st->dual_edge_sq_norms) LAUNCH(e, k_fill, cdiv(m, 256), 256, 0, e->w, m, 1.0);
   if (e->enable_pse && !st->primal_edge_sq_norms) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
+    if (e->sparse)
+      LAUNCH(e, k_price_csc<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, n, m, (const double*)nullptr, e->vflag,
+             e->gam);
+    else {
     LAUNCH(e, k_price_partial<1>, price_grid(e), PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
            (const int32_t*)nullptr, (int32_t)m, e->lane[0].partial);
     LAUNCH(e, k_price_finish, cdiv(nt, 256), 256, 0, e->lane[0].partial, (const int32_t*)nullptr, (int32_t)m, e->lda, n, m,
            (const double*)nullptr, e->vflag, e->gam, 1);
+    }
   }
   // column cache: an initial basis with structural columns (warm start) fetches them one by one
   e->h_slot_of_row.assign(m, -1);
@@ -1705,7 +1851,7 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
   cudaEventDestroy(b);
   *ms_per_launch = (double)ms / iters;
   // algorithmic bytes: 8 n s + 8 s + 8 n  with s = m, n = this shard's columns
-  *bytes_per_launch = 8 * e->n * (int64_t)m + 8 * (int64_t)m + 8 * e->n;
+  *bytes_per_launch = e->sparse ? 12 * e->nnz + 8 * (int64_t)m + 8 * e->nt : 8 * e->n * (int64_t)m + 8 * (int64_t)m + 8 * e->n;
   return MLP_OK;
 }
 

@@ -175,6 +175,18 @@ mlp_status mlp_solver_create_dense_sharded(int device, int64_t m, int64_t n_glob
   *out = s;
   return MLP_OK;
 }
+mlp_status mlp_solver_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
+                                    const double* vals, mlp_solver** out) {
+  *out = nullptr;
+  mlp_engine* e = nullptr;
+  ST(mlp_engine_create_sparse(device, m, n, nnz, row_ptr, col_idx, vals, &e));
+  mlp_solver* s = new mlp_solver();
+  s->eng = e;
+  s->m = m;
+  s->n = n;
+  *out = s;
+  return MLP_OK;
+}
 mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local) {
   return mlp_engine_upload_local_rows(s->eng, row0, nrows, rows_local);
 }
