@@ -258,10 +258,13 @@ struct mlp_engine {
 
   // lane synchronisation (see "host side")
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
+  int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
-  cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr;
+  cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr, ev_win = nullptr;
   int64_t spec_var = -1;  // variable whose v = B^-T alpha_q / N^T v were computed ahead by mlp_ftran_col
+  int64_t ftran_var = -1; // variable whose FTRAN (alpha, |alpha|^2) was queued right behind its selection
+  Cand* d_win = nullptr;  // winner header of the last candidate exchange
   size_t smem_optin = 48 << 10;
 
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -411,6 +414,144 @@ k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __rest
       o.x = acc0;
       o.y = acc1;
       *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col) = o;
+    }
+  }
+}
+
+// ---- bulk-copy (TMA) form of the same price-out --------------------------------------------------------------
+// The LDG kernel above needs 6 resident CTAs per SM (all registers) to keep enough bytes in flight; that starves the
+// latency-bound kernels of lane 1 that should run beside it.  Here the bytes in flight live in SHARED memory instead:
+// one CTA per SM, a producer warp gathers the listed rows with 1-D bulk copies (cp.async.bulk, 4 KB row segments,
+// L2 evict-first) into a TP_STAGES-deep ring guarded by mbarriers, eight consumer warps accumulate.  Work items,
+// chunking and the per-column accumulation order (list order within a chunk, thread t owns columns 2t, 2t+1 of the
+// tile) are those of k_price_partial, so the partial sums are bit-identical.
+constexpr int TP_ROWS = 8;                        // rows per stage
+constexpr int TP_STAGES = 6;                      // ring depth: 6 x 32 KB = 192 KB in flight per SM
+constexpr int TP_TILE_BYTES = PR_TILE * 8;        // 4 KB
+constexpr int TP_STAGE_BYTES = TP_ROWS * TP_TILE_BYTES;
+constexpr int TP_CONSUMERS = PR_THREADS;          // 8 warps
+constexpr int TP_THREADS = TP_CONSUMERS + 32;     // + producer warp
+constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_ROWS * 8 + 2 * TP_STAGES * 8 + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)  // L2 evict-first: A is streamed once per pivot
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1)
+k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
+                    const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
+                    double* __restrict__ partial) {
+  extern __shared__ __align__(128) unsigned char tp_smem[];
+  double* sdata = reinterpret_cast<double*>(tp_smem);
+  double* sw = reinterpret_cast<double*>(tp_smem + (size_t)TP_STAGES * TP_STAGE_BYTES);   // [stage][row] weights
+  uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_ROWS);
+  uint64_t* empty = full + TP_STAGES;
+  const int s = count_ptr ? *count_ptr : fixed_count;
+  const int C = price_chunks_for(s);
+  const int L = (s + C - 1) / C;
+  const int tiles = (int)((lda + PR_TILE - 1) / PR_TILE);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < TP_STAGES; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, TP_CONSUMERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t it = 0;  // stages handled so far by this role: slot = it % TP_STAGES, phase = (it / TP_STAGES) & 1
+  if (warp == TP_CONSUMERS / 32) {
+    // ---------------- producer warp: lane r < TP_ROWS fetches row r of the stage
+    for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
+      const int tile = item % tiles, chunk = item / tiles;
+      const int k0 = chunk * L, k1 = min(s, k0 + L);
+      const int64_t col0 = (int64_t)tile * PR_TILE;
+      const uint32_t tbytes = (uint32_t)(min((int64_t)PR_TILE, lda - col0) * 8);
+      for (int kb = k0; kb < k1; kb += TP_ROWS, ++it) {
+        const int nr = min(TP_ROWS, k1 - kb);
+        const int slot = it % TP_STAGES;
+        int32_t r = 0;
+        double wv = 0.0;
+        if (lane < nr) { r = rows[kb + lane]; wv = wts[kb + lane]; }  // issued before the wait: latency overlaps
+        mbar_wait(empty + slot, ((it / TP_STAGES) & 1) ^ 1);
+        if (lane < nr) sw[slot * TP_ROWS + lane] = wv;
+        __syncwarp();
+        if (lane == 0) mbar_arrive_expect_tx(full + slot, tbytes * nr);
+        __syncwarp();
+        if (lane < nr)
+          bulk_g2s(reinterpret_cast<unsigned char*>(sdata) + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * TP_TILE_BYTES,
+                   A + (int64_t)r * lda + col0, tbytes, full + slot);
+      }
+    }
+  } else {
+    // ---------------- consumers
+    const int t = threadIdx.x;
+    for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
+      const int tile = item % tiles, chunk = item / tiles;
+      const int k0 = chunk * L, k1 = min(s, k0 + L);
+      const int64_t col = ((int64_t)tile * PR_THREADS + t) * 2;
+      const bool active = col < lda;
+      double acc0 = 0.0, acc1 = 0.0;
+      for (int kb = k0; kb < k1; kb += TP_ROWS, ++it) {
+        const int nr = min(TP_ROWS, k1 - kb);
+        const int slot = it % TP_STAGES;
+        mbar_wait(full + slot, (it / TP_STAGES) & 1);
+        if (active) {
+          const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(sdata) +
+                                                              (size_t)slot * TP_STAGE_BYTES) + t;
+          const double* w = sw + slot * TP_ROWS;
+          if (nr == TP_ROWS) {
+            double2 v[TP_ROWS];
+#pragma unroll
+            for (int u = 0; u < TP_ROWS; ++u) v[u] = p[u * (TP_TILE_BYTES / 16)];
+#pragma unroll
+            for (int u = 0; u < TP_ROWS; ++u) {
+              const double wv = w[u];
+              acc0 += wv * v[u].x;
+              acc1 += wv * v[u].y;
+            }
+          } else {
+            for (int u = 0; u < nr; ++u) {
+              const double2 v = p[u * (TP_TILE_BYTES / 16)];
+              const double wv = w[u];
+              acc0 += wv * v.x;
+              acc1 += wv * v.y;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+      }
+      if (active) {
+        double2 o;
+        o.x = acc0;
+        o.y = acc1;
+        *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col) = o;
+      }
     }
   }
 }
@@ -609,6 +750,30 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
       out->f[0] = d[v];
       out->f[1] = xnb[v];
     }
+  }
+}
+
+// Arg-reduce of the gathered candidate headers ON THE DEVICE (larger key wins, ties go to the smaller `tie`: lowest
+// position, solver.rs:719) and copy of the winner's column into colq, so that the FTRAN of the entering column can be
+// queued behind the selection without a host round trip.  Every thread repeats the <= 8-way comparison.
+__global__ void __launch_bounds__(256) k_pick_winner(const char* __restrict__ recv, size_t xbytes, int world, int m,
+                                                      double* __restrict__ colq, Cand* __restrict__ win) {
+  int best = -1;
+  double err = 0.0;
+  for (int r = 0; r < world; ++r) {
+    const Cand* c = reinterpret_cast<const Cand*>(recv + (size_t)r * xbytes);
+    if (c->f[4] != 0.0) err = 1.0;
+    if (c->var < 0) continue;
+    if (best < 0) { best = r; continue; }
+    const Cand* b = reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
+    if (c->key > b->key || (c->key == b->key && c->tie < b->tie)) best = r;
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) colq[i] = best < 0 ? 0.0 : reinterpret_cast<const double*>(recv + (size_t)best * xbytes + sizeof(Cand))[i];
+  if (i == 0) {
+    if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
+    else *win = *reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
+    win->f[4] = err;
   }
 }
 
@@ -877,7 +1042,11 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
     LAUNCHS(e, ln.st, k_price_csc<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, e->m, slack_vals,
             e->vflag, out);
   } else {
-    LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
+    if (e->price_tma)
+      LAUNCHS(e, ln.st, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count,
+              ln.partial);
+    else
+      LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
     LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
             e->vflag, out, 0);
   }
@@ -1018,6 +1187,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
   e->h_pending_free.clear();
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   e->spec_var = -1;
+  e->ftran_var = -1;
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
   ST(ensure_eta_capacity(e, 2 * k + 32));
@@ -1067,8 +1237,14 @@ static mlp_status refactor_impl(mlp_engine* e) {
 
 // The exchange step: every shard's candidate header + candidate column are all-gathered, the winner is chosen with the
 // reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
+static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out);
+static mlp_status se_helper(mlp_engine* e, int64_t var);
+static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq);
+static constexpr int64_t VAR_PENDING = -2;
+
 static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   const int m = (int)e->m;
+  Lane& l0 = e->lane[0];
   if (e->sparse) {
     CU(cudaMemsetAsync(e->xsend + sizeof(Cand), 0, (size_t)m * sizeof(double), e->stream));
     LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, (int64_t)-1, (const Cand*)e->xsend,
@@ -1082,24 +1258,22 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
     ST(e->comm->allgather(e->xsend, e->xrecv, e->xbytes, e->stream));
     recv = e->xrecv;
   }
-  CU(cudaMemcpy2DAsync(e->h_cands, sizeof(Cand), recv, e->xbytes, sizeof(Cand), (size_t)e->world, cudaMemcpyDeviceToHost,
-                       e->stream));
-  CU(cudaStreamSynchronize(e->stream));
-  e->cnt.d2h_bytes += (int64_t)sizeof(Cand) * e->world;
-  int best = -1;
-  bool err = false;
-  for (int r = 0; r < e->world; ++r) {
-    const Cand& c = e->h_cands[r];
-    if (c.f[4] != 0.0) err = true;
-    if (c.var < 0) continue;
-    if (best < 0 || c.key > e->h_cands[best].key || (c.key == e->h_cands[best].key && c.tie < e->h_cands[best].tie)) best = r;
-  }
-  if (err) { set_err("non-finite steepest-edge norm on a shard"); return MLP_NONFINITE; }
-  if (best < 0) { winner->var = -1; e->colq_var = -1; return MLP_OK; }
-  *winner = e->h_cands[best];
-  CU(cudaMemcpyAsync(e->colq, recv + (size_t)best * e->xbytes + sizeof(Cand), (size_t)m * sizeof(double),
-                     cudaMemcpyDeviceToDevice, e->stream));
-  e->colq_var = winner->var;
+  LAUNCH(e, k_pick_winner, cdiv(m, 256), 256, 0, recv, e->xbytes, e->world, m, e->colq, e->d_win);
+  CU(cudaMemcpyAsync(e->h_cands, e->d_win, sizeof(Cand), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ev_win, e->stream));
+  // Both callers continue with calc_col_coeffs of the winner (solver.rs:750, 532): queue that FTRAN — and, with primal
+  // steepest edge, the v / N^T v chain — now, before the host has even seen which variable won.
+  ST(ftran(e, l0, e->colq, e->alpha));
+  compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+  ST(mark0(e));
+  e->spec_var = -1;
+  if (e->enable_pse && e->overlap) ST(se_helper(e, VAR_PENDING));
+  CU(cudaEventSynchronize(e->ev_win));  // the header only, not the chain queued behind it
+  e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
+  *winner = e->h_cands[0];
+  if (winner->f[4] != 0.0) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
+  e->colq_var = e->ftran_var = winner->var;
+  if (e->spec_var == VAR_PENDING) e->spec_var = winner->var;
   return MLP_OK;
 }
 
@@ -1140,7 +1314,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->rhs); dev_free(e->alpha); dev_free(e->rho); dev_free(e->tau); dev_free(e->vvec); dev_free(e->work_m);
   dev_free(e->work_mb); dev_free(e->colq); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val);
   dev_free(e->vlist_idx); dev_free(e->vlist_val); dev_free(e->scal); dev_free(e->icnt);
-  dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred);
+  dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred); dev_free(e->d_win);
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   for (int l = 0; l < 2; ++l) {
@@ -1156,6 +1330,7 @@ static void destroy_engine(mlp_engine* e) {
   if (e->s0_mark) cudaEventDestroy(e->s0_mark);
   if (e->s1_mark) cudaEventDestroy(e->s1_mark);
   if (e->ev_vbtran) cudaEventDestroy(e->ev_vbtran);
+  if (e->ev_win) cudaEventDestroy(e->ev_win);
   delete e->comm;
   if (e->lane[1].st && e->lane[1].st != e->lane[0].st) cudaStreamDestroy(e->lane[1].st);
   if (e->lane[0].st) cudaStreamDestroy(e->lane[0].st);
@@ -1191,6 +1366,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
+  if (const char* v = getenv("MLP_PRICE_TMA")) e->price_tma = atoi(v) != 0;
+  CU(cudaFuncSetAttribute(k_price_partial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   {  // lane 1 carries short latency-bound kernels that must slip in beside the price-out: highest priority
     int lo_p = 0, hi_p = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -1225,6 +1402,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->d_res = e->lane[0].d_res;
   A(dev_alloc(&e->rowcover, m));
   e->xbytes = sizeof(Cand) + (size_t)m * sizeof(double);
+  A(dev_alloc(&e->d_win, 1));
   A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * m + 64));
   if (st != MLP_OK) { destroy_engine(e); return st; }
   for (int l = 0; l < 2; ++l) CU(cudaHostAlloc((void**)&e->lane[l].h_res, sizeof(DevRes), cudaHostAllocDefault));
@@ -1235,6 +1413,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaEventCreateWithFlags(&e->s0_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->s1_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_vbtran, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&e->ev_win, cudaEventDisableTiming));
   if (!sparse) CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
   for (int l = 0; l < 2; ++l) {
     CU(cudaMemsetAsync(e->lane[l].red_counter, 0, 4 * sizeof(unsigned), e->stream));
@@ -1504,8 +1683,7 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
          l0.red_i, l0.red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
   Cand w;
   w.var = -1;
-  ST(exchange_candidates(e, &w));
-  ST(mark0(e));
+  ST(exchange_candidates(e, &w));  // records s0_mark ahead of the run-ahead tail
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
   out->pos = w.tie;
@@ -1519,8 +1697,10 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
 mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   if (!e || !e->initialized || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
+  if (e->ftran_var == var) return MLP_OK;  // queued right behind the selection of `var`
   Lane& l0 = e->lane[0];
   ST(begin0(e));
+  e->ftran_var = -1;
   ST(fetch_column(e, var));
   ST(ftran(e, l0, e->colq, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
@@ -1613,7 +1793,6 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w));
-  ST(mark0(e));
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
   out->coeff = w.f[0];
@@ -1659,6 +1838,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     if (e->overlap) CU(cudaStreamWaitEvent(l1.st, e->ev_vbtran, 0));  // the eta file is about to change
   }
   e->spec_var = -1;
+  e->ftran_var = -1;
   // lane 1: row half of the pivot, eta push
   double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->m;
   LAUNCHS(e, l1.st, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val,
