@@ -249,6 +249,7 @@ struct mlp_engine {
   int64_t k = 0, kcap = 0;
   int32_t *Jpos = nullptr, *Jslot = nullptr, *Rp = nullptr;  // kcap
   int32_t* rowcover = nullptr;                                 // m
+  int32_t *lu_aff = nullptr, *lu_perm = nullptr;              // panel row-permutation records (192), in-place permutation (kcap)
   double *Bcols = nullptr, *LUc = nullptr, *Cinv = nullptr;   // column cache m x kcap (slot-indexed); LU factors and (LU)^-1, kcap x kcap
   // eta file
   int64_t K = 0, Kcap = 0;
@@ -1140,6 +1141,8 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   }
   for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
   dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
+  dev_free(e->lu_aff); dev_free(e->lu_perm);
+  ST(dev_alloc(&e->lu_aff, 192)); ST(dev_alloc(&e->lu_perm, cap));
   e->Bcols = nb;
   e->kcap = cap;
   ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jslot, cap)); ST(dev_alloc(&e->Rp, cap));
@@ -1203,10 +1206,21 @@ static mlp_status refactor_impl(mlp_engine* e) {
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
     LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->m, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
     int* flags = e->d_res->flags;
-    for (int t = 0; t < (int)k; ++t) {
-      LAUNCH(e, k_lu_pivot, 1, 1024, 0, e->LUc, e->kcap, (int)k, t, e->Rp, flags);
-      const int rem = (int)k - t - 1;
-      if (rem > 0) LAUNCH(e, k_lu_update, dim3(cdiv(rem, 32), cdiv(rem, 8)), dim3(32, 8), 0, e->LUc, e->kcap, (int)k, t, flags);
+    for (int j0 = 0; j0 < (int)k;) {
+      const int rows = (int)k - j0;
+      // widest panel whose rows x nb block (+ row ids, permutation) fits in shared memory; else work in place in global memory
+      int nb = LU_NB, use_smem = 0;
+      for (int cand = LU_NB; cand >= 4; cand /= 2)
+        if ((size_t)rows * cand * 8 + (size_t)rows * 8 <= e->smem_optin) { nb = cand; use_smem = 1; break; }
+      nb = std::min(nb, rows);
+      const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * 8 : 0;
+      LAUNCH(e, k_lu_panel, 1, 1024, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, flags, e->lu_aff, e->lu_aff + 64, e->lu_aff + 128,
+             e->lu_perm, use_smem);
+      if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
+                              e->lu_aff + 128, flags);
+      const int rem = rows - nb;
+      if (rem > 0) LAUNCH(e, k_lu_trailing, dim3(cdiv(rem, LU_NC), cdiv(rem, 256)), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, flags);
+      j0 += nb;
     }
     {  // (L U)^-1, one CTA per column
       const size_t need = (size_t)k * sizeof(double);
@@ -1316,6 +1330,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->vlist_idx); dev_free(e->vlist_val); dev_free(e->scal); dev_free(e->icnt);
   dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred); dev_free(e->d_win);
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
+  dev_free(e->lu_aff); dev_free(e->lu_perm);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
@@ -1378,6 +1393,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   }
   e->smem_optin = std::min<size_t>((size_t)prop.sharedMemPerBlockOptin, (size_t)200 << 10);
   CU(cudaFuncSetAttribute(k_core_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin));
+  CU(cudaFuncSetAttribute(k_lu_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin));
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
   const int64_t nt = e->nt, gt = ng + m;

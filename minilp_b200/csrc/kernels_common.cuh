@@ -339,52 +339,166 @@ __global__ void k_btran_start(const double* __restrict__ c, const int32_t* __res
 // are taken in basis-position order and whose pivots follow the reference's threshold rule:
 // among rows with |x| >= 0.1 max|x| (lu.rs:224) — all have the same original-row count, lu.rs:225-229 —
 // the first in list order, i.e. the lowest original row index.
-__global__ void __launch_bounds__(1024) k_lu_pivot(double* __restrict__ C, int64_t ld, int k, int t,
-                                                    int32_t* __restrict__ Rp, int* __restrict__ flags) {
+//
+// Right-looking, blocked in panels of nb <= 32 columns, three launches per panel:
+//   k_lu_panel     one CTA factorizes the (k-j0) x nb panel held in shared memory (pivot search, row swap, scaling and
+//                  the rank-1 updates inside the panel), records the panel's row permutation;
+//   k_lu_swap_solve  one warp per column outside the panel applies that permutation and, right of the panel, solves
+//                  U12 = L11^-1 A12 in registers;
+//   k_lu_trailing  A22 -= L21 U12, thread per row with its L21 row in registers, 16 columns per CTA.
+// Every element sees the same operations in the same order as column-by-column elimination (t ascending, separate
+// multiply and subtract), so the factors are bit-identical to an unblocked factorization.
+constexpr int LU_NB = 32;
+__global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
+                                                    int32_t* __restrict__ Rp, int* __restrict__ flags,
+                                                    int32_t* __restrict__ aff_pos, int32_t* __restrict__ aff_src,
+                                                    int32_t* __restrict__ aff_cnt, int32_t* __restrict__ perm_glob, int use_smem) {
+  extern __shared__ __align__(16) unsigned char lu_smem[];
   __shared__ double smk[32];
   __shared__ long long smi[32];
   __shared__ double s_max;
-  __shared__ int s_piv;
-  if (flags[1]) return;
-  double* col = C + (int64_t)t * ld;
-  double mx = 0.0;
-  for (int i = t + threadIdx.x; i < k; i += blockDim.x) mx = fmax(mx, fabs(col[i]));
-  KeyIdx r = block_argmax(KeyIdx{mx, 0}, smk, smi);
-  if (threadIdx.x == 0) s_max = r.key;
-  __syncthreads();
-  const double max_abs = s_max;
-  if (!(max_abs >= 1e-8) || isinf(max_abs)) {  // lu.rs:207-211
-    if (threadIdx.x == 0) flags[1] = 1;
-    return;
-  }
-  // lowest original row among eligible: maximise -Rp
-  KeyIdx c{-INFINITY, LLONG_MAX};
-  for (int i = t + threadIdx.x; i < k; i += blockDim.x)
-    if (fabs(col[i]) >= 0.1 * max_abs) {
-      const double key = -(double)Rp[i];
-      if (better_max(key, i, c.key, c.idx)) { c.key = key; c.idx = i; }
+  __shared__ int s_piv, s_cnt, s_stop;
+  const int rows = k - j0, tid = threadIdx.x;
+  double* P;
+  int64_t pld;
+  int32_t *rp, *perm;
+  if (use_smem) {
+    P = reinterpret_cast<double*>(lu_smem);
+    pld = rows;
+    rp = reinterpret_cast<int32_t*>(P + (size_t)rows * nb);
+    perm = rp + rows;
+    for (int idx = tid; idx < rows * nb; idx += blockDim.x) {
+      const int r = idx % rows, c = idx / rows;
+      P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
     }
-  c = block_argmax(c, smk, smi);
-  if (threadIdx.x == 0) s_piv = (int)c.idx;
-  __syncthreads();
-  const int p = s_piv;
-  if (p != t) {
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-      const double a = C[(int64_t)j * ld + t], b = C[(int64_t)j * ld + p];
-      C[(int64_t)j * ld + t] = b;
-      C[(int64_t)j * ld + p] = a;
-    }
-    if (threadIdx.x == 0) { const int a = Rp[t]; Rp[t] = Rp[p]; Rp[p] = a; }
+    for (int r = tid; r < rows; r += blockDim.x) rp[r] = Rp[j0 + r];
+  } else {
+    P = C + (int64_t)j0 * ld + j0;
+    pld = ld;
+    rp = Rp + j0;
+    perm = perm_glob;
   }
+  for (int r = tid; r < rows; r += blockDim.x) perm[r] = r;
+  if (tid == 0) { s_cnt = 0; s_stop = flags[1]; }
   __syncthreads();
-  const double pv = col[t];
-  for (int i = t + 1 + threadIdx.x; i < k; i += blockDim.x) col[i] = col[i] / pv;  // lu.rs:261
+  for (int c = 0; c < nb && !s_stop; ++c) {
+    double* col = P + (size_t)c * pld;
+    double mx = 0.0;
+    for (int r = c + tid; r < rows; r += blockDim.x) mx = fmax(mx, fabs(col[r]));
+    KeyIdx rr = block_argmax(KeyIdx{mx, 0}, smk, smi);
+    if (tid == 0) {
+      s_max = rr.key;
+      if (!(rr.key >= 1e-8) || isinf(rr.key)) { flags[1] = 1; s_stop = 1; }  // lu.rs:207-211
+    }
+    __syncthreads();
+    if (s_stop) break;
+    const double max_abs = s_max;
+    KeyIdx cand{-INFINITY, LLONG_MAX};  // lowest original row among the eligible ones: maximise -Rp
+    for (int r = c + tid; r < rows; r += blockDim.x)
+      if (fabs(col[r]) >= 0.1 * max_abs) {
+        const double key = -(double)rp[r];
+        if (better_max(key, r, cand.key, cand.idx)) { cand.key = key; cand.idx = r; }
+      }
+    cand = block_argmax(cand, smk, smi);
+    if (tid == 0) s_piv = (int)cand.idx;
+    __syncthreads();
+    const int p = s_piv;
+    if (p != c) {
+      if (tid < nb) {
+        double* q = P + (size_t)tid * pld;
+        const double a = q[c], b = q[p];
+        q[c] = b;
+        q[p] = a;
+      } else if (tid == nb) {
+        const int a = rp[c]; rp[c] = rp[p]; rp[p] = a;
+        const int b = perm[c]; perm[c] = perm[p]; perm[p] = b;
+      }
+    }
+    __syncthreads();
+    const double pv = col[c];
+    for (int r = c + 1 + tid; r < rows; r += blockDim.x) col[r] = col[r] / pv;  // lu.rs:261
+    __syncthreads();
+    const int rr2 = rows - c - 1, nc2 = nb - c - 1;
+    for (int idx = tid; idx < rr2 * nc2; idx += blockDim.x) {
+      const int r = c + 1 + idx % rr2, cc = c + 1 + idx / rr2;
+      double* q = P + (size_t)cc * pld;
+      q[r] -= col[r] * q[c];
+    }
+    __syncthreads();
+  }
+  if (use_smem) {
+    for (int idx = tid; idx < rows * nb; idx += blockDim.x) {
+      const int r = idx % rows, c = idx / rows;
+      C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
+    }
+    for (int r = tid; r < rows; r += blockDim.x) Rp[j0 + r] = rp[r];
+  }
+  for (int r = tid; r < rows; r += blockDim.x)
+    if (perm[r] != r) {
+      const int slot = atomicAdd(&s_cnt, 1);
+      aff_pos[slot] = j0 + r;
+      aff_src[slot] = j0 + perm[r];
+    }
+  __syncthreads();
+  if (tid == 0) *aff_cnt = s_cnt;
 }
-__global__ void k_lu_update(double* __restrict__ C, int64_t ld, int k, int t, const int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) k_lu_swap_solve(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
+                                                        const int32_t* __restrict__ aff_pos, const int32_t* __restrict__ aff_src,
+                                                        const int32_t* __restrict__ aff_cnt, const int* __restrict__ flags) {
+  __shared__ double L11[LU_NB][LU_NB + 1];
   if (flags[1]) return;
-  const int i = t + 1 + blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = t + 1 + blockIdx.y * blockDim.y + threadIdx.y;
-  if (i < k && j < k) C[(int64_t)j * ld + i] -= C[(int64_t)t * ld + i] * C[(int64_t)j * ld + t];
+  for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
+    const int t = idx % nb, sc = idx / nb;
+    L11[t][sc] = C[(int64_t)(j0 + sc) * ld + j0 + t];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  int j = blockIdx.x * 8 + (threadIdx.x >> 5);  // index over the k - nb columns outside the panel
+  if (j >= k - nb) return;
+  if (j >= j0) j += nb;
+  double* colj = C + (int64_t)j * ld;
+  const int na = *aff_cnt;  // <= 2 nb
+  double v0 = 0.0, v1 = 0.0;
+  if (lane < na) v0 = colj[aff_src[lane]];
+  if (lane + 32 < na) v1 = colj[aff_src[lane + 32]];
+  __syncwarp();
+  if (lane < na) colj[aff_pos[lane]] = v0;
+  if (lane + 32 < na) colj[aff_pos[lane + 32]] = v1;
+  __syncwarp();
+  if (j < j0) return;
+  double a = lane < nb ? colj[j0 + lane] : 0.0;
+  for (int sc = 0; sc < nb; ++sc) {
+    const double us = __shfl_sync(FULLMASK, a, sc);
+    if (lane > sc && lane < nb) a -= L11[lane][sc] * us;
+  }
+  if (lane < nb) colj[j0 + lane] = a;
+}
+constexpr int LU_NC = 16;
+__global__ void __launch_bounds__(256) k_lu_trailing(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
+                                                      const int* __restrict__ flags) {
+  __shared__ double U[LU_NB][LU_NC];
+  if (flags[1]) return;
+  const int r0 = j0 + nb;
+  const int jbase = r0 + blockIdx.x * LU_NC;
+  const int ncol = min(LU_NC, k - jbase);
+  for (int idx = threadIdx.x; idx < nb * LU_NC; idx += blockDim.x) {
+    const int t = idx % nb, jj = idx / nb;
+    U[t][jj] = jj < ncol ? C[(int64_t)(jbase + jj) * ld + j0 + t] : 0.0;
+  }
+  __syncthreads();
+  const int r = r0 + blockIdx.y * blockDim.x + threadIdx.x;
+  if (r >= k) return;
+  double Lr[LU_NB];
+#pragma unroll
+  for (int t = 0; t < LU_NB; ++t) Lr[t] = t < nb ? C[(int64_t)(j0 + t) * ld + r] : 0.0;
+  for (int jj = 0; jj < ncol; ++jj) {
+    double* q = C + (int64_t)(jbase + jj) * ld + r;
+    double a = *q;
+#pragma unroll
+    for (int t = 0; t < LU_NB; ++t)
+      if (t < nb) a -= Lr[t] * U[t][jj];
+    *q = a;
+  }
 }
 // ------------------------------------------------------------------------------------------------ K3 primal ratio test
 // Harris pass 1 (solver.rs:782-795): max_step = min(max_step0, min_r (slack_r + EPS)/|alpha_r|)
