@@ -41,7 +41,7 @@ def full(src, dst, m=None, n=None):
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary ({os.path.basename(src)})\n\n")
-        f.write("`ncu --set full --clock-control none --import-source on -k regex:k_price_partial` over `bench.py`.\n\n")
+        f.write("`ncu --set full --clock-control none --import-source on -k regex:k_price_partial_tma` over `bench.py`.\n\n")
         for r in data:
             f.write(f"## launch id {r[0]}\n\n| metric | value | unit |\n|---|---:|---|\n")
             for w, i in idx:
@@ -55,7 +55,7 @@ def full(src, dst, m=None, n=None):
             u = units[i].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
         t = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-        json.dump({"m": int(m), "n": int(n), "dram_bytes_per_launch": t, "kernel": "k_price_partial<0>",
+        json.dump({"m": int(m), "n": int(n), "dram_bytes_per_launch": t, "kernel": big[hdr.index("Kernel Name")].split("(")[0],
                    "source": os.path.basename(dst)}, open(os.path.join(os.path.dirname(dst), "price_traffic.json"), "w"))
 
 
