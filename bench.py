@@ -35,7 +35,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--m", type=int, default=50000)
-    ap.add_argument("--n", type=int, default=50000)
+    ap.add_argument("--n", "--cols", dest="n", type=int, default=50000)
     ap.add_argument("--kind", type=int, default=0, help="synthetic LP family (0 = dense_pos, see DESIGN.md)")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-baseline-seconds", type=float, default=20.0,
@@ -141,7 +141,7 @@ def run_reference(a):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- our arm
@@ -315,14 +315,27 @@ def run_ours(a):
             "value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"first {piv} pivots of the same {m_used}x{a.n} LP ({sec:.1f}s of single-thread CPU work; the "
                        f"reference is single-threaded){note}"), "host_cores_available": cores}
-    print(json.dumps(line), flush=True)
+    emit(line)
     s.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the process's real stdout; everything else printed while the bench runs (NCCL's version
+    banner, library chatter) was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     a = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

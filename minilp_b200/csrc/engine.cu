@@ -260,6 +260,7 @@ struct mlp_engine {
   // lane synchronisation (see "host side")
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
   int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
+  int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
   cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr, ev_win = nullptr;
@@ -426,13 +427,16 @@ k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __rest
 // L2 evict-first) into a TP_STAGES-deep ring guarded by mbarriers, eight consumer warps accumulate.  Work items,
 // chunking and the per-column accumulation order (list order within a chunk, thread t owns columns 2t, 2t+1 of the
 // tile) are those of k_price_partial, so the partial sums are bit-identical.
-constexpr int TP_ROWS = 8;                        // rows per stage
+constexpr int TP_STAGE_BYTES = 32768;             // one stage: R rows x tile_cols x 8 B, R = 32768 / (tile_cols * 8) <= 32
 constexpr int TP_STAGES = 6;                      // ring depth: 6 x 32 KB = 192 KB in flight per SM
-constexpr int TP_TILE_BYTES = PR_TILE * 8;        // 4 KB
-constexpr int TP_STAGE_BYTES = TP_ROWS * TP_TILE_BYTES;
+constexpr int TP_MAXROWS = 32;                    // one row per producer lane
 constexpr int TP_CONSUMERS = PR_THREADS;          // 8 warps
 constexpr int TP_THREADS = TP_CONSUMERS + 32;     // + producer warp
-constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_ROWS * 8 + 2 * TP_STAGES * 8 + 16;
+constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_MAXROWS * 8 + 2 * TP_STAGES * 8 + 16;
+// Tile width: 512 columns (4 KB row segments).  Narrower tiles were measured and lose: 6.77 TB/s at 512, 6.19 at 256,
+// 4.30 at 128 columns (more, smaller bulk copies per byte); a narrow column block of a sharded engine has fewer work
+// items per SM, but the tail still has enough SMs active to saturate HBM.  MLP_PRICE_TILE overrides for experiments.
+static int price_tile_cols(int64_t, int) { return PR_TILE; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -468,16 +472,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
                     const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
-                    double* __restrict__ partial) {
+                    double* __restrict__ partial, int tile_cols) {
   extern __shared__ __align__(128) unsigned char tp_smem[];
-  double* sdata = reinterpret_cast<double*>(tp_smem);
   double* sw = reinterpret_cast<double*>(tp_smem + (size_t)TP_STAGES * TP_STAGE_BYTES);   // [stage][row] weights
-  uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_ROWS);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_MAXROWS);
   uint64_t* empty = full + TP_STAGES;
   const int s = count_ptr ? *count_ptr : fixed_count;
   const int C = price_chunks_for(s);
   const int L = (s + C - 1) / C;
-  const int tiles = (int)((lda + PR_TILE - 1) / PR_TILE);
+  const int tiles = (int)((lda + tile_cols - 1) / tile_cols);
+  const int tile_bytes = tile_cols * 8;
+  const int R = TP_STAGE_BYTES / tile_bytes;  // rows per stage: 8 / 16 / 32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int q = 0; q < TP_STAGES; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, TP_CONSUMERS / 32); }
@@ -486,62 +491,62 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
   __syncthreads();
   uint32_t it = 0;  // stages handled so far by this role: slot = it % TP_STAGES, phase = (it / TP_STAGES) & 1
   if (warp == TP_CONSUMERS / 32) {
-    // ---------------- producer warp: lane r < TP_ROWS fetches row r of the stage
+    // ---------------- producer warp: lane r < R fetches row r of the stage
     for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
       const int tile = item % tiles, chunk = item / tiles;
       const int k0 = chunk * L, k1 = min(s, k0 + L);
-      const int64_t col0 = (int64_t)tile * PR_TILE;
-      const uint32_t tbytes = (uint32_t)(min((int64_t)PR_TILE, lda - col0) * 8);
-      for (int kb = k0; kb < k1; kb += TP_ROWS, ++it) {
-        const int nr = min(TP_ROWS, k1 - kb);
+      const int64_t col0 = (int64_t)tile * tile_cols;
+      const uint32_t tbytes = (uint32_t)(min((int64_t)tile_cols, lda - col0) * 8);
+      for (int kb = k0; kb < k1; kb += R, ++it) {
+        const int nr = min(R, k1 - kb);
         const int slot = it % TP_STAGES;
         int32_t r = 0;
         double wv = 0.0;
         if (lane < nr) { r = rows[kb + lane]; wv = wts[kb + lane]; }  // issued before the wait: latency overlaps
         mbar_wait(empty + slot, ((it / TP_STAGES) & 1) ^ 1);
-        if (lane < nr) sw[slot * TP_ROWS + lane] = wv;
+        if (lane < nr) sw[slot * TP_MAXROWS + lane] = wv;
         __syncwarp();
         if (lane == 0) mbar_arrive_expect_tx(full + slot, tbytes * nr);
         __syncwarp();
         if (lane < nr)
-          bulk_g2s(reinterpret_cast<unsigned char*>(sdata) + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * TP_TILE_BYTES,
-                   A + (int64_t)r * lda + col0, tbytes, full + slot);
+          bulk_g2s(tp_smem + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * tile_bytes, A + (int64_t)r * lda + col0, tbytes,
+                   full + slot);
       }
     }
   } else {
-    // ---------------- consumers
+    // ---------------- consumers: thread t < tile_cols / 2 owns columns 2t, 2t+1 of the tile
     const int t = threadIdx.x;
+    const int rstride = tile_bytes / 16;  // double2 per row
     for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
       const int tile = item % tiles, chunk = item / tiles;
       const int k0 = chunk * L, k1 = min(s, k0 + L);
-      const int64_t col = ((int64_t)tile * PR_THREADS + t) * 2;
-      const bool active = col < lda;
+      const int64_t col = (int64_t)tile * tile_cols + 2 * t;
+      const bool active = 2 * t < tile_cols && col < lda;
       double acc0 = 0.0, acc1 = 0.0;
-      for (int kb = k0; kb < k1; kb += TP_ROWS, ++it) {
-        const int nr = min(TP_ROWS, k1 - kb);
+      for (int kb = k0; kb < k1; kb += R, ++it) {
+        const int nr = min(R, k1 - kb);
         const int slot = it % TP_STAGES;
         mbar_wait(full + slot, (it / TP_STAGES) & 1);
         if (active) {
-          const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(sdata) +
-                                                              (size_t)slot * TP_STAGE_BYTES) + t;
-          const double* w = sw + slot * TP_ROWS;
-          if (nr == TP_ROWS) {
-            double2 v[TP_ROWS];
+          const double2* p = reinterpret_cast<const double2*>(tp_smem + (size_t)slot * TP_STAGE_BYTES) + t;
+          const double* w = sw + slot * TP_MAXROWS;
+          int u0 = 0;
+          for (; u0 + 8 <= nr; u0 += 8) {
+            double2 v[8];
 #pragma unroll
-            for (int u = 0; u < TP_ROWS; ++u) v[u] = p[u * (TP_TILE_BYTES / 16)];
+            for (int u = 0; u < 8; ++u) v[u] = p[(u0 + u) * rstride];
 #pragma unroll
-            for (int u = 0; u < TP_ROWS; ++u) {
-              const double wv = w[u];
+            for (int u = 0; u < 8; ++u) {
+              const double wv = w[u0 + u];
               acc0 += wv * v[u].x;
               acc1 += wv * v[u].y;
             }
-          } else {
-            for (int u = 0; u < nr; ++u) {
-              const double2 v = p[u * (TP_TILE_BYTES / 16)];
-              const double wv = w[u];
-              acc0 += wv * v.x;
-              acc1 += wv * v.y;
-            }
+          }
+          for (; u0 < nr; ++u0) {
+            const double2 v = p[u0 * rstride];
+            const double wv = w[u0];
+            acc0 += wv * v.x;
+            acc1 += wv * v.y;
           }
         }
         __syncwarp();
@@ -1045,7 +1050,7 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   } else {
     if (e->price_tma)
       LAUNCHS(e, ln.st, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count,
-              ln.partial);
+              ln.partial, e->price_tile);
     else
       LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
     LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
@@ -1382,6 +1387,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("MLP_PRICE_TMA")) e->price_tma = atoi(v) != 0;
+  e->price_tile = price_tile_cols(e->lda, e->sm_count);
+  if (const char* v = getenv("MLP_PRICE_TILE")) { const int t = atoi(v); if (t == 128 || t == 256 || t == 512) e->price_tile = t; }
   CU(cudaFuncSetAttribute(k_price_partial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   {  // lane 1 carries short latency-bound kernels that must slip in beside the price-out: highest priority
     int lo_p = 0, hi_p = 0;
