@@ -259,19 +259,25 @@ struct mlp_engine {
 
   // lane synchronisation (see "host side")
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
+  int async_pivot = 1;  // MLP_ASYNC_PIVOT=0: mlp_pivot always waits for the device
   int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
   int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
   cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr, ev_win = nullptr;
   int64_t spec_var = -1;  // variable whose v = B^-T alpha_q / N^T v were computed ahead by mlp_ftran_col
+  bool sel_valid = false; // xsend holds the pricing candidate of the CURRENT state (left by k_update_select)
   int64_t ftran_var = -1; // variable whose FTRAN (alpha, |alpha|^2) was queued right behind its selection
   Cand* d_win = nullptr;  // winner header of the last candidate exchange
   size_t smem_optin = 48 << 10;
 
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t pev[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][begin/end]; slot 0 rho, 1 v
-  bool ppending[2] = {false, false};
+  // price-out timing, double-buffered by pivot parity: a pivot's events are read only after the NEXT selection has synced
+  cudaEvent_t pev[2][2][2] = {};  // [slot][parity][begin/end]; slot 0 rho, 1 v
+  bool ppending[2][2] = {};
+  int32_t* h_mail = nullptr;      // pinned: [parity*4 + 0] nnz(rho), [parity*4 + 1] nnz(v) of the timed launches
+  int64_t pivot_seq = 0;          // completed basis changes; parity = pivot_seq & 1
+  int64_t alpha_nnz_host = -1;    // nnz(alpha_q) as read back with the ratio test, -1: not known on the host
   int prof_on = 0;
   mlp_profile prof{};
 
@@ -592,8 +598,9 @@ __global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n,
 }
 // same, for the variable named by a candidate header that is still on the device (no host round trip)
 __global__ void k_cand_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int64_t c0, int64_t ng, int m,
-                                const Cand* __restrict__ cand, double* __restrict__ dst) {
+                                const Cand* __restrict__ cand, double* __restrict__ dst, Cand* __restrict__ win_out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && win_out) *win_out = *cand;  // single shard: the candidate IS the winner
   if (i >= m) return;
   const long long g = cand->var;
   if (g < 0) { dst[i] = 0.0; return; }
@@ -620,12 +627,19 @@ __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__
     if (cov >= 0) {
       const double* p = Bcols + i;
       int j = 0;
-      for (; j + 8 <= nj; j += 8) {
-        double v[8];
+      for (; j + 16 <= nj; j += 16) {  // 16 loads in flight, subtraction still in column order
+        double v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
+        for (int u = 0; u < 16; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc -= ts[j + u] * v[u];
+        for (int u = 0; u < 16; ++u) acc -= ts[j + u] * v[u];
+      }
+      for (; j + 4 <= nj; j += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc -= ts[j + u] * v[u];
       }
       for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)sl[j] * ldb];
     }
@@ -651,7 +665,16 @@ __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict_
   const int r0 = sidx * L, r1 = min(rows, r0 + L);
   const double* p = Bcols + (int64_t)Jslot[j] * ldb;
   double acc = 0.0;
-  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
+  int i = r0 + threadIdx.x;
+  const int st = blockDim.x;
+  for (; i + 7 * st < r1; i += 8 * st) {  // 8 row pairs in flight per thread, added in row order
+    double a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = p[i + u * st]; b[u] = x[i + u * st]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += a[u] * b[u];
+  }
+  for (; i < r1; i += st) acc += p[i] * x[i];
   const double tot = block_sum(acc, sm);
   if (threadIdx.x == 0) part[(int64_t)sidx * k + j] = tot;
 }
@@ -662,8 +685,10 @@ __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict_
 // load, the price-out and the set-up passes.
 // rhs.set(column) (solver.rs:672-675): dst is zero-filled by the caller; var < 0 comes from a candidate header.
 __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                               int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst) {
+                               int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst,
+                               Cand* __restrict__ win_out) {
   int64_t lv = lv_arg;
+  if (cand && win_out && blockIdx.x == 0 && threadIdx.x == 0) *win_out = *cand;
   if (cand) {
     if (cand->var < 0) return;
     lv = cand->var;  // single shard: local == global
@@ -907,65 +932,121 @@ __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ a
   }
   if (eta_col) eta_col[r] = (r == row) ? 1.0 - 1.0 / coeff : a / coeff;  // 1276-1280
 }
-// Variable half over this shard's variables: reduced costs (solver.rs:1073-1080) and primal steepest-edge norms
-// (1139-1150).  pivot_obj = d_q / coeff comes from the host (the entering column may live on another shard).
-__global__ void __launch_bounds__(256) k_pivot_vars(double* __restrict__ d, double* __restrict__ gam,
-                                                     const double* __restrict__ rc, const double* __restrict__ helper,
-                                                     const uint8_t* __restrict__ vflag, int64_t nt, int64_t q_local,
-                                                     double pivot_obj, double coeff, int pse, const double* __restrict__ scal,
-                                                     int* __restrict__ flags) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nt || v == q_local) return;
-  if (vflag[v] & MLP_BASIC) return;
-  const double c = rc[v];
-  if (c == 0.0) return;
-  d[v] -= pivot_obj * c;
-  if (pse) {
-    const double psn = scal[2] + 1.0;  // 1136
-    const double pcs = coeff * coeff;
-    const double g = gam[v] + (-2.0 * c * helper[v] / coeff + psn * c * c / pcs);  // 1144-1146
-    gam[v] = g;
-    if (!isfinite(g)) flags[0] = 1;
-  }
-}
-// Bookkeeping of Solver::pivot done by one thread: 1057-1058, 1066-1071, 1076, 1142, 1088-1091.
-// q / lv are GLOBAL ids; ql / lvl their local indices on this shard or -1.
-__global__ void k_pivot_swap(double* d, double* gam, double* xnb, uint8_t* vflag, int32_t* vpos, int32_t* bvar, double* loB,
-                             double* hiB, const double* lo, const double* hi, int64_t q, int64_t ql, int64_t lvl, int col, int row,
-                             double pivot_obj, double coeff, double leaving_new_val, int pse, const double* scal, int* flags,
-                             DevRes* res) {
-  const int lv = bvar[row];
-  loB[row] = lo[q];
-  hiB[row] = hi[q];
-  if (lvl >= 0) {
-    xnb[lvl] = leaving_new_val;
-    unsigned f = 0;  // nb_var_is_fixed stays with the non-basic position in the reference and is false on this path
-    if (leaving_new_val == lo[lv]) f |= MLP_AT_MIN;
-    if (leaving_new_val == hi[lv]) f |= MLP_AT_MAX;
-    vflag[lvl] = (uint8_t)f;
-    vpos[lvl] = col;
-    d[lvl] = -pivot_obj;
-    if (pse) {
-      const double g = (scal[2] + 1.0) / (coeff * coeff);
-      gam[lvl] = g;
-      if (!isfinite(g)) flags[0] = 1;
-    }
-  }
-  bvar[row] = (int32_t)q;
-  if (ql >= 0) {
-    vflag[ql] = MLP_BASIC;
-    vpos[ql] = row;
-  }
-  res->i[0] = lv;
-  res->flags[0] = flags[0];
-  res->flags[1] = flags[1];
-}
 __global__ void k_flip_var(double* xnb, uint8_t* vflag, const double* lo, const double* hi, int64_t q, int64_t ql, double new_val) {
   xnb[ql] = new_val;
   unsigned f = vflag[ql] & MLP_FIXED;
   if (new_val == lo[q]) f |= MLP_AT_MIN;
   if (new_val == hi[q]) f |= MLP_AT_MAX;
   vflag[ql] = (uint8_t)f;  // solver.rs:1038-1040
+}
+
+// The variable half of Solver::pivot and the NEXT pricing scan in one pass over this shard's variables (SURVEY K1
+// "fused update+select"): per variable — finish the N^T v price-out (sum of the chunk partials in chunk order, as
+// k_price_finish), update reduced cost and primal steepest-edge norm (k_pivot_vars), apply the basis swap to the two
+// variables concerned (k_pivot_swap), then score the variable for choose_pivot (k_select_primal) with its new state.
+// Block partial arg-max -> last block finishes and leaves the candidate header for the exchange step.
+struct UpdSel {
+  // price-out finish (pse only; sparse storage has helper already)
+  const double* partial; const int32_t* count_ptr; int64_t lda; const double* slack_vals; double* helper; int finish;
+  // pivot
+  int64_t q, ql, lvl, lv; int col, row; double pivot_obj, coeff, leaving_new_val; int pse;
+};
+__global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restrict__ d, double* __restrict__ gam,
+                                                        const double* __restrict__ rc, double* __restrict__ xnb,
+                                                        uint8_t* __restrict__ vflag, int32_t* __restrict__ vpos,
+                                                        int32_t* __restrict__ bvar, double* __restrict__ loB,
+                                                        double* __restrict__ hiB, const double* __restrict__ lo,
+                                                        const double* __restrict__ hi, int64_t nt, int64_t n, int64_t m,
+                                                        int64_t c0, int64_t ng, const double* __restrict__ scal,
+                                                        int* __restrict__ flags, double* __restrict__ red_f,
+                                                        long long* __restrict__ red_i, unsigned* counter, DevRes* res, Cand* out) {
+  __shared__ double smk[32];
+  __shared__ long long smi[32];
+  KeyIdx best{-INFINITY, LLONG_MAX};
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nt) {
+    unsigned f = vflag[v];
+    double h = 0.0;
+    if (a.pse) {
+      if (a.finish) {
+        if (v < n) {
+          const int C = price_chunks_for(*a.count_ptr);
+          for (int c = 0; c < C; ++c) h += a.partial[(int64_t)c * a.lda + v];
+        } else h = a.slack_vals[v - n];
+        if (f & MLP_BASIC) h = 0.0;
+        a.helper[v] = h;
+      } else h = a.helper[v];
+    }
+    double dv = d[v], gv = gam[v];
+    if (v == a.lvl) {  // the leaving variable takes the non-basic slot (solver.rs:1066-1071, 1076, 1142)
+      xnb[v] = a.leaving_new_val;
+      f = 0;
+      if (a.leaving_new_val == lo[a.lv]) f |= MLP_AT_MIN;
+      if (a.leaving_new_val == hi[a.lv]) f |= MLP_AT_MAX;
+      vflag[v] = (uint8_t)f;
+      vpos[v] = a.col;
+      dv = -a.pivot_obj;
+      d[v] = dv;
+      if (a.pse) {
+        gv = (scal[2] + 1.0) / (a.coeff * a.coeff);
+        gam[v] = gv;
+        if (!isfinite(gv)) flags[0] = 1;
+      }
+    } else if (v == a.ql) {  // the entering variable becomes basic (1088-1091)
+      f = MLP_BASIC;
+      vflag[v] = MLP_BASIC;
+      vpos[v] = a.row;
+    } else if (!(f & MLP_BASIC)) {
+      const double c = rc[v];
+      if (c != 0.0) {
+        dv -= a.pivot_obj * c;  // 1073-1080
+        d[v] = dv;
+        if (a.pse) {
+          const double psn = scal[2] + 1.0;  // 1136
+          gv = gv + (-2.0 * c * h / a.coeff + psn * c * c / (a.coeff * a.coeff));  // 1144-1146
+          gam[v] = gv;
+          if (!isfinite(gv)) flags[0] = 1;
+        }
+      }
+    }
+    if (v == 0) {  // row-side bookkeeping, identical on every shard (1057-1058, 1088)
+      loB[a.row] = lo[a.q];
+      hiB[a.row] = hi[a.q];
+      res->i[0] = bvar[a.row];  // the device's idea of the leaving variable, cross-checked by the host
+      bvar[a.row] = (int32_t)a.q;
+    }
+    // choose_pivot's scan (696-739) on the updated state
+    if (!(f & MLP_BASIC) && !(((f & MLP_AT_MIN) && dv > -EPS) || ((f & MLP_AT_MAX) && dv < EPS))) {
+      best.key = a.pse ? dv * dv / gv : fabs(dv);
+      best.idx = ((long long)vpos[v] << 32) | (long long)v;
+    }
+  }
+  best = block_argmax(best, smk, smi);
+  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
+  if (!last_block(counter)) return;
+  KeyIdx b{-INFINITY, LLONG_MAX};
+  for (int qd = threadIdx.x; qd < (int)gridDim.x; qd += blockDim.x) {
+    const double k = __ldcg(red_f + qd);
+    const long long i = __ldcg(red_i + qd);
+    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
+  }
+  b = block_argmax(b, smk, smi);
+  if (threadIdx.x == 0) {
+    *counter = 0;
+    const int nf = *((volatile int*)flags);
+    res->flags[0] = nf;
+    res->flags[1] = flags[1];
+    out->f[4] = (double)nf;
+    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
+    else {
+      const long long vv = b.idx & 0xffffffffLL;
+      out->key = b.key;
+      out->tie = b.idx >> 32;
+      out->var = vv < n ? c0 + vv : ng + (vv - n);
+      out->f[0] = __ldcg(d + vv);
+      out->f[1] = __ldcg(xnb + vv);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ init kernels
@@ -1040,9 +1121,10 @@ static int price_grid(const mlp_engine* e) { return e->sm_count * e->price_ctas;
 
 // out (local variable index) = N^T w over the listed rows (+ slack part), basic entries zeroed
 static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const double* wts, const int32_t* count_ptr,
-                             int fixed_count, const double* slack_vals, double* out, int prof_slot = -1) {
+                             int fixed_count, const double* slack_vals, double* out, int prof_slot = -1, bool finish = true) {
   const bool prof = e->prof_on && prof_slot >= 0;
-  if (prof) CU(cudaEventRecord(e->pev[prof_slot][0], ln.st));
+  const int par = (int)(e->pivot_seq & 1);
+  if (prof) CU(cudaEventRecord(e->pev[prof_slot][par][0], ln.st));
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
     LAUNCHS(e, ln.st, k_price_csc<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, e->m, slack_vals,
@@ -1053,24 +1135,30 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
               ln.partial, e->price_tile);
     else
       LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
-    LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m, slack_vals,
-            e->vflag, out, 0);
+    // finish == false: the chunk partials are reduced by the consumer (k_update_select) instead
+    if (finish)
+      LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m,
+              slack_vals, e->vflag, out, 0);
   }
   if (prof) {
-    CU(cudaEventRecord(e->pev[prof_slot][1], ln.st));
-    e->ppending[prof_slot] = true;
+    CU(cudaEventRecord(e->pev[prof_slot][par][1], ln.st));
+    // support size of this launch, for the algorithmic byte count: lands in pinned memory in stream order
+    if (count_ptr) CU(cudaMemcpyAsync(e->h_mail + par * 4 + prof_slot, count_ptr, sizeof(int32_t), cudaMemcpyDeviceToHost, ln.st));
+    else e->h_mail[par * 4 + prof_slot] = fixed_count;
+    e->ppending[prof_slot][par] = true;
   }
   return MLP_OK;
 }
-// after both lanes are idle: fold pending price-out timings into the profile
-static mlp_status collect_profile(mlp_engine* e, int64_t s_rho, int64_t s_v) {
+// fold the finished price-out timings of one parity into the profile (their events must have completed: called after a
+// host sync that is ordered behind them)
+static mlp_status collect_profile(mlp_engine* e, int par) {
   for (int slot = 0; slot < 2; ++slot) {
-    if (!e->ppending[slot]) continue;
-    e->ppending[slot] = false;
+    if (!e->ppending[slot][par]) continue;
+    e->ppending[slot][par] = false;
     float ms = 0.f;
-    CU(cudaEventSynchronize(e->pev[slot][1]));
-    CU(cudaEventElapsedTime(&ms, e->pev[slot][0], e->pev[slot][1]));
-    const int64_t sz = slot == 0 ? s_rho : s_v;
+    CU(cudaEventSynchronize(e->pev[slot][par][1]));
+    CU(cudaEventElapsedTime(&ms, e->pev[slot][par][0], e->pev[slot][par][1]));
+    const int64_t sz = e->h_mail[par * 4 + slot];
     const int64_t bytes = e->sparse ? 12 * e->nnz + 8 * e->m + 8 * e->nt : 8 * e->n * sz + 8 * sz + 8 * e->n;
     if (slot == 0) { e->prof.price_rho_ms += ms; e->prof.price_rho_launches += 1; e->prof.price_rho_bytes += bytes; }
     else { e->prof.price_v_ms += ms; e->prof.price_v_launches += 1; e->prof.price_v_bytes += bytes; }
@@ -1264,20 +1352,19 @@ static constexpr int64_t VAR_PENDING = -2;
 static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   const int m = (int)e->m;
   Lane& l0 = e->lane[0];
+  // single shard: the candidate's column goes straight into colq and its header is the winner
+  double* dst = e->world > 1 ? (double*)(e->xsend + sizeof(Cand)) : e->colq;
+  Cand* win = e->world > 1 ? nullptr : e->d_win;
   if (e->sparse) {
-    CU(cudaMemsetAsync(e->xsend + sizeof(Cand), 0, (size_t)m * sizeof(double), e->stream));
-    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, (int64_t)-1, (const Cand*)e->xsend,
-           (double*)(e->xsend + sizeof(Cand)));
+    CU(cudaMemsetAsync(dst, 0, (size_t)m * sizeof(double), e->stream));
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, (int64_t)-1, (const Cand*)e->xsend, dst, win);
   } else {
-    LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend,
-           (double*)(e->xsend + sizeof(Cand)));
+    LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend, dst, win);
   }
-  char* recv = e->xsend;
   if (e->world > 1) {
     ST(e->comm->allgather(e->xsend, e->xrecv, e->xbytes, e->stream));
-    recv = e->xrecv;
+    LAUNCH(e, k_pick_winner, cdiv(m, 256), 256, 0, e->xrecv, e->xbytes, e->world, m, e->colq, e->d_win);
   }
-  LAUNCH(e, k_pick_winner, cdiv(m, 256), 256, 0, recv, e->xbytes, e->world, m, e->colq, e->d_win);
   CU(cudaMemcpyAsync(e->h_cands, e->d_win, sizeof(Cand), cudaMemcpyDeviceToHost, e->stream));
   CU(cudaEventRecord(e->ev_win, e->stream));
   // Both callers continue with calc_col_coeffs of the winner (solver.rs:750, 532): queue that FTRAN — and, with primal
@@ -1287,7 +1374,9 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   ST(mark0(e));
   e->spec_var = -1;
   if (e->enable_pse && e->overlap) ST(se_helper(e, VAR_PENDING));
+  e->alpha_nnz_host = -1;
   CU(cudaEventSynchronize(e->ev_win));  // the header only, not the chain queued behind it
+  if (e->prof_on) ST(collect_profile(e, (int)((e->pivot_seq & 1) ^ 1)));  // the previous pivot is complete by now
   e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
   *winner = e->h_cands[0];
   if (winner->f[4] != 0.0) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
@@ -1303,7 +1392,7 @@ static mlp_status fetch_column(mlp_engine* e, int64_t var) {
   const int64_t lv = to_local(e, var);
   if (e->sparse) {
     CU(cudaMemsetAsync(e->colq, 0, (size_t)m * sizeof(double), e->stream));
-    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, lv, (const Cand*)nullptr, e->colq);
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, lv, (const Cand*)nullptr, e->colq, (Cand*)nullptr);
   } else if (lv >= 0) LAUNCH(e, k_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, m, lv, e->colq);
   if (e->world > 1 && var < e->ng) ST(e->comm->broadcast(e->colq, (size_t)m * sizeof(double), owner_of(e, var), e->stream));
   e->colq_var = var;
@@ -1318,7 +1407,7 @@ static mlp_status se_helper(mlp_engine* e, int64_t var) {
   ST(btran(e, l0, e->work_m, -1, e->vvec));
   CU(cudaEventRecord(e->ev_vbtran, l0.st));
   compact(e, l0, e->vvec, e->vlist_idx, e->vlist_val, e->icnt + 2, e->scal + 3);
-  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper, 1));
+  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper, 1, false));
   e->spec_var = var;
   return MLP_OK;
 }
@@ -1346,7 +1435,8 @@ static void destroy_engine(mlp_engine* e) {
   }
   if (e->h_cands) cudaFreeHost(e->h_cands);
   for (int i = 0; i < 4; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) if (e->pev[i][j]) cudaEventDestroy(e->pev[i][j]);
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int q = 0; q < 2; ++q) if (e->pev[i][j][q]) cudaEventDestroy(e->pev[i][j][q]);
+  if (e->h_mail) cudaFreeHost(e->h_mail);
   if (e->s0_mark) cudaEventDestroy(e->s0_mark);
   if (e->s1_mark) cudaEventDestroy(e->s1_mark);
   if (e->ev_vbtran) cudaEventDestroy(e->ev_vbtran);
@@ -1385,6 +1475,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
+  if (const char* v = getenv("MLP_ASYNC_PIVOT")) e->async_pivot = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("MLP_PRICE_TMA")) e->price_tma = atoi(v) != 0;
   e->price_tile = price_tile_cols(e->lda, e->sm_count);
@@ -1418,7 +1509,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
     Lane& ln = e->lane[l];
     A(dev_alloc(&ln.wm, m));
     A(dev_alloc(&ln.partial, (size_t)PR_MAXC * e->lda));
-    A(dev_alloc(&ln.red_f, 4096)); A(dev_alloc(&ln.red_i, 4096)); A(dev_alloc(&ln.red_counter, 4));
+    const size_t nred = std::max<size_t>(4096, (size_t)cdiv(nt, 256) + 1);  // k_update_select: one partial per 256 variables
+    A(dev_alloc(&ln.red_f, nred)); A(dev_alloc(&ln.red_i, nred)); A(dev_alloc(&ln.red_counter, 4));
     A(dev_alloc(&ln.seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&ln.seg_ss, (size_t)cdiv(m, CP_SEG) + 1));
     A(dev_alloc(&ln.d_res, 1));
   }
@@ -1432,7 +1524,9 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->h_res = e->lane[0].h_res;
   CU(cudaHostAlloc((void**)&e->h_cands, sizeof(Cand) * world, cudaHostAllocDefault));
   for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&e->ev[i]));
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) CU(cudaEventCreate(&e->pev[i][j]));
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2; ++j) for (int q = 0; q < 2; ++q) CU(cudaEventCreate(&e->pev[i][j][q]));
+  CU(cudaHostAlloc((void**)&e->h_mail, 8 * sizeof(int32_t), cudaHostAllocDefault));
+  std::memset(e->h_mail, 0, 8 * sizeof(int32_t));
   CU(cudaEventCreateWithFlags(&e->s0_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->s1_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_vbtran, cudaEventDisableTiming));
@@ -1636,6 +1730,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (st->dual_edge_sq_norms) ST(h2d(e, e->w, st->dual_edge_sq_norms, m * 8));
   CU(cudaStreamSynchronize(e->stream));
   e->spec_var = -1;
+  e->sel_valid = false;
   if (!st->basic_var_vals) {
     double* part = e->world > 1 ? e->work_m : e->xred;
     if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->xnb, part);
@@ -1684,6 +1779,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
 mlp_status mlp_engine_set_primal_steepest_edge(mlp_engine* e, int32_t enable) {
   if (!e) return MLP_INVALID;
   e->enable_pse = enable;
+  e->sel_valid = false;  // the score changes from d^2/gamma to |d| (solver.rs:713-716)
   return MLP_OK;
 }
 
@@ -1702,8 +1798,10 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
   const int grid = std::min(cdiv(e->nt, 256), 1024);
   Lane& l0 = e->lane[0];
   ST(begin0(e));
-  LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->n, e->c0, e->ng, e->enable_pse, l0.red_f,
-         l0.red_i, l0.red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
+  if (!e->sel_valid)
+    LAUNCH(e, k_select_primal, grid, 256, 0, e->d, e->gam, e->vflag, e->vpos, e->nt, e->n, e->c0, e->ng, e->enable_pse, l0.red_f,
+           l0.red_i, l0.red_counter, e->xnb, e->d_res->flags, (Cand*)e->xsend);
+  e->sel_valid = false;
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w));  // records s0_mark ahead of the run-ahead tail
@@ -1724,6 +1822,7 @@ mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   Lane& l0 = e->lane[0];
   ST(begin0(e));
   e->ftran_var = -1;
+  e->alpha_nnz_host = -1;
   ST(fetch_column(e, var));
   ST(ftran(e, l0, e->colq, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
@@ -1744,8 +1843,10 @@ mlp_status mlp_ratio_primal(mlp_engine* e, int32_t sign, double max_step0, mlp_l
           l1.red_counter, e->scal);
   LAUNCHS(e, l1.st, k_ratio_primal_2, grid, 256, 0, e->alpha, e->xB, e->loB, e->hiB, (int)e->m, sign, e->scal, l1.red_f, l1.red_i,
           l1.red_counter, l1.d_res);
+  CU(cudaMemcpyAsync(&l1.d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, l1.st));  // nnz(alpha_q)
   ST(mark1(e));
   ST(fetch_res(e, l1));
+  e->alpha_nnz_host = (int64_t)(int32_t)(l1.h_res->i[1] & 0xffffffffLL);
   out->row = l1.h_res->i[0];
   out->coeff = l1.h_res->f[0];
   out->leaving_new_val = l1.h_res->f[1];
@@ -1802,6 +1903,7 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925)
   Lane& l0 = e->lane[0];
   ST(begin0(e));
+  e->sel_valid = false;  // the candidate buffer is reused for the dual ratio test
   double bv = 0.0;
   ST(d2h(e, &bv, e->xB + row, sizeof(double)));
   const int lds = leaving_new_val > bv ? 1 : 0;
@@ -1838,6 +1940,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   out->lu_nnz = e->lu_nnz;
   if (!pi->has_elem) {  // solver.rs:1031-1042
     ST(begin0(e));
+    e->sel_valid = false;
     LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, -1, pi->entering_new_val, pi->entering_diff,
            1.0, 0, 0, e->scal, (double*)nullptr, e->d_res->flags);
     if (ql >= 0) LAUNCH(e, k_flip_var, 1, 1, 0, e->xnb, e->vflag, e->lo, e->hi, q, ql, pi->entering_new_val);
@@ -1878,10 +1981,17 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   ST(mark1(e));
   // lane 0: variable half
   ST(begin0(e));
-  LAUNCH(e, k_pivot_vars, cdiv(e->nt, 256), 256, 0, e->d, e->gam, e->rc, e->helper, e->vflag, e->nt, ql, pivot_obj, pi->coeff,
-         e->enable_pse, e->scal, e->d_res->flags);
-  LAUNCH(e, k_pivot_swap, 1, 1, 0, e->d, e->gam, e->xnb, e->vflag, e->vpos, e->bvar, e->loB, e->hiB, e->lo, e->hi, q, ql, lvl,
-         (int)pi->col, row, pivot_obj, pi->coeff, pi->leaving_new_val, e->enable_pse, e->scal, e->d_res->flags, e->d_res);
+  {
+    UpdSel a;
+    a.partial = l0.partial; a.count_ptr = e->icnt + 2; a.lda = e->lda; a.slack_vals = e->vvec; a.helper = e->helper;
+    a.finish = e->sparse ? 0 : 1;
+    a.q = q; a.ql = ql; a.lvl = lvl; a.lv = lv; a.col = (int)pi->col; a.row = row;
+    a.pivot_obj = pivot_obj; a.coeff = pi->coeff; a.leaving_new_val = pi->leaving_new_val; a.pse = e->enable_pse;
+    LAUNCH(e, k_update_select, cdiv(e->nt, 256), 256, 0, a, e->d, e->gam, e->rc, e->xnb, e->vflag, e->vpos, e->bvar, e->loB,
+           e->hiB, e->lo, e->hi, e->nt, e->n, e->m, e->c0, e->ng, e->scal, e->d_res->flags, l0.red_f, l0.red_i, l0.red_counter,
+           e->d_res, (Cand*)e->xsend);
+    e->sel_valid = true;  // the next choose_pivot scan is already done
+  }
   // column cache: the leaving structural column frees its slot, the entering one takes a slot
   if (e->h_slot_of_row[row] >= 0) { e->h_pending_free.push_back(e->h_slot_of_row[row]); e->h_slot_of_row[row] = -1; }
   if (q < e->ng) {
@@ -1896,15 +2006,24 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     e->h_slot_of_row[row] = slot;
   }
   e->h_bvar[row] = q;
-  // one device->host read per pivot: status flags, leaving var, nnz(alpha)
-  CU(cudaMemcpyAsync(&e->d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
-  if (e->prof_on) {
-    CU(cudaMemcpyAsync(&e->d_res->i[2], e->icnt + 0, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
-    CU(cudaMemcpyAsync(&e->d_res->i[3], e->icnt + 2, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
+  const int par = (int)(e->pivot_seq & 1);
+  e->pivot_seq += 1;
+  if (!do_refactor && e->alpha_nnz_host >= 0 && e->async_pivot) {
+    // Primal loop: everything the host needs is already known — the leaving variable from its mirror, nnz(alpha_q) from
+    // the ratio test's read-back — so the call returns without waiting for the device; a non-finite norm surfaces with
+    // the next selection (candidate header f[4]).  The host is then free to queue the next pivot's chain behind this one.
+    ST(mark0(e));
+    out->leaving_var = lv;
+    out->col_nnz = e->alpha_nnz_host;
+    e->alpha_nnz_host = -1;
+    out->eta_count = e->K;
+    return MLP_OK;
   }
+  // one device->host read: status flags, leaving var, nnz(alpha)
+  CU(cudaMemcpyAsync(&e->d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
   ST(mark0(e));
   ST(fetch_res(e, l0));
-  if (e->prof_on) ST(collect_profile(e, e->h_res->i[2] & 0xffffffffLL, e->h_res->i[3] & 0xffffffffLL));
+  if (e->prof_on) ST(collect_profile(e, par));
   out->leaving_var = e->h_res->i[0];
   out->col_nnz = (int64_t)(int32_t)(e->h_res->i[1] & 0xffffffffLL);
   if (out->leaving_var != lv) { set_err("pivot: host/device basis mirrors diverged"); return MLP_INVALID; }
@@ -1926,6 +2045,7 @@ mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {
   Lane& l0 = e->lane[0];
   ST(begin0(e));
   e->spec_var = -1;
+  e->sel_valid = false;
   if (e->K > 0) ST(refactor_impl(e));  // solver.rs:1200-1203
   LAUNCH(e, k_gather_cB, cdiv(m, 256), 256, 0, e->cobj, e->bvar, m, e->work_m);
   ST(btran(e, l0, e->work_m, -1, e->vvec));  // multipliers y (1205-1214)
@@ -2020,13 +2140,19 @@ mlp_status mlp_event_elapsed_ms(mlp_engine* e, int32_t a, int32_t b, double* ms)
 }
 mlp_status mlp_profile_enable(mlp_engine* e, int32_t on) {
   if (!e) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  if (e->prof_on) for (int par = 0; par < 2; ++par) ST(collect_profile(e, par));
   e->prof_on = on;
-  e->ppending[0] = e->ppending[1] = false;
+  std::memset(e->ppending, 0, sizeof(e->ppending));
   if (on) e->prof = mlp_profile{};
   return MLP_OK;
 }
 mlp_status mlp_profile_get(mlp_engine* e, mlp_profile* out) {
   if (!e || !out) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  for (int par = 0; par < 2; ++par) ST(collect_profile(e, par));
   *out = e->prof;
   return MLP_OK;
 }

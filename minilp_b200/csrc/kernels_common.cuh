@@ -105,13 +105,18 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restri
     seg_ss[blockIdx.x] = ss;
   }
   if (!last_block(counter)) return;
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {  // fixed order: lane-strided partial sums, then the shuffle tree
     int c = 0;
     double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) { c += __ldcg(seg_cnt + b); t += __ldcg(seg_ss + b); }
-    *count = c;
-    *sumsq = t;
-    *counter = 0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += 32) { c += __ldcg(seg_cnt + b); t += __ldcg(seg_ss + b); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(FULLMASK, c, o);
+    t = warp_sum(t);
+    if (threadIdx.x == 0) {
+      *count = c;
+      *sumsq = t;
+      *counter = 0;
+    }
   }
 }
 __global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restrict__ x, int m, const int32_t* __restrict__ seg_cnt,
@@ -249,12 +254,19 @@ __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M
     if (i < rows) {
       const double* p = M + (int64_t)j0 * ld + i;
       int j = 0;
-      for (; j + 8 <= nj; j += 8) {
-        double v[8];
+      for (; j + 16 <= nj; j += 16) {  // 16 loads in flight, subtraction still in column order
+        double v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = p[(int64_t)(j + u) * ld];
+        for (int u = 0; u < 16; ++u) v[u] = p[(int64_t)(j + u) * ld];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc -= ts[j + u] * v[u];
+        for (int u = 0; u < 16; ++u) acc -= ts[j + u] * v[u];
+      }
+      for (; j + 4 <= nj; j += 4) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = p[(int64_t)(j + u) * ld];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc -= ts[j + u] * v[u];
       }
       for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)j * ld];
     }
@@ -274,7 +286,16 @@ __global__ void __launch_bounds__(256) k_gemv_t_part(const double* __restrict__ 
   const int r0 = sidx * L, r1 = min(rows, r0 + L);
   const double* p = M + (int64_t)j * ld;
   double acc = 0.0;
-  for (int i = r0 + threadIdx.x; i < r1; i += blockDim.x) acc += p[i] * x[i];
+  int i = r0 + threadIdx.x;
+  const int st = blockDim.x;
+  for (; i + 7 * st < r1; i += 8 * st) {  // 8 row pairs in flight per thread, added in row order
+    double a[8], b[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { a[u] = p[i + u * st]; b[u] = x[i + u * st]; }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc += a[u] * b[u];
+  }
+  for (; i < r1; i += st) acc += p[i] * x[i];
   const double tot = block_sum(acc, sm);
   if (threadIdx.x == 0) part[(int64_t)sidx * cols + j] = tot;
 }
