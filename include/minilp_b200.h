@@ -188,6 +188,30 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* info, mlp_pivot_result
 /* recalc_obj_coeffs (solver.rs:1199-1231): y = B^-T c_B, d_N = c_N - N^T y, objective from scratch. */
 mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val);
 
+/* ---- incremental API: the engine half of Solver::fix_var (solver.rs:378-415), unfix_var (418-438),
+ * add_constraint (549-634) and add_gomory_cut (440-460).  Dense single-shard engines. */
+typedef struct mlp_var_info {
+  uint32_t flags;      /* MLP_BASIC or MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED */
+  int64_t pos_or_row;  /* VarState::Basic(row) / NonBasic(col), solver.rs:60-64 */
+  double obj_coeff;    /* nb_var_obj_coeffs[col] (0 for a basic variable) */
+  double value;        /* Solver::get_value, 371-376 */
+} mlp_var_info;
+mlp_status mlp_get_var(mlp_engine* e, int64_t var, mlp_var_info* out);
+/* nb_var_states[col] / nb_var_is_fixed[col] of a non-basic variable (405-411, 420-428) */
+mlp_status mlp_set_nb_state(mlp_engine* e, int64_t var, uint32_t flags);
+typedef struct mlp_add_row_result {
+  int64_t row, slack_var;
+  double basic_val;  /* basic_var_vals.push(rhs - lhs_val), 591 */
+  double rhs;        /* stored right-hand side (differs from the argument when slack coefficients were substituted) */
+  int64_t lu_nnz;    /* after basis_solver.reset, 612 */
+} mlp_add_row_result;
+/* Appends the row  coeffs . x + slack_coeffs . s + s_new = rhs  with s_new in [slack_min, slack_max] (563-571), makes
+ * s_new basic, refactorizes (612) and extends the steepest-edge norms by the new tableau row (615-630).
+ * coeffs: n doubles (structural variables); slack_coeffs: m doubles or NULL — coefficients on EXISTING slack variables, as
+ * a Gomory cut has; they are eliminated through s_i = rhs_i - a_i x, so slack columns stay unit columns. */
+mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double* slack_coeffs, double slack_min,
+                              double slack_max, double rhs, mlp_add_row_result* out);
+
 /* Downloads (device -> caller buffer).  Var-indexed arrays have n+m entries, row-indexed m. */
 typedef enum mlp_array {
   MLP_ARR_OBJ_COEFFS = 0,   /* d, by var (valid where non-basic) */
@@ -271,6 +295,14 @@ mlp_status mlp_solver_values(mlp_solver* s, double* out);
 int64_t mlp_solver_trace_len(mlp_solver* s);
 int64_t mlp_solver_get_trace(mlp_solver* s, int64_t first, int64_t count, double* out);
 void mlp_solver_set_record_trace(mlp_solver* s, int32_t on);
+/* Solution::add_constraint / fix_var / unfix_var / add_gomory_cut (lib.rs:368-423) on a solved problem.
+ * add_constraint: `count` (variable, coefficient) pairs over structural variables, cmp_op 0 Eq / 1 Le / 2 Ge.
+ * Status MLP_INFEASIBLE where the reference returns Err(Infeasible); *was_fixed mirrors unfix_var's bool. */
+mlp_status mlp_solver_add_constraint(mlp_solver* s, int64_t count, const int64_t* vars, const double* coeffs, int32_t cmp_op,
+                                     double rhs);
+mlp_status mlp_solver_fix_var(mlp_solver* s, int64_t var, double val);
+mlp_status mlp_solver_unfix_var(mlp_solver* s, int64_t var, int32_t* was_fixed);
+mlp_status mlp_solver_add_gomory_cut(mlp_solver* s, int64_t var);
 /* host mirrors of nb_vars (n) and basic_vars (m) */
 mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out);
 mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out);

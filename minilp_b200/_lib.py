@@ -49,6 +49,14 @@ class PivotResult(C.Structure):
     _fields_ = [("leaving_var", i64), ("col_nnz", i64), ("eta_count", i64), ("lu_nnz", i64), ("refactored", i32)]
 
 
+class VarInfo(C.Structure):
+    _fields_ = [("flags", C.c_uint32), ("pos_or_row", i64), ("obj_coeff", f64), ("value", f64)]
+
+
+class AddRowResult(C.Structure):
+    _fields_ = [("row", i64), ("slack_var", i64), ("basic_val", f64), ("rhs", f64), ("lu_nnz", i64)]
+
+
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", i64), ("h2d_bytes", i64), ("d2h_bytes", i64), ("refactors", i64), ("etas_pushed", i64),
                 ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64)]
@@ -88,6 +96,13 @@ SIGNATURES = {
     "mlp_ratio_dual": (i32, [vp, i64, f64, C.POINTER(DualEntering)]),
     "mlp_pivot": (i32, [vp, C.POINTER(PivotInfo), C.POINTER(PivotResult)]),
     "mlp_recalc_obj_coeffs": (i32, [vp, pd]),
+    "mlp_get_var": (i32, [vp, i64, C.POINTER(VarInfo)]),
+    "mlp_set_nb_state": (i32, [vp, i64, C.c_uint32]),
+    "mlp_engine_add_row": (i32, [vp, pd, pd, f64, f64, f64, C.POINTER(AddRowResult)]),
+    "mlp_solver_add_constraint": (i32, [vp, i64, pi64, pd, i32, f64]),
+    "mlp_solver_fix_var": (i32, [vp, i64, f64]),
+    "mlp_solver_unfix_var": (i32, [vp, i64, pi32]),
+    "mlp_solver_add_gomory_cut": (i32, [vp, i64]),
     "mlp_download_f64": (i32, [vp, i32, pd, i64]),
     "mlp_download_basic_vars": (i32, [vp, pi64]),
     "mlp_download_var_state": (i32, [vp, pu8, pi32]),

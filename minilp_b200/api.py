@@ -444,12 +444,52 @@ class Problem:
 
 
 class Solution:
-    """lib.rs:313-355 (objective, var_value, iteration).  The incremental methods (add_constraint, fix_var,
-    unfix_var, add_gomory_cut: lib.rs:368-423) are SURVEY.md §8 row f2 ("next") and are not built yet."""
+    """lib.rs:313-423: objective, var_value, iteration and the incremental methods.  The reference's
+    incremental methods consume `self` and return the new solution; here they update in place and return self.
+    Not mirrored: `Clone` (lib.rs:313) — a device deep copy of the engine is not built yet."""
 
     def __init__(self, solver, direction, num_vars):
         self.solver, self.direction, self.num_vars = solver, direction, num_vars
         self._vals = solver.values()
+
+    def _refresh(self):
+        s = self.solver
+        s.m = int(_lib.lib().mlp_solver_num_constraints(s._s))
+        s.engine.m = s.m
+        self._vals = s.values()
+        return self
+
+    def add_constraint(self, expr, cmp_op, rhs):
+        """lib.rs:368-382 -> Solver::add_constraint (solver.rs:549-634)."""
+        expr = sorted((int(v), float(c)) for v, c in expr)
+        vs = [v for v, _ in expr]
+        if len(set(vs)) != len(vs):
+            raise ValueError("variable added more than once to a constraint")  # CsVec::new panics (lib.rs:376)
+        if any(v < 0 or v >= self.num_vars for v in vs):
+            raise ValueError("unknown variable")
+        va = np.array(vs, dtype=np.int64)
+        co = np.array([c for _, c in expr], dtype=np.float64)
+        _check(_lib.lib().mlp_solver_add_constraint(self.solver._s, len(vs), _p(va, pi64), _p(co), int(cmp_op), float(rhs)))
+        return self._refresh()
+
+    def fix_var(self, var, val):
+        """lib.rs:391-395 -> Solver::fix_var (solver.rs:378-415)."""
+        assert 0 <= var < self.num_vars
+        _check(_lib.lib().mlp_solver_fix_var(self.solver._s, int(var), float(val)))
+        return self._refresh()
+
+    def unfix_var(self, var):
+        """lib.rs:400-404 -> Solver::unfix_var (solver.rs:418-438).  Returns (solution, was_fixed)."""
+        assert 0 <= var < self.num_vars
+        was = C.c_int32(0)
+        _check(_lib.lib().mlp_solver_unfix_var(self.solver._s, int(var), C.byref(was)))
+        return self._refresh(), bool(was.value)
+
+    def add_gomory_cut(self, var):
+        """lib.rs:419-423 -> Solver::add_gomory_cut (solver.rs:440-460); the variable must be basic."""
+        assert 0 <= var < self.num_vars
+        _check(_lib.lib().mlp_solver_add_gomory_cut(self.solver._s, int(var)))
+        return self._refresh()
 
     def objective(self):
         v = self.solver.cur_obj_val

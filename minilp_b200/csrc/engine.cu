@@ -208,6 +208,8 @@ struct mlp_engine {
   // variables are replicated on every shard.  LOCAL variable index: structural g -> g-c0, slack ng+i -> n+i.
   // Everything the ABI shows is GLOBAL.  world == 1: c0 = 0, n = ng.
   int64_t m = 0, n = 0, nt = 0, lda = 0, ng = 0, c0 = 0;
+  int64_t mld = 0;  // row capacity (>= m): allocation length of every row-indexed array and leading dimension of Bcols / E;
+                    // rows are appended by mlp_engine_add_row (Solver::add_constraint) without re-laying anything out
   Comm* comm = nullptr;
   int rank = 0, world = 1;
   int sm_count = 148;
@@ -1101,6 +1103,59 @@ __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __re
   if (r < m) out[r] = cobj[bvar[r]];
 }
 
+// ------------------------------------------------------------------------------------------------ incremental API (row f2)
+// Solver::add_constraint (solver.rs:549-634) pieces.  A cut may carry coefficients g_i on slack variables
+// (add_gomory_cut, 440-460); slack columns stay unit columns here, so s_i = rhs_i - a_i x is substituted:
+// row' = c - A^T g, rhs' = rhs - g . rhs_old (the same constraint; see DESIGN.md §9 for what that changes).
+__global__ void k_row_combine(double* __restrict__ row, const double* __restrict__ partial, const int32_t* __restrict__ count_ptr,
+                              int64_t lda, int64_t n) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int C = price_chunks_for(*count_ptr);
+  double t = 0.0;
+  for (int c = 0; c < C; ++c) t += partial[(int64_t)c * lda + j];
+  row[j] -= t;
+}
+// out[0] = base - sum_i a_i b_i (single CTA, deterministic); used for rhs' and for the new basic value rhs - a . x
+__global__ void __launch_bounds__(1024) k_sub_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t cnt, double base,
+                                                   const double* __restrict__ base_ptr, double* __restrict__ out) {
+  __shared__ double sm[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += a[i] * b[i];
+  const double tot = block_sum(acc, sm);
+  if (threadIdx.x == 0) out[0] = (base_ptr ? *base_ptr : base) - tot;
+}
+// current value of every structural variable (Solver::get_value, 371-376) as a dense vector
+__global__ void k_struct_values(const double* __restrict__ xnb, const double* __restrict__ xB, const uint8_t* __restrict__ vflag,
+                                const int32_t* __restrict__ vpos, int64_t n, double* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[j] = (vflag[j] & MLP_BASIC) ? xB[vpos[j]] : xnb[j];
+}
+// state of the appended row and of its slack variable (563-571, 591)
+__global__ void k_new_row_state(int64_t r, int64_t lv, int64_t gv, double smin, double smax, const double* __restrict__ val,
+                                const double* __restrict__ rhs_new, double* lo, double* hi, double* cobj, double* d, double* gam,
+                                double* xnb, uint8_t* vflag, int32_t* vpos, int32_t* bvar, double* xB, double* loB, double* hiB,
+                                double* w, double* rhs, int32_t* rowcover) {
+  lo[gv] = smin; hi[gv] = smax; cobj[gv] = 0.0;
+  d[lv] = 0.0; gam[lv] = 0.0; xnb[lv] = 0.0;
+  vflag[lv] = MLP_BASIC; vpos[lv] = (int32_t)r;
+  bvar[r] = (int32_t)gv; xB[r] = *val; loB[r] = smin; hiB[r] = smax; w[r] = 1.0; rhs[r] = *rhs_new;
+  rowcover[r] = (int32_t)r;
+}
+// the cached basis columns get their entry of the new row
+__global__ void k_bcols_new_row(const double* __restrict__ rowA, const int32_t* __restrict__ slots, const int32_t* __restrict__ vars,
+                                int cnt, int64_t ldb, int64_t r, double* __restrict__ Bcols) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) Bcols[(int64_t)slots[t] * ldb + r] = rowA[vars[t]];
+}
+// primal_edge_sq_norms[c] += coeff^2 over the new tableau row (618-622)
+__global__ void k_add_sq(double* __restrict__ gam, const double* __restrict__ rc, const uint8_t* __restrict__ vflag, int64_t nt) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nt && !(vflag[v] & MLP_BASIC)) gam[v] += rc[v] * rc[v];
+}
+__global__ void k_copy1(double* dst, const double* src) { *dst = *src; }
+__global__ void k_set_var_state(uint8_t* vflag, int64_t lv, unsigned f) { vflag[lv] = (uint8_t)f; }
+
 // ================================================================================================ host side
 // Two lanes (streams).  API calls keep sequential semantics through two marks: s0_mark is recorded on lane 0 at the end of
 // the non-speculative part of every lane-0 call, s1_mark on lane 1 at the end of every lane-1 call; a call on one lane
@@ -1189,11 +1244,11 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
-  LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->m, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
+  LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
           e->Jslot, out);
   if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
     LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
-    LAUNCHS(e, ln.st, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->m, m, K, ln.tK, out);
+    LAUNCHS(e, ln.st, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->mld, m, K, ln.tK, out);
   }
   return MLP_OK;
 }
@@ -1203,15 +1258,15 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
 static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   if (K > 0) {  // etas in reverse, 1325-1333: u = E^T c, s = (I+G)^-T u, c[r_j] -= s_j
-    if (unit_row >= 0) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->m, unit_row, K, ln.tK);
-    else gemv_t(e, ln, e->E, e->m, m, K, c, ln.gt_part_K, nullptr, nullptr, ln.tK, 0);
+    if (unit_row >= 0) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->mld, unit_row, K, ln.tK);
+    else gemv_t(e, ln, e->E, e->mld, m, K, c, ln.gt_part_K, nullptr, nullptr, ln.tK, 0);
     LAUNCHS(e, ln.st, k_mv_t<true>, cdiv(K, 8), 256, 0, e->Ginv, e->Kcap, K, ln.tK, (const int32_t*)nullptr, ln.tK2);
     LAUNCHS(e, ln.st, k_eta_scatter, cdiv(K, 256), 256, 0, ln.tK2, e->etaR, e->etaPrev, e->etaHead, K, c);
   }
   LAUNCHS(e, ln.st, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, ln.wm);
   if (k > 0) {
     const int S = gemv_split(e, m, k);
-    LAUNCHS(e, ln.st, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->m, m, k, e->Jslot, ln.wm, ln.gt_part_k);
+    LAUNCHS(e, ln.st, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->mld, m, k, e->Jslot, ln.wm, ln.gt_part_k);
     LAUNCHS(e, ln.st, k_gemv_t_fin, cdiv(k, 256), 256, 0, ln.gt_part_k, S, k, c, e->Jpos, ln.xk, 1);
     // y = L^-T U^-T rhs (lu_factors_transp, lu.rs:108-115) = (C^-1)^T rhs, scattered to the core's constraint rows
     LAUNCHS(e, ln.st, k_mv_t<false>, cdiv(k, 8), 256, 0, e->Cinv, e->kcap, k, ln.xk, e->Rp, out);
@@ -1223,13 +1278,13 @@ static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double
 // arenas costs tens of milliseconds, so capacity grows by doubling and rarely; the cache content survives growth.
 static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
-  int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->m)))));
+  int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->mld)))));
   while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   double* nb = nullptr;
-  ST(dev_alloc(&nb, (size_t)e->m * cap));
+  ST(dev_alloc(&nb, (size_t)e->mld * cap));
   if (e->Bcols && e->kcap > 0) {
-    CU(cudaMemcpyAsync(nb, e->Bcols, (size_t)e->m * e->kcap * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(nb, e->Bcols, (size_t)e->mld * e->kcap * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
   for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
@@ -1249,12 +1304,12 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
 }
 static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
   if (K <= e->Kcap && e->E) return MLP_OK;
-  int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->m))));
+  int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->mld))));
   while (cap < K) cap *= 2;
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   e->Kcap = cap;
-  ST(dev_alloc(&e->E, (size_t)e->m * cap)); ST(dev_alloc(&e->Ginv, (size_t)cap * cap)); ST(dev_alloc(&e->gK, cap));
+  ST(dev_alloc(&e->E, (size_t)e->mld * cap)); ST(dev_alloc(&e->Ginv, (size_t)cap * cap)); ST(dev_alloc(&e->gK, cap));
   ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap));
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
@@ -1297,7 +1352,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
     ST(h2d(e, e->Jslot, jslot.data(), k * sizeof(int32_t)));
     ST(h2d(e, e->Rp, R.data(), k * sizeof(int32_t)));
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
-    LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->m, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
+    LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
     int* flags = e->d_res->flags;
     for (int j0 = 0; j0 < (int)k;) {
       const int rows = (int)k - j0;
@@ -1494,31 +1549,35 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaFuncSetAttribute(k_lu_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem_optin));
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
-  const int64_t nt = e->nt, gt = ng + m;
-  if (!sparse) A(dev_alloc(&e->A, (size_t)m * e->lda));
+  // Row capacity: Solution::add_constraint / add_gomory_cut (lib.rs:368-423) append rows; every row-indexed array is
+  // allocated for mld rows so that appending one costs O(n), not a re-layout.
+  e->mld = sparse ? m : m + std::max<int64_t>(64, m / 8);
+  if (const char* v = getenv("MLP_ROW_RESERVE")) e->mld = m + std::max<int64_t>(0, atoll(v));
+  const int64_t ml = e->mld, ntc = e->n + ml, gt = ng + ml;
+  if (!sparse) A(dev_alloc(&e->A, (size_t)ml * e->lda));
   A(dev_alloc(&e->lo, gt)); A(dev_alloc(&e->hi, gt)); A(dev_alloc(&e->cobj, gt));
-  A(dev_alloc(&e->d, nt)); A(dev_alloc(&e->gam, nt)); A(dev_alloc(&e->xnb, nt));
-  A(dev_alloc(&e->vflag, nt)); A(dev_alloc(&e->vpos, nt)); A(dev_alloc(&e->bvar, m));
-  A(dev_alloc(&e->xB, m)); A(dev_alloc(&e->loB, m)); A(dev_alloc(&e->hiB, m)); A(dev_alloc(&e->w, m)); A(dev_alloc(&e->rhs, m));
-  A(dev_alloc(&e->alpha, m)); A(dev_alloc(&e->rho, m)); A(dev_alloc(&e->tau, m)); A(dev_alloc(&e->vvec, m));
-  A(dev_alloc(&e->work_m, m)); A(dev_alloc(&e->work_mb, m)); A(dev_alloc(&e->colq, m));
-  A(dev_alloc(&e->rc, nt)); A(dev_alloc(&e->helper, nt));
-  A(dev_alloc(&e->list_idx, m)); A(dev_alloc(&e->list_val, m)); A(dev_alloc(&e->vlist_idx, m)); A(dev_alloc(&e->vlist_val, m));
+  A(dev_alloc(&e->d, ntc)); A(dev_alloc(&e->gam, ntc)); A(dev_alloc(&e->xnb, ntc));
+  A(dev_alloc(&e->vflag, ntc)); A(dev_alloc(&e->vpos, ntc)); A(dev_alloc(&e->bvar, ml));
+  A(dev_alloc(&e->xB, ml)); A(dev_alloc(&e->loB, ml)); A(dev_alloc(&e->hiB, ml)); A(dev_alloc(&e->w, ml)); A(dev_alloc(&e->rhs, ml));
+  A(dev_alloc(&e->alpha, ml)); A(dev_alloc(&e->rho, ml)); A(dev_alloc(&e->tau, ml)); A(dev_alloc(&e->vvec, ml));
+  A(dev_alloc(&e->work_m, ml)); A(dev_alloc(&e->work_mb, ml)); A(dev_alloc(&e->colq, ml));
+  A(dev_alloc(&e->rc, ntc)); A(dev_alloc(&e->helper, ntc));
+  A(dev_alloc(&e->list_idx, ml)); A(dev_alloc(&e->list_val, ml)); A(dev_alloc(&e->vlist_idx, ml)); A(dev_alloc(&e->vlist_val, ml));
   A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
-    A(dev_alloc(&ln.wm, m));
+    A(dev_alloc(&ln.wm, ml));
     A(dev_alloc(&ln.partial, (size_t)PR_MAXC * e->lda));
-    const size_t nred = std::max<size_t>(4096, (size_t)cdiv(nt, 256) + 1);  // k_update_select: one partial per 256 variables
+    const size_t nred = std::max<size_t>(4096, (size_t)cdiv(ntc, 256) + 1);  // k_update_select: one partial per 256 variables
     A(dev_alloc(&ln.red_f, nred)); A(dev_alloc(&ln.red_i, nred)); A(dev_alloc(&ln.red_counter, 4));
-    A(dev_alloc(&ln.seg_cnt, (size_t)cdiv(m, CP_SEG) + 1)); A(dev_alloc(&ln.seg_ss, (size_t)cdiv(m, CP_SEG) + 1));
+    A(dev_alloc(&ln.seg_cnt, (size_t)cdiv(ml, CP_SEG) + 1)); A(dev_alloc(&ln.seg_ss, (size_t)cdiv(ml, CP_SEG) + 1));
     A(dev_alloc(&ln.d_res, 1));
   }
   e->d_res = e->lane[0].d_res;
-  A(dev_alloc(&e->rowcover, m));
-  e->xbytes = sizeof(Cand) + (size_t)m * sizeof(double);
+  A(dev_alloc(&e->rowcover, ml));
+  e->xbytes = sizeof(Cand) + (size_t)ml * sizeof(double);
   A(dev_alloc(&e->d_win, 1));
-  A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * m + 64));
+  A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * ml + 64));
   if (st != MLP_OK) { destroy_engine(e); return st; }
   for (int l = 0; l < 2; ++l) CU(cudaHostAlloc((void**)&e->lane[l].h_res, sizeof(DevRes), cudaHostAllocDefault));
   e->h_res = e->lane[0].h_res;
@@ -1531,14 +1590,14 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaEventCreateWithFlags(&e->s1_mark, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_vbtran, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&e->ev_win, cudaEventDisableTiming));
-  if (!sparse) CU(cudaMemsetAsync(e->A, 0, (size_t)m * e->lda * sizeof(double), e->stream));
+  if (!sparse) CU(cudaMemsetAsync(e->A, 0, (size_t)e->mld * e->lda * sizeof(double), e->stream));
   for (int l = 0; l < 2; ++l) {
     CU(cudaMemsetAsync(e->lane[l].red_counter, 0, 4 * sizeof(unsigned), e->stream));
     CU(cudaMemsetAsync(e->lane[l].d_res, 0, sizeof(DevRes), e->stream));
   }
-  CU(cudaMemsetAsync(e->gam, 0, nt * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->helper, 0, nt * sizeof(double), e->stream));
-  CU(cudaMemsetAsync(e->rc, 0, nt * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->gam, 0, ntc * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->helper, 0, ntc * sizeof(double), e->stream));
+  CU(cudaMemsetAsync(e->rc, 0, ntc * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->xsend, 0, e->xbytes, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   e->h_bvar.assign(m, 0);
@@ -1766,7 +1825,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
       ST(fetch_column(e, e->h_bvar[r]));
       const int32_t slot = e->h_free_slots.back();
       e->h_free_slots.pop_back();
-      CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * m, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+      CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
       e->h_slot_of_row[r] = slot;
     }
   }
@@ -1966,13 +2025,13 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   e->spec_var = -1;
   e->ftran_var = -1;
   // lane 1: row half of the pivot, eta push
-  double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->m;
+  double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->mld;
   LAUNCHS(e, l1.st, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val,
           pi->entering_diff, pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags);
   if (!do_refactor) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
-    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->m, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, prev);
+    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, prev);
     LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
     e->h_last_eta_of_row[row] = K;
     e->K += 1;
@@ -2002,7 +2061,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     }
     const int32_t slot = e->h_free_slots.back();
     e->h_free_slots.pop_back();
-    CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->m, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
     e->h_slot_of_row[row] = slot;
   }
   e->h_bvar[row] = q;
@@ -2035,6 +2094,105 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     out->lu_nnz = e->lu_nnz;
   }
   out->eta_count = e->K;
+  return MLP_OK;
+}
+
+// ---------------------------------------------------------------------------------- incremental API
+mlp_status mlp_get_var(mlp_engine* e, int64_t var, mlp_var_info* out) {
+  if (!e || !e->initialized || !out || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
+  if (e->world != 1) { set_err("mlp_get_var: single-shard engines only"); return MLP_INVALID; }
+  CU(cudaSetDevice(e->device));
+  ST(begin0(e));
+  const int64_t lv = to_local(e, var);
+  uint8_t f = 0;
+  int32_t pos = 0;
+  ST(d2h(e, &f, e->vflag + lv, 1));
+  ST(d2h(e, &pos, e->vpos + lv, 4));
+  out->flags = f;
+  out->pos_or_row = pos;
+  if (f & MLP_BASIC) {
+    out->obj_coeff = 0.0;
+    ST(d2h(e, &out->value, e->xB + pos, 8));
+  } else {
+    ST(d2h(e, &out->obj_coeff, e->d + lv, 8));
+    ST(d2h(e, &out->value, e->xnb + lv, 8));
+  }
+  return MLP_OK;
+}
+mlp_status mlp_set_nb_state(mlp_engine* e, int64_t var, uint32_t flags) {
+  if (!e || !e->initialized || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
+  if (e->world != 1) { set_err("mlp_set_nb_state: single-shard engines only"); return MLP_INVALID; }
+  CU(cudaSetDevice(e->device));
+  ST(begin0(e));
+  e->sel_valid = false;
+  LAUNCH(e, k_set_var_state, 1, 1, 0, e->vflag, to_local(e, var), flags & (MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED));
+  return mark0(e);
+}
+
+mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double* slack_coeffs, double slack_min, double slack_max,
+                              double rhs, mlp_add_row_result* out) {
+  if (!e || !e->initialized || !coeffs || !out) return MLP_INVALID;
+  if (e->sparse || e->world != 1) { set_err("add_row: dense single-shard engines only (row f2 is partly built)"); return MLP_INVALID; }
+  if (e->m >= e->mld) { set_err("add_row: row capacity exhausted (MLP_ROW_RESERVE)"); return MLP_NOMEM; }
+  CU(cudaSetDevice(e->device));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  Lane& l0 = e->lane[0];
+  const int64_t m = e->m, n = e->n, r = m, lv = n + r, gv = e->ng + r;
+  e->sel_valid = false;
+  e->spec_var = e->ftran_var = -1;
+  e->colq_var = -1;
+  double* rowA = e->A + r * e->lda;
+  ST(h2d(e, rowA, coeffs, n * 8));
+  double* d_rhs_new = e->scal + 7;
+  if (slack_coeffs) {
+    ST(h2d(e, e->work_m, slack_coeffs, m * 8));
+    compact(e, l0, e->work_m, e->list_idx, e->list_val, e->icnt, e->scal + 8);
+    if (e->price_tma)
+      LAUNCH(e, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, e->list_idx, e->list_val, e->icnt, 0, l0.partial,
+             e->price_tile);
+    else
+      LAUNCH(e, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, e->list_idx, e->list_val, e->icnt, 0, l0.partial);
+    LAUNCH(e, k_row_combine, cdiv(n, 256), 256, 0, rowA, l0.partial, e->icnt, e->lda, n);
+    LAUNCH(e, k_sub_dot, 1, 1024, 0, e->work_m, e->rhs, m, rhs, (const double*)nullptr, d_rhs_new);
+  } else {
+    ST(h2d(e, d_rhs_new, &rhs, 8));
+  }
+  // basic value of the new slack: rhs - a . x over the structural variables (583-591)
+  LAUNCH(e, k_struct_values, cdiv(n, 256), 256, 0, e->xnb, e->xB, e->vflag, e->vpos, n, e->helper);
+  LAUNCH(e, k_sub_dot, 1, 1024, 0, rowA, e->helper, n, 0.0, d_rhs_new, e->scal + 9);
+  LAUNCH(e, k_new_row_state, 1, 1, 0, r, lv, gv, slack_min, slack_max, e->scal + 9, d_rhs_new, e->lo, e->hi, e->cobj, e->d, e->gam,
+         e->xnb, e->vflag, e->vpos, e->bvar, e->xB, e->loB, e->hiB, e->w, e->rhs, e->rowcover);
+  {  // cached basis columns: entry of the new row
+    std::vector<int32_t> slots, vars;
+    for (int64_t p = 0; p < m; ++p)
+      if (e->h_slot_of_row[p] >= 0) { slots.push_back(e->h_slot_of_row[p]); vars.push_back((int32_t)e->h_bvar[p]); }
+    if (!slots.empty()) {
+      ST(h2d(e, e->vlist_idx, slots.data(), slots.size() * 4));
+      ST(h2d(e, e->list_idx, vars.data(), vars.size() * 4));
+      LAUNCH(e, k_bcols_new_row, cdiv((int64_t)slots.size(), 256), 256, 0, rowA, e->vlist_idx, e->list_idx, (int)slots.size(), e->mld,
+             r, e->Bcols);
+    }
+    CU(cudaStreamSynchronize(e->stream));
+  }
+  e->m += 1;
+  e->nt += 1;
+  e->h_bvar.push_back(gv);
+  e->h_slot_of_row.push_back(-1);
+  e->h_last_eta_of_row.push_back(-1);
+  ST(refactor_impl(e));  // basis_solver.reset (612)
+  ST(mark0(e));
+  if (e->enable_pse || e->enable_dse) {  // 615-630: the new tableau row extends the steepest-edge norms
+    ST(mlp_calc_row_coeffs(e, r));
+    ST(begin0(e));
+    if (e->enable_pse) LAUNCH(e, k_add_sq, cdiv(e->nt, 256), 256, 0, e->gam, e->rc, e->vflag, e->nt);
+    if (e->enable_dse) LAUNCH(e, k_copy1, 1, 1, 0, e->w + r, e->scal + 1);
+    ST(mark0(e));
+  }
+  out->row = r;
+  out->slack_var = gv;
+  out->lu_nnz = e->lu_nnz;
+  ST(d2h(e, &out->basic_val, e->xB + r, 8));
+  ST(d2h(e, &out->rhs, e->rhs + r, 8));
   return MLP_OK;
 }
 

@@ -351,6 +351,148 @@ mlp_status mlp_solver_run(mlp_solver* s, int64_t max_pivots, int32_t* done) {
   return rc;
 }
 
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ incremental API (row f2)
+// restore_feasibility (solver.rs:513-547) / optimize (487-511) run to completion, as the incremental entry points do.
+static mlp_status restore_feasibility(mlp_solver* s) {
+  for (;;) {
+    int moved = 0;
+    ST(dual_iteration(s, &moved));
+    if (!moved) break;
+  }
+  s->is_primal_feasible = true;
+  return MLP_OK;
+}
+static mlp_status optimize(mlp_solver* s) {
+  for (;;) {
+    int moved = 0;
+    ST(primal_iteration(s, &moved));
+    if (!moved) break;
+  }
+  s->is_dual_feasible = true;
+  return MLP_OK;
+}
+static bool finished(const mlp_solver* s) { return s && s->initialized && s->stage == 4; }
+
+// Solver::add_constraint (solver.rs:549-634); slack_coeffs (m doubles or null) only from add_gomory_cut.
+static mlp_status add_constraint_impl(mlp_solver* s, const std::vector<double>& coeffs, const double* slack_coeffs, bool empty,
+                                      int32_t cmp_op, double rhs) {
+  if (!finished(s) || !s->is_primal_feasible || !s->is_dual_feasible) return MLP_INVALID;  // assert! 555-556
+  if (empty) {  // 558-570
+    const bool taut = cmp_op == 0 ? 0.0 == rhs : cmp_op == 1 ? 0.0 <= rhs : 0.0 >= rhs;
+    return taut ? MLP_OK : MLP_INFEASIBLE;
+  }
+  double smin, smax;  // 573-577
+  if (cmp_op == 1) { smin = 0.0; smax = kInf; }
+  else if (cmp_op == 2) { smin = -kInf; smax = 0.0; }
+  else { smin = 0.0; smax = 0.0; }
+  mlp_add_row_result ar;
+  ST(mlp_engine_add_row(s->eng, coeffs.data(), slack_coeffs, smin, smax, rhs, &ar));
+  s->orig_obj_coeffs.push_back(0.0);  // 579-585
+  s->orig_var_mins.push_back(smin);
+  s->orig_var_maxs.push_back(smax);
+  s->basic_vars.push_back(ar.slack_var);
+  s->m += 1;
+  s->eta_nnz = 0;
+  s->lu_nnz = ar.lu_nnz;
+  s->is_primal_feasible = false;  // 632-633
+  return restore_feasibility(s);
+}
+
+extern "C" {
+mlp_status mlp_solver_add_constraint(mlp_solver* s, int64_t count, const int64_t* vars, const double* coeffs, int32_t cmp_op,
+                                     double rhs) {
+  if (!s || count < 0 || (count > 0 && (!vars || !coeffs))) return MLP_INVALID;
+  std::vector<double> row((size_t)s->n, 0.0);
+  for (int64_t t = 0; t < count; ++t) {
+    if (vars[t] < 0 || vars[t] >= s->n) return MLP_INVALID;
+    row[(size_t)vars[t]] = coeffs[t];  // CsVec::new rejects duplicates (lib.rs:376); the Python mirror checks before calling
+  }
+  return add_constraint_impl(s, row, nullptr, count == 0, cmp_op, rhs);
+}
+
+// Solver::fix_var, solver.rs:378-415
+mlp_status mlp_solver_fix_var(mlp_solver* s, int64_t var, double val) {
+  if (!finished(s) || var < 0 || var >= s->n) return MLP_INVALID;
+  if (val < s->orig_var_mins[var] || val > s->orig_var_maxs[var]) return MLP_INFEASIBLE;  // 379-381
+  mlp_var_info vi;
+  ST(mlp_get_var(s->eng, var, &vi));
+  if (vi.flags & MLP_BASIC) {  // 384-392: pivot it out of the basis at the value `val`
+    const int64_t row = vi.pos_or_row;
+    ST(mlp_calc_row_coeffs(s->eng, row));
+    mlp_dual_entering de;
+    ST(mlp_ratio_dual(s->eng, row, val, &de));
+    if (de.var < 0) return MLP_INFEASIBLE;  // 1019
+    const double entering_diff = (vi.value - val) / de.coeff;  // 1005
+    const double entering_new_val = de.cur_val + entering_diff;
+    ST(mlp_ftran_col(s->eng, de.var));
+    ST(do_pivot(s, 0, de.var, de.pos, de.obj_coeff, entering_new_val, entering_diff, true, row, de.coeff, val));
+  } else {  // 394-404: move the non-basic variable, no basis change (not a pivot: no trace record)
+    const int64_t col = vi.pos_or_row;
+    ST(mlp_ftran_col(s->eng, var));
+    const double diff = val - vi.value;
+    mlp_pivot_info pi;
+    std::memset(&pi, 0, sizeof(pi));
+    pi.entering_var = var;
+    pi.col = col;
+    pi.entering_new_val = val;
+    pi.entering_diff = diff;
+    pi.has_elem = 0;
+    mlp_pivot_result pr;
+    ST(mlp_pivot(s->eng, &pi, &pr));
+    s->cur_obj_val += diff * vi.obj_coeff;  // 401
+    s->nb_var_vals[col] = val;
+  }
+  ST(mlp_set_nb_state(s->eng, var, MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED));  // 407-411
+  s->is_primal_feasible = false;
+  return restore_feasibility(s);
+}
+
+// Solver::unfix_var, solver.rs:418-438
+mlp_status mlp_solver_unfix_var(mlp_solver* s, int64_t var, int32_t* was_fixed) {
+  if (was_fixed) *was_fixed = 0;
+  if (!finished(s) || var < 0 || var >= s->n) return MLP_INVALID;
+  mlp_var_info vi;
+  ST(mlp_get_var(s->eng, var, &vi));
+  if ((vi.flags & MLP_BASIC) || !(vi.flags & MLP_FIXED)) return MLP_OK;
+  const uint32_t f = (vi.value == s->orig_var_mins[var] ? MLP_AT_MIN : 0u) | (vi.value == s->orig_var_maxs[var] ? MLP_AT_MAX : 0u);
+  ST(mlp_set_nb_state(s->eng, var, f));  // 424-428
+  s->is_dual_feasible = false;
+  ST(optimize(s));  // 432: .unwrap() in the reference — an error status here is that panic
+  if (was_fixed) *was_fixed = 1;
+  return MLP_OK;
+}
+
+// Solver::add_gomory_cut, solver.rs:440-460
+mlp_status mlp_solver_add_gomory_cut(mlp_solver* s, int64_t var) {
+  if (!finished(s) || var < 0 || var >= s->n) return MLP_INVALID;
+  mlp_var_info vi;
+  ST(mlp_get_var(s->eng, var, &vi));
+  if (!(vi.flags & MLP_BASIC)) return MLP_INVALID;  // panic!("var is not basic"), 458
+  const int64_t row = vi.pos_or_row, nt = s->n + s->m;
+  ST(mlp_calc_row_coeffs(s->eng, row));
+  std::vector<double> rc((size_t)nt), flags_dummy;
+  ST(mlp_download_f64(s->eng, MLP_ARR_ROW_COEFFS, rc.data(), nt));
+  std::vector<uint8_t> fl((size_t)nt);
+  std::vector<int32_t> pos((size_t)nt);
+  ST(mlp_download_var_state(s->eng, fl.data(), pos.data()));
+  std::vector<double> cut((size_t)s->n, 0.0), cut_slack((size_t)s->m, 0.0);
+  bool any_slack = false, any = false;
+  for (int64_t v = 0; v < nt; ++v) {  // 444-448 over the non-zeros of row_coeffs
+    if ((fl[v] & MLP_BASIC) || rc[v] == 0.0) continue;
+    const double c = std::floor(rc[v]) - rc[v];
+    any = true;
+    if (v < s->n) cut[(size_t)v] = c;
+    else { cut_slack[(size_t)(v - s->n)] = c; any_slack = any_slack || c != 0.0; }
+  }
+  const double cut_bound = std::floor(vi.value) - vi.value;  // 450
+  return add_constraint_impl(s, cut, any_slack ? cut_slack.data() : nullptr, !any, 1 /* Le */, cut_bound);
+}
+}  // extern "C"
+
+extern "C" {
+
 double mlp_solver_cur_obj_val(mlp_solver* s) { return s->cur_obj_val; }
 int64_t mlp_solver_pivots_done(mlp_solver* s) { return s->pivots_done; }
 int64_t mlp_solver_num_vars(mlp_solver* s) { return s->n; }
