@@ -212,6 +212,9 @@ typedef struct mlp_add_row_result {
 mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double* slack_coeffs, double slack_min,
                               double slack_max, double rhs, mlp_add_row_result* out);
 
+/* Solver: Clone (solver.rs:14; Solution: Clone, lib.rs:313): device-to-device deep copy, factors and eta file included. */
+mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out);
+
 /* Downloads (device -> caller buffer).  Var-indexed arrays have n+m entries, row-indexed m. */
 typedef enum mlp_array {
   MLP_ARR_OBJ_COEFFS = 0,   /* d, by var (valid where non-basic) */
@@ -303,6 +306,7 @@ mlp_status mlp_solver_add_constraint(mlp_solver* s, int64_t count, const int64_t
 mlp_status mlp_solver_fix_var(mlp_solver* s, int64_t var, double val);
 mlp_status mlp_solver_unfix_var(mlp_solver* s, int64_t var, int32_t* was_fixed);
 mlp_status mlp_solver_add_gomory_cut(mlp_solver* s, int64_t var);
+mlp_status mlp_solver_clone(mlp_solver* s, mlp_solver** out);
 /* host mirrors of nb_vars (n) and basic_vars (m) */
 mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out);
 mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out);

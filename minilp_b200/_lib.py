@@ -96,6 +96,8 @@ SIGNATURES = {
     "mlp_ratio_dual": (i32, [vp, i64, f64, C.POINTER(DualEntering)]),
     "mlp_pivot": (i32, [vp, C.POINTER(PivotInfo), C.POINTER(PivotResult)]),
     "mlp_recalc_obj_coeffs": (i32, [vp, pd]),
+    "mlp_engine_clone": (i32, [vp, C.POINTER(vp)]),
+    "mlp_solver_clone": (i32, [vp, C.POINTER(vp)]),
     "mlp_get_var": (i32, [vp, i64, C.POINTER(VarInfo)]),
     "mlp_set_nb_state": (i32, [vp, i64, C.c_uint32]),
     "mlp_engine_add_row": (i32, [vp, pd, pd, f64, f64, f64, C.POINTER(AddRowResult)]),

@@ -313,6 +313,16 @@ class Solver:
         s.direction = direction
         return s
 
+    def clone(self):
+        """Solver: Clone (solver.rs:14) — device-to-device deep copy."""
+        h = C.c_void_p()
+        _check(_lib.lib().mlp_solver_clone(self._s, C.byref(h)))
+        c = object.__new__(Solver)
+        c._s, c.m, c.n, c.rank, c.world = h, self.m, self.n, 0, 1
+        c.engine = Engine(C.c_void_p(_lib.lib().mlp_solver_engine(h)), self.m, self.n)
+        c.direction = getattr(self, "direction", None)
+        return c
+
     def run(self, max_pivots=-1):
         done = C.c_int32(0)
         _check(_lib.lib().mlp_solver_run(self._s, max_pivots, C.byref(done)))
@@ -445,12 +455,15 @@ class Problem:
 
 class Solution:
     """lib.rs:313-423: objective, var_value, iteration and the incremental methods.  The reference's
-    incremental methods consume `self` and return the new solution; here they update in place and return self.
-    Not mirrored: `Clone` (lib.rs:313) — a device deep copy of the engine is not built yet."""
+    incremental methods consume `self` and return the new solution; here they update in place and return self;
+    `clone()` is `Solution: Clone` (lib.rs:313)."""
 
     def __init__(self, solver, direction, num_vars):
         self.solver, self.direction, self.num_vars = solver, direction, num_vars
         self._vals = solver.values()
+
+    def clone(self):
+        return Solution(self.solver.clone(), self.direction, self.num_vars)
 
     def _refresh(self):
         s = self.solver

@@ -1276,10 +1276,11 @@ static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double
 
 // Column cache / LU arenas.  First allocation is generous (~1 GB of basis columns): cudaFree/cudaMalloc of the big
 // arenas costs tens of milliseconds, so capacity grows by doubling and rarely; the cache content survives growth.
-static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
+static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = false) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->mld)))));
   while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
+  if (exact) cap = k;        // clone: same leading dimensions as the source
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   double* nb = nullptr;
   ST(dev_alloc(&nb, (size_t)e->mld * cap));
@@ -1302,10 +1303,11 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k) {
   }
   return MLP_OK;
 }
-static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K) {
+static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = false) {
   if (K <= e->Kcap && e->E) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->mld))));
   while (cap < K) cap *= 2;
+  if (exact) cap = K;
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   e->Kcap = cap;
@@ -1503,7 +1505,7 @@ static void destroy_engine(mlp_engine* e) {
 }
 
 static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out,
-                                bool sparse = false) {
+                                bool sparse = false, int64_t mld_override = 0) {
   *out = nullptr;
   if (m <= 0 || ng <= 0 || m > 0x7fffffff || ng + m > 0x7fffffff || world < 1 || rank < 0 || rank >= world) {
     set_err("bad dimensions");
@@ -1553,6 +1555,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   // allocated for mld rows so that appending one costs O(n), not a re-layout.
   e->mld = sparse ? m : m + std::max<int64_t>(64, m / 8);
   if (const char* v = getenv("MLP_ROW_RESERVE")) e->mld = m + std::max<int64_t>(0, atoll(v));
+  if (mld_override >= m) e->mld = mld_override;
   const int64_t ml = e->mld, ntc = e->n + ml, gt = ng + ml;
   if (!sparse) A(dev_alloc(&e->A, (size_t)ml * e->lda));
   A(dev_alloc(&e->lo, gt)); A(dev_alloc(&e->hi, gt)); A(dev_alloc(&e->cobj, gt));
@@ -2193,6 +2196,70 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
   out->lu_nnz = e->lu_nnz;
   ST(d2h(e, &out->basic_val, e->xB + r, 8));
   ST(d2h(e, &out->rhs, e->rhs + r, 8));
+  return MLP_OK;
+}
+
+// Solver: Clone (solver.rs:14, used by Solution: Clone lib.rs:313): device-to-device deep copy of the whole engine state,
+// basis factors and eta file included, so the copy continues bit-identically.
+mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
+  if (!src || !out || !src->initialized) return MLP_INVALID;
+  *out = nullptr;
+  if (src->world != 1) { set_err("clone: single-shard engines only"); return MLP_INVALID; }
+  CU(cudaSetDevice(src->device));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(src->lane[l].st));
+  mlp_engine* e = nullptr;
+  ST(create_engine(src->device, src->m, src->ng, 0, 1, nullptr, &e, src->sparse, src->mld));
+  mlp_status st = MLP_OK;
+  auto cp = [&](void* dst, const void* from, size_t bytes) {
+    if (st == MLP_OK && bytes && cudaMemcpyAsync(dst, from, bytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) {
+      set_err("clone: device copy failed");
+      st = MLP_CUDA_ERROR;
+    }
+  };
+  auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
+  const size_t ml = (size_t)src->mld, ntc = (size_t)src->n + ml, gt = (size_t)src->ng + ml;
+  if (src->sparse) {
+    e->nnz = src->nnz;
+    e->h_csc_ptr = src->h_csc_ptr;
+    const size_t z = (size_t)src->nnz;
+    A(dev_alloc(&e->csr_ptr, src->m + 1)); A(dev_alloc(&e->csr_idx, z)); A(dev_alloc(&e->csr_val, z));
+    A(dev_alloc(&e->csc_ptr, src->n + 1)); A(dev_alloc(&e->csc_idx, z)); A(dev_alloc(&e->csc_val, z));
+    cp(e->csr_ptr, src->csr_ptr, (src->m + 1) * 8); cp(e->csr_idx, src->csr_idx, z * 4); cp(e->csr_val, src->csr_val, z * 8);
+    cp(e->csc_ptr, src->csc_ptr, (src->n + 1) * 8); cp(e->csc_idx, src->csc_idx, z * 4); cp(e->csc_val, src->csc_val, z * 8);
+  } else cp(e->A, src->A, ml * (size_t)src->lda * 8);
+  cp(e->lo, src->lo, gt * 8); cp(e->hi, src->hi, gt * 8); cp(e->cobj, src->cobj, gt * 8);
+  cp(e->d, src->d, ntc * 8); cp(e->gam, src->gam, ntc * 8); cp(e->xnb, src->xnb, ntc * 8);
+  cp(e->vflag, src->vflag, ntc); cp(e->vpos, src->vpos, ntc * 4); cp(e->bvar, src->bvar, ml * 4);
+  cp(e->xB, src->xB, ml * 8); cp(e->loB, src->loB, ml * 8); cp(e->hiB, src->hiB, ml * 8); cp(e->w, src->w, ml * 8);
+  cp(e->rhs, src->rhs, ml * 8); cp(e->rowcover, src->rowcover, ml * 4);
+  cp(e->alpha, src->alpha, ml * 8); cp(e->rho, src->rho, ml * 8); cp(e->rc, src->rc, ntc * 8); cp(e->helper, src->helper, ntc * 8);
+  cp(e->scal, src->scal, 16 * 8); cp(e->icnt, src->icnt, 16 * 4);
+  cp(e->d_res, src->d_res, sizeof(DevRes));
+  if (st == MLP_OK && src->kcap > 0) {
+    A(ensure_lu_capacity(e, src->kcap, true));
+    if (st == MLP_OK && e->kcap != src->kcap) { set_err("clone: capacity mismatch"); st = MLP_INVALID; }
+    const size_t kc = (size_t)src->kcap;
+    cp(e->Jpos, src->Jpos, kc * 4); cp(e->Jslot, src->Jslot, kc * 4); cp(e->Rp, src->Rp, kc * 4);
+    cp(e->Bcols, src->Bcols, ml * kc * 8); cp(e->LUc, src->LUc, kc * kc * 8); cp(e->Cinv, src->Cinv, kc * kc * 8);
+  }
+  if (st == MLP_OK && src->Kcap > 0) {
+    A(ensure_eta_capacity(e, src->Kcap, true));
+    if (st == MLP_OK && e->Kcap != src->Kcap) { set_err("clone: capacity mismatch"); st = MLP_INVALID; }
+    const size_t Kc = (size_t)src->Kcap;
+    cp(e->E, src->E, ml * (size_t)src->K * 8); cp(e->Ginv, src->Ginv, Kc * Kc * 8);
+    cp(e->etaR, src->etaR, Kc * 4); cp(e->etaPrev, src->etaPrev, Kc * 4); cp(e->etaHead, src->etaHead, Kc * 4);
+  }
+  if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("clone: copy failed"); st = MLP_CUDA_ERROR; }
+  if (st != MLP_OK) { destroy_engine(e); return st; }
+  e->nt = src->nt;
+  e->k = src->k; e->K = src->K; e->lu_nnz = src->lu_nnz;
+  e->enable_pse = src->enable_pse; e->enable_dse = src->enable_dse;
+  e->h_bvar = src->h_bvar; e->h_slot_of_row = src->h_slot_of_row; e->h_free_slots = src->h_free_slots;
+  e->h_pending_free = src->h_pending_free; e->h_last_eta_of_row = src->h_last_eta_of_row;
+  e->cnt = src->cnt;
+  e->initialized = true;
+  ST(mark0(e));
+  *out = e;
   return MLP_OK;
 }
 

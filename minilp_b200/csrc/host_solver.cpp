@@ -412,6 +412,18 @@ mlp_status mlp_solver_add_constraint(mlp_solver* s, int64_t count, const int64_t
   return add_constraint_impl(s, row, nullptr, count == 0, cmp_op, rhs);
 }
 
+// Solution: Clone (lib.rs:313-318)
+mlp_status mlp_solver_clone(mlp_solver* s, mlp_solver** out) {
+  if (!s || !out) return MLP_INVALID;
+  *out = nullptr;
+  mlp_engine* e = nullptr;
+  ST(mlp_engine_clone(s->eng, &e));
+  mlp_solver* c = new mlp_solver(*s);
+  c->eng = e;
+  *out = c;
+  return MLP_OK;
+}
+
 // Solver::fix_var, solver.rs:378-415
 mlp_status mlp_solver_fix_var(mlp_solver* s, int64_t var, double val) {
   if (!finished(s) || var < 0 || var >= s->n) return MLP_INVALID;

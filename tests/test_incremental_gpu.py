@@ -40,6 +40,27 @@ def test_lib_fix_unfix_var():
         p.solve().fix_var(v1, 3.5)  # outside the bounds, solver.rs:379-381
 
 
+def test_clone_continues_identically():
+    """Solution: Clone (lib.rs:313): the reference's tests branch off one solved problem with clone()."""
+    p, v1, v2 = fix_unfix_problem()
+    orig = p.solve()
+    a = orig.clone().fix_var(v1, 0.5)
+    assert (a[v1], a[v2], a.objective()) == (0.5, 3.0, 6.5)
+    b = orig.clone().fix_var(v2, 2.5)
+    assert (b[v1], b[v2], b.objective()) == (1.5, 2.5, 6.5)
+    assert (orig[v1], orig[v2], orig.objective()) == (1.0, 3.0, 7.0)  # the source is untouched
+    # mid-solve clone of a larger LP (factors + eta file copied): both continue to the same end, pivot for pivot
+    lp = mb.synth_dense(3, 80, 120, 5)
+    s = mb.Solver.from_dense(lp)
+    s.run(37)
+    c = s.clone()
+    assert s.run() and c.run()
+    assert np.array_equal(s.trace(), c.trace())
+    assert s.cur_obj_val == c.cur_obj_val and np.array_equal(s.values(), c.values())
+    s.close()
+    c.close()
+
+
 def add_constraint_problem():
     p = mb.Problem(mb.OptimizationDirection.Minimize)
     v1 = p.add_var(2.0, (0.0, INF))
