@@ -1106,7 +1106,7 @@ __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __re
 // ------------------------------------------------------------------------------------------------ incremental API (row f2)
 // Solver::add_constraint (solver.rs:549-634) pieces.  A cut may carry coefficients g_i on slack variables
 // (add_gomory_cut, 440-460); slack columns stay unit columns here, so s_i = rhs_i - a_i x is substituted:
-// row' = c - A^T g, rhs' = rhs - g . rhs_old (the same constraint; see DESIGN.md §9 for what that changes).
+// row' = c - A^T g, rhs' = rhs - g . rhs_old (the same constraint; see DESIGN.md §8 for what that changes).
 __global__ void k_row_combine(double* __restrict__ row, const double* __restrict__ partial, const int32_t* __restrict__ count_ptr,
                               int64_t lda, int64_t n) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

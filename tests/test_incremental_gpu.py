@@ -175,7 +175,7 @@ def test_incremental_ops_match_oracle(kind, m, n, seed):
 
 
 def test_gomory_cuts_match_oracle_objective():
-    """Gomory cuts carry slack coefficients; the engine eliminates them (DESIGN.md §9), which changes the dual
+    """Gomory cuts carry slack coefficients; the engine eliminates them (DESIGN.md §8), which changes the dual
     steepest-edge weights of later pivots: end states are compared, not the sequence."""
     lp, g, r = both(0, 30, 40, 4)
     for _ in range(3):
