@@ -189,6 +189,7 @@ struct Lane {
   double *xk = nullptr, *xk2 = nullptr;  // kcap: core right-hand side / solution
   double *tK = nullptr, *tK2 = nullptr;  // Kcap: eta scalars
   double* wm = nullptr;                   // m
+  double* gpart = nullptr;                // TALL_MAXG x mld: column-group partials of the tall-skinny products
   double *gt_part_k = nullptr, *gt_part_K = nullptr;
   int32_t* seg_cnt = nullptr;
   double* seg_ss = nullptr;
@@ -647,6 +648,22 @@ __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__
     }
   }
   if (cov >= 0) out[cov] = acc;
+  if (i < k) out[Jpos[i]] = xk[i];
+}
+// FTRAN tail after a column-group split (k_tall_part): alpha_slack = a_S - sum_g part[g], alpha[Jpos[t]] = x[t]
+__global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int64_t pld, int m, int k,
+                                     const double* __restrict__ xk, const double* __restrict__ rhs0,
+                                     const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
+                                     double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) {
+    const int cov = rowcover[i];
+    if (cov >= 0) {
+      double tsum = 0.0;
+      for (int g = 0; g < G; ++g) tsum += part[(int64_t)g * pld + i];
+      out[cov] = rhs0[i] - tsum;
+    }
+  }
   if (i < k) out[Jpos[i]] = xk[i];
 }
 // core C = D[R,:] (k x k, column-major) from the column cache
@@ -1228,8 +1245,15 @@ static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, doub
   if (idx) LAUNCHS(e, ln.st, k_compact_write, nseg, CP_SEG, 0, x, m, ln.seg_cnt, idx, val);
 }
 static int gemv_split(const mlp_engine* e, int rows, int cols) {
-  int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(2 * (int64_t)e->sm_count, cols)));
+  // enough (column, row-slice) CTAs to fill every SM's thread slots (8 CTAs of 256 threads)
+  int S = std::max(1, std::min(GT_MAXSPLIT, cdiv(8 * (int64_t)e->sm_count, cols)));
   return std::min(S, std::max(1, rows / 2048));
+}
+constexpr int TALL_MAXG = 16;
+// column groups for the thread-per-row products: fill the SMs' thread slots, at least 32 columns per group
+static int tall_groups(const mlp_engine* e, int rows, int cols) {
+  const int want = cdiv((int64_t)e->sm_count * 2048, std::max(rows, 1));
+  return std::max(1, std::min(std::min(TALL_MAXG, want), cols / 32));
 }
 static void gemv_t(mlp_engine* e, Lane& ln, const double* M, int64_t ld, int rows, int cols, const double* x, double* part,
                    const double* base, const int32_t* base_idx, double* out, int negate) {
@@ -1244,11 +1268,23 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
-  LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
-          e->Jslot, out);
+  const int Gk = tall_groups(e, m, k);
+  if (Gk > 1) {
+    LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), Gk), 256, 0, e->Bcols, e->mld, m, k, ln.xk, e->Jslot, e->rowcover, ln.gpart, e->mld);
+    LAUNCHS(e, ln.st, k_ftran_finish_parts, cdiv(std::max(m, k), 256), 256, 0, ln.gpart, Gk, e->mld, m, k, ln.xk, rhs0, e->rowcover,
+            e->Jpos, out);
+  } else
+    LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
+            e->Jslot, out);
   if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
     LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
-    LAUNCHS(e, ln.st, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->mld, m, K, ln.tK, out);
+    const int GK = tall_groups(e, m, K);
+    if (GK > 1) {
+      LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), GK), 256, 0, e->E, e->mld, m, K, ln.tK, (const int32_t*)nullptr,
+              (const int32_t*)nullptr, ln.gpart, e->mld);
+      LAUNCHS(e, ln.st, k_sub_parts, cdiv(m, 256), 256, 0, ln.gpart, GK, e->mld, m, out);
+    } else
+      LAUNCHS(e, ln.st, k_gemv_n_sub, cdiv(m, 256), 256, 0, e->E, e->mld, m, K, ln.tK, out);
   }
   return MLP_OK;
 }
@@ -1485,7 +1521,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
-    dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.wm); dev_free(ln.gt_part_k);
+    dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.wm); dev_free(ln.gpart); dev_free(ln.gt_part_k);
     dev_free(ln.gt_part_K); dev_free(ln.seg_cnt); dev_free(ln.seg_ss); dev_free(ln.red_f); dev_free(ln.red_i);
     dev_free(ln.red_counter); dev_free(ln.partial); dev_free(ln.d_res);
     if (ln.h_res) cudaFreeHost(ln.h_res);
@@ -1570,6 +1606,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
     A(dev_alloc(&ln.wm, ml));
+    A(dev_alloc(&ln.gpart, (size_t)16 * ml));
     A(dev_alloc(&ln.partial, (size_t)PR_MAXC * e->lda));
     const size_t nred = std::max<size_t>(4096, (size_t)cdiv(ntc, 256) + 1);  // k_update_select: one partial per 256 variables
     A(dev_alloc(&ln.red_f, nred)); A(dev_alloc(&ln.red_i, nred)); A(dev_alloc(&ln.red_counter, 4));

@@ -274,6 +274,50 @@ __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M
   if (i < rows) y[i] = acc;
 }
 
+// Column-group split of the same tall-skinny products for wide basis blocks: with one thread per row a 50k-row pass
+// has only ~340 threads per SM, too few loads in flight to saturate HBM once cols grows into the hundreds.  Grid
+// (row tiles, G): CTA (x, g) accumulates column group g into part[g][i]; the finishing kernels add the G partials in
+// group order.   col(j) = slots ? slots[j] : j;   rows with rowmask[i] < 0 are skipped.
+__global__ void __launch_bounds__(256) k_tall_part(const double* __restrict__ M, int64_t ld, int rows, int cols,
+                                                    const double* __restrict__ t, const int32_t* __restrict__ slots,
+                                                    const int32_t* __restrict__ rowmask, double* __restrict__ part, int64_t pld) {
+  __shared__ double ts[512];
+  __shared__ int32_t sl[512];
+  const int G = gridDim.y, g = blockIdx.y;
+  const int cg = (cols + G - 1) / G;
+  const int c0 = g * cg, c1 = min(cols, c0 + cg);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < rows && (!rowmask || rowmask[i] >= 0);
+  double acc = 0.0;
+  for (int j0 = c0; j0 < c1; j0 += 512) {
+    const int nj = min(512, c1 - j0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < nj; q += blockDim.x) { ts[q] = t[j0 + q]; sl[q] = slots ? slots[j0 + q] : j0 + q; }
+    __syncthreads();
+    if (act) {
+      const double* p = M + i;
+      int j = 0;
+      for (; j + 16 <= nj; j += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = p[(int64_t)sl[j + u] * ld];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc += ts[j + u] * v[u];
+      }
+      for (; j < nj; ++j) acc += ts[j] * p[(int64_t)sl[j] * ld];
+    }
+  }
+  if (i < rows) part[(int64_t)g * pld + i] = acc;
+}
+// y[i] -= sum_g part[g][i]
+__global__ void k_sub_parts(const double* __restrict__ part, int G, int64_t pld, int rows, double* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double tsum = 0.0;
+  for (int g = 0; g < G; ++g) tsum += part[(int64_t)g * pld + i];
+  y[i] -= tsum;
+}
+
 // out[j] = base[idx[j]] - sum_i M[i + j*ld] * x[i]   (negate) or the plain dot products.
 // Grid (cols, S): CTA (j, s) reduces row slice s of column j; k_gemv_t_fin adds the S partials in order.
 // Used for BTRAN: u = E^T rhs (solver.rs:1326-1330) and the right-hand side of the core solve.
