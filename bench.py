@@ -294,8 +294,8 @@ def run_ours(a):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "m": a.m, "n": a.n,
                    "l2": f"inputs_exceed_l2 (8*m*n/N = {8 * a.m * nloc / 1e9:.1f} GB of A are read per GPU per pivot)",
-                   "parallelism": (f"columns sharded over {world} GPUs ({nloc} each), basis replicated, one NCCL all-gather "
-                                   "(candidate + entering column) per pivot") if world > 1 else "single GPU",
+                   "parallelism": (f"columns sharded over {world} GPUs ({nloc} each), basis replicated, one candidate exchange "
+                                   f"per pivot ({e.exchange_kind()})") if world > 1 else "single GPU",
                    "pivots_before_timed_region": p0, "optimal_reached": bool(done),
                    "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
                    "refactors_in_region": c1["refactors"] - c0["refactors"], "setup": setup,

@@ -79,6 +79,10 @@ mlp_status mlp_nccl_get_unique_id(void* out128);
 mlp_status mlp_local_group_create(int32_t world, void** out);
 void mlp_local_group_destroy(void* group);
 mlp_status mlp_engine_local_range(mlp_engine* e, int64_t* col_begin, int64_t* col_end);
+/* How the per-pivot candidate exchange runs: 0 single shard, 1 NCCL all-gather, 2 in-process group, 3 one kernel over
+ * NVLink peer memory (CUDA IPC; chosen automatically with MLP_COMM_NCCL when every rank can map every peer, MLP_P2P=0
+ * disables it). */
+int32_t mlp_engine_exchange_kind(mlp_engine* e);
 void mlp_engine_destroy(mlp_engine* e);
 /* Stream `nrows` consecutive rows of A from HOST memory, starting at row0: full rows of n_global doubles (a sharded
  * engine takes its own column slice) ... */

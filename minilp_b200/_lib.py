@@ -81,6 +81,7 @@ SIGNATURES = {
     "mlp_local_group_create": (i32, [i32, C.POINTER(vp)]),
     "mlp_local_group_destroy": (None, [vp]),
     "mlp_engine_local_range": (i32, [vp, pi64, pi64]),
+    "mlp_engine_exchange_kind": (i32, [vp]),
     "mlp_engine_upload_local_rows": (i32, [vp, i64, i64, pd]),
     "mlp_engine_upload_rows": (i32, [vp, i64, i64, pd]),
     "mlp_engine_init_state": (i32, [vp, C.POINTER(InitState)]),

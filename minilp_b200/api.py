@@ -152,6 +152,9 @@ class Engine:
         self.col_begin, self.col_end, self.n_global = b.value, e.value, n_global
         self.n = e.value - b.value
 
+    def exchange_kind(self):
+        return {0: "none", 1: "nccl_allgather", 2: "in_process", 3: "nvlink_peer_memory"}[int(_lib.lib().mlp_engine_exchange_kind(self._e))]
+
     def global_ids(self):
         """GLOBAL variable index of every local variable slot."""
         return np.concatenate([np.arange(self.col_begin, self.col_end), self.n_global + np.arange(self.m)])

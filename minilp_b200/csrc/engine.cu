@@ -272,6 +272,12 @@ struct mlp_engine {
   bool sel_valid = false; // xsend holds the pricing candidate of the CURRENT state (left by k_update_select)
   int64_t ftran_var = -1; // variable whose FTRAN (alpha, |alpha|^2) was queued right behind its selection
   Cand* d_win = nullptr;  // winner header of the last candidate exchange
+  // peer-memory exchange (k_exchange_p2p): own buffer = 2 columns (by exchange parity) + 2 x world mailbox slots
+  bool p2p = false;
+  char* pbuf = nullptr;
+  char* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t pcol_bytes = 0, pbox_off = 0;
+  unsigned long long xseq = 0;
   size_t smem_optin = 48 << 10;
 
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -823,6 +829,69 @@ __global__ void __launch_bounds__(256) k_pick_winner(const char* __restrict__ re
   if (i == 0) {
     if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
     else *win = *reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
+    win->f[4] = err;
+  }
+}
+
+// The same exchange as ONE kernel over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): every
+// rank stores its 64-byte candidate header into a mailbox slot of every peer and raises the slot's sequence flag
+// (system-scope fence in between); every rank then polls its OWN mailbox, arg-reduces the headers, and pulls the
+// winner's column (8 m bytes) straight out of the owner's memory.  Compared with the all-gather it moves one column
+// instead of `world` and has no collective launch latency.  Buffers and mailboxes are double-buffered by exchange
+// parity: a rank can be at most one exchange ahead of a peer, because finishing exchange s needs every peer's flag s.
+struct PeerTable { char* base[8]; };
+constexpr int P2P_SLOT = 128;  // 64 B header + flag, padded
+__global__ void __launch_bounds__(256) k_exchange_p2p(PeerTable pt, int rank, int world, unsigned long long seq, int parity,
+                                                       const Cand* __restrict__ mine, int m, size_t col_bytes, size_t box_off,
+                                                       double* __restrict__ colq, Cand* __restrict__ win) {
+  __shared__ Cand hdr[8];
+  __shared__ int s_best;
+  __shared__ int s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  if (blockIdx.x == 0 && threadIdx.x < world) {  // publish into peer `threadIdx.x`
+    char* slot = pt.base[threadIdx.x] + box_off + ((size_t)parity * world + rank) * P2P_SLOT;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(mine);
+    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(slot);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) dst[q] = src[q];
+    __threadfence_system();
+    dst[8] = seq;
+  }
+  __syncthreads();
+  if (threadIdx.x < world) {  // wait for peer `threadIdx.x`'s header in my own mailbox
+    const char* slot = pt.base[rank] + box_off + ((size_t)parity * world + threadIdx.x) * P2P_SLOT;
+    const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(slot);
+    const long long t0 = clock64();
+    bool ok = true;
+    while (src[8] != seq) {
+      if (clock64() - t0 > 120000000000LL) { ok = false; break; }  // ~60 s: a peer died; report instead of hanging forever
+      __nanosleep(64);
+    }
+    __threadfence_system();
+    unsigned long long* d = reinterpret_cast<unsigned long long*>(&hdr[threadIdx.x]);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d[q] = src[q];
+    if (!ok) s_bad = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int best = -1;
+    for (int r = 0; r < world; ++r) {
+      if (hdr[r].var < 0) continue;
+      if (best < 0 || hdr[r].key > hdr[best].key || (hdr[r].key == hdr[best].key && hdr[r].tie < hdr[best].tie)) best = r;
+    }
+    s_best = s_bad ? -1 : best;
+  }
+  __syncthreads();
+  const int best = s_best;
+  const double* src = best < 0 ? nullptr : reinterpret_cast<const double*>(pt.base[best] + (size_t)parity * col_bytes);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+    colq[i] = best < 0 ? 0.0 : __ldcv(src + i);  // peer memory: never served from a stale cache line
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double err = s_bad ? 2.0 : 0.0;
+    for (int r = 0; r < world; ++r) if (hdr[r].f[4] != 0.0 && err == 0.0) err = 1.0;
+    if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
+    else *win = hdr[best];
     win->f[4] = err;
   }
 }
@@ -1447,6 +1516,7 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   Lane& l0 = e->lane[0];
   // single shard: the candidate's column goes straight into colq and its header is the winner
   double* dst = e->world > 1 ? (double*)(e->xsend + sizeof(Cand)) : e->colq;
+  if (e->world > 1 && e->p2p) dst = (double*)(e->pbuf + (size_t)((e->xseq + 1) & 1) * e->pcol_bytes);  // this exchange's parity
   Cand* win = e->world > 1 ? nullptr : e->d_win;
   if (e->sparse) {
     CU(cudaMemsetAsync(dst, 0, (size_t)m * sizeof(double), e->stream));
@@ -1454,7 +1524,13 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   } else {
     LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend, dst, win);
   }
-  if (e->world > 1) {
+  if (e->world > 1 && e->p2p) {
+    PeerTable pt;
+    for (int r = 0; r < 8; ++r) pt.base[r] = e->peer_base[r];
+    e->xseq += 1;
+    LAUNCH(e, k_exchange_p2p, 64, 256, 0, pt, e->rank, e->world, e->xseq, (int)(e->xseq & 1), (const Cand*)e->xsend, m,
+           e->pcol_bytes, e->pbox_off, e->colq, e->d_win);
+  } else if (e->world > 1) {
     ST(e->comm->allgather(e->xsend, e->xrecv, e->xbytes, e->stream));
     LAUNCH(e, k_pick_winner, cdiv(m, 256), 256, 0, e->xrecv, e->xbytes, e->world, m, e->colq, e->d_win);
   }
@@ -1472,6 +1548,7 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   if (e->prof_on) ST(collect_profile(e, (int)((e->pivot_seq & 1) ^ 1)));  // the previous pivot is complete by now
   e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
   *winner = e->h_cands[0];
+  if (winner->f[4] == 2.0) { set_err("peer-memory exchange timed out: a rank stopped participating"); return MLP_CUDA_ERROR; }
   if (winner->f[4] != 0.0) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   e->colq_var = e->ftran_var = winner->var;
   if (e->spec_var == VAR_PENDING) e->spec_var = winner->var;
@@ -1505,6 +1582,66 @@ static mlp_status se_helper(mlp_engine* e, int64_t var) {
   return MLP_OK;
 }
 
+// Map every rank's exchange buffer into this process (CUDA IPC over NVLink).  All ranks agree on the outcome through an
+// all-gather of their success flags; on any failure everyone keeps the NCCL all-gather path.
+static void setup_p2p(mlp_engine* e, NcclComm* nc) {
+  if (const char* v = getenv("MLP_P2P")) if (atoi(v) == 0) return;
+  if (e->world > 8) return;
+  struct Msg { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+  static_assert(sizeof(Msg) == 128, "Msg layout");
+  const size_t col = ((size_t)e->mld * sizeof(double) + 255) / 256 * 256;
+  const size_t total = 2 * col + 2 * (size_t)e->world * P2P_SLOT;
+  Msg mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.ok = 1;
+  if (cudaMalloc((void**)&e->pbuf, total) != cudaSuccess) { cudaGetLastError(); e->pbuf = nullptr; mine.ok = 0; }
+  if (mine.ok && cudaMemset(e->pbuf, 0, total) != cudaSuccess) mine.ok = 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.h, e->pbuf) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  Msg* d_msgs = nullptr;
+  std::vector<Msg> all((size_t)e->world);
+  bool coll_ok = cudaMalloc((void**)&d_msgs, sizeof(Msg) * (e->world + 1)) == cudaSuccess;
+  if (coll_ok) {
+    cudaMemcpyAsync(d_msgs + e->world, &mine, sizeof(Msg), cudaMemcpyHostToDevice, e->stream);
+    coll_ok = nc->allgather(d_msgs + e->world, d_msgs, sizeof(Msg), e->stream) == MLP_OK;
+    cudaMemcpyAsync(all.data(), d_msgs, sizeof(Msg) * e->world, cudaMemcpyDeviceToHost, e->stream);
+    coll_ok = cudaStreamSynchronize(e->stream) == cudaSuccess && coll_ok;
+    cudaFree(d_msgs);
+  }
+  bool ok = coll_ok;
+  for (int r = 0; ok && r < e->world; ++r) ok = all[(size_t)r].ok != 0;
+  int opened = 1;
+  if (ok) {
+    for (int r = 0; r < e->world; ++r) {
+      if (r == e->rank) { e->peer_base[r] = e->pbuf; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; break; }
+      e->peer_base[r] = (char*)p;
+    }
+  }
+  // second agreement round: did everyone manage to map everyone?
+  int* d_flag = nullptr;
+  std::vector<int> flags((size_t)e->world, 0);
+  int my_flag = ok && opened;
+  if (coll_ok && cudaMalloc((void**)&d_flag, sizeof(int) * (e->world + 1)) == cudaSuccess) {
+    cudaMemcpyAsync(d_flag + e->world, &my_flag, sizeof(int), cudaMemcpyHostToDevice, e->stream);
+    const bool g = nc->allgather(d_flag + e->world, d_flag, sizeof(int), e->stream) == MLP_OK;
+    cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * e->world, cudaMemcpyDeviceToHost, e->stream);
+    const bool s2 = cudaStreamSynchronize(e->stream) == cudaSuccess;
+    cudaFree(d_flag);
+    bool every = g && s2;
+    for (int r = 0; every && r < e->world; ++r) every = flags[(size_t)r] != 0;
+    e->p2p = every;
+  }
+  e->pcol_bytes = col;
+  e->pbox_off = 2 * col;
+  if (!e->p2p) {
+    for (int r = 0; r < 8; ++r) {
+      if (e->peer_base[r] && e->peer_base[r] != e->pbuf) cudaIpcCloseMemHandle(e->peer_base[r]);
+      e->peer_base[r] = nullptr;
+    }
+  }
+}
+
 static void destroy_engine(mlp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
@@ -1516,6 +1653,8 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->work_mb); dev_free(e->colq); dev_free(e->rc); dev_free(e->helper); dev_free(e->list_idx); dev_free(e->list_val);
   dev_free(e->vlist_idx); dev_free(e->vlist_val); dev_free(e->scal); dev_free(e->icnt);
   dev_free(e->xsend); dev_free(e->xrecv); dev_free(e->xred); dev_free(e->d_win);
+  for (int r = 0; r < 8; ++r) if (e->peer_base[r] && e->peer_base[r] != e->pbuf) cudaIpcCloseMemHandle(e->peer_base[r]);
+  dev_free(e->pbuf);
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   dev_free(e->lu_aff); dev_free(e->lu_perm);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
@@ -1751,9 +1890,16 @@ mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_glob
       comm = c;
     } else { set_err("unknown comm kind"); return MLP_INVALID; }
   }
-  return create_engine(device, m, n_global, rank, world, comm, out);
+  ST(create_engine(device, m, n_global, rank, world, comm, out));
+  if (world > 1 && comm_kind == MLP_COMM_NCCL) setup_p2p(*out, (NcclComm*)comm);  // best effort: falls back to the all-gather
+  return MLP_OK;
 }
 void mlp_engine_destroy(mlp_engine* e) { destroy_engine(e); }
+int32_t mlp_engine_exchange_kind(mlp_engine* e) {
+  if (!e || e->world <= 1) return 0;
+  if (e->p2p) return 3;
+  return dynamic_cast<NcclComm*>(e->comm) ? 1 : 2;
+}
 mlp_status mlp_engine_local_range(mlp_engine* e, int64_t* begin, int64_t* end) {
   if (!e) return MLP_INVALID;
   *begin = e->c0;

@@ -28,6 +28,9 @@ def main():
         lp = mb.synth_dense(kind, m, n, seed)
         uid = fresh_uid()
         s = mb.Solver.from_dense(lp, device=local, rank=rank, world=world, comm=uid)
+        kinds = [None] * world
+        dist.all_gather_object(kinds, s.engine.exchange_kind())
+        assert len(set(kinds)) == 1, kinds  # every rank took the same exchange path
         assert s.run()
         ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
         assert ref.continue_solve()
@@ -37,7 +40,7 @@ def main():
         objs = [None] * world
         dist.all_gather_object(objs, s.cur_obj_val)
         assert all(o == objs[0] for o in objs), objs
-        print(f"NCCL_OK rank {rank}/{world} kind {kind}: {s.pivots_done} pivots obj {s.cur_obj_val:.12g}", flush=True)
+        print(f"NCCL_OK rank {rank}/{world} kind {kind} via {kinds[0]}: {s.pivots_done} pivots obj {s.cur_obj_val:.12g}", flush=True)
         s.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -95,8 +95,10 @@ def test_sharded_budgeted_run_stays_in_lockstep():
     assert shards[0]["trace"].shape[0] == 25
 
 
-def test_nccl_two_processes_match_oracle():
-    """One process per GPU over NCCL (the deployment shape); needs two devices."""
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_nccl_two_processes_match_oracle(p2p):
+    """One process per GPU (the deployment shape); needs two devices.  p2p=1: candidate exchange as one kernel
+    over NVLink peer memory; p2p=0: NCCL all-gather."""
     import os
     import subprocess
     import sys
@@ -105,6 +107,7 @@ def test_nccl_two_processes_match_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "_nccl_worker.py")],
-                         capture_output=True, text=True, timeout=600, cwd=root)
+                         capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, MLP_P2P=p2p))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("NCCL_OK") == 6, out.stdout[-3000:] + out.stderr[-3000:]
+    assert ("via nvlink_peer_memory" if p2p == "1" else "via nccl_allgather") in out.stdout, out.stdout[-2000:]
