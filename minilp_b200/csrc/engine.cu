@@ -225,6 +225,18 @@ struct mlp_engine {
   int32_t *csr_idx = nullptr, *csc_idx = nullptr;         // nnz
   double *csr_val = nullptr, *csc_val = nullptr;          // nnz
   std::vector<int64_t> h_csc_ptr;                         // host copy: column counts for LUFactors::nnz
+  int32_t *corevar = nullptr, *corepos = nullptr, *rowcore = nullptr;  // kcap, n, m: see k_ftran_finish_csr
+  int64_t corevar_k = 0;                                  // entries of corevar currently marked in corepos
+  // segment table of the CSC copy (<= CSC_SEG entries of one column per segment) and the core's slice of it
+  int64_t nseg = 0;
+  int32_t* seg_col = nullptr;      // nseg
+  int64_t* seg_off = nullptr;      // nseg
+  int64_t* col_seg = nullptr;      // n+1
+  double* seg_sum = nullptr;       // nseg
+  std::vector<int64_t> h_col_seg;  // host copy
+  int32_t *cseg_id = nullptr, *cseg_first = nullptr;  // core segments (capacity cseg_cap) / kcap+1
+  double* csum[2] = {nullptr, nullptr};                // per lane
+  int64_t cseg_cap = 0, ncseg = 0;
   double *lo = nullptr, *hi = nullptr, *cobj = nullptr;  // ng+m, GLOBAL index, replicated
   double *d = nullptr, *gam = nullptr, *xnb = nullptr;   // n+m, local index
   uint8_t* vflag = nullptr;                               // n+m
@@ -726,29 +738,46 @@ __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* _
   for (int64_t t = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < e; t += (int64_t)gridDim.x * blockDim.x) dst[idx[t]] = val[t];
 }
 // Price-out over the CSC copy (calc_row_coeffs 685-692, update_primal_sq_norms 1117-1132, recalc_obj_coeffs 1216-1222,
-// column norms 297-299): one warp per column gathers the DENSE multiplier vector w at the column's row indices —
-// 12 bytes per stored entry, rows ascending within a column, fixed shuffle tree: bit-reproducible, no atomics.
+// column norms 297-299): gathers the DENSE multiplier vector w at each column's row indices — 12 bytes per stored entry.
+// Column lengths are power-law distributed (one column of a netlib-like LP can hold 10^5 entries), so the unit of work is
+// a SEGMENT of at most CSC_SEG consecutive entries of one column (table built once at creation): pass 1, one warp per
+// segment, rows ascending, fixed shuffle tree; pass 2 adds a column's segment sums in order.  Bit-reproducible, no atomics.
 // MODE 0: out[v] = sum_i A[i,v] w[i] (slack v: w[v-n]; basic v: 0)     MODE 1: out[v] = |a_v|^2 + 1
+constexpr int CSC_SEG = 1024;
 template <int MODE>
-__global__ void __launch_bounds__(256) k_price_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                   const double* __restrict__ val, int64_t n, int64_t m,
-                                                   const double* __restrict__ w, const uint8_t* __restrict__ vflag,
-                                                   double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_price_csc_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                       const double* __restrict__ val, const int32_t* __restrict__ seg_col,
+                                                       const int64_t* __restrict__ seg_off, int64_t nseg,
+                                                       const double* __restrict__ w, const uint8_t* __restrict__ vflag,
+                                                       double* __restrict__ seg_sum) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t v = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); v < n; v += warps) {
-    if (MODE == 0 && (vflag[v] & MLP_BASIC)) { if (lane == 0) out[v] = 0.0; continue; }
-    const int64_t b = ptr[v], e = ptr[v + 1];
+  for (int64_t sg = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); sg < nseg; sg += warps) {
+    const int v = seg_col[sg];
     double acc = 0.0;
-    for (int64_t t = b + lane; t < e; t += 32) {
-      const double a = __ldcs(val + t);
-      acc += (MODE == 0) ? a * w[__ldcs(idx + t)] : a * a;
+    if (MODE == 1 || !(vflag[v] & MLP_BASIC)) {
+      const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
+      for (int64_t t = b + lane; t < e; t += 32) {
+        const double a = __ldcs(val + t);
+        acc += (MODE == 0) ? a * w[__ldcs(idx + t)] : a * a;
+      }
+      acc = warp_sum(acc);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) out[v] = (MODE == 1) ? acc + 1.0 : acc;
+    if (lane == 0) seg_sum[sg] = acc;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x)
-    out[n + i] = (MODE == 1) ? 2.0 : ((vflag[n + i] & MLP_BASIC) ? 0.0 : w[i]);
+}
+template <int MODE>
+__global__ void __launch_bounds__(256) k_price_csc_fin(const int64_t* __restrict__ col_seg, const double* __restrict__ seg_sum,
+                                                       int64_t n, int64_t m, const double* __restrict__ w,
+                                                       const uint8_t* __restrict__ vflag, double* __restrict__ out) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) {
+    double t = 0.0;
+    for (int64_t sg = col_seg[v]; sg < col_seg[v + 1]; ++sg) t += seg_sum[sg];
+    out[v] = (MODE == 1) ? t + 1.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : t);
+  } else if (v < n + m) {
+    out[v] = (MODE == 1) ? 2.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : w[v - n]);
+  }
 }
 // rows of A x_N over the CSR copy (solver.rs:234-238): one warp per row
 __global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
@@ -761,6 +790,79 @@ __global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__
   for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) acc += val[t] * xnb[idx[t]];
   acc = warp_sum(acc);
   if (lane == 0) out[r] = acc;
+}
+
+// The three places where the basis machinery touches the basic structural columns, read from the sparse matrix itself
+// instead of a dense m x k column cache (12 bytes per stored entry instead of 8 m k):
+//   corevar[t]  structural variable of core column t        corepos[v]  core column of variable v, or -1
+//   rowcore[i]  core row of constraint row i (i in R), or -1
+// FTRAN tail: alpha[cov_i] = a_i - sum_{j in row i, j in the core} A[i,j] x[corepos[j]]  (warp per CSR row)
+__global__ void __launch_bounds__(256) k_ftran_finish_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                          const double* __restrict__ val, int m, int k,
+                                                          const double* __restrict__ xk, const double* __restrict__ rhs0,
+                                                          const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
+                                                          const int32_t* __restrict__ corepos, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt < k) out[Jpos[gt]] = xk[gt];
+  const int64_t i = gt >> 5;
+  if (i >= m) return;
+  const int cov = rowcover[i];
+  if (cov < 0) return;
+  double acc = 0.0;
+  for (int64_t t = ptr[i] + lane; t < ptr[i + 1]; t += 32) {
+    const int c = corepos[idx[t]];
+    if (c >= 0) acc += val[t] * xk[c];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[cov] = rhs0[i] - acc;
+}
+// BTRAN core right-hand side: x[t] = c[Jpos[t]] - sum_i A[i, corevar[t]] cov[i], over the segments of the core columns
+// (cseg_id[j] = global segment, cseg_first[t] = first entry of core column t in that list; built at each refactorization)
+__global__ void __launch_bounds__(256) k_core_rhs_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                      const double* __restrict__ val, const int32_t* __restrict__ seg_col,
+                                                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
+                                                      int ncseg, const double* __restrict__ cov, double* __restrict__ csum) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= ncseg) return;
+  const int64_t sg = cseg_id[j];
+  const int v = seg_col[sg];
+  const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
+  double acc = 0.0;
+  for (int64_t q = b + lane; q < e; q += 32) acc += val[q] * cov[idx[q]];
+  acc = warp_sum(acc);
+  if (lane == 0) csum[j] = acc;
+}
+__global__ void k_core_rhs_fin(const double* __restrict__ csum, const int32_t* __restrict__ cseg_first, int k,
+                               const double* __restrict__ c, const int32_t* __restrict__ Jpos, double* __restrict__ x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= k) return;
+  double tsum = 0.0;
+  for (int j = cseg_first[t]; j < cseg_first[t + 1]; ++j) tsum += csum[j];
+  x[t] = c[Jpos[t]] - tsum;
+}
+// core C = D[R,:]: scatter the stored entries of each core column that fall into core rows (C zero-filled before)
+__global__ void __launch_bounds__(256) k_extract_core_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                          const double* __restrict__ val, const int32_t* __restrict__ seg_col,
+                                                          const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
+                                                          int ncseg, const int32_t* __restrict__ corepos,
+                                                          const int32_t* __restrict__ rowcore, double* __restrict__ C, int64_t ld) {
+  const int lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= ncseg) return;
+  const int64_t sg = cseg_id[j];
+  const int v = seg_col[sg];
+  const int t = corepos[v];
+  const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
+  for (int64_t q = b + lane; q < e; q += 32) {
+    const int r = rowcore[idx[q]];
+    if (r >= 0) C[(int64_t)t * ld + r] = val[q];
+  }
+}
+__global__ void k_set_corepos(int32_t* __restrict__ corepos, const int32_t* __restrict__ corevar, int k, int clear) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < k) corepos[corevar[t]] = clear ? -1 : t;
 }
 
 // ------------------------------------------------------------------------------------------------ K1 pricing scan
@@ -1268,8 +1370,10 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   if (prof) CU(cudaEventRecord(e->pev[prof_slot][par][0], ln.st));
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
-    LAUNCHS(e, ln.st, k_price_csc<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, e->m, slack_vals,
-            e->vflag, out);
+    double* ssum = &ln == &e->lane[0] ? e->seg_sum : e->seg_sum + e->nseg;
+    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->nseg,
+            slack_vals, e->vflag, ssum);
+    LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, slack_vals, e->vflag, out);
   } else {
     if (e->price_tma)
       LAUNCHS(e, ln.st, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count,
@@ -1338,7 +1442,10 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
   const int Gk = tall_groups(e, m, k);
-  if (Gk > 1) {
+  if (e->sparse) {
+    LAUNCHS(e, ln.st, k_ftran_finish_csr, cdiv(std::max<int64_t>((int64_t)m * 32, k), 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val,
+            m, k, ln.xk, rhs0, e->rowcover, e->Jpos, e->corepos, out);
+  } else if (Gk > 1) {
     LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), Gk), 256, 0, e->Bcols, e->mld, m, k, ln.xk, e->Jslot, e->rowcover, ln.gpart, e->mld);
     LAUNCHS(e, ln.st, k_ftran_finish_parts, cdiv(std::max(m, k), 256), 256, 0, ln.gpart, Gk, e->mld, m, k, ln.xk, rhs0, e->rowcover,
             e->Jpos, out);
@@ -1370,9 +1477,16 @@ static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double
   }
   LAUNCHS(e, ln.st, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, ln.wm);
   if (k > 0) {
-    const int S = gemv_split(e, m, k);
-    LAUNCHS(e, ln.st, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->mld, m, k, e->Jslot, ln.wm, ln.gt_part_k);
-    LAUNCHS(e, ln.st, k_gemv_t_fin, cdiv(k, 256), 256, 0, ln.gt_part_k, S, k, c, e->Jpos, ln.xk, 1);
+    if (e->sparse) {
+      double* cs = e->csum[&ln == &e->lane[0] ? 0 : 1];
+      LAUNCHS(e, ln.st, k_core_rhs_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
+              (int)e->ncseg, ln.wm, cs);
+      LAUNCHS(e, ln.st, k_core_rhs_fin, cdiv(k, 256), 256, 0, cs, e->cseg_first, k, c, e->Jpos, ln.xk);
+    } else {
+      const int S = gemv_split(e, m, k);
+      LAUNCHS(e, ln.st, k_core_rhs_part, dim3((unsigned)k, (unsigned)S), 256, 0, e->Bcols, e->mld, m, k, e->Jslot, ln.wm, ln.gt_part_k);
+      LAUNCHS(e, ln.st, k_gemv_t_fin, cdiv(k, 256), 256, 0, ln.gt_part_k, S, k, c, e->Jpos, ln.xk, 1);
+    }
     // y = L^-T U^-T rhs (lu_factors_transp, lu.rs:108-115) = (C^-1)^T rhs, scattered to the core's constraint rows
     LAUNCHS(e, ln.st, k_mv_t<false>, cdiv(k, 8), 256, 0, e->Cinv, e->kcap, k, ln.xk, e->Rp, out);
   }
@@ -1388,8 +1502,8 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
   if (exact) cap = k;        // clone: same leading dimensions as the source
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   double* nb = nullptr;
-  ST(dev_alloc(&nb, (size_t)e->mld * cap));
-  if (e->Bcols && e->kcap > 0) {
+  ST(dev_alloc(&nb, e->sparse ? 1 : (size_t)e->mld * cap));  // sparse storage reads the basic columns from the matrix itself
+  if (!e->sparse && e->Bcols && e->kcap > 0) {
     CU(cudaMemcpyAsync(nb, e->Bcols, (size_t)e->mld * e->kcap * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
   }
@@ -1397,6 +1511,15 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
   dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   dev_free(e->lu_aff); dev_free(e->lu_perm);
   ST(dev_alloc(&e->lu_aff, 192)); ST(dev_alloc(&e->lu_perm, cap));
+  if (e->sparse) {
+    if (e->corevar_k > 0) {  // un-mark with the old list before it is freed
+      LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
+      CU(cudaStreamSynchronize(e->stream));
+      e->corevar_k = 0;
+    }
+    dev_free(e->corevar); dev_free(e->cseg_first);
+    ST(dev_alloc(&e->corevar, cap)); ST(dev_alloc(&e->cseg_first, cap + 1));
+  }
   e->Bcols = nb;
   e->kcap = cap;
   ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jslot, cap)); ST(dev_alloc(&e->Rp, cap));
@@ -1429,12 +1552,13 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = fal
 // BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.
 static mlp_status refactor_impl(mlp_engine* e) {
   const int64_t m = e->m, ng = e->ng;
-  std::vector<int32_t> jpos, jslot, rowcover(m, -1), R;
+  std::vector<int32_t> jpos, jslot, jvar, rowcover(m, -1), R;
   for (int64_t p = 0; p < m; ++p) {
     const int64_t v = e->h_bvar[p];
     if (v < ng) {
       jpos.push_back((int32_t)p);
-      if (e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
+      jvar.push_back((int32_t)v);
+      if (!e->sparse && e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
       jslot.push_back(e->h_slot_of_row[p]);
     } else rowcover[v - ng] = (int32_t)p;
   }
@@ -1458,8 +1582,39 @@ static mlp_status refactor_impl(mlp_engine* e) {
     ST(h2d(e, e->Jpos, jpos.data(), k * sizeof(int32_t)));
     ST(h2d(e, e->Jslot, jslot.data(), k * sizeof(int32_t)));
     ST(h2d(e, e->Rp, R.data(), k * sizeof(int32_t)));
+    std::vector<int32_t> rowcore;
+    if (e->sparse) {
+      if (e->corevar_k > 0) LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
+      ST(h2d(e, e->corevar, jvar.data(), k * sizeof(int32_t)));
+      LAUNCH(e, k_set_corepos, cdiv(k, 256), 256, 0, e->corepos, e->corevar, (int)k, 0);
+      e->corevar_k = k;
+      rowcore.assign(m, -1);
+      for (int64_t i = 0; i < k; ++i) rowcore[R[i]] = (int32_t)i;
+      ST(h2d(e, e->rowcore, rowcore.data(), m * sizeof(int32_t)));
+      // the core's segments
+      std::vector<int32_t> cid, cfirst((size_t)k + 1, 0);
+      for (int64_t t = 0; t < k; ++t) {
+        cfirst[t] = (int32_t)cid.size();
+        for (int64_t sg = e->h_col_seg[jvar[t]]; sg < e->h_col_seg[jvar[t] + 1]; ++sg) cid.push_back((int32_t)sg);
+      }
+      cfirst[k] = (int32_t)cid.size();
+      e->ncseg = (int64_t)cid.size();
+      if (e->ncseg > e->cseg_cap) {
+        dev_free(e->cseg_id); dev_free(e->csum[0]); dev_free(e->csum[1]);
+        e->cseg_cap = std::max<int64_t>(2 * e->ncseg, 4096);
+        ST(dev_alloc(&e->cseg_id, e->cseg_cap)); ST(dev_alloc(&e->csum[0], e->cseg_cap)); ST(dev_alloc(&e->csum[1], e->cseg_cap));
+      }
+      ST(h2d(e, e->cseg_id, cid.data(), cid.size() * sizeof(int32_t)));
+      ST(h2d(e, e->cseg_first, cfirst.data(), cfirst.size() * sizeof(int32_t)));
+      CU(cudaStreamSynchronize(e->stream));
+    }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
-    LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
+    if (e->sparse) {
+      CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
+      LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
+             (int)e->ncseg, e->corepos, e->rowcore, e->LUc, e->kcap);
+    } else
+      LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
     int* flags = e->d_res->flags;
     for (int j0 = 0; j0 < (int)k;) {
       const int rows = (int)k - j0;
@@ -1485,6 +1640,10 @@ static mlp_status refactor_impl(mlp_engine* e) {
     ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
   } else {
+    if (e->sparse && e->corevar_k > 0) {
+      LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
+      e->corevar_k = 0;
+    }
     CU(cudaStreamSynchronize(e->stream));
   }
   // LUFactors::nnz (lu.rs:52-54) of the reference's factors of this basis: every stored entry of the k structural basic
@@ -1647,6 +1806,9 @@ static void destroy_engine(mlp_engine* e) {
   cudaSetDevice(e->device);
   for (int l = 0; l < 2; ++l) if (e->lane[l].st) cudaStreamSynchronize(e->lane[l].st);
   dev_free(e->csr_ptr); dev_free(e->csc_ptr); dev_free(e->csr_idx); dev_free(e->csc_idx); dev_free(e->csr_val); dev_free(e->csc_val);
+  dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
+  dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
+  dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
   dev_free(e->rhs); dev_free(e->alpha); dev_free(e->rho); dev_free(e->tau); dev_free(e->vvec); dev_free(e->work_m);
@@ -1856,6 +2018,25 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
   auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
   A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
   A(dev_alloc(&e->csc_ptr, n + 1)); A(dev_alloc(&e->csc_idx, nnz)); A(dev_alloc(&e->csc_val, nnz));
+  A(dev_alloc(&e->corepos, n)); A(dev_alloc(&e->rowcore, m));
+  std::vector<int32_t> sgc;
+  std::vector<int64_t> sgo, cseg((size_t)n + 1, 0);
+  for (int64_t j = 0; j < n; ++j) {
+    cseg[j] = (int64_t)sgc.size();
+    int64_t b = cptr[j];
+    do { sgc.push_back((int32_t)j); sgo.push_back(b); b += CSC_SEG; } while (b < cptr[j + 1]);  // an empty column keeps one empty segment
+  }
+  cseg[n] = (int64_t)sgc.size();
+  e->nseg = (int64_t)sgc.size();
+  e->h_col_seg = cseg;
+  A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg)); A(dev_alloc(&e->col_seg, n + 1));
+  A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
+  if (st == MLP_OK) {
+    A(h2d(e, e->seg_col, sgc.data(), e->nseg * sizeof(int32_t)));
+    A(h2d(e, e->seg_off, sgo.data(), e->nseg * sizeof(int64_t)));
+    A(h2d(e, e->col_seg, cseg.data(), (n + 1) * sizeof(int64_t)));
+  }
+  if (st == MLP_OK && cudaMemsetAsync(e->corepos, 0xff, n * sizeof(int32_t), e->stream) != cudaSuccess) st = MLP_CUDA_ERROR;
   if (st == MLP_OK) {
     A(h2d(e, e->csr_ptr, row_ptr, (m + 1) * sizeof(int64_t)));
     A(h2d(e, e->csr_idx, col_idx, nnz * sizeof(int32_t)));
@@ -1987,8 +2168,11 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   if (e->enable_pse && !st->primal_edge_sq_norms) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
     if (e->sparse)
-      LAUNCH(e, k_price_csc<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, n, m, (const double*)nullptr, e->vflag,
-             e->gam);
+    {
+      LAUNCH(e, k_price_csc_seg<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->nseg,
+             (const double*)nullptr, e->vflag, e->seg_sum);
+      LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, (const double*)nullptr, e->vflag, e->gam);
+    }
     else {
     LAUNCH(e, k_price_partial<1>, price_grid(e), PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
            (const int32_t*)nullptr, (int32_t)m, e->lane[0].partial);
@@ -2011,7 +2195,8 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
       ST(fetch_column(e, e->h_bvar[r]));
       const int32_t slot = e->h_free_slots.back();
       e->h_free_slots.pop_back();
-      CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+      if (!e->sparse)
+        CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
       e->h_slot_of_row[r] = slot;
     }
   }
@@ -2247,7 +2432,8 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     }
     const int32_t slot = e->h_free_slots.back();
     e->h_free_slots.pop_back();
-    CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
+    if (!e->sparse)
+      CU(cudaMemcpyAsync(e->Bcols + (size_t)slot * e->mld, e->colq, (size_t)m * 8, cudaMemcpyDeviceToDevice, e->stream));
     e->h_slot_of_row[row] = slot;
   }
   e->h_bvar[row] = q;
@@ -2387,7 +2573,7 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
 mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   if (!src || !out || !src->initialized) return MLP_INVALID;
   *out = nullptr;
-  if (src->world != 1) { set_err("clone: single-shard engines only"); return MLP_INVALID; }
+  if (src->world != 1 || src->sparse) { set_err("clone: dense single-shard engines only"); return MLP_INVALID; }
   CU(cudaSetDevice(src->device));
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(src->lane[l].st));
   mlp_engine* e = nullptr;
