@@ -277,7 +277,8 @@ def run_ours(a):
         dist.destroy_process_group()
         return
     roofline = {
-        "bound": "hbm", "kernel": "k_price_partial<0> + k_price_finish (N^T v of update_primal_sq_norms, solver.rs:1117-1132)",
+        "bound": "hbm", "kernel": "k_price_partial_tma (bulk-copy ring; chunk partials reduced inside k_update_select): N^T v of "
+                                   "update_primal_sq_norms, solver.rs:1117-1132",
         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(a, nloc),
         "peak_source": peak_src, "launches_timed": prof["price_v_launches"],
         "avg_launch_ms": prof["price_v_ms"] / nv, "algorithmic_bytes_per_launch": prof["price_v_bytes"] / nv,
@@ -299,12 +300,17 @@ def run_ours(a):
                    "pivots_before_timed_region": p0, "optimal_reached": bool(done),
                    "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
                    "refactors_in_region": c1["refactors"] - c0["refactors"], "setup": setup,
-                   "objective_after": s.cur_obj_val},
+                   "objective_after": s.cur_obj_val,
+                   "engine_switches": {k: os.environ[k] for k in ("MLP_FUSED", "MLP_FUSED_MAX", "MLP_LANE1_LDG", "MLP_OVERLAP",
+                                                                  "MLP_PRICE_TMA", "MLP_P2P") if k in os.environ}},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT,
                 "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),
                 "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(steps, 1),
-                "wall_s": wall, "refactor_wall_s": refac_s},
+                "wall_s": wall, "refactor_wall_s": refac_s,
+                # the same pivots with the one-time upload of A (pinned host -> HBM, before the loop) charged to them
+                "value_incl_matrix_upload": steps / (wall + setup["h2d_upload_s"]),
+                "matrix_upload_bytes": setup["h2d_upload_bytes"]},
         "gpu_launches": (c1["kernel_launches"] - c0["kernel_launches"]) * world,
         "roofline": roofline,
     }

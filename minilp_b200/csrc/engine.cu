@@ -64,6 +64,7 @@ struct Cand {
 static_assert(sizeof(Cand) == 64, "Cand must be 64 bytes");
 
 #include "kernels_common.cuh"
+#include "chain_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------ communicators
 // The pivot path has ONE real exchange step per pivot: the arg-reduce of the per-shard pricing
@@ -270,6 +271,14 @@ struct mlp_engine {
   int64_t K = 0, Kcap = 0;
   double *E = nullptr, *Ginv = nullptr, *gK = nullptr;  // eta columns m x Kcap; (I+G)^-1 Kcap x Kcap; coupling row of the newest eta
   int32_t *etaR = nullptr, *etaPrev = nullptr, *etaHead = nullptr;
+  int32_t* etaLast = nullptr;  // mld: index of the newest eta whose leaving row is r, -1 if none (head of k_eta_scatter's chain)
+  // fused FTRAN -> BTRAN chain (chain_fused.cuh)
+  int fused = 1;               // MLP_FUSED=0: separate kernels
+  int fused_max = FZ_MAX;      // largest k / K that takes the fused chain (MLP_FUSED_MAX lowers it: tests of the hand-over)
+  double* fz_scratch = nullptr;
+  int32_t* fz_cta_cnt = nullptr;
+  double* fz_cta_ss = nullptr;
+  unsigned* fz_bar = nullptr;
   int64_t lu_nnz = 0;
 
   // lane synchronisation (see "host side")
@@ -277,6 +286,7 @@ struct mlp_engine {
   int async_pivot = 1;  // MLP_ASYNC_PIVOT=0: mlp_pivot always waits for the device
   int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
   int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE)
+  int lane1_ldg = 1;    // lane 1 prices out with the LDG kernel while lane 0 runs the bulk-copy one (MLP_LANE1_LDG=0: both bulk-copy)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
   cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr, ev_win = nullptr;
@@ -898,7 +908,7 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
   b = block_argmax(b, smk, smi);
   if (threadIdx.x == 0) {
     *counter = 0;
-    out->f[4] = (double)flags[0];
+    out->f[4] = flags[2] ? 2.0 : (double)flags[0];
     if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
     else {
       const long long v = b.idx & 0xffffffffLL;
@@ -1075,7 +1085,7 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
   b = block_argmax(b, smk, smi);
   if (threadIdx.x == 0) {
     *counter = 0;
-    out->f[4] = (double)flags[0];
+    out->f[4] = flags[2] ? 2.0 : (double)flags[0];
     if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
     else {
       const long long g = b.idx;
@@ -1226,7 +1236,7 @@ __global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restr
     const int nf = *((volatile int*)flags);
     res->flags[0] = nf;
     res->flags[1] = flags[1];
-    out->f[4] = (double)nf;
+    out->f[4] = flags[2] ? 2.0 : (double)nf;
     if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
     else {
       const long long vv = b.idx & 0xffffffffLL;
@@ -1375,11 +1385,17 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
             slack_vals, e->vflag, ssum);
     LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, slack_vals, e->vflag, out);
   } else {
-    if (e->price_tma)
+    // Lane 1 (the tableau-row price-out, support <= k+1 rows) runs BESIDE lane 0's dense N^T v price-out.  The bulk-copy
+    // kernel holds 194 KB of shared memory per SM, so a second instance cannot become resident until the first one has
+    // finished (measured: the rho price-out waited 2.6 ms per pivot, and with it the whole tail of lane 1).  The LDG form
+    // needs no shared-memory ring and slips in next to it; its partial sums are bit-identical.
+    const bool beside = e->overlap && e->lane1_ldg && e->enable_pse && &ln == &e->lane[1];  // pse: lane 0 is pricing out too
+    if (e->price_tma && !beside)
       LAUNCHS(e, ln.st, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count,
               ln.partial, e->price_tile);
     else
-      LAUNCHS(e, ln.st, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts, count_ptr, fixed_count, ln.partial);
+      LAUNCHS(e, ln.st, k_price_partial<0>, beside ? e->sm_count * 2 : price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts,
+              count_ptr, fixed_count, ln.partial);
     // finish == false: the chunk partials are reduced by the consumer (k_update_select) instead
     if (finish)
       LAUNCHS(e, ln.st, k_price_finish, cdiv(e->nt, 256), 256, 0, ln.partial, count_ptr, fixed_count, e->lda, e->n, e->m,
@@ -1576,6 +1592,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
   e->k = k;
   e->K = 0;
   CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
+  CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)e->mld * sizeof(int32_t), e->stream));  // eta file is empty: no chains
   std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
   ST(h2d(e, e->rowcover, rowcover.data(), m * sizeof(int32_t)));
   if (k > 0) {
@@ -1667,6 +1684,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
 // reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
 static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out);
 static mlp_status se_helper(mlp_engine* e, int64_t var);
+static bool chain_fusable(const mlp_engine* e);
+static mlp_status chain_fused(mlp_engine* e, int64_t var);
 static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq);
 static constexpr int64_t VAR_PENDING = -2;
 
@@ -1697,17 +1716,20 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   CU(cudaEventRecord(e->ev_win, e->stream));
   // Both callers continue with calc_col_coeffs of the winner (solver.rs:750, 532): queue that FTRAN — and, with primal
   // steepest edge, the v / N^T v chain — now, before the host has even seen which variable won.
-  ST(ftran(e, l0, e->colq, e->alpha));
-  compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
-  ST(mark0(e));
   e->spec_var = -1;
-  if (e->enable_pse && e->overlap) ST(se_helper(e, VAR_PENDING));
+  if (chain_fusable(e)) ST(chain_fused(e, VAR_PENDING));
+  else {
+    ST(ftran(e, l0, e->colq, e->alpha));
+    compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+    ST(mark0(e));
+    if (e->enable_pse && e->overlap) ST(se_helper(e, VAR_PENDING));
+  }
   e->alpha_nnz_host = -1;
   CU(cudaEventSynchronize(e->ev_win));  // the header only, not the chain queued behind it
   if (e->prof_on) ST(collect_profile(e, (int)((e->pivot_seq & 1) ^ 1)));  // the previous pivot is complete by now
   e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
   *winner = e->h_cands[0];
-  if (winner->f[4] == 2.0) { set_err("peer-memory exchange timed out: a rank stopped participating"); return MLP_CUDA_ERROR; }
+  if (winner->f[4] == 2.0) { set_err("device-side rendezvous timed out (peer-memory exchange: a rank stopped participating; or a grid barrier of the fused chain)"); return MLP_CUDA_ERROR; }
   if (winner->f[4] != 0.0) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   e->colq_var = e->ftran_var = winner->var;
   if (e->spec_var == VAR_PENDING) e->spec_var = winner->var;
@@ -1736,6 +1758,51 @@ static mlp_status se_helper(mlp_engine* e, int64_t var) {
   ST(btran(e, l0, e->work_m, -1, e->vvec));
   CU(cudaEventRecord(e->ev_vbtran, l0.st));
   compact(e, l0, e->vvec, e->vlist_idx, e->vlist_val, e->icnt + 2, e->scal + 3);
+  ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper, 1, false));
+  e->spec_var = var;
+  return MLP_OK;
+}
+
+// The same chain as ftran + compact + se_helper, as one cooperative launch (chain_fused.cuh) followed by the price-out.
+static bool chain_fusable(const mlp_engine* e) {
+  return e->fused && !e->sparse && e->enable_pse && e->overlap && e->k <= e->fused_max && e->K <= e->fused_max;
+}
+static int fz_slices(const mlp_engine* e, int cols) {
+  // about two (column, slice) units per warp of the grid; a slice keeps >= 512 rows.  Depends only on m, cols and the SM
+  // count, so every shard of a column-sharded engine reduces in the same order.
+  const int64_t W = (int64_t)e->sm_count * FZ_WARPS;
+  const int want = cdiv(2 * W, std::max(cols, 1));
+  const int cap = (int)std::max<int64_t>(1, std::min<int64_t>(FZ_MAXS, e->m / 512));
+  return std::max(1, std::min(want, cap));
+}
+static mlp_status chain_fused(mlp_engine* e, int64_t var) {
+  Lane& l0 = e->lane[0];
+  ChainArgs a;
+  a.m = (int)e->m; a.k = (int)e->k; a.K = (int)e->K;
+  a.S_k = fz_slices(e, a.k); a.S_K = fz_slices(e, a.K);
+  a.mld = e->mld; a.kcap = e->kcap; a.Kcap = e->Kcap;
+  a.Cinv = e->Cinv; a.Ginv = e->Ginv; a.Bcols = e->Bcols; a.E = e->E; a.colq = e->colq;
+  a.Rp = e->Rp; a.Jpos = e->Jpos; a.Jslot = e->Jslot; a.rowcover = e->rowcover;
+  a.etaR = e->etaR; a.etaPrev = e->etaPrev; a.etaLast = e->etaLast;
+  a.alpha = e->alpha; a.vvec = e->vvec; a.cov = l0.wm;
+  double* z = e->fz_scratch;
+  a.px = z; z += FZ_G * FZ_MAX;
+  a.pt = z; z += FZ_G * FZ_MAX;
+  a.pu = z; z += FZ_MAXS * FZ_MAX;
+  a.pr = z; z += FZ_MAXS * FZ_MAX;
+  a.uK = z; z += FZ_MAX;
+  a.sK = z; z += FZ_MAX;
+  a.rk = z;
+  a.cta_cnt = e->fz_cta_cnt; a.cta_ss = e->fz_cta_ss;
+  a.seg_cnt = l0.seg_cnt; a.seg_ss = l0.seg_ss;
+  a.vidx = e->vlist_idx; a.vval = e->vlist_val;
+  a.icnt = e->icnt; a.scal = e->scal;
+  a.bar = e->fz_bar; a.flags = e->d_res->flags;
+  void* args[] = {&a};
+  CU(cudaLaunchCooperativeKernel((const void*)k_chain_primal, dim3((unsigned)e->sm_count), dim3(FZ_T), args, 0, l0.st));
+  e->cnt.kernel_launches += 1;
+  ST(mark0(e));                              // alpha_q, nnz(alpha_q), |alpha_q|^2 are final: lane 1 may start the ratio test
+  CU(cudaEventRecord(e->ev_vbtran, l0.st));  // ... and the eta file has been read for the last time
   ST(price_list(e, l0, e->vlist_idx, e->vlist_val, e->icnt + 2, 0, e->vvec, e->helper, 1, false));
   e->spec_var = var;
   return MLP_OK;
@@ -1820,6 +1887,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   dev_free(e->lu_aff); dev_free(e->lu_perm);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
+  dev_free(e->etaLast); dev_free(e->fz_scratch); dev_free(e->fz_cta_cnt); dev_free(e->fz_cta_ss); dev_free(e->fz_bar);
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
     dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.wm); dev_free(ln.gpart); dev_free(ln.gt_part_k);
@@ -1872,6 +1940,16 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   if (const char* v = getenv("MLP_ASYNC_PIVOT")) e->async_pivot = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("MLP_PRICE_TMA")) e->price_tma = atoi(v) != 0;
+  if (const char* v = getenv("MLP_LANE1_LDG")) e->lane1_ldg = atoi(v) != 0;
+  if (const char* v = getenv("MLP_FUSED")) e->fused = atoi(v) != 0;
+  if (const char* v = getenv("MLP_FUSED_MAX")) e->fused_max = std::max(0, std::min(FZ_MAX, atoi(v)));
+  {  // the fused chain needs a cooperative launch of one CTA per SM
+    int nb = 0;
+    if (!prop.cooperativeLaunch || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_chain_primal, FZ_T, 0) != cudaSuccess || nb < 1) {
+      cudaGetLastError();
+      e->fused = 0;
+    }
+  }
   e->price_tile = price_tile_cols(e->lda, e->sm_count);
   if (const char* v = getenv("MLP_PRICE_TILE")) { const int t = atoi(v); if (t == 128 || t == 256 || t == 512) e->price_tile = t; }
   CU(cudaFuncSetAttribute(k_price_partial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
@@ -1916,6 +1994,9 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   }
   e->d_res = e->lane[0].d_res;
   A(dev_alloc(&e->rowcover, ml));
+  A(dev_alloc(&e->etaLast, ml));
+  A(dev_alloc(&e->fz_scratch, (size_t)(2 * FZ_G + 2 * FZ_MAXS + 3) * FZ_MAX));
+  A(dev_alloc(&e->fz_cta_cnt, (size_t)e->sm_count)); A(dev_alloc(&e->fz_cta_ss, (size_t)e->sm_count)); A(dev_alloc(&e->fz_bar, 4));
   e->xbytes = sizeof(Cand) + (size_t)ml * sizeof(double);
   A(dev_alloc(&e->d_win, 1));
   A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * ml + 64));
@@ -1936,6 +2017,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
     CU(cudaMemsetAsync(e->lane[l].red_counter, 0, 4 * sizeof(unsigned), e->stream));
     CU(cudaMemsetAsync(e->lane[l].d_res, 0, sizeof(DevRes), e->stream));
   }
+  CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)ml * sizeof(int32_t), e->stream));
+  CU(cudaMemsetAsync(e->fz_bar, 0, 4 * sizeof(unsigned), e->stream));
   CU(cudaMemsetAsync(e->gam, 0, ntc * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->helper, 0, ntc * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->rc, 0, ntc * sizeof(double), e->stream));
@@ -2254,11 +2337,12 @@ mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   e->ftran_var = -1;
   e->alpha_nnz_host = -1;
   ST(fetch_column(e, var));
+  e->spec_var = -1;
+  if (chain_fusable(e)) return chain_fused(e, var);
   ST(ftran(e, l0, e->colq, e->alpha));
   // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
   compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
   ST(mark0(e));
-  e->spec_var = -1;
   if (e->enable_pse && e->overlap) ST(se_helper(e, var));  // runs ahead of the ratio test on lane 0
   return MLP_OK;
 }
@@ -2402,7 +2486,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (!do_refactor) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
-    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, prev);
+    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
     LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
     e->h_last_eta_of_row[row] = K;
     e->K += 1;
@@ -2617,6 +2701,7 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
     const size_t Kc = (size_t)src->Kcap;
     cp(e->E, src->E, ml * (size_t)src->K * 8); cp(e->Ginv, src->Ginv, Kc * Kc * 8);
     cp(e->etaR, src->etaR, Kc * 4); cp(e->etaPrev, src->etaPrev, Kc * 4); cp(e->etaHead, src->etaHead, Kc * 4);
+    cp(e->etaLast, src->etaLast, ml * 4);
   }
   if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("clone: copy failed"); st = MLP_CUDA_ERROR; }
   if (st != MLP_OK) { destroy_engine(e); return st; }

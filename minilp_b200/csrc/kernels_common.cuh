@@ -686,13 +686,14 @@ __global__ void __launch_bounds__(256) k_select_row_dual(const double* __restric
 // Coupling row of a new eta K: g[j] = E_j[r_K] (j < K), a strided gather of row r_K of E, plus the per-row chains used by
 // k_eta_scatter — see DESIGN.md "eta chain in closed form".
 __global__ void k_eta_grow(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ g,
-                           int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int prev) {
+                           int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int32_t* etaLast, int prev) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < K) g[j] = E[(int64_t)j * lde + rK];
   if (j == 0) {
     etaR[K] = rK;
     etaPrev[K] = prev;
     etaHead[K] = 1;
+    etaLast[rK] = K;
     if (prev >= 0) etaHead[prev] = 0;
   }
 }

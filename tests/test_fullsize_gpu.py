@@ -1,0 +1,114 @@
+"""BASELINE config 3 at FULL size (50 000 x 50 000 dense, 20 GB of A in HBM): the oracle cannot run here in seconds, so
+the engine is checked through size-independent properties of the revised simplex method:
+
+  * B^-1 is one matrix: the pivot element computed column-wise (FTRAN, alpha_q[r]) equals the one computed row-wise
+    (BTRAN + price-out, row_coeffs[q]) — solver.rs:671-677 vs 680-693;
+  * the basic solution satisfies  A x + s = rhs  (try_new's invariant, solver.rs:234-238, kept by every pivot 1049-1055);
+  * the objective the pivots accumulate (solver.rs:1027) equals c.x recomputed from the solution, and never increases
+    over primal pivots;
+  * refactorization (BasisSolver::reset, 1286-1303) does not change B^-1 a_q;
+  * the run is reproducible bit for bit.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import minilp_b200 as mb
+
+pytestmark = pytest.mark.gpu
+
+M = N = 50000
+KIND, SEED = 0, 1
+PIVOTS = 40
+
+
+def _enough_memory():
+    try:
+        import torch
+        free, _ = torch.cuda.mem_get_info(0)
+        return free > 30 * (1 << 30)
+    except Exception:
+        return False
+
+
+def build(m, n, kind, seed):
+    d, obj, mins, maxs, ops, rhs = mb.synth_vectors(kind, m, n, seed)
+    s = mb.Solver(m, n)
+    threads = os.cpu_count() or 1
+    step = max(1, (256 << 20) // (8 * n))
+    for r0 in range(0, m, step):
+        nr = min(step, m - r0)
+        s.upload_rows(r0, mb.synth_rows(kind, m, n, seed, r0, nr, threads))
+    s.init(-obj if d == mb.OptimizationDirection.Maximize else obj, mins, maxs, ops, rhs)
+    s.direction = d
+    return s, obj, rhs
+
+
+def matvec_rows(m, n, kind, seed, x):
+    """A x on the host, regenerating A in row blocks (the generator is a pure function of (seed, i, j))."""
+    out = np.empty(m)
+    threads = os.cpu_count() or 1
+    step = max(1, (256 << 20) // (8 * n))
+    for r0 in range(0, m, step):
+        nr = min(step, m - r0)
+        out[r0:r0 + nr] = mb.synth_rows(kind, m, n, seed, r0, nr, threads) @ x
+    return out
+
+
+@pytest.mark.skipif(not _enough_memory(), reason="needs ~25 GB of free HBM")
+def test_config3_full_size_properties():
+    s, obj, rhs = build(M, N, KIND, SEED)
+    e = s.engine
+    assert not s.run(PIVOTS)
+    tr = s.trace()
+    assert tr.shape[0] == PIVOTS
+    # objective (internal minimisation form) never increases over primal pivots
+    objs = tr[:, 7]
+    assert np.all(np.diff(objs) <= 1e-9 * np.maximum(1.0, np.abs(objs[1:]))), "primal objective went up"
+    c = e.counters()
+    assert c["k_structural"] > 0 and c["refactors"] >= 2
+
+    # --- A x + s = rhs and the accumulated objective
+    fl, pos = e.var_state()
+    xnb, xb = e.download(2), e.download(3)
+    val = np.where(fl & 4, xb[np.clip(pos, 0, M - 1)], xnb)  # MLP_BASIC == 4: value sits in basic_var_vals[row]
+    assert (fl & 4).sum() == M
+    x, slack = val[:N], val[N:]
+    assert np.array_equal(x, s.values())
+    ax = matvec_rows(M, N, KIND, SEED, x)
+    resid = np.abs(ax + slack - rhs)
+    assert resid.max() <= 1e-9 * max(1.0, np.abs(rhs).max()), f"A x + s - rhs: {resid.max()}"
+    cx = float(-obj @ x)  # Maximize: the solver minimises -c.x (lib.rs:235-238)
+    assert abs(cx - s.cur_obj_val) <= 1e-9 * max(1.0, abs(cx)), (cx, s.cur_obj_val)
+
+    # --- pivot element two ways, for a few (non-basic column, row) pairs
+    nbv = s.nb_vars()
+    rng = np.random.default_rng(5)
+    structural_rows = np.flatnonzero(s.basic_vars() < N)
+    for col in rng.choice(N, 3, replace=False):
+        var = int(nbv[col])
+        e.ftran_col(var)
+        alpha = e.download(5)
+        rows = [int(np.argmax(np.abs(alpha))), int(structural_rows[0]), int(rng.integers(M))]
+        for r in rows:
+            e.calc_row_coeffs(r)
+            rc = e.download(7)
+            lv = var if var < N else N + (var - N)
+            assert abs(rc[lv] - alpha[r]) <= 1e-9 * max(1.0, abs(alpha[r])), (var, r, rc[lv], alpha[r])
+
+    # --- refactorization keeps B^-1 a_q
+    var = int(nbv[123])
+    e.ftran_col(var)
+    a1 = e.download(5)
+    e.refactor()
+    e.ftran_col(var)
+    a2 = e.download(5)
+    assert np.all(np.abs(a1 - a2) <= 1e-9 * np.maximum(1.0, np.abs(a1)))
+    s.close()
+
+    # --- reproducible bit for bit
+    s2, _, _ = build(M, N, KIND, SEED)
+    s2.run(PIVOTS)
+    assert np.array_equal(s2.trace(), tr)
+    s2.close()
