@@ -272,6 +272,17 @@ mlp_status mlp_profile_get(mlp_engine* e, mlp_profile* out);
  * multiplier vector over all m rows; returns the mean device time of one launch pair in milliseconds. */
 mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_launch, int64_t* bytes_per_launch);
 
+/* Tuning knobs of the device path (experiments and A/B measurements; none of them changes a result beyond the rounding
+ * of re-ordered reductions).  Takes effect from the next call on.  The same knobs are read from the environment when an
+ * engine is created (MLP_PRICE_TILE, MLP_LANE1_LDG, MLP_FUSED, MLP_FUSED_MAX). */
+enum {
+  MLP_TUNE_PRICE_TILE = 0, /* columns per tile of the bulk-copy price-out: 128, 256, 512, 1024, 2048 */
+  MLP_TUNE_LANE1_LDG = 1,  /* 1: the tableau-row price-out runs as the LDG kernel beside lane 0's bulk-copy kernel */
+  MLP_TUNE_FUSED = 2,      /* 1: FTRAN -> BTRAN chain of a primal pivot as one cooperative kernel */
+  MLP_TUNE_FUSED_MAX = 3   /* largest k / K that takes the fused chain (<= 512) */
+};
+mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value);
+
 /* ===================================================================== host control loop */
 /* C++ mirror of the reference's Solver control flow (try_new 108-369, initial_solve 470-485,
  * optimize 487-511, restore_feasibility 513-547, choose_pivot 695-853, pivot's host half) written

@@ -237,6 +237,11 @@ class Engine:
         _check(_lib.lib().mlp_profile_get(self._e, C.byref(p)))
         return {k: getattr(p, k) for k, _ in Profile._fields_}
 
+    TUNE = {"price_tile": 0, "lane1_ldg": 1, "fused": 2, "fused_max": 3}
+
+    def set_tuning(self, knob, value):
+        _check(_lib.lib().mlp_engine_set_tuning(self._e, self.TUNE[knob], int(value)))
+
     def bench_price_dense(self, iters):
         ms, by = C.c_double(), C.c_int64()
         _check(_lib.lib().mlp_bench_price_dense(self._e, iters, C.byref(ms), C.byref(by)))

@@ -506,6 +506,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+// NV = column pairs per consumer thread: a tile is up to NV * 512 columns wide (NV * 4 KB row segments).  Thread t owns
+// column pairs t, t + 256, ... of the tile; every column still accumulates its rows in list order.
+template <int NV>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
                     const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
@@ -551,50 +554,70 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
       }
     }
   } else {
-    // ---------------- consumers: thread t < tile_cols / 2 owns columns 2t, 2t+1 of the tile
+    // ---------------- consumers: thread t owns column pairs t + 256 v (v < NV) of the tile
     const int t = threadIdx.x;
     const int rstride = tile_bytes / 16;  // double2 per row
+    constexpr int RU = 8 / NV;            // rows per unrolled batch: 8 loads in flight per thread
     for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
       const int tile = item % tiles, chunk = item / tiles;
       const int k0 = chunk * L, k1 = min(s, k0 + L);
       const int64_t col = (int64_t)tile * tile_cols + 2 * t;
-      const bool active = 2 * t < tile_cols && col < lda;
-      double acc0 = 0.0, acc1 = 0.0;
+      bool active[NV];
+      double acc0[NV], acc1[NV];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        active[v] = 2 * (t + TP_CONSUMERS * v) < tile_cols && col + 2 * TP_CONSUMERS * v < lda;
+        acc0[v] = 0.0;
+        acc1[v] = 0.0;
+      }
       for (int kb = k0; kb < k1; kb += R, ++it) {
         const int nr = min(R, k1 - kb);
         const int slot = it % TP_STAGES;
         mbar_wait(full + slot, (it / TP_STAGES) & 1);
-        if (active) {
+        if (active[0]) {
           const double2* p = reinterpret_cast<const double2*>(tp_smem + (size_t)slot * TP_STAGE_BYTES) + t;
           const double* w = sw + slot * TP_MAXROWS;
           int u0 = 0;
-          for (; u0 + 8 <= nr; u0 += 8) {
-            double2 v[8];
+          for (; u0 + RU <= nr; u0 += RU) {
+            double2 x[RU][NV];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = p[(u0 + u) * rstride];
+            for (int u = 0; u < RU; ++u)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+              for (int v = 0; v < NV; ++v)
+                if (NV == 1 || active[v]) x[u][v] = p[(u0 + u) * rstride + TP_CONSUMERS * v];
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
               const double wv = w[u0 + u];
-              acc0 += wv * v[u].x;
-              acc1 += wv * v[u].y;
+#pragma unroll
+              for (int v = 0; v < NV; ++v)
+                if (NV == 1 || active[v]) {
+                  acc0[v] += wv * x[u][v].x;
+                  acc1[v] += wv * x[u][v].y;
+                }
             }
           }
           for (; u0 < nr; ++u0) {
-            const double2 v = p[u0 * rstride];
             const double wv = w[u0];
-            acc0 += wv * v.x;
-            acc1 += wv * v.y;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+              if (NV == 1 || active[v]) {
+                const double2 x = p[u0 * rstride + TP_CONSUMERS * v];
+                acc0[v] += wv * x.x;
+                acc1[v] += wv * x.y;
+              }
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + slot);
       }
-      if (active) {
-        double2 o;
-        o.x = acc0;
-        o.y = acc1;
-        *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col) = o;
-      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        if (active[v]) {
+          double2 o;
+          o.x = acc0[v];
+          o.y = acc1[v];
+          *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col + 2 * TP_CONSUMERS * v) = o;
+        }
     }
   }
 }
@@ -1371,6 +1394,16 @@ static mlp_status fetch_res(mlp_engine* e, Lane& ln) {
   return MLP_OK;
 }
 static int price_grid(const mlp_engine* e) { return e->sm_count * e->price_ctas; }
+static void launch_price_tma(mlp_engine* e, cudaStream_t st, const int32_t* rows, const double* wts, const int32_t* count_ptr,
+                             int fixed_count, double* partial) {
+  const int tc = e->price_tile;
+  if (tc > 1024)
+    LAUNCHS(e, st, k_price_partial_tma<4>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+  else if (tc > 512)
+    LAUNCHS(e, st, k_price_partial_tma<2>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+  else
+    LAUNCHS(e, st, k_price_partial_tma<1>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+}
 
 // out (local variable index) = N^T w over the listed rows (+ slack part), basic entries zeroed
 static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const double* wts, const int32_t* count_ptr,
@@ -1391,8 +1424,7 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
     // needs no shared-memory ring and slips in next to it; its partial sums are bit-identical.
     const bool beside = e->overlap && e->lane1_ldg && e->enable_pse && &ln == &e->lane[1];  // pse: lane 0 is pricing out too
     if (e->price_tma && !beside)
-      LAUNCHS(e, ln.st, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count,
-              ln.partial, e->price_tile);
+      launch_price_tma(e, ln.st, rows, wts, count_ptr, fixed_count, ln.partial);
     else
       LAUNCHS(e, ln.st, k_price_partial<0>, beside ? e->sm_count * 2 : price_grid(e), PR_THREADS, 0, e->A, e->lda, rows, wts,
               count_ptr, fixed_count, ln.partial);
@@ -1951,8 +1983,10 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
     }
   }
   e->price_tile = price_tile_cols(e->lda, e->sm_count);
-  if (const char* v = getenv("MLP_PRICE_TILE")) { const int t = atoi(v); if (t == 128 || t == 256 || t == 512) e->price_tile = t; }
-  CU(cudaFuncSetAttribute(k_price_partial_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+  if (const char* v = getenv("MLP_PRICE_TILE")) { const int t = atoi(v); if (t == 128 || t == 256 || t == 512 || t == 1024 || t == 2048) e->price_tile = t; }
+  CU(cudaFuncSetAttribute(k_price_partial_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+  CU(cudaFuncSetAttribute(k_price_partial_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+  CU(cudaFuncSetAttribute(k_price_partial_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   {  // lane 1 carries short latency-bound kernels that must slip in beside the price-out: highest priority
     int lo_p = 0, hi_p = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -2604,8 +2638,7 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
     ST(h2d(e, e->work_m, slack_coeffs, m * 8));
     compact(e, l0, e->work_m, e->list_idx, e->list_val, e->icnt, e->scal + 8);
     if (e->price_tma)
-      LAUNCH(e, k_price_partial_tma, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, e->list_idx, e->list_val, e->icnt, 0, l0.partial,
-             e->price_tile);
+      launch_price_tma(e, e->stream, e->list_idx, e->list_val, e->icnt, 0, l0.partial);
     else
       LAUNCH(e, k_price_partial<0>, price_grid(e), PR_THREADS, 0, e->A, e->lda, e->list_idx, e->list_val, e->icnt, 0, l0.partial);
     LAUNCH(e, k_row_combine, cdiv(n, 256), 256, 0, rowA, l0.partial, e->icnt, e->lda, n);
@@ -2833,6 +2866,33 @@ mlp_status mlp_profile_get(mlp_engine* e, mlp_profile* out) {
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   for (int par = 0; par < 2; ++par) ST(collect_profile(e, par));
   *out = e->prof;
+  return MLP_OK;
+}
+
+mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value) {
+  if (!e) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  switch (knob) {
+    case MLP_TUNE_PRICE_TILE:
+      if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048) { set_err("set_tuning: tile"); return MLP_INVALID; }
+      e->price_tile = value;
+      break;
+    case MLP_TUNE_LANE1_LDG: e->lane1_ldg = value != 0; break;
+    case MLP_TUNE_FUSED: {
+      int nb = 0;
+      if (value && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_chain_primal, FZ_T, 0) != cudaSuccess || nb < 1)) {
+        cudaGetLastError();
+        set_err("set_tuning: the fused chain cannot be launched cooperatively on this device");
+        return MLP_INVALID;
+      }
+      e->fused = value != 0;
+      break;
+    }
+    case MLP_TUNE_FUSED_MAX: e->fused_max = std::max(0, std::min(FZ_MAX, (int)value)); break;
+    default: set_err("set_tuning: unknown knob"); return MLP_INVALID;
+  }
+  e->spec_var = -1;
   return MLP_OK;
 }
 

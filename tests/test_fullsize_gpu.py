@@ -73,7 +73,7 @@ def test_config3_full_size_properties():
     fl, pos = e.var_state()
     xnb, xb = e.download(2), e.download(3)
     val = np.where(fl & 4, xb[np.clip(pos, 0, M - 1)], xnb)  # MLP_BASIC == 4: value sits in basic_var_vals[row]
-    assert (fl & 4).sum() == M
+    assert int(((fl & 4) != 0).sum()) == M
     x, slack = val[:N], val[N:]
     assert np.array_equal(x, s.values())
     ax = matvec_rows(M, N, KIND, SEED, x)

@@ -56,8 +56,12 @@ def test_fused_chain_equals_separate_kernels_per_pivot(kind, m, n, seed, steps):
         assert df == du, f"termination differs at pivot {it}"
         sf, su = state(f), state(u)
         assert np.array_equal(sf["basic"], su["basic"]) and np.array_equal(sf["nb"], su["nb"]), f"basis differs at pivot {it}"
-        for key in ("d", "gam", "xnb", "xb", "w", "alpha", "helper"):
+        for key in ("d", "gam", "xnb", "xb", "w", "alpha"):
             assert close(sf[key], su[key], 1e-9), f"{key} differs at pivot {it}"
+        # N^T v sums ~m products of size |v| |A|: entries that cancel to ~0 carry the absolute error of the big ones,
+        # so the helper is compared relative to its largest entry
+        hs = max(1.0, float(np.abs(su["helper"]).max()))
+        assert np.all(np.abs(sf["helper"] - su["helper"]) <= 1e-9 * hs), f"helper differs at pivot {it}"
         if df:
             break
     cf, cu = f.engine.counters(), u.engine.counters()
