@@ -274,14 +274,17 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
 
 /* Tuning knobs of the device path (experiments and A/B measurements; none of them changes a result beyond the rounding
  * of re-ordered reductions).  Takes effect from the next call on.  The same knobs are read from the environment when an
- * engine is created (MLP_PRICE_TILE, MLP_LANE1_LDG, MLP_FUSED, MLP_FUSED_MAX). */
+ * engine is created (MLP_PRICE_TILE, MLP_PRICE_SPLIT, MLP_LANE1_LDG, MLP_FUSED, MLP_FUSED_MAX). */
 enum {
-  MLP_TUNE_PRICE_TILE = 0, /* columns per tile of the bulk-copy price-out: 128, 256, 512, 1024, 2048 */
+  MLP_TUNE_PRICE_TILE = 0, /* columns per tile of the bulk-copy price-out: a multiple of 64 in [128, 2048]; 0 = automatic.
+                              Resets the split to 1. */
   MLP_TUNE_LANE1_LDG = 1,  /* 1: the tableau-row price-out runs as the LDG kernel beside lane 0's bulk-copy kernel */
   MLP_TUNE_FUSED = 2,      /* 1: FTRAN -> BTRAN chain of a primal pivot as one cooperative kernel */
-  MLP_TUNE_FUSED_MAX = 3   /* largest k / K that takes the fused chain (<= 512) */
+  MLP_TUNE_FUSED_MAX = 3,  /* largest k / K that takes the fused chain (<= 512) */
+  MLP_TUNE_PRICE_SPLIT = 4 /* column slices (1, 2, 4) per work item of the price-out's last, partial round */
 };
 mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value);
+mlp_status mlp_engine_get_tuning(mlp_engine* e, int32_t knob, int32_t* value);
 
 /* ===================================================================== host control loop */
 /* C++ mirror of the reference's Solver control flow (try_new 108-369, initial_solve 470-485,

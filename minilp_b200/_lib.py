@@ -114,6 +114,7 @@ SIGNATURES = {
     "mlp_engine_sync": (i32, [vp]),
     "mlp_bench_price_dense": (i32, [vp, i32, pd, pi64]),
     "mlp_engine_set_tuning": (i32, [vp, i32, i32]),
+    "mlp_engine_get_tuning": (i32, [vp, i32, C.POINTER(i32)]),
     "mlp_event_mark": (i32, [vp, i32]),
     "mlp_event_elapsed_ms": (i32, [vp, i32, i32, pd]),
     "mlp_profile_enable": (i32, [vp, i32]),

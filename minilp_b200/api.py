@@ -237,10 +237,17 @@ class Engine:
         _check(_lib.lib().mlp_profile_get(self._e, C.byref(p)))
         return {k: getattr(p, k) for k, _ in Profile._fields_}
 
-    TUNE = {"price_tile": 0, "lane1_ldg": 1, "fused": 2, "fused_max": 3}
+    TUNE = {"price_tile": 0, "lane1_ldg": 1, "fused": 2, "fused_max": 3, "price_split": 4}
 
     def set_tuning(self, knob, value):
         _check(_lib.lib().mlp_engine_set_tuning(self._e, self.TUNE[knob], int(value)))
+
+    def get_tuning(self, knob=None):
+        if knob is None:
+            return {k: self.get_tuning(k) for k in self.TUNE}
+        v = C.c_int32()
+        _check(_lib.lib().mlp_engine_get_tuning(self._e, self.TUNE[knob], C.byref(v)))
+        return v.value
 
     def bench_price_dense(self, iters):
         ms, by = C.c_double(), C.c_int64()

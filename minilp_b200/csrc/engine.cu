@@ -285,7 +285,8 @@ struct mlp_engine {
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
   int async_pivot = 1;  // MLP_ASYNC_PIVOT=0: mlp_pivot always waits for the device
   int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
-  int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE)
+  int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE; default: choose_price_tiling)
+  int price_split = 1;  // column slices per item of the last, partial round (MLP_PRICE_SPLIT)
   int lane1_ldg = 1;    // lane 1 prices out with the LDG kernel while lane 0 runs the bulk-copy one (MLP_LANE1_LDG=0: both bulk-copy)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
@@ -473,7 +474,41 @@ constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_M
 // Tile width: 512 columns (4 KB row segments).  Narrower tiles were measured and lose: 6.77 TB/s at 512, 6.19 at 256,
 // 4.30 at 128 columns (more, smaller bulk copies per byte); a narrow column block of a sharded engine has fewer work
 // items per SM, but the tail still has enough SMs active to saturate HBM.  MLP_PRICE_TILE overrides for experiments.
-static int price_tile_cols(int64_t, int) { return PR_TILE; }
+// Choice of the tiling (host): widths are multiples of 64 columns in [128, 2048]; the cost of a candidate is its number of
+// rounds weighted by the measured efficiency of its row-segment width (B200, profiles/r01d_price_sweep.md: isolated dense
+// N^T v, GB/s) and by how much of a 32 KB stage whole rows of that width fill.  The chunk count is taken for a dense
+// multiplier (support = m), the case that matters: v = B^-T alpha_q.
+static double price_width_gbps(int w) {
+  static const int W[5] = {128, 256, 512, 1024, 2048};
+  static const double B[5] = {4400.0, 5230.0, 6880.0, 7320.0, 7250.0};
+  if (w <= W[0]) return B[0];
+  for (int i = 1; i < 5; ++i)
+    if (w <= W[i]) return B[i - 1] + (B[i] - B[i - 1]) * (double)(w - W[i - 1]) / (double)(W[i] - W[i - 1]);
+  return B[4];
+}
+static double price_width_cost(int w) {  // time per (row x tile) of width w, arbitrary units
+  const int R = std::min(TP_MAXROWS, TP_STAGE_BYTES / (w * 8));
+  const double fill = (double)R * w * 8 / TP_STAGE_BYTES;  // bytes in flight per stage relative to a full one
+  return (double)w / (price_width_gbps(w) * (0.75 + 0.25 * fill));
+}
+static void choose_price_tiling(int64_t lda, int64_t m, int G, int* tile, int* split) {
+  const int C = price_chunks_for((int)std::min<int64_t>(m, INT_MAX));
+  double best = 1e300;
+  *tile = PR_TILE;
+  *split = 1;
+  for (int64_t T = std::max<int64_t>(1, (lda + 2047) / 2048); T <= lda; ++T) {
+    const int w = (int)(((lda + T - 1) / T + 63) / 64 * 64);
+    if (w > 2048) continue;
+    if (w < 384) break;
+    const int64_t tiles = (lda + w - 1) / w, items = tiles * C, full = items / G, left = items - full * G;
+    for (int sp = 1; sp <= 4; sp *= 2) {
+      if (w / sp < 128) continue;
+      double cost = (double)full * price_width_cost(w);
+      if (left) cost += (double)((left * sp + G - 1) / G) * price_width_cost(w / sp);
+      if (cost < best) { best = cost; *tile = w; *split = sp; }
+    }
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -507,12 +542,43 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // NV = column pairs per consumer thread: a tile is up to NV * 512 columns wide (NV * 4 KB row segments).  Thread t owns
-// column pairs t, t + 256, ... of the tile; every column still accumulates its rows in list order.
+// column pairs t, t + 256, ... of the tile; every column still accumulates its rows in list order, so the partial sums
+// do not depend on the tiling.
+//
+// Work items and load balance.  An item is (column tile, support chunk); CTA b takes items b, b + G, ... (G CTAs).  With
+// tiles * C items the last round is only partly filled — at 50k columns and 1024-column tiles 3136 items are 21.2
+// rounds, i.e. 4 % of the kernel runs with 80 % of the SMs idle.  So only the items of the FULL rounds keep the whole tile
+// width; the items of the last, partial round are cut into `split` column slices each, which spreads that round over
+// all CTAs again (narrower row segments are less efficient, but only the tail pays that).
+struct PriceItem {
+  int chunk;
+  int64_t col0;
+  int cols;   // columns actually present (0: the slice lies beyond the matrix)
+  int width;  // nominal width: row stride of the stage in shared memory
+};
+__device__ __forceinline__ PriceItem price_item(int idx, int main_items, int tiles, int tile_cols, int split, int64_t lda) {
+  PriceItem it;
+  int item, sub = 0;
+  it.width = tile_cols;
+  if (idx < main_items) item = idx;
+  else {
+    const int j = idx - main_items;
+    item = main_items + j / split;
+    sub = j % split;
+    it.width = tile_cols / split;
+  }
+  it.chunk = item / tiles;
+  it.col0 = (int64_t)(item % tiles) * tile_cols + (int64_t)sub * it.width;
+  const int64_t tile_end = min(lda, (int64_t)(item % tiles + 1) * tile_cols);
+  const int64_t c = min((int64_t)it.width, tile_end - it.col0);
+  it.cols = c > 0 ? (int)c : 0;
+  return it;
+}
 template <int NV>
 __global__ void __launch_bounds__(TP_THREADS, 1)
 k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
                     const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
-                    double* __restrict__ partial, int tile_cols) {
+                    double* __restrict__ partial, int tile_cols, int split) {
   extern __shared__ __align__(128) unsigned char tp_smem[];
   double* sw = reinterpret_cast<double*>(tp_smem + (size_t)TP_STAGES * TP_STAGE_BYTES);   // [stage][row] weights
   uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_MAXROWS);
@@ -521,8 +587,9 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
   const int C = price_chunks_for(s);
   const int L = (s + C - 1) / C;
   const int tiles = (int)((lda + tile_cols - 1) / tile_cols);
-  const int tile_bytes = tile_cols * 8;
-  const int R = TP_STAGE_BYTES / tile_bytes;  // rows per stage: 8 / 16 / 32
+  const int items = tiles * C;
+  const int main_items = items / (int)gridDim.x * (int)gridDim.x;
+  const int total = main_items + (items - main_items) * split;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int q = 0; q < TP_STAGES; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, TP_CONSUMERS / 32); }
@@ -532,11 +599,13 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
   uint32_t it = 0;  // stages handled so far by this role: slot = it % TP_STAGES, phase = (it / TP_STAGES) & 1
   if (warp == TP_CONSUMERS / 32) {
     // ---------------- producer warp: lane r < R fetches row r of the stage
-    for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
-      const int tile = item % tiles, chunk = item / tiles;
-      const int k0 = chunk * L, k1 = min(s, k0 + L);
-      const int64_t col0 = (int64_t)tile * tile_cols;
-      const uint32_t tbytes = (uint32_t)(min((int64_t)tile_cols, lda - col0) * 8);
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      const PriceItem pi = price_item(idx, main_items, tiles, tile_cols, split, lda);
+      if (pi.cols == 0) continue;
+      const int k0 = pi.chunk * L, k1 = min(s, k0 + L);
+      const int tile_bytes = pi.width * 8;
+      const int R = min(TP_MAXROWS, TP_STAGE_BYTES / tile_bytes);  // rows per stage
+      const uint32_t tbytes = (uint32_t)pi.cols * 8u;
       for (int kb = k0; kb < k1; kb += R, ++it) {
         const int nr = min(R, k1 - kb);
         const int slot = it % TP_STAGES;
@@ -549,24 +618,27 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
         if (lane == 0) mbar_arrive_expect_tx(full + slot, tbytes * nr);
         __syncwarp();
         if (lane < nr)
-          bulk_g2s(tp_smem + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * tile_bytes, A + (int64_t)r * lda + col0, tbytes,
+          bulk_g2s(tp_smem + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * tile_bytes, A + (int64_t)r * lda + pi.col0, tbytes,
                    full + slot);
       }
     }
   } else {
     // ---------------- consumers: thread t owns column pairs t + 256 v (v < NV) of the tile
     const int t = threadIdx.x;
-    const int rstride = tile_bytes / 16;  // double2 per row
     constexpr int RU = 8 / NV;            // rows per unrolled batch: 8 loads in flight per thread
-    for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
-      const int tile = item % tiles, chunk = item / tiles;
-      const int k0 = chunk * L, k1 = min(s, k0 + L);
-      const int64_t col = (int64_t)tile * tile_cols + 2 * t;
+    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
+      const PriceItem pi = price_item(idx, main_items, tiles, tile_cols, split, lda);
+      if (pi.cols == 0) continue;
+      const int k0 = pi.chunk * L, k1 = min(s, k0 + L);
+      const int tile_bytes = pi.width * 8;
+      const int R = min(TP_MAXROWS, TP_STAGE_BYTES / tile_bytes);
+      const int rstride = tile_bytes / 16;  // double2 per row
+      const int64_t col = pi.col0 + 2 * t;
       bool active[NV];
       double acc0[NV], acc1[NV];
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
-        active[v] = 2 * (t + TP_CONSUMERS * v) < tile_cols && col + 2 * TP_CONSUMERS * v < lda;
+        active[v] = 2 * (t + TP_CONSUMERS * v) < pi.cols;
         acc0[v] = 0.0;
         acc1[v] = 0.0;
       }
@@ -616,7 +688,7 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
           double2 o;
           o.x = acc0[v];
           o.y = acc1[v];
-          *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col + 2 * TP_CONSUMERS * v) = o;
+          *reinterpret_cast<double2*>(partial + (int64_t)pi.chunk * lda + col + 2 * TP_CONSUMERS * v) = o;
         }
     }
   }
@@ -1396,13 +1468,13 @@ static mlp_status fetch_res(mlp_engine* e, Lane& ln) {
 static int price_grid(const mlp_engine* e) { return e->sm_count * e->price_ctas; }
 static void launch_price_tma(mlp_engine* e, cudaStream_t st, const int32_t* rows, const double* wts, const int32_t* count_ptr,
                              int fixed_count, double* partial) {
-  const int tc = e->price_tile;
+  const int tc = e->price_tile, sp = e->price_split;
   if (tc > 1024)
-    LAUNCHS(e, st, k_price_partial_tma<4>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+    LAUNCHS(e, st, k_price_partial_tma<4>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
   else if (tc > 512)
-    LAUNCHS(e, st, k_price_partial_tma<2>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+    LAUNCHS(e, st, k_price_partial_tma<2>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
   else
-    LAUNCHS(e, st, k_price_partial_tma<1>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc);
+    LAUNCHS(e, st, k_price_partial_tma<1>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
 }
 
 // out (local variable index) = N^T w over the listed rows (+ slack part), basic entries zeroed
@@ -1982,8 +2054,15 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
       e->fused = 0;
     }
   }
-  e->price_tile = price_tile_cols(e->lda, e->sm_count);
-  if (const char* v = getenv("MLP_PRICE_TILE")) { const int t = atoi(v); if (t == 128 || t == 256 || t == 512 || t == 1024 || t == 2048) e->price_tile = t; }
+  choose_price_tiling(e->lda, m, e->sm_count, &e->price_tile, &e->price_split);
+  if (const char* v = getenv("MLP_PRICE_TILE")) {
+    const int t = atoi(v);
+    if (t >= 128 && t <= 2048 && t % 64 == 0) { e->price_tile = t; e->price_split = 1; }
+  }
+  if (const char* v = getenv("MLP_PRICE_SPLIT")) {
+    const int t = atoi(v);
+    if ((t == 1 || t == 2 || t == 4) && e->price_tile / t >= 128 && (e->price_tile / t) % 16 == 0) e->price_split = t;
+  }
   CU(cudaFuncSetAttribute(k_price_partial_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   CU(cudaFuncSetAttribute(k_price_partial_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   CU(cudaFuncSetAttribute(k_price_partial_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
@@ -2875,8 +2954,17 @@ mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value) {
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   switch (knob) {
     case MLP_TUNE_PRICE_TILE:
-      if (value != 128 && value != 256 && value != 512 && value != 1024 && value != 2048) { set_err("set_tuning: tile"); return MLP_INVALID; }
+      if (value == 0) { choose_price_tiling(e->lda, e->m, e->sm_count, &e->price_tile, &e->price_split); break; }  // automatic
+      if (value < 128 || value > 2048 || value % 64 != 0) { set_err("set_tuning: tile width must be a multiple of 64 in [128, 2048]"); return MLP_INVALID; }
       e->price_tile = value;
+      e->price_split = 1;
+      break;
+    case MLP_TUNE_PRICE_SPLIT:
+      if ((value != 1 && value != 2 && value != 4) || e->price_tile / value < 128 || (e->price_tile / value) % 16 != 0) {
+        set_err("set_tuning: split must be 1, 2 or 4 and leave slices of >= 128 columns");
+        return MLP_INVALID;
+      }
+      e->price_split = value;
       break;
     case MLP_TUNE_LANE1_LDG: e->lane1_ldg = value != 0; break;
     case MLP_TUNE_FUSED: {
@@ -2893,6 +2981,19 @@ mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value) {
     default: set_err("set_tuning: unknown knob"); return MLP_INVALID;
   }
   e->spec_var = -1;
+  return MLP_OK;
+}
+
+mlp_status mlp_engine_get_tuning(mlp_engine* e, int32_t knob, int32_t* value) {
+  if (!e || !value) return MLP_INVALID;
+  switch (knob) {
+    case MLP_TUNE_PRICE_TILE: *value = e->price_tile; break;
+    case MLP_TUNE_PRICE_SPLIT: *value = e->price_split; break;
+    case MLP_TUNE_LANE1_LDG: *value = e->lane1_ldg; break;
+    case MLP_TUNE_FUSED: *value = e->fused; break;
+    case MLP_TUNE_FUSED_MAX: *value = e->fused_max; break;
+    default: set_err("get_tuning: unknown knob"); return MLP_INVALID;
+  }
   return MLP_OK;
 }
 

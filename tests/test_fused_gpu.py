@@ -112,3 +112,27 @@ def test_lane1_price_kernel_choice_is_bit_identical():
         assert np.array_equal(a.engine.download(which), b.engine.download(which))
     a.close()
     b.close()
+
+
+def test_price_tilings_are_bit_identical():
+    """Tile width and tail split of the bulk-copy price-out only change which CTA sums which columns: every column adds
+    its rows in list order within the same support chunks, so the product has the same bits under every tiling."""
+    lp = mb.synth_dense(0, 700, 3000, 4)
+    s = make(lp)
+    s.run(25)
+    e = s.engine
+    ref = None
+    for tile, split in [(512, 1), (1024, 1), (1024, 4), (2048, 2), (704, 1), (1088, 1), (128, 1), (256, 2), (1536, 4)]:
+        e.set_tuning("price_tile", tile)
+        e.set_tuning("price_split", split)
+        assert e.get_tuning("price_tile") == tile and e.get_tuning("price_split") == split
+        e.bench_price_dense(1)
+        h = e.download(10)
+        assert np.any(h != 0.0)
+        if ref is None:
+            ref = h
+            assert np.allclose(h[:3000], 0.5 * lp.a.sum(axis=0) * (h[:3000] != 0), rtol=1e-12)
+        assert np.array_equal(h, ref), (tile, split)
+    e.set_tuning("price_tile", 0)  # automatic again
+    assert s.run()
+    s.close()
