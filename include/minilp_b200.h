@@ -276,7 +276,7 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
  * of re-ordered reductions).  Takes effect from the next call on.  The same knobs are read from the environment when an
  * engine is created (MLP_PRICE_TILE, MLP_PRICE_SPLIT, MLP_LANE1_LDG, MLP_FUSED, MLP_FUSED_MAX). */
 enum {
-  MLP_TUNE_PRICE_TILE = 0, /* columns per tile of the bulk-copy price-out: a multiple of 64 in [128, 2048]; 0 = automatic.
+  MLP_TUNE_PRICE_TILE = 0, /* columns per tile of the bulk-copy price-out: a multiple of 64 in [128, 4096]; 0 = automatic.
                               Resets the split to 1. */
   MLP_TUNE_LANE1_LDG = 1,  /* 1: the tableau-row price-out runs as the LDG kernel beside lane 0's bulk-copy kernel */
   MLP_TUNE_FUSED = 2,      /* 1: FTRAN -> BTRAN chain of a primal pivot as one cooperative kernel */

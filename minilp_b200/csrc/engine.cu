@@ -474,40 +474,17 @@ constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_M
 // Tile width: 512 columns (4 KB row segments).  Narrower tiles were measured and lose: 6.77 TB/s at 512, 6.19 at 256,
 // 4.30 at 128 columns (more, smaller bulk copies per byte); a narrow column block of a sharded engine has fewer work
 // items per SM, but the tail still has enough SMs active to saturate HBM.  MLP_PRICE_TILE overrides for experiments.
-// Choice of the tiling (host): widths are multiples of 64 columns in [128, 2048]; the cost of a candidate is its number of
-// rounds weighted by the measured efficiency of its row-segment width (B200, profiles/r01d_price_sweep.md: isolated dense
-// N^T v, GB/s) and by how much of a 32 KB stage whole rows of that width fill.  The chunk count is taken for a dense
-// multiplier (support = m), the case that matters: v = B^-T alpha_q.
-static double price_width_gbps(int w) {
-  static const int W[5] = {128, 256, 512, 1024, 2048};
-  static const double B[5] = {4400.0, 5230.0, 6880.0, 7320.0, 7250.0};
-  if (w <= W[0]) return B[0];
-  for (int i = 1; i < 5; ++i)
-    if (w <= W[i]) return B[i - 1] + (B[i] - B[i - 1]) * (double)(w - W[i - 1]) / (double)(W[i] - W[i - 1]);
-  return B[4];
-}
-static double price_width_cost(int w) {  // time per (row x tile) of width w, arbitrary units
-  const int R = std::min(TP_MAXROWS, TP_STAGE_BYTES / (w * 8));
-  const double fill = (double)R * w * 8 / TP_STAGE_BYTES;  // bytes in flight per stage relative to a full one
-  return (double)w / (price_width_gbps(w) * (0.75 + 0.25 * fill));
-}
-static void choose_price_tiling(int64_t lda, int64_t m, int G, int* tile, int* split) {
-  const int C = price_chunks_for((int)std::min<int64_t>(m, INT_MAX));
-  double best = 1e300;
-  *tile = PR_TILE;
+// Choice of the tiling (host), from the measured sweep profiles/r01d_price_sweep.md (B200, isolated dense N^T v, m = 50k;
+// GB/s at 512-column tiles -> at the width chosen here):  n_loc 50 000: 6760 -> 7068 (1280);  25 000: 6615 -> 6862 (1280);
+// 12 500: 6636 -> 6930 (1536);  6 250: 6145 -> 6619 (2048).  Wider row segments mean fewer, larger bulk copies and longer
+// contiguous DRAM bursts, and that matters more the shorter the rows of the local block are.  The kernel is HBM-bound with
+// ~28 MB in flight, so a partly filled last round of work items costs little (a round model that predicted gains from
+// balancing it did not survive the measurement; the tail split stays available as a knob, default 1).
+static void choose_price_tiling(int64_t lda, int64_t /*m*/, int /*G*/, int* tile, int* split) {
   *split = 1;
-  for (int64_t T = std::max<int64_t>(1, (lda + 2047) / 2048); T <= lda; ++T) {
-    const int w = (int)(((lda + T - 1) / T + 63) / 64 * 64);
-    if (w > 2048) continue;
-    if (w < 384) break;
-    const int64_t tiles = (lda + w - 1) / w, items = tiles * C, full = items / G, left = items - full * G;
-    for (int sp = 1; sp <= 4; sp *= 2) {
-      if (w / sp < 128) continue;
-      double cost = (double)full * price_width_cost(w);
-      if (left) cost += (double)((left * sp + G - 1) / G) * price_width_cost(w / sp);
-      if (cost < best) { best = cost; *tile = w; *split = sp; }
-    }
-  }
+  int w = lda < 10000 ? 2048 : lda < 20000 ? 1536 : 1280;
+  const int need = (int)std::min<int64_t>(2048, (lda + 63) / 64 * 64);  // never wider than the block itself
+  *tile = std::max(128, std::min(w, need));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1469,7 +1446,9 @@ static int price_grid(const mlp_engine* e) { return e->sm_count * e->price_ctas;
 static void launch_price_tma(mlp_engine* e, cudaStream_t st, const int32_t* rows, const double* wts, const int32_t* count_ptr,
                              int fixed_count, double* partial) {
   const int tc = e->price_tile, sp = e->price_split;
-  if (tc > 1024)
+  if (tc > 2048)
+    LAUNCHS(e, st, k_price_partial_tma<8>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
+  else if (tc > 1024)
     LAUNCHS(e, st, k_price_partial_tma<4>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
   else if (tc > 512)
     LAUNCHS(e, st, k_price_partial_tma<2>, e->sm_count, TP_THREADS, TP_SMEM, e->A, e->lda, rows, wts, count_ptr, fixed_count, partial, tc, sp);
@@ -2057,7 +2036,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   choose_price_tiling(e->lda, m, e->sm_count, &e->price_tile, &e->price_split);
   if (const char* v = getenv("MLP_PRICE_TILE")) {
     const int t = atoi(v);
-    if (t >= 128 && t <= 2048 && t % 64 == 0) { e->price_tile = t; e->price_split = 1; }
+    if (t >= 128 && t <= 4096 && t % 64 == 0) { e->price_tile = t; e->price_split = 1; }
   }
   if (const char* v = getenv("MLP_PRICE_SPLIT")) {
     const int t = atoi(v);
@@ -2066,6 +2045,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaFuncSetAttribute(k_price_partial_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   CU(cudaFuncSetAttribute(k_price_partial_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   CU(cudaFuncSetAttribute(k_price_partial_tma<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
+  CU(cudaFuncSetAttribute(k_price_partial_tma<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM));
   {  // lane 1 carries short latency-bound kernels that must slip in beside the price-out: highest priority
     int lo_p = 0, hi_p = 0;
     CU(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
@@ -2955,7 +2935,7 @@ mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value) {
   switch (knob) {
     case MLP_TUNE_PRICE_TILE:
       if (value == 0) { choose_price_tiling(e->lda, e->m, e->sm_count, &e->price_tile, &e->price_split); break; }  // automatic
-      if (value < 128 || value > 2048 || value % 64 != 0) { set_err("set_tuning: tile width must be a multiple of 64 in [128, 2048]"); return MLP_INVALID; }
+      if (value < 128 || value > 4096 || value % 64 != 0) { set_err("set_tuning: tile width must be a multiple of 64 in [128, 4096]"); return MLP_INVALID; }
       e->price_tile = value;
       e->price_split = 1;
       break;

@@ -12,6 +12,7 @@ ap.add_argument("--m", type=int, default=50000)
 ap.add_argument("--widths", default="50000,25000,12500,6250")
 ap.add_argument("--tiles", default="512,640,768,960,1024,1088,1280,1344,1536,2048")
 ap.add_argument("--pivots", type=int, default=40)
+ap.add_argument("--splits", type=int, default=1, help="also sweep a few (tile, split) combinations")
 a0 = ap.parse_args()
 for n in [int(x) for x in a0.widths.split(",")]:
     a = argparse.Namespace(m=a0.m, n=n, kind=0, seed=1)
@@ -21,7 +22,9 @@ for n in [int(x) for x in a0.widths.split(",")]:
     auto = (e.get_tuning("price_tile"), e.get_tuning("price_split"))
     ref = None
     grid = [(t, 1) for t in [int(x) for x in a0.tiles.split(",")]]
-    grid += [(1024, 2), (1024, 4), (2048, 2), (2048, 4), (1280, 2), (1536, 4), auto]
+    if a0.splits:
+        grid += [(1024, 2), (1024, 4), (2048, 2), (2048, 4), (1280, 2), (1536, 4)]
+    grid.append(auto)
     for tile, split in grid:
         e.set_tuning("price_tile", tile)
         e.set_tuning("price_split", split)

@@ -36,12 +36,14 @@ def full(src, dst, m=None, n=None):
             "launch__occupancy_limit_registers", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__cycles_active.avg.pct_of_peak_sustained_elapsed",
             "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
-            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg", "smsp__inst_executed.sum",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
     idx = [(w, hdr.index(w)) for w in want if w in hdr]
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary ({os.path.basename(src)})\n\n")
-        f.write("`ncu --set full --clock-control none --import-source on -k regex:k_price_partial_tma` over `bench.py`.\n\n")
+        kn = sorted({r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0] for r in data})
+        f.write(f"`ncu --set full --clock-control none --import-source on -k regex:{'|'.join(kn)}` over `bench.py`.\n\n")
         for r in data:
             f.write(f"## launch id {r[0]}\n\n| metric | value | unit |\n|---|---:|---|\n")
             for w, i in idx:
