@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--m", type=int, default=50000)
+    ap.add_argument("--m", "--rows", dest="m", type=int, default=50000)  # under torchrun use --rows / --cols (its parser grabs --m)
     ap.add_argument("--n", "--cols", dest="n", type=int, default=50000)
     ap.add_argument("--kind", type=int, default=0, help="synthetic LP family (0 = dense_pos, see DESIGN.md)")
     ap.add_argument("--seed", type=int, default=1)

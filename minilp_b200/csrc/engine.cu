@@ -310,6 +310,8 @@ struct mlp_engine {
   int32_t* h_mail = nullptr;      // pinned: [parity*4 + 0] nnz(rho), [parity*4 + 1] nnz(v) of the timed launches
   int64_t pivot_seq = 0;          // completed basis changes; parity = pivot_seq & 1
   int64_t alpha_nnz_host = -1;    // nnz(alpha_q) as read back with the ratio test, -1: not known on the host
+  int64_t dual_row_host = -1;     // row whose basic value mlp_select_row_dual just returned (-1: none), and that value:
+  double dual_row_val = 0.0;      // spares mlp_ratio_dual a device->host round trip per dual pivot
   int prof_on = 0;
   mlp_profile prof{};
 
@@ -474,16 +476,17 @@ constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_M
 // Tile width: 512 columns (4 KB row segments).  Narrower tiles were measured and lose: 6.77 TB/s at 512, 6.19 at 256,
 // 4.30 at 128 columns (more, smaller bulk copies per byte); a narrow column block of a sharded engine has fewer work
 // items per SM, but the tail still has enough SMs active to saturate HBM.  MLP_PRICE_TILE overrides for experiments.
-// Choice of the tiling (host), from the measured sweep profiles/r01d_price_sweep.md (B200, isolated dense N^T v, m = 50k;
-// GB/s at 512-column tiles -> at the width chosen here):  n_loc 50 000: 6760 -> 7068 (1280);  25 000: 6615 -> 6862 (1280);
-// 12 500: 6636 -> 6930 (1536);  6 250: 6145 -> 6619 (2048).  Wider row segments mean fewer, larger bulk copies and longer
-// contiguous DRAM bursts, and that matters more the shorter the rows of the local block are.  The kernel is HBM-bound with
-// ~28 MB in flight, so a partly filled last round of work items costs little (a round model that predicted gains from
-// balancing it did not survive the measurement; the tail split stays available as a knob, default 1).
+// Choice of the tiling (host), from the measured sweeps in profiles/r01d_price_sweep.md (B200, isolated dense N^T v,
+// m = 50k; GB/s at 512-column tiles -> at the width chosen here):  n_loc 50 000: 6760 -> 7068 (1280);  25 000: 6735 -> 7070
+// (1280);  12 500: 6668 -> 7102 (4096);  6 250: 6125 -> 6998 (4096).  Wider row segments mean fewer, larger bulk copies and
+// longer contiguous DRAM bursts, and that matters more the shorter the rows of the local block are; widths whose rows fill
+// a 32 KB stage badly (2560 columns = 20 KB: one row per stage) lose the bytes in flight again.  The kernel is HBM-bound
+// with ~28 MB in flight, so a partly filled last round of work items costs little (a round model that predicted gains
+// from balancing it did not survive the measurement; the tail split stays available as a knob, default 1).
 static void choose_price_tiling(int64_t lda, int64_t /*m*/, int /*G*/, int* tile, int* split) {
   *split = 1;
-  int w = lda < 10000 ? 2048 : lda < 20000 ? 1536 : 1280;
-  const int need = (int)std::min<int64_t>(2048, (lda + 63) / 64 * 64);  // never wider than the block itself
+  const int w = lda < 20000 ? 4096 : 1280;
+  const int need = (int)std::min<int64_t>(4096, (lda + 63) / 64 * 64);  // never wider than the block itself
   *tile = std::max(128, std::min(w, need));
 }
 
@@ -2333,6 +2336,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   CU(cudaStreamSynchronize(e->stream));
   e->spec_var = -1;
   e->sel_valid = false;
+  e->dual_row_host = -1;
   if (!st->basic_var_vals) {
     double* part = e->world > 1 ? e->work_m : e->xred;
     if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->xnb, part);
@@ -2501,6 +2505,8 @@ mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
   out->val = e->h_res->f[0];
   out->min = e->h_res->f[1];
   out->max = e->h_res->f[2];
+  e->dual_row_host = out->row;
+  e->dual_row_val = out->val;
   return MLP_OK;
 }
 
@@ -2511,8 +2517,8 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   Lane& l0 = e->lane[0];
   ST(begin0(e));
   e->sel_valid = false;  // the candidate buffer is reused for the dual ratio test
-  double bv = 0.0;
-  ST(d2h(e, &bv, e->xB + row, sizeof(double)));
+  double bv = e->dual_row_val;  // basic_var_vals[row] as choose_pivot_row_dual saw it; x_B has not changed since
+  if (e->dual_row_host != row) ST(d2h(e, &bv, e->xB + row, sizeof(double)));
   const int lds = leaving_new_val > bv ? 1 : 0;
   const int grid = std::min(cdiv(e->nt, 256), 1024);
   LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, l0.red_f, l0.red_counter, e->scal);
@@ -2545,6 +2551,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   out->col_nnz = 0;
   out->refactored = 0;
   out->lu_nnz = e->lu_nnz;
+  e->dual_row_host = -1;  // x_B is about to change
   if (!pi->has_elem) {  // solver.rs:1031-1042
     ST(begin0(e));
     e->sel_valid = false;
@@ -2690,6 +2697,7 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
   e->sel_valid = false;
   e->spec_var = e->ftran_var = -1;
   e->colq_var = -1;
+  e->dual_row_host = -1;
   double* rowA = e->A + r * e->lda;
   ST(h2d(e, rowA, coeffs, n * 8));
   double* d_rhs_new = e->scal + 7;
