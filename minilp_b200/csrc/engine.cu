@@ -1727,7 +1727,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
         if ((size_t)rows * cand * 8 + (size_t)rows * 8 <= e->smem_optin) { nb = cand; use_smem = 1; break; }
       nb = std::min(nb, rows);
       const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * 8 : 0;
-      LAUNCH(e, k_lu_panel, 1, 1024, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, flags, e->lu_aff, e->lu_aff + 64, e->lu_aff + 128,
+      const int pt = std::max(64, std::min(1024, (rows + 31) / 32 * 32));  // one row per thread
+      LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, flags, e->lu_aff, e->lu_aff + 64, e->lu_aff + 128,
              e->lu_perm, use_smem);
       if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
                               e->lu_aff + 128, flags);

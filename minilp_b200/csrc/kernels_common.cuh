@@ -431,11 +431,14 @@ __device__ __forceinline__ KeyIdx warp_argmax_all(KeyIdx v) {
   return v;
 }
 // The panel factorization is column-sequential — per column: pivot search (two reductions: max |x|, then the lowest
-// original row among the rows within 0.1 of it), row swap, rank-1 update of the rest of the panel — so its cost is the
-// number of CTA barriers per column: 4 here (9 in the first version: 91 us per 32-column panel at 570 rows, 70 % of a
-// refactorization).  The division by the pivot (lu.rs:261) is not stored during the loop: step c is the only one that
-// uses column c as L, it divides on the fly, and the quotients are stored once for the whole panel at the end (row c,
-// which holds the pivots, is final after step c; later swaps permute whole rows, and the division is element-wise).
+// original row among the rows within 0.1 of it), row swap, scaling and rank-1 update of the rest of the panel.  Two things
+// bound it: CTA barriers per column (4 here, 9 in the first version) and the instruction count of the update.  The
+// update is mapped one ROW per thread (thread r divides its entry of column c by the pivot, lu.rs:261, stores it and
+// walks the remaining <= 31 columns of its row): no integer div/mod per element as in a flat (row, column) index, no
+// element is touched by two threads, stride-1 shared-memory accesses, the pivot row is a broadcast.  The launch uses
+// as many threads as the panel has rows (<= 1024), so the barriers stay cheap for small cores.
+// (measured at 216 rows: flat index 2.8 us per column; flat index with 4 barriers and the division taken on the fly
+// 4.9 us — the f64 divisions cost more than the barriers saved; this form: see profiles/.)
 __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
                                                     int32_t* __restrict__ Rp, int* __restrict__ flags,
                                                     int32_t* __restrict__ aff_pos, int32_t* __restrict__ aff_src,
@@ -453,10 +456,8 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     pld = rows;
     rp = reinterpret_cast<int32_t*>(P + (size_t)rows * nb);
     perm = rp + rows;
-    for (int idx = tid; idx < rows * nb; idx += blockDim.x) {
-      const int r = idx % rows, c = idx / rows;
-      P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
-    }
+    for (int c = 0; c < nb; ++c)
+      for (int r = tid; r < rows; r += blockDim.x) P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
     for (int r = tid; r < rows; r += blockDim.x) rp[r] = Rp[j0 + r];
   } else {
     P = C + (int64_t)j0 * ld + j0;
@@ -468,10 +469,9 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
   if (tid == 0) s_cnt = 0;
   bool stop = flags[1] != 0;  // uniform: flags[1] only changes inside this kernel, by a uniform decision
   __syncthreads();
-  int done_cols = 0;  // columns whose pivot has been chosen (their quotients are stored after the loop)
   for (int c = 0; c < nb && !stop; ++c) {
     double* col = P + (size_t)c * pld;
-    // pivot search 1: max |x| below the diagonal (lu.rs:194-206)
+    // pivot search 1: max |x| from the diagonal down (lu.rs:194-206)
     double mx = 0.0;
     for (int r = c + tid; r < rows; r += blockDim.x) mx = fmax(mx, fabs(col[r]));
     mx = warp_max_all(mx);
@@ -509,31 +509,21 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
       }
     }
     __syncthreads();
-    // rank-1 update of the rest of the panel with l_r = x_r / pivot taken on the fly
+    // scaling and rank-1 update, one row per thread
     const double pv = col[c];
-    const int rr2 = rows - c - 1, nc2 = nb - c - 1;
-    for (int idx = tid; idx < rr2 * nc2; idx += blockDim.x) {
-      const int r = c + 1 + idx % rr2, cc = c + 1 + idx / rr2;
-      double* q = P + (size_t)cc * pld;
-      q[r] -= (col[r] / pv) * q[c];
+    for (int r = c + 1 + tid; r < rows; r += blockDim.x) {
+      const double l = col[r] / pv;  // lu.rs:261
+      col[r] = l;
+      for (int cc = c + 1; cc < nb; ++cc) {
+        double* q = P + (size_t)cc * pld;
+        q[r] -= l * q[c];
+      }
     }
-    done_cols = c + 1;
     __syncthreads();
   }
-  // quotients of every factorized column (lu.rs:261)
-  for (int idx = tid; idx < rows * done_cols; idx += blockDim.x) {
-    const int r = idx % rows, c = idx / rows;
-    if (r > c) {
-      double* col = P + (size_t)c * pld;
-      col[r] = col[r] / col[c];
-    }
-  }
-  __syncthreads();
   if (use_smem) {
-    for (int idx = tid; idx < rows * nb; idx += blockDim.x) {
-      const int r = idx % rows, c = idx / rows;
-      C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
-    }
+    for (int c = 0; c < nb; ++c)
+      for (int r = tid; r < rows; r += blockDim.x) C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
     for (int r = tid; r < rows; r += blockDim.x) Rp[j0 + r] = rp[r];
   }
   for (int r = tid; r < rows; r += blockDim.x)

@@ -75,3 +75,12 @@ def test_gloo_world2_pricing_argreduce():
                          capture_output=True, text=True, env=env, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("GLOO_OK") == 2, out.stdout + out.stderr
+
+
+def test_tuning_knobs_match_the_header():
+    """api.Engine.TUNE mirrors the MLP_TUNE_* enum of include/minilp_b200.h."""
+    import re
+    from minilp_b200.api import Engine
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "minilp_b200.h")).read()
+    enum = dict((k.lower(), int(v)) for k, v in re.findall(r"MLP_TUNE_([A-Z0-9_]+)\s*=\s*(\d+)", hdr))
+    assert enum == Engine.TUNE
