@@ -414,40 +414,44 @@ __global__ void k_btran_start(const double* __restrict__ c, const int32_t* __res
 // Every element sees the same operations in the same order as column-by-column elimination (t ascending, separate
 // multiply and subtract), so the factors are bit-identical to an unblocked factorization.
 constexpr int LU_NB = 32;
-// Butterfly reductions: every lane ends up with the result, so the block-level result needs ONE barrier (each warp
-// writes its partial, barrier, every warp reduces the <= 32 partials again) instead of three.
-__device__ __forceinline__ double warp_max_all(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULLMASK, v, o));
-  return v;
+// Warp reductions of the pivot search through the integer reduce unit (redux.sync: one instruction instead of a
+// five-step shuffle tree per 32-bit word); every lane gets the result.
+// max of non-negative doubles: for x >= 0 the IEEE bit pattern orders like the value.
+__device__ __forceinline__ double warp_max_nonneg(double x) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+  const unsigned mh = __reduce_max_sync(FULLMASK, hi);
+  const unsigned ml = __reduce_max_sync(FULLMASK, hi == mh ? lo : 0u);
+  return __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
 }
-__device__ __forceinline__ KeyIdx warp_argmax_all(KeyIdx v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double k = __shfl_xor_sync(FULLMASK, v.key, o);
-    const long long i = __shfl_xor_sync(FULLMASK, v.idx, o);
-    if (better_max(k, i, v.key, v.idx)) { v.key = k; v.idx = i; }
-  }
-  return v;
+// arg-min of distinct non-negative keys (UINT_MAX: none): returns the payload of the lane holding the smallest key
+__device__ __forceinline__ int warp_argmin_u32(unsigned key, int payload, unsigned* min_out) {
+  const unsigned mk = __reduce_min_sync(FULLMASK, key);
+  const unsigned who = __ballot_sync(FULLMASK, key == mk);
+  *min_out = mk;
+  return __shfl_sync(FULLMASK, payload, __ffs(who) - 1);
 }
 // The panel factorization is column-sequential — per column: pivot search (two reductions: max |x|, then the lowest
-// original row among the rows within 0.1 of it), row swap, scaling and rank-1 update of the rest of the panel.  Two things
-// bound it: CTA barriers per column (4 here, 9 in the first version) and the instruction count of the update.  The
-// update is mapped one ROW per thread (thread r divides its entry of column c by the pivot, lu.rs:261, stores it and
-// walks the remaining <= 31 columns of its row): no integer div/mod per element as in a flat (row, column) index, no
-// element is touched by two threads, stride-1 shared-memory accesses, the pivot row is a broadcast.  The launch uses
-// as many threads as the panel has rows (<= 1024), so the barriers stay cheap for small cores.
-// (measured at 216 rows: flat index 2.8 us per column; flat index with 4 barriers and the division taken on the fly
-// 4.9 us — the f64 divisions cost more than the barriers saved; this form: see profiles/.)
+// original row among the rows within 0.1 of it), row swap, scaling and rank-1 update of the rest of the panel — so it is
+// bound by the LATENCY of one column step, not by throughput.  Per column: 4 CTA barriers (9 in the first version), the
+// two reductions go through redux.sync, and the update is mapped one ROW per thread (thread r divides its entry of
+// column c by the pivot, lu.rs:261, stores it and walks the remaining <= 31 columns of its row four at a time with all
+// loads issued ahead of the stores): no integer div/mod per element as with a flat (row, column) index, no element is
+// touched by two threads, stride-1 shared-memory accesses, the pivot row is a broadcast.  The launch uses as many
+// threads as the panel has rows (<= 1024), which keeps the barriers cheap for small cores.
+// Measured per 32-column panel at ~200 rows: 91 us (flat index, 9 barriers) -> 81 us (row per thread, shuffle trees)
+// -> see profiles/ for this form.  The arithmetic and the pivot rule are unchanged: factors are bit-identical.
 __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
                                                     int32_t* __restrict__ Rp, int* __restrict__ flags,
                                                     int32_t* __restrict__ aff_pos, int32_t* __restrict__ aff_src,
                                                     int32_t* __restrict__ aff_cnt, int32_t* __restrict__ perm_glob, int use_smem) {
   extern __shared__ __align__(16) unsigned char lu_smem[];
-  __shared__ double redk[2][32];
-  __shared__ long long redi[2][32];
+  __shared__ double redk[32];
+  __shared__ unsigned redrp[32];
+  __shared__ int redr[32];
   __shared__ int s_cnt;
   const int rows = k - j0, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
+  const int T = blockDim.x;
   double* P;
   int64_t pld;
   int32_t *rp, *perm;
@@ -457,46 +461,50 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     rp = reinterpret_cast<int32_t*>(P + (size_t)rows * nb);
     perm = rp + rows;
     for (int c = 0; c < nb; ++c)
-      for (int r = tid; r < rows; r += blockDim.x) P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
-    for (int r = tid; r < rows; r += blockDim.x) rp[r] = Rp[j0 + r];
+      for (int r = tid; r < rows; r += T) P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
+    for (int r = tid; r < rows; r += T) rp[r] = Rp[j0 + r];
   } else {
     P = C + (int64_t)j0 * ld + j0;
     pld = ld;
     rp = Rp + j0;
     perm = perm_glob;
   }
-  for (int r = tid; r < rows; r += blockDim.x) perm[r] = r;
+  for (int r = tid; r < rows; r += T) perm[r] = r;
   if (tid == 0) s_cnt = 0;
   bool stop = flags[1] != 0;  // uniform: flags[1] only changes inside this kernel, by a uniform decision
   __syncthreads();
   for (int c = 0; c < nb && !stop; ++c) {
     double* col = P + (size_t)c * pld;
-    // pivot search 1: max |x| from the diagonal down (lu.rs:194-206)
+    // pivot search 1: max |x| from the diagonal down (lu.rs:194-206); a NaN never wins (fmax semantics)
     double mx = 0.0;
-    for (int r = c + tid; r < rows; r += blockDim.x) mx = fmax(mx, fabs(col[r]));
-    mx = warp_max_all(mx);
-    if (lane == 0) redk[0][wid] = mx;
+    for (int r = c + tid; r < rows; r += T) {
+      const double x = fabs(col[r]);
+      if (x > mx) mx = x;
+    }
+    mx = warp_max_nonneg(mx);
+    if (lane == 0) redk[wid] = mx;
     __syncthreads();
-    const double max_abs = warp_max_all(lane < nw ? redk[0][lane] : 0.0);
+    const double max_abs = warp_max_nonneg(lane < nw ? redk[lane] : 0.0);
     if (!(max_abs >= 1e-8) || isinf(max_abs)) {  // lu.rs:207-211; uniform across the CTA
       if (tid == 0) flags[1] = 1;
       stop = true;
       break;
     }
-    // pivot search 2: lowest original row among the eligible ones (maximise -Rp)
-    KeyIdx cand{-INFINITY, LLONG_MAX};
-    for (int r = c + tid; r < rows; r += blockDim.x)
-      if (fabs(col[r]) >= 0.1 * max_abs) {
-        const double key = -(double)rp[r];
-        if (better_max(key, r, cand.key, cand.idx)) { cand.key = key; cand.idx = r; }
+    // pivot search 2: lowest original row among the eligible ones (original rows are distinct)
+    unsigned bk = 0xffffffffu;
+    int br = -1;
+    const double thr = 0.1 * max_abs;
+    for (int r = c + tid; r < rows; r += T)
+      if (fabs(col[r]) >= thr) {
+        const unsigned key = (unsigned)rp[r];
+        if (key < bk) { bk = key; br = r; }
       }
-    cand = warp_argmax_all(cand);
-    if (lane == 0) { redk[1][wid] = cand.key; redi[1][wid] = cand.idx; }
+    unsigned wk;
+    const int wr = warp_argmin_u32(bk, br, &wk);
+    if (lane == 0) { redrp[wid] = wk; redr[wid] = wr; }
     __syncthreads();
-    KeyIdx b{-INFINITY, LLONG_MAX};
-    if (lane < nw) { b.key = redk[1][lane]; b.idx = redi[1][lane]; }
-    b = warp_argmax_all(b);
-    const int p = (int)b.idx;
+    unsigned dummy;
+    const int p = warp_argmin_u32(lane < nw ? redrp[lane] : 0xffffffffu, lane < nw ? redr[lane] : -1, &dummy);
     if (p != c) {
       if (tid < nb) {
         double* q = P + (size_t)tid * pld;
@@ -511,10 +519,27 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     __syncthreads();
     // scaling and rank-1 update, one row per thread
     const double pv = col[c];
-    for (int r = c + 1 + tid; r < rows; r += blockDim.x) {
+    for (int r = c + 1 + tid; r < rows; r += T) {
       const double l = col[r] / pv;  // lu.rs:261
       col[r] = l;
-      for (int cc = c + 1; cc < nb; ++cc) {
+      int cc = c + 1;
+      for (; cc + 4 <= nb; cc += 4) {
+        double* q0 = P + (size_t)cc * pld;
+        double* q1 = q0 + pld;
+        double* q2 = q1 + pld;
+        double* q3 = q2 + pld;
+        const double u0 = q0[c], u1 = q1[c], u2 = q2[c], u3 = q3[c];
+        double x0 = q0[r], x1 = q1[r], x2 = q2[r], x3 = q3[r];
+        x0 -= l * u0;
+        x1 -= l * u1;
+        x2 -= l * u2;
+        x3 -= l * u3;
+        q0[r] = x0;
+        q1[r] = x1;
+        q2[r] = x2;
+        q3[r] = x3;
+      }
+      for (; cc < nb; ++cc) {
         double* q = P + (size_t)cc * pld;
         q[r] -= l * q[c];
       }
@@ -523,10 +548,10 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
   }
   if (use_smem) {
     for (int c = 0; c < nb; ++c)
-      for (int r = tid; r < rows; r += blockDim.x) C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
-    for (int r = tid; r < rows; r += blockDim.x) Rp[j0 + r] = rp[r];
+      for (int r = tid; r < rows; r += T) C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
+    for (int r = tid; r < rows; r += T) Rp[j0 + r] = rp[r];
   }
-  for (int r = tid; r < rows; r += blockDim.x)
+  for (int r = tid; r < rows; r += T)
     if (perm[r] != r) {
       const int slot = atomicAdd(&s_cnt, 1);
       aff_pos[slot] = j0 + r;
