@@ -1739,7 +1739,10 @@ static mlp_status refactor_impl(mlp_engine* e) {
     {  // (L U)^-1, one CTA per column
       const size_t need = (size_t)k * sizeof(double);
       const int use_smem = need <= e->smem_optin ? 1 : 0;
-      LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
+      if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
     }
     ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }

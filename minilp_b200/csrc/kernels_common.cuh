@@ -225,6 +225,78 @@ __global__ void __launch_bounds__(256) k_core_inverse(const double* __restrict__
     __syncthreads();
   }
 }
+// The same substitution for k <= 256 RPT with every thread owning FIXED rows (tid, tid + 256, ...) so that the entries of
+// the NEXT factor column can be fetched one step ahead: in k_core_inverse each of the ~2k sequential steps waits for a
+// global load of its column (L2 latency, ~650 cycles per step: 138 us at k = 207); here that latency is off the
+// critical path and a step costs one shared-memory round trip and a barrier.  Same operations in the same order.
+template <int RPT>
+__global__ void __launch_bounds__(256) k_core_inverse_pf(const double* __restrict__ LU, int64_t ld, int k, double* __restrict__ Cinv,
+                                                          const int* __restrict__ flags) {
+  extern __shared__ double smem_v[];
+  if (flags[1]) return;
+  const int j = blockIdx.x, tid = threadIdx.x;
+  double* out = Cinv + (int64_t)j * ld;
+  double* v = smem_v;
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + 256 * q;
+    if (i < k) v[i] = (i == j) ? 1.0 : 0.0;
+  }
+  double nxt[RPT];
+  // L y = e_j (unit diagonal; y_i = 0 for i < j)
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + 256 * q;
+    nxt[q] = (i < k && i > j) ? LU[(int64_t)j * ld + i] : 0.0;
+  }
+  __syncthreads();
+  for (int t = j; t < k - 1; ++t) {
+    double cur[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      cur[q] = nxt[q];
+      const int i = tid + 256 * q;
+      nxt[q] = (t + 2 < k && i < k && i > t + 1) ? LU[(int64_t)(t + 1) * ld + i] : 0.0;  // column of the next step
+    }
+    const double vt = v[t];
+    if (vt != 0.0) {
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int i = tid + 256 * q;
+        if (i < k && i > t) v[i] -= cur[q] * vt;
+      }
+    }
+    __syncthreads();
+  }
+  // U x = y
+  double dnx = LU[(int64_t)(k - 1) * ld + (k - 1)];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int i = tid + 256 * q;
+    nxt[q] = (i < k - 1) ? LU[(int64_t)(k - 1) * ld + i] : 0.0;
+  }
+  for (int t = k - 1; t >= 0; --t) {
+    double cur[RPT];
+    const double diag = dnx;
+    if (t > 0) dnx = LU[(int64_t)(t - 1) * ld + (t - 1)];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      cur[q] = nxt[q];
+      const int i = tid + 256 * q;
+      nxt[q] = (t > 0 && i < t - 1) ? LU[(int64_t)(t - 1) * ld + i] : 0.0;
+    }
+    const double vt = v[t] / diag;
+    if (vt != 0.0) {
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        const int i = tid + 256 * q;
+        if (i < t) v[i] -= cur[q] * vt;
+      }
+    }
+    if (tid == 0) out[t] = vt;
+    __syncthreads();
+  }
+}
 // New row K of (I+G)^-1 when eta K with coupling row g (g[i] = E_i[r_K], i < K) is appended:
 // [[T,0],[g^T,1]]^-1 = [[T^-1,0],[-g^T T^-1,1]].  One warp per column.
 __global__ void __launch_bounds__(256) k_eta_inv_row(const double* __restrict__ g, double* __restrict__ Ginv, int64_t ld, int K) {
@@ -460,9 +532,18 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     pld = rows;
     rp = reinterpret_cast<int32_t*>(P + (size_t)rows * nb);
     perm = rp + rows;
-    for (int c = 0; c < nb; ++c)
-      for (int r = tid; r < rows; r += T) P[(size_t)c * pld + r] = C[(int64_t)(j0 + c) * ld + j0 + r];
-    for (int r = tid; r < rows; r += T) rp[r] = Rp[j0 + r];
+    for (int r = tid; r < rows; r += T) {  // 8 global loads in flight per thread (a plain loop serialises them: ~12 us per panel)
+      const double* src = C + (int64_t)j0 * ld + j0 + r;
+      for (int c0 = 0; c0 < nb; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = c0 + u < nb ? src[(int64_t)(c0 + u) * ld] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u < nb) P[(size_t)(c0 + u) * pld + r] = v[u];
+      }
+      rp[r] = Rp[j0 + r];
+    }
   } else {
     P = C + (int64_t)j0 * ld + j0;
     pld = ld;
@@ -547,9 +628,18 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     __syncthreads();
   }
   if (use_smem) {
-    for (int c = 0; c < nb; ++c)
-      for (int r = tid; r < rows; r += T) C[(int64_t)(j0 + c) * ld + j0 + r] = P[(size_t)c * pld + r];
-    for (int r = tid; r < rows; r += T) Rp[j0 + r] = rp[r];
+    for (int r = tid; r < rows; r += T) {
+      double* dst = C + (int64_t)j0 * ld + j0 + r;
+      for (int c0 = 0; c0 < nb; c0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = c0 + u < nb ? P[(size_t)(c0 + u) * pld + r] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c0 + u < nb) dst[(int64_t)(c0 + u) * ld] = v[u];
+      }
+      Rp[j0 + r] = rp[r];
+    }
   }
   for (int r = tid; r < rows; r += T)
     if (perm[r] != r) {
