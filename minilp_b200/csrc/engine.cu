@@ -226,6 +226,9 @@ struct mlp_engine {
   int32_t *csr_idx = nullptr, *csc_idx = nullptr;         // nnz
   double *csr_val = nullptr, *csc_val = nullptr;          // nnz
   std::vector<int64_t> h_csc_ptr;                         // host copy: column counts for LUFactors::nnz
+  std::vector<int64_t> h_csr_ptr;                         // host copy of the CSR matrix: Solution::add_constraint appends a row and
+  std::vector<int32_t> h_csr_idx;                         // rebuilds the CSC copy and the segment table from it, as the reference
+  std::vector<double> h_csr_val;                          // rebuilds its CSR and CSC (solver.rs:598-610)
   int32_t *corevar = nullptr, *corepos = nullptr, *rowcore = nullptr;  // kcap, n, m: see k_ftran_finish_csr
   int64_t corevar_k = 0;                                  // entries of corevar currently marked in corepos
   // segment table of the CSC copy (<= CSC_SEG entries of one column per segment) and the core's slice of it
@@ -2068,7 +2071,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   auto A = [&](mlp_status s) { if (st == MLP_OK) st = s; };
   // Row capacity: Solution::add_constraint / add_gomory_cut (lib.rs:368-423) append rows; every row-indexed array is
   // allocated for mld rows so that appending one costs O(n), not a re-layout.
-  e->mld = sparse ? m : m + std::max<int64_t>(64, m / 8);
+  e->mld = m + std::max<int64_t>(64, m / 8);
   if (const char* v = getenv("MLP_ROW_RESERVE")) e->mld = m + std::max<int64_t>(0, atoll(v));
   if (mld_override >= m) e->mld = mld_override;
   const int64_t ml = e->mld, ntc = e->n + ml, gt = ng + ml;
@@ -2166,42 +2169,30 @@ mlp_status mlp_nccl_get_unique_id(void* out128) {
 mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out) {
   return create_engine(device, m, n, 0, 1, nullptr, out);
 }
-mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
-                                    const double* vals, mlp_engine** out) {
-  *out = nullptr;
-  if (!row_ptr || !col_idx || !vals || nnz < 0 || m <= 0 || n <= 0 || row_ptr[0] != 0 || row_ptr[m] != nnz) {
-    set_err("create_sparse: bad CSR");
-    return MLP_INVALID;
-  }
-  // CsMat::to_csc (solver.rs:253): counting transpose, rows ascending within a column (sparse.rs:230-269 does the same)
+// (Re)build everything the engine derives from the host CSR copy (h_csr_*): the CSC copy — CsMat::to_csc (solver.rs:253,
+// 610), a counting transpose with rows ascending within a column (sparse.rs:230-269 does the same) —, the segment table
+// of the CSC copy, and the device arrays.  m = number of rows of the CSR copy.
+static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
+  const int64_t n = e->n, nnz = (int64_t)e->h_csr_idx.size();
+  const int64_t* row_ptr = e->h_csr_ptr.data();
+  const int32_t* col_idx = e->h_csr_idx.data();
+  const double* vals = e->h_csr_val.data();
   std::vector<int64_t> cptr((size_t)n + 1, 0);
-  for (int64_t t = 0; t < nnz; ++t) {
-    if (col_idx[t] < 0 || col_idx[t] >= n) { set_err("create_sparse: column index out of range"); return MLP_INVALID; }
-    cptr[(size_t)col_idx[t] + 1] += 1;
-  }
+  for (int64_t t = 0; t < nnz; ++t) cptr[(size_t)col_idx[t] + 1] += 1;
   for (int64_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
   std::vector<int32_t> cidx((size_t)nnz);
   std::vector<double> cval((size_t)nnz);
   {
     std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
-    for (int64_t i = 0; i < m; ++i) {
-      if (row_ptr[i + 1] < row_ptr[i]) { set_err("create_sparse: row_ptr not monotone"); return MLP_INVALID; }
+    for (int64_t i = 0; i < m; ++i)
       for (int64_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
         const int64_t d = fill[col_idx[t]]++;
         cidx[d] = (int32_t)i;
         cval[d] = vals[t];
       }
-    }
   }
-  mlp_engine* e = nullptr;
-  ST(create_engine(device, m, n, 0, 1, nullptr, &e, true));
   e->nnz = nnz;
   e->h_csc_ptr = cptr;
-  mlp_status st = MLP_OK;
-  auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
-  A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
-  A(dev_alloc(&e->csc_ptr, n + 1)); A(dev_alloc(&e->csc_idx, nnz)); A(dev_alloc(&e->csc_val, nnz));
-  A(dev_alloc(&e->corepos, n)); A(dev_alloc(&e->rowcore, m));
   std::vector<int32_t> sgc;
   std::vector<int64_t> sgo, cseg((size_t)n + 1, 0);
   for (int64_t j = 0; j < n; ++j) {
@@ -2212,15 +2203,19 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
   cseg[n] = (int64_t)sgc.size();
   e->nseg = (int64_t)sgc.size();
   e->h_col_seg = cseg;
+  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  dev_free(e->csr_ptr); dev_free(e->csr_idx); dev_free(e->csr_val); dev_free(e->csc_ptr); dev_free(e->csc_idx); dev_free(e->csc_val);
+  dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum);
+  mlp_status st = MLP_OK;
+  auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
+  A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
+  A(dev_alloc(&e->csc_ptr, n + 1)); A(dev_alloc(&e->csc_idx, nnz)); A(dev_alloc(&e->csc_val, nnz));
   A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg)); A(dev_alloc(&e->col_seg, n + 1));
   A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
   if (st == MLP_OK) {
     A(h2d(e, e->seg_col, sgc.data(), e->nseg * sizeof(int32_t)));
     A(h2d(e, e->seg_off, sgo.data(), e->nseg * sizeof(int64_t)));
     A(h2d(e, e->col_seg, cseg.data(), (n + 1) * sizeof(int64_t)));
-  }
-  if (st == MLP_OK && cudaMemsetAsync(e->corepos, 0xff, n * sizeof(int32_t), e->stream) != cudaSuccess) st = MLP_CUDA_ERROR;
-  if (st == MLP_OK) {
     A(h2d(e, e->csr_ptr, row_ptr, (m + 1) * sizeof(int64_t)));
     A(h2d(e, e->csr_idx, col_idx, nnz * sizeof(int32_t)));
     A(h2d(e, e->csr_val, vals, nnz * sizeof(double)));
@@ -2228,7 +2223,30 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
     A(h2d(e, e->csc_idx, cidx.data(), nnz * sizeof(int32_t)));
     A(h2d(e, e->csc_val, cval.data(), nnz * sizeof(double)));
   }
-  if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("create_sparse: upload failed"); st = MLP_CUDA_ERROR; }
+  if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("sparse upload failed"); st = MLP_CUDA_ERROR; }
+  return st;  // host vectors go out of scope only after the synchronize
+}
+mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
+                                    const double* vals, mlp_engine** out) {
+  *out = nullptr;
+  if (!row_ptr || !col_idx || !vals || nnz < 0 || m <= 0 || n <= 0 || row_ptr[0] != 0 || row_ptr[m] != nnz) {
+    set_err("create_sparse: bad CSR");
+    return MLP_INVALID;
+  }
+  for (int64_t i = 0; i < m; ++i)
+    if (row_ptr[i + 1] < row_ptr[i]) { set_err("create_sparse: row_ptr not monotone"); return MLP_INVALID; }
+  for (int64_t t = 0; t < nnz; ++t)
+    if (col_idx[t] < 0 || col_idx[t] >= n) { set_err("create_sparse: column index out of range"); return MLP_INVALID; }
+  mlp_engine* e = nullptr;
+  ST(create_engine(device, m, n, 0, 1, nullptr, &e, true));
+  e->h_csr_ptr.assign(row_ptr, row_ptr + m + 1);
+  e->h_csr_idx.assign(col_idx, col_idx + nnz);
+  e->h_csr_val.assign(vals, vals + nnz);
+  mlp_status st = MLP_OK;
+  auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
+  A(dev_alloc(&e->corepos, n)); A(dev_alloc(&e->rowcore, e->mld));
+  if (st == MLP_OK && cudaMemsetAsync(e->corepos, 0xff, n * sizeof(int32_t), e->stream) != cudaSuccess) st = MLP_CUDA_ERROR;
+  A(sparse_upload(e, m));
   if (st != MLP_OK) { destroy_engine(e); return st; }
   *out = e;
   return MLP_OK;
@@ -2692,7 +2710,7 @@ mlp_status mlp_set_nb_state(mlp_engine* e, int64_t var, uint32_t flags) {
 mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double* slack_coeffs, double slack_min, double slack_max,
                               double rhs, mlp_add_row_result* out) {
   if (!e || !e->initialized || !coeffs || !out) return MLP_INVALID;
-  if (e->sparse || e->world != 1) { set_err("add_row: dense single-shard engines only (row f2 is partly built)"); return MLP_INVALID; }
+  if (e->world != 1) { set_err("add_row: single-shard engines only (row f2 is partly built)"); return MLP_INVALID; }
   if (e->m >= e->mld) { set_err("add_row: row capacity exhausted (MLP_ROW_RESERVE)"); return MLP_NOMEM; }
   CU(cudaSetDevice(e->device));
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
@@ -2702,6 +2720,72 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
   e->spec_var = e->ftran_var = -1;
   e->colq_var = -1;
   e->dual_row_host = -1;
+  if (e->sparse) {
+    // Sparse storage: the row is appended to the host CSR copy and the CSC copy, the segment table and the device
+    // arrays are rebuilt from it — O(nnz), what the reference does per added constraint (solver.rs:598-610 rebuilds
+    // its CSR row by row and calls to_csc).  The scalar work of 563-591 is done on the host in index order.
+    std::vector<double> row(coeffs, coeffs + n);
+    double rhs_new = rhs;
+    if (slack_coeffs) {  // Gomory cut: substitute s_i = rhs_i - a_i x (see the dense path and DESIGN.md §8)
+      std::vector<double> rhs_old((size_t)m), t((size_t)n, 0.0);
+      ST(d2h(e, rhs_old.data(), e->rhs, m * 8));
+      double dot = 0.0;
+      for (int64_t i = 0; i < m; ++i) {
+        const double g = slack_coeffs[i];
+        if (g == 0.0) continue;
+        for (int64_t q = e->h_csr_ptr[i]; q < e->h_csr_ptr[i + 1]; ++q) t[(size_t)e->h_csr_idx[q]] += g * e->h_csr_val[q];
+        dot += g * rhs_old[(size_t)i];
+      }
+      for (int64_t j = 0; j < n; ++j) row[(size_t)j] -= t[(size_t)j];
+      rhs_new = rhs - dot;
+    }
+    // basic value of the new slack: rhs - a . x over the structural variables (583-591), in index order
+    std::vector<double> xnb((size_t)e->nt), xb((size_t)m);
+    std::vector<uint8_t> fl((size_t)e->nt);
+    std::vector<int32_t> pos((size_t)e->nt);
+    ST(d2h(e, xnb.data(), e->xnb, e->nt * 8));
+    ST(d2h(e, xb.data(), e->xB, m * 8));
+    ST(d2h(e, fl.data(), e->vflag, e->nt));
+    ST(d2h(e, pos.data(), e->vpos, e->nt * 4));
+    double ax = 0.0;
+    int64_t row_nnz = 0;
+    for (int64_t j = 0; j < n; ++j) {
+      const double c = row[(size_t)j];
+      if (c == 0.0) continue;
+      ++row_nnz;
+      ax += c * ((fl[(size_t)j] & MLP_BASIC) ? xb[(size_t)pos[(size_t)j]] : xnb[(size_t)j]);
+    }
+    const double val = rhs_new - ax;
+    for (int64_t j = 0; j < n; ++j)
+      if (row[(size_t)j] != 0.0) { e->h_csr_idx.push_back((int32_t)j); e->h_csr_val.push_back(row[(size_t)j]); }
+    e->h_csr_ptr.push_back(e->h_csr_ptr.back() + row_nnz);
+    ST(sparse_upload(e, m + 1));
+    double two[2] = {rhs_new, val};
+    ST(h2d(e, e->scal + 7, two, sizeof(two)));  // [7] rhs of the new row, [8] its basic value
+    LAUNCH(e, k_new_row_state, 1, 1, 0, r, lv, gv, slack_min, slack_max, e->scal + 8, e->scal + 7, e->lo, e->hi, e->cobj, e->d, e->gam,
+           e->xnb, e->vflag, e->vpos, e->bvar, e->xB, e->loB, e->hiB, e->w, e->rhs, e->rowcover);
+    CU(cudaStreamSynchronize(e->stream));
+    e->m += 1;
+    e->nt += 1;
+    e->h_bvar.push_back(gv);
+    e->h_slot_of_row.push_back(-1);
+    e->h_last_eta_of_row.push_back(-1);
+    ST(refactor_impl(e));  // basis_solver.reset (612)
+    ST(mark0(e));
+    if (e->enable_pse || e->enable_dse) {  // 615-630: the new tableau row extends the steepest-edge norms
+      ST(mlp_calc_row_coeffs(e, r));
+      ST(begin0(e));
+      if (e->enable_pse) LAUNCH(e, k_add_sq, cdiv(e->nt, 256), 256, 0, e->gam, e->rc, e->vflag, e->nt);
+      if (e->enable_dse) LAUNCH(e, k_copy1, 1, 1, 0, e->w + r, e->scal + 1);
+      ST(mark0(e));
+    }
+    out->row = r;
+    out->slack_var = gv;
+    out->lu_nnz = e->lu_nnz;
+    ST(d2h(e, &out->basic_val, e->xB + r, 8));
+    ST(d2h(e, &out->rhs, e->rhs + r, 8));
+    return MLP_OK;
+  }
   double* rowA = e->A + r * e->lda;
   ST(h2d(e, rowA, coeffs, n * 8));
   double* d_rhs_new = e->scal + 7;
@@ -2761,7 +2845,7 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
 mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   if (!src || !out || !src->initialized) return MLP_INVALID;
   *out = nullptr;
-  if (src->world != 1 || src->sparse) { set_err("clone: dense single-shard engines only"); return MLP_INVALID; }
+  if (src->world != 1) { set_err("clone: single-shard engines only"); return MLP_INVALID; }
   CU(cudaSetDevice(src->device));
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(src->lane[l].st));
   mlp_engine* e = nullptr;
@@ -2775,14 +2859,11 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   };
   auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
   const size_t ml = (size_t)src->mld, ntc = (size_t)src->n + ml, gt = (size_t)src->ng + ml;
-  if (src->sparse) {
-    e->nnz = src->nnz;
-    e->h_csc_ptr = src->h_csc_ptr;
-    const size_t z = (size_t)src->nnz;
-    A(dev_alloc(&e->csr_ptr, src->m + 1)); A(dev_alloc(&e->csr_idx, z)); A(dev_alloc(&e->csr_val, z));
-    A(dev_alloc(&e->csc_ptr, src->n + 1)); A(dev_alloc(&e->csc_idx, z)); A(dev_alloc(&e->csc_val, z));
-    cp(e->csr_ptr, src->csr_ptr, (src->m + 1) * 8); cp(e->csr_idx, src->csr_idx, z * 4); cp(e->csr_val, src->csr_val, z * 8);
-    cp(e->csc_ptr, src->csc_ptr, (src->n + 1) * 8); cp(e->csc_idx, src->csc_idx, z * 4); cp(e->csc_val, src->csc_val, z * 8);
+  if (src->sparse) {  // matrix, CSC copy and segment table from the host CSR copy; then the core marks of the current factors
+    e->h_csr_ptr = src->h_csr_ptr; e->h_csr_idx = src->h_csr_idx; e->h_csr_val = src->h_csr_val;
+    A(dev_alloc(&e->corepos, (size_t)src->n)); A(dev_alloc(&e->rowcore, ml));
+    if (st == MLP_OK) A(sparse_upload(e, src->m));
+    cp(e->corepos, src->corepos, (size_t)src->n * 4); cp(e->rowcore, src->rowcore, ml * 4);
   } else cp(e->A, src->A, ml * (size_t)src->lda * 8);
   cp(e->lo, src->lo, gt * 8); cp(e->hi, src->hi, gt * 8); cp(e->cobj, src->cobj, gt * 8);
   cp(e->d, src->d, ntc * 8); cp(e->gam, src->gam, ntc * 8); cp(e->xnb, src->xnb, ntc * 8);
@@ -2797,7 +2878,18 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
     if (st == MLP_OK && e->kcap != src->kcap) { set_err("clone: capacity mismatch"); st = MLP_INVALID; }
     const size_t kc = (size_t)src->kcap;
     cp(e->Jpos, src->Jpos, kc * 4); cp(e->Jslot, src->Jslot, kc * 4); cp(e->Rp, src->Rp, kc * 4);
-    cp(e->Bcols, src->Bcols, ml * kc * 8); cp(e->LUc, src->LUc, kc * kc * 8); cp(e->Cinv, src->Cinv, kc * kc * 8);
+    if (!src->sparse) cp(e->Bcols, src->Bcols, ml * kc * 8);
+    cp(e->LUc, src->LUc, kc * kc * 8); cp(e->Cinv, src->Cinv, kc * kc * 8);
+    if (src->sparse) {
+      cp(e->corevar, src->corevar, kc * 4); cp(e->cseg_first, src->cseg_first, (kc + 1) * 4);
+      e->corevar_k = src->corevar_k;
+      e->ncseg = src->ncseg;
+      if (src->cseg_cap > 0) {
+        e->cseg_cap = src->cseg_cap;
+        A(dev_alloc(&e->cseg_id, (size_t)e->cseg_cap)); A(dev_alloc(&e->csum[0], (size_t)e->cseg_cap)); A(dev_alloc(&e->csum[1], (size_t)e->cseg_cap));
+        cp(e->cseg_id, src->cseg_id, (size_t)src->ncseg * 4);
+      }
+    }
   }
   if (st == MLP_OK && src->Kcap > 0) {
     A(ensure_eta_capacity(e, src->Kcap, true));

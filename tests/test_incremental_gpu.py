@@ -1,6 +1,6 @@
 """Solution::add_constraint / fix_var / unfix_var / add_gomory_cut (lib.rs:368-423) on the device
 engine — the reference's own tests (lib.rs:544-645; `clone()` replaced by re-solving) and differential runs against the
-oracle on mid-size LPs."""
+oracle on mid-size LPs — for both storages of the matrix (dense rows in HBM; CSR + CSC)."""
 import numpy as np
 import pytest
 
@@ -12,6 +12,7 @@ from test_parity_gpu import close
 pytestmark = pytest.mark.gpu
 INF = float("inf")
 Le, Ge, Eq = mb.ComparisonOp.Le, mb.ComparisonOp.Ge, mb.ComparisonOp.Eq
+STORAGES = pytest.mark.parametrize("storage", ["dense", "sparse"])
 
 
 def fix_unfix_problem():
@@ -23,9 +24,11 @@ def fix_unfix_problem():
     return p, v1, v2
 
 
-def test_lib_fix_unfix_var():
+@STORAGES
+def test_lib_fix_unfix_var(storage):
     """lib.rs:544-576"""
     p, v1, v2 = fix_unfix_problem()
+    _solve, p.solve = p.solve, lambda: _solve(storage=storage)
     sol = p.solve().fix_var(v1, 0.5)
     assert (sol[v1], sol[v2], sol.objective()) == (0.5, 3.0, 6.5)
     sol, was = sol.unfix_var(v1)
@@ -40,10 +43,11 @@ def test_lib_fix_unfix_var():
         p.solve().fix_var(v1, 3.5)  # outside the bounds, solver.rs:379-381
 
 
-def test_clone_continues_identically():
+@STORAGES
+def test_clone_continues_identically(storage):
     """Solution: Clone (lib.rs:313): the reference's tests branch off one solved problem with clone()."""
     p, v1, v2 = fix_unfix_problem()
-    orig = p.solve()
+    orig = p.solve(storage=storage)
     a = orig.clone().fix_var(v1, 0.5)
     assert (a[v1], a[v2], a.objective()) == (0.5, 3.0, 6.5)
     b = orig.clone().fix_var(v2, 2.5)
@@ -51,7 +55,12 @@ def test_clone_continues_identically():
     assert (orig[v1], orig[v2], orig.objective()) == (1.0, 3.0, 7.0)  # the source is untouched
     # mid-solve clone of a larger LP (factors + eta file copied): both continue to the same end, pivot for pivot
     lp = mb.synth_dense(3, 80, 120, 5)
-    s = mb.Solver.from_dense(lp)
+    if storage == "sparse":
+        rp = np.arange(0, 80 * 120 + 1, 120, dtype=np.int64)
+        ci = np.tile(np.arange(120, dtype=np.int32), 80)
+        s = mb.Solver.from_csr(lp.direction, 80, 120, rp, ci, lp.a.ravel(), lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
+    else:
+        s = mb.Solver.from_dense(lp)
     s.run(37)
     c = s.clone()
     assert s.run() and c.run()
@@ -70,9 +79,11 @@ def add_constraint_problem():
     return p, v1, v2
 
 
-def test_lib_add_constraint():
+@STORAGES
+def test_lib_add_constraint(storage):
     """lib.rs:579-621"""
     p, v1, v2 = add_constraint_problem()
+    _solve, p.solve = p.solve, lambda: _solve(storage=storage)
     sol = p.solve().add_constraint([(v1, -1.0), (v2, 1.0)], Le, 0.0)
     assert (sol[v1], sol[v2], sol.objective()) == (1.0, 1.0, 3.0)
     sol = p.solve().fix_var(v2, 1.5).add_constraint([(v1, -1.0), (v2, 1.0)], Le, 0.0)
@@ -89,14 +100,15 @@ def test_lib_add_constraint():
         p.solve().add_constraint([(v1, 1.0), (v2, 1.0)], Ge, 5.0)  # contradicts x + y <= 4
 
 
-def test_lib_gomory_cut():
+@STORAGES
+def test_lib_gomory_cut(storage):
     """lib.rs:624-645"""
     p = mb.Problem(mb.OptimizationDirection.Minimize)
     v1 = p.add_var(0.0, (0.0, INF))
     v2 = p.add_var(-1.0, (0.0, INF))
     p.add_constraint([(v1, 3.0), (v2, 2.0)], Le, 6.0)
     p.add_constraint([(v1, -3.0), (v2, 2.0)], Le, 0.0)
-    sol = p.solve()
+    sol = p.solve(storage=storage)
     assert (sol[v1], sol[v2], sol.objective()) == (1.0, 1.5, -1.5)
     sol = sol.add_gomory_cut(v2)
     assert abs(sol[v1] - 2.0 / 3.0) < 1e-8 and abs(sol[v2] - 1.0) < 1e-12 and abs(sol.objective() + 1.0) < 1e-12
@@ -104,7 +116,7 @@ def test_lib_gomory_cut():
     assert abs(sol[v1] - 1.0) < 1e-8 and abs(sol[v2] - 1.0) < 1e-12 and abs(sol.objective() + 1.0) < 1e-12
 
 
-def both(kind, m, n, seed):
+def both(kind, m, n, seed, storage="dense"):
     lp = mb.synth_dense(kind, m, n, seed)
     p = mb.Problem(lp.direction)
     q = oracle.Problem(lp.direction)
@@ -115,7 +127,7 @@ def both(kind, m, n, seed):
         e = [(j, float(lp.a[i, j])) for j in range(n)]
         p.add_constraint(e, int(lp.ops[i]), lp.rhs[i])
         q.add_constraint(e, int(lp.ops[i]), lp.rhs[i])
-    return lp, p.solve(storage="dense"), q.solve(tie_lowest_index=True)
+    return lp, p.solve(storage=storage), q.solve(tie_lowest_index=True)
 
 
 def same(g, r):
@@ -125,9 +137,10 @@ def same(g, r):
     assert tg.shape[0] == tr.shape[0] and np.array_equal(tg[:, [1, 3, 4]], tr[:, [1, 3, 4]]), "basis sequence differs"
 
 
+@STORAGES
 @pytest.mark.parametrize("kind,m,n,seed", [(0, 40, 60, 1), (3, 50, 50, 2), (1, 30, 45, 3)])
-def test_incremental_ops_match_oracle(kind, m, n, seed):
-    lp, g, r = both(kind, m, n, seed)
+def test_incremental_ops_match_oracle(kind, m, n, seed, storage):
+    lp, g, r = both(kind, m, n, seed, storage)
     same(g, r)
     rng = np.random.default_rng(seed)
     x = r.values()
@@ -174,10 +187,11 @@ def test_incremental_ops_match_oracle(kind, m, n, seed):
         same(g, r)
 
 
-def test_gomory_cuts_match_oracle_objective():
+@STORAGES
+def test_gomory_cuts_match_oracle_objective(storage):
     """Gomory cuts carry slack coefficients; the engine eliminates them, which changes the dual
     steepest-edge weights of later pivots: end states are compared, not the sequence."""
-    lp, g, r = both(0, 30, 40, 4)
+    lp, g, r = both(0, 30, 40, 4, storage)
     for _ in range(3):
         x = r.values()
         frac = np.abs(x - np.round(x))
