@@ -193,7 +193,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* info, mlp_pivot_result
 mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val);
 
 /* ---- incremental API: the engine half of Solver::fix_var (solver.rs:378-415), unfix_var (418-438),
- * add_constraint (549-634) and add_gomory_cut (440-460).  Dense single-shard engines. */
+ * add_constraint (549-634) and add_gomory_cut (440-460).  Single-shard engines, dense or sparse storage. */
 typedef struct mlp_var_info {
   uint32_t flags;      /* MLP_BASIC or MLP_AT_MIN | MLP_AT_MAX | MLP_FIXED */
   int64_t pos_or_row;  /* VarState::Basic(row) / NonBasic(col), solver.rs:60-64 */
