@@ -1,7 +1,7 @@
 """BASELINE config 2: 1000 x 1000 dense LP, FTRAN / BTRAN / price kernels only — device time per call (CUDA events
 through the ABI's marks, median of 50) next to the oracle port's probes on one host core."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import minilp_b200 as mb
 import oracle

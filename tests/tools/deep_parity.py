@@ -2,7 +2,7 @@
 the basis to hold more than 512 structural columns and the eta file more than 512 columns, i.e. past the limits of the
 fused chain (production thresholds, not the MLP_FUSED_MAX test knob).  Prints one JSON line per case."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import minilp_b200 as mb
 import oracle

@@ -1,8 +1,8 @@
 """BASELINE config 4 at scale: netlib-like sparse LP via MPS on one B200 vs the oracle port on one host core.
-   python scripts/sparse_scale.py [--m 100000 --n 100000 --col-nnz 100 --pivots 2000]
+   python tests/tools/sparse_scale.py [--m 100000 --n 100000 --col-nnz 100 --pivots 2000]
 Prints one JSON line (not a bench.py line: config 4 is a parity case, this is its measured footnote)."""
 import argparse, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import minilp_b200 as mb
 from minilp_b200 import mps, synth
