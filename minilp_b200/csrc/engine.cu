@@ -1479,7 +1479,9 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
     // kernel holds 194 KB of shared memory per SM, so a second instance cannot become resident until the first one has
     // finished (measured: the rho price-out waited 2.6 ms per pivot, and with it the whole tail of lane 1).  The LDG form
     // needs no shared-memory ring and slips in next to it; its partial sums are bit-identical.
-    const bool beside = e->overlap && e->lane1_ldg && e->enable_pse && &ln == &e->lane[1];  // pse: lane 0 is pricing out too
+    // (only while lane 0's N^T v of the same pivot is queued or running — spec_var — i.e. in the primal loop; in the dual
+    // loop the tableau row is priced out before the entering column is known and has the GPU to itself)
+    const bool beside = e->overlap && e->lane1_ldg && e->enable_pse && e->spec_var != -1 && &ln == &e->lane[1];
     if (e->price_tma && !beside)
       launch_price_tma(e, ln.st, rows, wts, count_ptr, fixed_count, ln.partial);
     else
