@@ -44,6 +44,12 @@ def parse_args():
     return ap.parse_args()
 
 
+def bench_config(a):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "m": a.m, "n": a.n, "kind": a.kind, "seed": a.seed,
+            "l2": "inputs_exceed_l2 (8*m*n bytes of A are read per pivot, split over the GPUs)"}
+
+
 def workload_name(a):
     fam = {0: "dense_pos", 1: "dense_box", 2: "dense_cover", 3: "dense_mixed"}[a.kind]
     return f"{fam} {a.m}x{a.n} seed {a.seed} (BASELINE config 3: full pivot loop with eta updates)"
@@ -107,7 +113,7 @@ def cpu_port_run(a, warmup, steps, budget_s, threads_for_gen):
         m = max(1000, a.m // 4)
         note = f" (host could not hold {a.m}x{a.n}: {type(exc).__name__}; rows cut to {m})"
         s = oracle.DenseSolver.synth(a.kind, m, a.n, a.seed, threads=threads_for_gen)
-    s.set_record_trace(False)
+    s.set_record_trace(True)  # the oracle's pivots of this very LP are the parity reference of the bench line
     if warmup > 0:
         s.continue_solve(warmup)
     done_p, sec = 0, 0.0
@@ -117,7 +123,26 @@ def cpu_port_run(a, warmup, steps, budget_s, threads_for_gen):
         done_p += 1
         if fin:
             break
-    return done_p, sec, m, note
+    ties = {"tied_pivots": s.tied_pivots, "near_tie_pivots": s.near_tie_pivots, "tie_events": s.tie_events}
+    return done_p, sec, m, note, s.trace().copy(), ties
+
+
+def parity_against(trace_gpu, trace_cpu, ties, m_used, m):
+    """Pivot-for-pivot comparison of the engine's trace with the oracle's (reference tie rule) on the same LP: phase, entering
+    variable, its position, leaving row, leaving variable must be equal; objective after each pivot within 1e-8 relative."""
+    if m_used != m:
+        return {"pivots_compared": 0, "note": "oracle ran a smaller LP (host memory)"}
+    k = int(min(trace_gpu.shape[0], trace_cpu.shape[0]))
+    if k == 0:
+        return {"pivots_compared": 0}
+    same = np.all(trace_gpu[:k, :5] == trace_cpu[:k, :5], axis=1)
+    first = -1 if same.all() else int(np.argmin(same))
+    upto = k if first < 0 else first
+    og, oc = trace_gpu[:upto, 7], trace_cpu[:upto, 7]
+    rel = float(np.max(np.abs(og - oc) / np.maximum(1.0, np.abs(oc)))) if upto else None
+    return {"pivots_compared": k, "first_divergence": first, "oracle_tie_events": ties["tie_events"],
+            "oracle_tied_pivots": ties["tied_pivots"], "oracle_near_tie_pivots": ties["near_tie_pivots"],
+            "obj_rel_diff": rel, "tolerance": 1e-8, "oracle": "oracle/ C++ port, reference tie rule, same LP from the slack basis"}
 
 
 def run_reference(a):
@@ -125,8 +150,8 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    wu = min(a.warmup, 1)
-    piv, sec, m_used, note = cpu_port_run(a, wu, a.steps, a.ref_budget_seconds, cores)
+    wu = a.warmup
+    piv, sec, m_used, note, _, _ = cpu_port_run(a, wu, a.steps, a.ref_budget_seconds, cores)
     val = piv / sec if sec > 0 else 0.0
     sample = (f"{piv} consecutive pivots after {wu} warm-up pivot(s) from the slack basis of the same {m_used}x{a.n} LP, "
               f"time-capped at {a.ref_budget_seconds:.0f}s{note}; matrix generation and try_new excluded")
@@ -134,8 +159,9 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": piv, "warmup": wu,
         "ms_per_step": 1000.0 * sec / max(piv, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "m": m_used, "n": a.n, "l2": "inputs_exceed_l2",
-                   "note": "reference = C++ port of minilp's Rust solver (oracle/), no Rust toolchain in the image"},
+        "config": bench_config(a),
+        "run_detail": {"m_used": m_used,
+                       "note": "reference = C++ port of minilp's Rust solver (oracle/), no Rust toolchain in the image"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                          "host_cores_available": cores},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -293,8 +319,8 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
         "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "m": a.m, "n": a.n,
-                   "l2": f"inputs_exceed_l2 (8*m*n/N = {8 * a.m * nloc / 1e9:.1f} GB of A are read per GPU per pivot)",
+        "config": bench_config(a),
+        "run_detail": {"a_bytes_per_gpu_per_pivot": 8 * a.m * nloc,
                    "parallelism": (f"columns sharded over {world} GPUs ({nloc} each), basis replicated, one candidate exchange "
                                    f"per pivot ({e.exchange_kind()})") if world > 1 else "single GPU",
                    "pivots_before_timed_region": p0, "optimal_reached": bool(done),
@@ -318,7 +344,9 @@ def run_ours(a):
         cores = os.cpu_count() or 1
         # the very first pivot of the port is ~7x slower than the following ones (first touch of its work vectors and of the
         # 20 GB matrix): it is run untimed, as the --impl reference arm does
-        piv, sec, m_used, note = cpu_port_run(a, 1, 1000, a.cpu_baseline_seconds, cores)
+        piv, sec, m_used, note, tr_cpu, ties = cpu_port_run(a, 1, 1000, a.cpu_baseline_seconds, cores)
+        line["parity"] = parity_against(s.trace(), tr_cpu, ties, m_used, a.m)
+        line["parity"]["engine_ties"] = s.tie_stats()
         line["cpu_baseline"] = {
             "value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"pivots 2..{piv + 1} of the same {m_used}x{a.n} LP after one untimed pivot ({sec:.1f}s of single-thread "

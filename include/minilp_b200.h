@@ -126,7 +126,6 @@ typedef struct mlp_entering {
   double obj_coeff; /* nb_var_obj_coeffs[pos] */
   double score;
   double cur_val;   /* nb_var_vals[pos] */
-  double var_min, var_max; /* unused (0): the host keeps orig_var_mins / orig_var_maxs, solver.rs:19-20 */
 } mlp_entering;
 mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out);
 
@@ -142,6 +141,10 @@ typedef struct mlp_leaving {
   double coeff;           /* pivot_coeff */
   double leaving_new_val; /* 813-819 */
   double basic_val;       /* basic_var_vals[row] (828) */
+  /* How contested the pass-2 winner was (804-823 keep the FIRST maximal |coeff| in col_coeffs list order, sparse.rs:75-80;
+   * the engine keeps the lowest row): other eligible rows whose |coeff| equals the winner's exactly / within 1e-9 relative.
+   * ties == 0 means the choice does not depend on the scan order. */
+  int64_t ties, near_ties;
 } mlp_leaving;
 mlp_status mlp_ratio_primal(mlp_engine* e, int32_t entering_diff_sign, double max_step0, mlp_leaving* out);
 
@@ -164,6 +167,7 @@ typedef struct mlp_dual_entering {
   double coeff;     /* pivot_coeff */
   double obj_coeff; /* nb_var_obj_coeffs[pos] */
   double cur_val;   /* nb_var_vals[pos] */
+  int64_t ties, near_ties; /* as in mlp_leaving, for pass 2 at 982-1002 (the engine keeps the lowest variable index) */
 } mlp_dual_entering;
 mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out);
 
@@ -191,6 +195,11 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* info, mlp_pivot_result
 
 /* recalc_obj_coeffs (solver.rs:1199-1231): y = B^-T c_B, d_N = c_N - N^T y, objective from scratch. */
 mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val);
+
+/* recalc_basic_var_vals (solver.rs:1177-1197; dead code in the reference, asked for by the TODO at 1024-1025): x_B =
+ * B^-1 (rhs - N x_N) from scratch, refactorizing first when etas exist.  SURVEY.md §8 row f4: never called unless the
+ * host asks (mlp_solver_set_recalc_period), so the default path is the reference's. */
+mlp_status mlp_recalc_basic_vals(mlp_engine* e);
 
 /* ---- incremental API: the engine half of Solver::fix_var (solver.rs:378-415), unfix_var (418-438),
  * add_constraint (549-634) and add_gomory_cut (440-460).  Single-shard engines, dense or sparse storage. */
@@ -245,6 +254,8 @@ typedef struct mlp_counters {
   int64_t k_structural; /* structural columns in the last factorized basis */
   int64_t lu_nnz;       /* LUFactors::nnz of the current factors (lu.rs:52-54) */
   int64_t eta_count;    /* eta_matrices.len() */
+  int64_t ratio_ties;      /* ratio tests (primal or dual) whose pass-2 winner was tied exactly */
+  int64_t ratio_near_ties; /* ... or within 1e-9 relative (includes the exact ones) */
 } mlp_counters;
 mlp_status mlp_get_counters(mlp_engine* e, mlp_counters* out);
 /* cudaStream_t of the engine (as void*), for CUDA-event timing by the caller. */
@@ -328,6 +339,14 @@ mlp_status mlp_solver_clone(mlp_solver* s, mlp_solver** out);
 /* host mirrors of nb_vars (n) and basic_vars (m) */
 mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out);
 mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out);
+/* Row f4: every `period` pivots (0, the default = never = the reference's behaviour) recompute x_B and — unless the
+ * artificial objective of solver.rs:261 is in place — d and the objective from scratch. */
+void mlp_solver_set_recalc_period(mlp_solver* s, int64_t period);
+int64_t mlp_solver_recalcs_done(mlp_solver* s);
+/* Pivots whose ratio-test winner was contested (see mlp_leaving.ties): out4 = { pivots tied exactly, pivots tied within
+ * 1e-9, index of the first exactly tied pivot or -1, index of the first near-tied pivot or -1 }.  All zero / -1 means the
+ * pivot sequence does not depend on the reference's list-order rule (sparse.rs:75-80 with solver.rs:811, 996). */
+void mlp_solver_tie_stats(mlp_solver* s, int64_t out4[4]);
 /* seconds of wall clock spent inside mlp_solver_run so far, and of that inside refactorizations */
 void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds);
 

@@ -24,12 +24,11 @@ class InitState(C.Structure):
 
 
 class Entering(C.Structure):
-    _fields_ = [("var", i64), ("pos", i64), ("obj_coeff", f64), ("score", f64), ("cur_val", f64), ("var_min", f64),
-                ("var_max", f64)]
+    _fields_ = [("var", i64), ("pos", i64), ("obj_coeff", f64), ("score", f64), ("cur_val", f64)]
 
 
 class Leaving(C.Structure):
-    _fields_ = [("row", i64), ("coeff", f64), ("leaving_new_val", f64), ("basic_val", f64)]
+    _fields_ = [("row", i64), ("coeff", f64), ("leaving_new_val", f64), ("basic_val", f64), ("ties", i64), ("near_ties", i64)]
 
 
 class DualRow(C.Structure):
@@ -37,7 +36,8 @@ class DualRow(C.Structure):
 
 
 class DualEntering(C.Structure):
-    _fields_ = [("var", i64), ("pos", i64), ("coeff", f64), ("obj_coeff", f64), ("cur_val", f64)]
+    _fields_ = [("var", i64), ("pos", i64), ("coeff", f64), ("obj_coeff", f64), ("cur_val", f64), ("ties", i64),
+                ("near_ties", i64)]
 
 
 class PivotInfo(C.Structure):
@@ -59,7 +59,7 @@ class AddRowResult(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", i64), ("h2d_bytes", i64), ("d2h_bytes", i64), ("refactors", i64), ("etas_pushed", i64),
-                ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64)]
+                ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64), ("ratio_ties", i64), ("ratio_near_ties", i64)]
 
 
 class Profile(C.Structure):
@@ -97,6 +97,9 @@ SIGNATURES = {
     "mlp_ratio_dual": (i32, [vp, i64, f64, C.POINTER(DualEntering)]),
     "mlp_pivot": (i32, [vp, C.POINTER(PivotInfo), C.POINTER(PivotResult)]),
     "mlp_recalc_obj_coeffs": (i32, [vp, pd]),
+    "mlp_recalc_basic_vals": (i32, [vp]),
+    "mlp_solver_set_recalc_period": (None, [vp, i64]),
+    "mlp_solver_recalcs_done": (i64, [vp]),
     "mlp_engine_clone": (i32, [vp, C.POINTER(vp)]),
     "mlp_solver_clone": (i32, [vp, C.POINTER(vp)]),
     "mlp_get_var": (i32, [vp, i64, C.POINTER(VarInfo)]),
@@ -138,6 +141,7 @@ SIGNATURES = {
     "mlp_solver_get_nb_vars": (i32, [vp, pi64]),
     "mlp_solver_get_basic_vars": (i32, [vp, pi64]),
     "mlp_solver_timers": (None, [vp, pd, pd]),
+    "mlp_solver_tie_stats": (None, [vp, pi64]),
     "mlp_shard_range": (None, [i64, i32, i32, pi64, pi64]),
     "mlp_reduce_candidates": (i32, [pd, pi64, pi64, i32]),
     "mlp_synth_rows": (None, [i32, i64, i64, C.c_uint64, i64, i64, i32, pd]),
@@ -147,16 +151,12 @@ SIGNATURES = {
 
 
 def build(force=False):
-    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    """Compile the CUDA extension in-tree for sm_100a (nvcc cross-compiles without a GPU).  make decides what is stale:
+    its prerequisite list names every source, so no second list can fall out of date here."""
     csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("engine.cu", "kernels_common.cuh", "host_solver.cpp", "synth.cpp", "Makefile")]
-    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "minilp_b200.h"))
-    if (not force and os.path.exists(LIB_PATH)
-            and os.path.getmtime(LIB_PATH) >= max(os.path.getmtime(s) for s in srcs)):
-        return LIB_PATH
-    subprocess.check_call(["make", "-C", csrc, "-s"])
+    cmd = ["make", "-C", csrc, "-s"] + (["-B"] if force else [])
+    subprocess.check_call(cmd)
     return LIB_PATH
-
 
 def lib():
     """Load libminilp_b200.so; fails loudly if it is missing (there is no Python/CPU fallback)."""

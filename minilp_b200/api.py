@@ -191,6 +191,10 @@ class Engine:
         _check(_lib.lib().mlp_ratio_dual(self._e, row, leaving_new_val, C.byref(out)))
         return out
 
+    def recalc_basic_vals(self):
+        """recalc_basic_var_vals (solver.rs:1177-1197): x_B from scratch (row f4)."""
+        _check(_lib.lib().mlp_recalc_basic_vals(self._e))
+
     def refactor(self):
         z = C.c_int64()
         _check(_lib.lib().mlp_refactor(self._e, C.byref(z)))
@@ -360,6 +364,14 @@ class Solver:
     def set_record_trace(self, on):
         _lib.lib().mlp_solver_set_record_trace(self._s, int(on))
 
+    def set_recalc_period(self, period):
+        """Row f4: recompute x_B and d from scratch every `period` pivots (0 = never, the reference's behaviour)."""
+        _lib.lib().mlp_solver_set_recalc_period(self._s, int(period))
+
+    @property
+    def recalcs_done(self):
+        return int(_lib.lib().mlp_solver_recalcs_done(self._s))
+
     def nb_vars(self):
         out = np.empty(self.n, dtype=np.int64)
         _check(_lib.lib().mlp_solver_get_nb_vars(self._s, _p(out, pi64)))
@@ -369,6 +381,12 @@ class Solver:
         out = np.empty(self.m, dtype=np.int64)
         _check(_lib.lib().mlp_solver_get_basic_vars(self._s, _p(out, pi64)))
         return out
+
+    def tie_stats(self):
+        """Pivots whose ratio-test winner was contested: dict(tied_pivots, near_tie_pivots, first_tied_pivot, first_near_tie_pivot)."""
+        out = np.zeros(4, dtype=np.int64)
+        _lib.lib().mlp_solver_tie_stats(self._s, _p(out, pi64))
+        return dict(zip(("tied_pivots", "near_tie_pivots", "first_tied_pivot", "first_near_tie_pivot"), (int(x) for x in out)))
 
     def timers(self):
         a, b = C.c_double(), C.c_double()
@@ -535,13 +553,18 @@ class Solution:
 
 class _TrivialSolution:
     """No constraints survive try_new (all tautological): the reference's loops make no pivot unless a variable
-    can improve without bound (solver.rs:841-844)."""
+    can improve without bound (solver.rs:841-844).  The incremental methods of lib.rs:368-423 work here too, as they do on
+    the reference's Solution of an unconstrained problem: the first real constraint builds the device engine."""
 
-    def __init__(self, p, n):
+    def __init__(self, p, n, fixed=None):
         self.direction, self.num_vars = p.direction, n
+        self._p = p
+        self._fixed = dict(fixed or {})  # var -> value (Solver::fix_var on a non-basic variable, solver.rs:394-411)
         vals, obj = [], 0.0
-        for c, mn, mx in zip(p.obj_coeffs, p.var_mins, p.var_maxs):
-            if mn == mx:
+        for j, (c, mn, mx) in enumerate(zip(p.obj_coeffs, p.var_mins, p.var_maxs)):
+            if j in self._fixed:
+                x = self._fixed[j]
+            elif mn == mx:
                 x = mn
             elif c > 0:
                 x = mn
@@ -562,3 +585,46 @@ class _TrivialSolution:
         return float(self._vals[var])
 
     __getitem__ = var_value
+
+    def __iter__(self):
+        return iter(enumerate(self._vals.tolist()))
+
+    def clone(self):
+        return _TrivialSolution(self._copy_problem(), self.num_vars, self._fixed)
+
+    def _copy_problem(self):
+        q = Problem(self._p.direction)
+        q.obj_coeffs, q.var_mins, q.var_maxs = list(self._p.obj_coeffs), list(self._p.var_mins), list(self._p.var_maxs)
+        q.constraints = list(self._p.constraints)
+        return q
+
+    def add_constraint(self, expr, cmp_op, rhs):
+        """lib.rs:368-382.  An empty expression is a tautology or infeasible (solver.rs:558-570); anything else makes this a
+        constrained problem: it is solved on the device and the variables fixed so far are fixed there again."""
+        q = self._copy_problem()
+        q.add_constraint(expr, cmp_op, rhs)
+        sol = q.solve()
+        for v, val in self._fixed.items():
+            sol = sol.fix_var(v, val)
+        return sol
+
+    def fix_var(self, var, val):
+        """lib.rs:391-395 / solver.rs:378-415 for a non-basic variable (every variable is non-basic here)."""
+        assert 0 <= var < self.num_vars
+        if val < self._p.var_mins[var] or val > self._p.var_maxs[var]:
+            raise Infeasible("value outside the variable's bounds")  # solver.rs:379-381
+        f = dict(self._fixed)
+        f[var] = float(val)
+        return _TrivialSolution(self._p, self.num_vars, f)
+
+    def unfix_var(self, var):
+        """lib.rs:400-404 / solver.rs:418-438: (solution, was_fixed)."""
+        assert 0 <= var < self.num_vars
+        if var not in self._fixed:
+            return self, False
+        f = dict(self._fixed)
+        del f[var]
+        return _TrivialSolution(self._p, self.num_vars, f), True
+
+    def add_gomory_cut(self, var):
+        raise ValueError("var is not basic")  # solver.rs:458 panics: without constraints no variable is basic

@@ -55,6 +55,8 @@ struct DevRes {  // small result block, mirrored in pinned host memory
 };
 // Selection candidate exchanged between column shards: 64-byte header, followed in the exchange buffer by the
 // candidate's column of [A|I] (m doubles).  Ordering: larger key wins, ties go to the smaller `tie`.
+// tie = (position or variable index) << 32 | tie counts of the dual ratio test (pack_ties; 0 for pricing candidates): the
+// high word is unique per candidate, so the low word never decides the order.
 struct Cand {
   double key;
   long long tie;
@@ -991,7 +993,7 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
     else {
       const long long v = b.idx & 0xffffffffLL;
       out->key = b.key;
-      out->tie = b.idx >> 32;
+      out->tie = (b.idx >> 32) << 32;
       out->var = v < n ? c0 + v : ng + (v - n);
       out->f[0] = d[v];
       out->f[1] = xnb[v];
@@ -999,6 +1001,16 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
   }
 }
 
+// low word of the winner's `tie` after absorbing a losing candidate of another shard: that candidate and its own ties
+// count towards the winner's when the keys agree exactly (low 16 bits) / within NEAR_TIE (next 16 bits)
+__host__ __device__ __forceinline__ long long merge_ties(long long wt, double wk, long long ct, double ck) {
+  long long e = wt & 0xffff, n = (wt >> 16) & 0xffff;
+  if (ck == wk) e += 1 + (ct & 0xffff);
+  if (ck >= wk * (1.0 - 1e-9)) n += 1 + ((ct >> 16) & 0xffff);
+  if (e > 65535) e = 65535;
+  if (n > 65535) n = 65535;
+  return (wt & ~0xffffffffLL) | (n << 16) | e;
+}
 // Arg-reduce of the gathered candidate headers ON THE DEVICE (larger key wins, ties go to the smaller `tie`: lowest
 // position, solver.rs:719) and copy of the winner's column into colq, so that the FTRAN of the entering column can be
 // queued behind the selection without a host round trip.  Every thread repeats the <= 8-way comparison.
@@ -1018,7 +1030,14 @@ __global__ void __launch_bounds__(256) k_pick_winner(const char* __restrict__ re
   if (i < m) colq[i] = best < 0 ? 0.0 : reinterpret_cast<const double*>(recv + (size_t)best * xbytes + sizeof(Cand))[i];
   if (i == 0) {
     if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
-    else *win = *reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
+    else {
+      Cand w = *reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
+      for (int r = 0; r < world; ++r) {  // ties of the winner across shards (dual ratio test)
+        const Cand* c = reinterpret_cast<const Cand*>(recv + (size_t)r * xbytes);
+        if (r != best && c->var >= 0) w.tie = merge_ties(w.tie, w.key, c->tie, c->key);
+      }
+      *win = w;
+    }
     win->f[4] = err;
   }
 }
@@ -1081,7 +1100,12 @@ __global__ void __launch_bounds__(256) k_exchange_p2p(PeerTable pt, int rank, in
     double err = s_bad ? 2.0 : 0.0;
     for (int r = 0; r < world; ++r) if (hdr[r].f[4] != 0.0 && err == 0.0) err = 1.0;
     if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
-    else *win = hdr[best];
+    else {
+      Cand w = hdr[best];
+      for (int r = 0; r < world; ++r)
+        if (r != best && hdr[r].var >= 0) w.tie = merge_ties(w.tie, w.key, hdr[r].tie, hdr[r].key);
+      *win = w;
+    }
     win->f[4] = err;
   }
 }
@@ -1130,7 +1154,8 @@ __global__ void k_min_small(const double* __restrict__ vals, int cnt, double* __
   for (int q = 0; q < cnt; ++q) b = fmin(b, vals[q]);
   *out = b;
 }
-// pass 2: exact ties in |coeff| go to the lowest GLOBAL variable index (the reference: first-touch order)
+// pass 2: exact ties in |coeff| go to the lowest GLOBAL variable index (the reference: first-touch order) and
+// are counted (candidate header `tie`, low word)
 __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__ rc, const double* __restrict__ d,
                                                        const uint8_t* __restrict__ vflag, const int32_t* __restrict__ vpos,
                                                        const double* __restrict__ xnb, int64_t nt, int64_t n, int64_t c0,
@@ -1139,8 +1164,9 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
                                                        unsigned* counter, const int* __restrict__ flags, Cand* out) {
   __shared__ double smk[32];
   __shared__ long long smi[32];
+  __shared__ long long smc[32];
   const double max_step = scal[0];
-  KeyIdx best{-INFINITY, LLONG_MAX};
+  KeyIdxC best{-INFINITY, LLONG_MAX, 0, 0};
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
     const unsigned f = vflag[v];
     if (f & MLP_BASIC) continue;
@@ -1149,18 +1175,23 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
     const double oc = clamp_obj(d[v], f);
     const double cur = fabs(oc) / fabs(coeff);  // 993
     const long long g = v < n ? c0 + v : ng + (v - n);
-    if (cur <= max_step && better_max(fabs(coeff), g, best.key, best.idx)) { best.key = fabs(coeff); best.idx = g; }
+    if (cur <= max_step) kic_merge(best, fabs(coeff), g, 1, 1);
   }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
+  best = block_argmax_c(best, smk, smi, smc);
+  if (threadIdx.x == 0) {
+    red_f[blockIdx.x] = best.key;
+    red_i[blockIdx.x] = best.idx;
+    red_i[RED_CNT_OFF + blockIdx.x] = ((long long)best.ex << 32) | (unsigned)best.nr;
+  }
   if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
+  KeyIdxC b{-INFINITY, LLONG_MAX, 0, 0};
   for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
     const double k = __ldcg(red_f + q);
     const long long i = __ldcg(red_i + q);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
+    const long long c = __ldcg(red_i + RED_CNT_OFF + q);
+    kic_merge(b, k, i, (int)(c >> 32), (int)(c & 0xffffffffLL));
   }
-  b = block_argmax(b, smk, smi);
+  b = block_argmax_c(b, smk, smi, smc);
   if (threadIdx.x == 0) {
     *counter = 0;
     out->f[4] = flags[2] ? 2.0 : (double)flags[0];
@@ -1169,7 +1200,7 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
       const long long g = b.idx;
       const long long v = g >= ng ? n + (g - ng) : g - c0;
       out->key = b.key;
-      out->tie = g;
+      out->tie = (g << 32) | pack_ties(b.ex, b.nr);
       out->var = g;
       out->f[0] = rc[v];
       out->f[1] = d[v];
@@ -1319,7 +1350,7 @@ __global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restr
     else {
       const long long vv = b.idx & 0xffffffffLL;
       out->key = b.key;
-      out->tie = b.idx >> 32;
+      out->tie = (b.idx >> 32) << 32;
       out->var = vv < n ? c0 + vv : ng + (vv - n);
       out->f[0] = __ldcg(d + vv);
       out->f[1] = __ldcg(xnb + vv);
@@ -2005,7 +2036,9 @@ static void destroy_engine(mlp_engine* e) {
 }
 
 static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out,
-                                bool sparse = false, int64_t mld_override = 0) {
+                                bool sparse = false, int64_t mld_override = 0);
+static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int world, Comm* comm, mlp_engine** out,
+                                bool sparse, int64_t mld_override) {
   *out = nullptr;
   if (m <= 0 || ng <= 0 || m > 0x7fffffff || ng + m > 0x7fffffff || world < 1 || rank < 0 || rank >= world) {
     set_err("bad dimensions");
@@ -2017,8 +2050,12 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
     delete comm;
     return MLP_NO_DEVICE;
   }
-  CU(cudaSetDevice(device));
+  if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); delete comm; return MLP_CUDA_ERROR; }
   mlp_engine* e = new mlp_engine();
+  struct Guard {  // every early return below releases the engine, its streams and the communicator
+    mlp_engine* e;
+    ~Guard() { if (e) destroy_engine(e); }
+  } guard{e};
   e->device = device;
   e->sparse = sparse;
   e->comm = comm;
@@ -2105,7 +2142,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->xbytes = sizeof(Cand) + (size_t)ml * sizeof(double);
   A(dev_alloc(&e->d_win, 1));
   A(dev_alloc(&e->xsend, e->xbytes)); A(dev_alloc(&e->xrecv, e->xbytes * world)); A(dev_alloc(&e->xred, (size_t)world * ml + 64));
-  if (st != MLP_OK) { destroy_engine(e); return st; }
+  if (st != MLP_OK) return st;
   for (int l = 0; l < 2; ++l) CU(cudaHostAlloc((void**)&e->lane[l].h_res, sizeof(DevRes), cudaHostAllocDefault));
   e->h_res = e->lane[0].h_res;
   CU(cudaHostAlloc((void**)&e->h_cands, sizeof(Cand) * world, cudaHostAllocDefault));
@@ -2132,6 +2169,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->h_bvar.assign(m, 0);
   e->h_slot_of_row.assign(m, -1);
   e->h_last_eta_of_row.assign(m, -1);
+  guard.e = nullptr;
   *out = e;
   return MLP_OK;
 }
@@ -2441,11 +2479,10 @@ mlp_status mlp_select_entering_primal(mlp_engine* e, mlp_entering* out) {
   ST(exchange_candidates(e, &w));  // records s0_mark ahead of the run-ahead tail
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
-  out->pos = w.tie;
+  out->pos = w.tie >> 32;
   out->score = w.key;
   out->obj_coeff = w.f[0];
   out->cur_val = w.f[1];
-  out->var_min = out->var_max = 0.0;  // the host keeps orig_var_mins / orig_var_maxs (solver.rs:19-20)
   return MLP_OK;
 }
 
@@ -2486,6 +2523,10 @@ mlp_status mlp_ratio_primal(mlp_engine* e, int32_t sign, double max_step0, mlp_l
   out->coeff = l1.h_res->f[0];
   out->leaving_new_val = l1.h_res->f[1];
   out->basic_val = l1.h_res->f[2];
+  out->ties = l1.h_res->i[2];
+  out->near_ties = l1.h_res->i[3];
+  if (out->row >= 0 && out->ties > 0) e->cnt.ratio_ties += 1;
+  if (out->row >= 0 && out->near_ties > 0) e->cnt.ratio_near_ties += 1;
   return MLP_OK;
 }
 
@@ -2561,11 +2602,20 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   out->obj_coeff = w.f[1];
   out->cur_val = w.f[2];
   out->pos = (int64_t)w.f[3];
+  out->ties = w.tie & 0xffff;
+  out->near_ties = (w.tie >> 16) & 0xffff;
+  if (out->ties > 0) e->cnt.ratio_ties += 1;
+  if (out->near_ties > 0) e->cnt.ratio_near_ties += 1;
   return MLP_OK;
 }
 
 mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* out) {
   if (!e || !e->initialized || !pi || !out) return MLP_INVALID;
+  if (pi->entering_var < 0 || pi->entering_var >= e->ng + e->m || pi->col < 0 || pi->col >= e->ng ||
+      (pi->has_elem && (pi->row < 0 || pi->row >= e->m))) {
+    set_err("pivot: entering_var / col / row out of range");
+    return MLP_INVALID;
+  }
   CU(cudaSetDevice(e->device));
   const int m = (int)e->m;
   Lane &l0 = e->lane[0], &l1 = e->lane[1];
@@ -2678,6 +2728,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
 }
 
 // ---------------------------------------------------------------------------------- incremental API
+static mlp_status grow_rows(mlp_engine* e);
 mlp_status mlp_get_var(mlp_engine* e, int64_t var, mlp_var_info* out) {
   if (!e || !e->initialized || !out || var < 0 || var >= e->ng + e->m) return MLP_INVALID;
   if (e->world != 1) { set_err("mlp_get_var: single-shard engines only"); return MLP_INVALID; }
@@ -2713,9 +2764,9 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
                               double rhs, mlp_add_row_result* out) {
   if (!e || !e->initialized || !coeffs || !out) return MLP_INVALID;
   if (e->world != 1) { set_err("add_row: single-shard engines only (row f2 is partly built)"); return MLP_INVALID; }
-  if (e->m >= e->mld) { set_err("add_row: row capacity exhausted (MLP_ROW_RESERVE)"); return MLP_NOMEM; }
   CU(cudaSetDevice(e->device));
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  if (e->m >= e->mld) ST(grow_rows(e));
   Lane& l0 = e->lane[0];
   const int64_t m = e->m, n = e->n, r = m, lv = n + r, gv = e->ng + r;
   e->sel_valid = false;
@@ -2843,18 +2894,29 @@ mlp_status mlp_engine_add_row(mlp_engine* e, const double* coeffs, const double*
 }
 
 // Solver: Clone (solver.rs:14, used by Solution: Clone lib.rs:313): device-to-device deep copy of the whole engine state,
-// basis factors and eta file included, so the copy continues bit-identically.
-mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
+// basis factors and eta file included, so the copy continues bit-identically.  new_mld > src->mld re-lays the row-indexed
+// arrays out for a larger row capacity (grow_rows below); the leading dimension of Bcols / E changes with it.
+static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** out) {
   if (!src || !out || !src->initialized) return MLP_INVALID;
   *out = nullptr;
   if (src->world != 1) { set_err("clone: single-shard engines only"); return MLP_INVALID; }
+  if (new_mld < src->mld) return MLP_INVALID;
   CU(cudaSetDevice(src->device));
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(src->lane[l].st));
   mlp_engine* e = nullptr;
-  ST(create_engine(src->device, src->m, src->ng, 0, 1, nullptr, &e, src->sparse, src->mld));
+  ST(create_engine(src->device, src->m, src->ng, 0, 1, nullptr, &e, src->sparse, new_mld));
   mlp_status st = MLP_OK;
   auto cp = [&](void* dst, const void* from, size_t bytes) {
     if (st == MLP_OK && bytes && cudaMemcpyAsync(dst, from, bytes, cudaMemcpyDeviceToDevice, e->stream) != cudaSuccess) {
+      set_err("clone: device copy failed");
+      st = MLP_CUDA_ERROR;
+    }
+  };
+  // column-major block with leading dimension = row capacity: `cols` columns of src->mld rows each
+  auto cp_cols = [&](double* dst, const double* from, size_t cols) {
+    if (st != MLP_OK || !cols) return;
+    if (cudaMemcpy2DAsync(dst, (size_t)e->mld * 8, from, (size_t)src->mld * 8, (size_t)src->mld * 8, cols, cudaMemcpyDeviceToDevice,
+                          e->stream) != cudaSuccess) {
       set_err("clone: device copy failed");
       st = MLP_CUDA_ERROR;
     }
@@ -2863,7 +2925,7 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   const size_t ml = (size_t)src->mld, ntc = (size_t)src->n + ml, gt = (size_t)src->ng + ml;
   if (src->sparse) {  // matrix, CSC copy and segment table from the host CSR copy; then the core marks of the current factors
     e->h_csr_ptr = src->h_csr_ptr; e->h_csr_idx = src->h_csr_idx; e->h_csr_val = src->h_csr_val;
-    A(dev_alloc(&e->corepos, (size_t)src->n)); A(dev_alloc(&e->rowcore, ml));
+    A(dev_alloc(&e->corepos, (size_t)src->n)); A(dev_alloc(&e->rowcore, (size_t)e->mld));
     if (st == MLP_OK) A(sparse_upload(e, src->m));
     cp(e->corepos, src->corepos, (size_t)src->n * 4); cp(e->rowcore, src->rowcore, ml * 4);
   } else cp(e->A, src->A, ml * (size_t)src->lda * 8);
@@ -2880,7 +2942,7 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
     if (st == MLP_OK && e->kcap != src->kcap) { set_err("clone: capacity mismatch"); st = MLP_INVALID; }
     const size_t kc = (size_t)src->kcap;
     cp(e->Jpos, src->Jpos, kc * 4); cp(e->Jslot, src->Jslot, kc * 4); cp(e->Rp, src->Rp, kc * 4);
-    if (!src->sparse) cp(e->Bcols, src->Bcols, ml * kc * 8);
+    if (!src->sparse) cp_cols(e->Bcols, src->Bcols, kc);
     cp(e->LUc, src->LUc, kc * kc * 8); cp(e->Cinv, src->Cinv, kc * kc * 8);
     if (src->sparse) {
       cp(e->corevar, src->corevar, kc * 4); cp(e->cseg_first, src->cseg_first, (kc + 1) * 4);
@@ -2897,7 +2959,7 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
     A(ensure_eta_capacity(e, src->Kcap, true));
     if (st == MLP_OK && e->Kcap != src->Kcap) { set_err("clone: capacity mismatch"); st = MLP_INVALID; }
     const size_t Kc = (size_t)src->Kcap;
-    cp(e->E, src->E, ml * (size_t)src->K * 8); cp(e->Ginv, src->Ginv, Kc * Kc * 8);
+    cp_cols(e->E, src->E, (size_t)src->K); cp(e->Ginv, src->Ginv, Kc * Kc * 8);
     cp(e->etaR, src->etaR, Kc * 4); cp(e->etaPrev, src->etaPrev, Kc * 4); cp(e->etaHead, src->etaHead, Kc * 4);
     cp(e->etaLast, src->etaLast, ml * 4);
   }
@@ -2906,6 +2968,10 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   e->nt = src->nt;
   e->k = src->k; e->K = src->K; e->lu_nnz = src->lu_nnz;
   e->enable_pse = src->enable_pse; e->enable_dse = src->enable_dse;
+  // the tuning state decides how reductions are tiled: the copy must round exactly like its source
+  e->price_tma = src->price_tma; e->price_tile = src->price_tile; e->price_split = src->price_split;
+  e->lane1_ldg = src->lane1_ldg; e->price_ctas = src->price_ctas; e->fused = src->fused; e->fused_max = src->fused_max;
+  e->async_pivot = src->async_pivot;
   e->h_bvar = src->h_bvar; e->h_slot_of_row = src->h_slot_of_row; e->h_free_slots = src->h_free_slots;
   e->h_pending_free = src->h_pending_free; e->h_last_eta_of_row = src->h_last_eta_of_row;
   e->cnt = src->cnt;
@@ -2913,6 +2979,49 @@ mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) {
   ST(mark0(e));
   *out = e;
   return MLP_OK;
+}
+mlp_status mlp_engine_clone(mlp_engine* src, mlp_engine** out) { return src ? clone_engine(src, src->mld, out) : MLP_INVALID; }
+
+// Row capacity exhausted (Solution::add_constraint / add_gomory_cut have no limit in the reference, lib.rs:368-423): double
+// it.  Every row-indexed array and the leading dimension of Bcols / E depend on it, so the state is copied into a freshly
+// laid-out engine (the clone path) whose guts then replace this handle's; the caller's pointer stays valid.
+static mlp_status grow_rows(mlp_engine* e) {
+  mlp_engine* bigger = nullptr;
+  const int64_t want = e->mld + std::max<int64_t>(64, e->mld / 2);
+  ST(clone_engine(e, want, &bigger));
+  std::swap(*e, *bigger);
+  destroy_engine(bigger);
+  return MLP_OK;
+}
+
+// f4: recalc_basic_var_vals (solver.rs:1177-1197; dead code there, the TODO at 1024-1025 asks for it every ~1000
+// pivots): x_B = B^-1 (rhs - N x_N) from scratch.  Off unless the caller asks (mlp_solver_set_recalc_period).
+__global__ void k_masked_xnb(const double* __restrict__ xnb, const uint8_t* __restrict__ vflag, int64_t nt, double* __restrict__ out) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nt) out[v] = (vflag[v] & MLP_BASIC) ? 0.0 : xnb[v];
+}
+__global__ void k_sub_vec(double* __restrict__ y, const double* __restrict__ x, int64_t cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) y[i] -= x[i];
+}
+mlp_status mlp_recalc_basic_vals(mlp_engine* e) {
+  if (!e || !e->initialized) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  const int64_t m = e->m, n = e->n, nt = e->nt;
+  Lane& l0 = e->lane[0];
+  ST(begin0(e));
+  e->spec_var = -1;
+  e->dual_row_host = -1;
+  if (e->K > 0) ST(refactor_impl(e));  // 1188-1191
+  LAUNCH(e, k_masked_xnb, cdiv(nt, 256), 256, 0, e->xnb, e->vflag, nt, e->helper);
+  double* part = e->world > 1 ? e->work_m : e->xred;
+  if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->helper, part);
+  else LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->helper, part);
+  if (e->world > 1) ST(e->comm->allgather(part, e->xred, (size_t)m * sizeof(double), e->stream));
+  LAUNCH(e, k_init_basic_vals, cdiv(m, 256), 256, 0, e->xred, e->world, (int)m, e->rhs, e->work_mb);  // rhs - A x_N (structural part)
+  LAUNCH(e, k_sub_vec, cdiv(m, 256), 256, 0, e->work_mb, e->helper + n, m);                           // non-basic slacks: unit columns
+  ST(ftran(e, l0, e->work_mb, e->xB));  // lu_factors.solve_dense (1193-1195): by constraint row in, by basis position out
+  return mark0(e);
 }
 
 mlp_status mlp_recalc_obj_coeffs(mlp_engine* e, double* cur_obj_val) {

@@ -42,8 +42,20 @@ struct mlp_solver {
   bool record_trace = true;
   std::vector<PivotRecord> trace;
   double run_seconds = 0.0, refactor_seconds = 0.0;
+  // pivots whose ratio-test winner (pass 2 of 804-823 / 982-1002) was tied exactly / within 1e-9: where the reference's
+  // list-order rule and the engine's lowest-index rule can part ways
+  int64_t tied_pivots = 0, near_tie_pivots = 0, first_tied_pivot = -1, first_near_tie_pivot = -1;
+  // f4: every recalc_period pivots (0 = never, the reference's behaviour) recompute x_B and d from scratch — the TODO at
+  // solver.rs:1024-1025 — with recalc_basic_var_vals (1177-1197) and recalc_obj_coeffs (1199-1231)
+  int64_t recalc_period = 0, recalcs_done = 0;
+  bool artificial_obj = false;  // solver.rs:261: while the artificial objective is in place d must not be recomputed from c
   bool initialized = false;
 };
+
+static void note_ties(mlp_solver* s, int64_t ties, int64_t near_ties) {
+  if (ties > 0) { s->tied_pivots += 1; if (s->first_tied_pivot < 0) s->first_tied_pivot = s->pivots_done; }
+  if (near_ties > 0) { s->near_tie_pivots += 1; if (s->first_near_tie_pivot < 0) s->first_near_tie_pivot = s->pivots_done; }
+}
 
 #define ST(x)                        \
   do {                               \
@@ -105,6 +117,19 @@ static mlp_status do_pivot(mlp_solver* s, int phase, int64_t entering_var, int64
   return MLP_OK;
 }
 
+// f4, between two iterations of either loop
+static mlp_status maybe_recalc(mlp_solver* s, bool dual_loop) {
+  if (s->recalc_period <= 0 || s->pivots_done == 0 || s->pivots_done % s->recalc_period != 0) return MLP_OK;
+  ST(mlp_recalc_basic_vals(s->eng));
+  if (!(dual_loop && s->artificial_obj)) ST(mlp_recalc_obj_coeffs(s->eng, &s->cur_obj_val));
+  mlp_counters c;
+  mlp_get_counters(s->eng, &c);
+  s->eta_nnz = 0;  // both refactorize whenever etas exist (1188-1191, 1200-1203)
+  s->lu_nnz = c.lu_nnz;
+  s->recalcs_done += 1;
+  return MLP_OK;
+}
+
 // One iteration of optimize() (solver.rs:497-498): choose_pivot (695-853) + pivot. *moved = 0 at the optimum.
 static mlp_status primal_iteration(mlp_solver* s, int* moved) {
   mlp_entering en;
@@ -117,6 +142,7 @@ static mlp_status primal_iteration(mlp_solver* s, int* moved) {
   mlp_leaving lv;
   ST(mlp_ratio_primal(s->eng, entering_diff_sign ? 1 : 0, std::fabs(entering_other_val - entering_cur_val), &lv));  // 782-823
   if (lv.row >= 0) {
+    note_ties(s, lv.ties, lv.near_ties);
     ST(mlp_calc_row_coeffs(s->eng, lv.row));                                           // 826
     const double entering_diff = (lv.basic_val - lv.leaving_new_val) / lv.coeff;       // 828
     const double entering_new_val = entering_cur_val + entering_diff;                  // 829
@@ -142,6 +168,7 @@ static mlp_status dual_iteration(mlp_solver* s, int* moved) {
   mlp_dual_entering de;
   ST(mlp_ratio_dual(s->eng, dr.row, leaving_new_val, &de));  // 531
   if (de.var < 0) return MLP_INFEASIBLE;                      // 1019
+  note_ties(s, de.ties, de.near_ties);
   const double entering_diff = (dr.val - leaving_new_val) / de.coeff;  // 1005
   const double entering_new_val = de.cur_val + entering_diff;          // 1006
   ST(mlp_ftran_col(s->eng, de.var));                                   // 532
@@ -285,12 +312,15 @@ mlp_status mlp_solver_init(mlp_solver* s, const double* obj, const double* mins,
     ST(mlp_engine_init_state(s->eng, &st));
   }
   s->cur_obj_val = need_artificial_obj ? 0.0 : obj_val;  // 302
+  s->artificial_obj = need_artificial_obj;
   s->is_primal_feasible = is_primal_feasible;
   s->is_dual_feasible = is_dual_feasible;
   s->eta_nnz = 0;
   ST(mlp_refactor(s->eng, &s->lu_nnz));  // value of lu_factors.nnz() for the slack basis
   s->stage = 0;
   s->pivots_done = 0;
+  s->tied_pivots = s->near_tie_pivots = 0;
+  s->first_tied_pivot = s->first_near_tie_pivot = -1;
   s->trace.clear();
   s->initialized = true;
   return MLP_OK;
@@ -313,6 +343,8 @@ mlp_status mlp_solver_run(mlp_solver* s, int64_t max_pivots, int32_t* done) {
           rc = dual_iteration(s, &moved);
           if (rc != MLP_OK) break;
           if (!moved) { s->is_primal_feasible = true; s->stage = 2; break; }
+          rc = maybe_recalc(s, true);
+          if (rc != MLP_OK) break;
         }
         if (rc == MLP_OK && s->stage == 1) go = false;
         break;
@@ -335,6 +367,8 @@ mlp_status mlp_solver_run(mlp_solver* s, int64_t max_pivots, int32_t* done) {
           rc = primal_iteration(s, &moved);
           if (rc != MLP_OK) break;
           if (!moved) { s->is_dual_feasible = true; s->stage = 4; break; }
+          rc = maybe_recalc(s, false);
+          if (rc != MLP_OK) break;
         }
         if (rc == MLP_OK && s->stage == 3) go = false;
         break;
@@ -436,6 +470,7 @@ mlp_status mlp_solver_fix_var(mlp_solver* s, int64_t var, double val) {
     mlp_dual_entering de;
     ST(mlp_ratio_dual(s->eng, row, val, &de));
     if (de.var < 0) return MLP_INFEASIBLE;  // 1019
+    note_ties(s, de.ties, de.near_ties);
     const double entering_diff = (vi.value - val) / de.coeff;  // 1005
     const double entering_new_val = de.cur_val + entering_diff;
     ST(mlp_ftran_col(s->eng, de.var));
@@ -524,6 +559,7 @@ mlp_status mlp_solver_values(mlp_solver* s, double* out) {  // Solver::get_value
 int64_t mlp_solver_trace_len(mlp_solver* s) { return (int64_t)s->trace.size(); }
 int64_t mlp_solver_get_trace(mlp_solver* s, int64_t first, int64_t count, double* out) {
   int64_t k = 0;
+  if (!s || !out || first < 0 || count < 0) return 0;
   for (int64_t i = first; i < first + count && i < (int64_t)s->trace.size(); ++i, ++k) {
     const PivotRecord& r = s->trace[(size_t)i];
     double* o = out + k * 13;
@@ -541,6 +577,14 @@ mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out) {
 mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out) {
   std::memcpy(out, s->basic_vars.data(), s->m * sizeof(int64_t));
   return MLP_OK;
+}
+void mlp_solver_set_recalc_period(mlp_solver* s, int64_t period) { s->recalc_period = period > 0 ? period : 0; }
+int64_t mlp_solver_recalcs_done(mlp_solver* s) { return s->recalcs_done; }
+void mlp_solver_tie_stats(mlp_solver* s, int64_t out4[4]) {
+  out4[0] = s->tied_pivots;
+  out4[1] = s->near_tie_pivots;
+  out4[2] = s->first_tied_pivot;
+  out4[3] = s->first_near_tie_pivot;
 }
 void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds) {
   *run_seconds = s->run_seconds;

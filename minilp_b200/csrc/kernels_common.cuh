@@ -48,6 +48,58 @@ __device__ __forceinline__ KeyIdx block_argmax(KeyIdx v, double* smk, long long*
   }
   return r;
 }
+// Arg-max that also counts how contested the winner is (pass 2 of the two Harris ratio tests, solver.rs:804-823 and
+// 982-1002, where the reference resolves an exact tie in |coeff| by list order): ex = candidates whose key equals the
+// winner's exactly, nr = candidates within NEAR_TIE relative of it; both include the winner.  The merge is exact for ex;
+// nr may over-count slightly (a candidate within NEAR_TIE of a runner-up that is itself within NEAR_TIE of the winner).
+constexpr double NEAR_TIE = 1e-9;
+struct KeyIdxC {
+  double key;
+  long long idx;
+  int ex, nr;
+};
+__device__ __forceinline__ void kic_merge(KeyIdxC& a, double bk, long long bi, int bex, int bnr) {
+  if (bi == LLONG_MAX) return;
+  if (a.idx == LLONG_MAX) { a.key = bk; a.idx = bi; a.ex = bex; a.nr = bnr; return; }
+  if (better_max(bk, bi, a.key, a.idx)) {
+    const int ex = bex + (a.key == bk ? a.ex : 0), nr = bnr + (a.key >= bk * (1.0 - NEAR_TIE) ? a.nr : 0);
+    a.key = bk; a.idx = bi; a.ex = ex; a.nr = nr;
+  } else {
+    a.ex += (bk == a.key ? bex : 0);
+    a.nr += (bk >= a.key * (1.0 - NEAR_TIE) ? bnr : 0);
+  }
+}
+__device__ __forceinline__ KeyIdxC warp_argmax_c(KeyIdxC v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double k = __shfl_down_sync(FULLMASK, v.key, o);
+    const long long i = __shfl_down_sync(FULLMASK, v.idx, o);
+    const int ex = __shfl_down_sync(FULLMASK, v.ex, o), nr = __shfl_down_sync(FULLMASK, v.nr, o);
+    kic_merge(v, k, i, ex, nr);
+  }
+  return v;
+}
+// smc: >= 32 long long (packed counts)
+__device__ __forceinline__ KeyIdxC block_argmax_c(KeyIdxC v, double* smk, long long* smi, long long* smc) {
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_argmax_c(v);
+  __syncthreads();
+  if (lane == 0) { smk[wid] = v.key; smi[wid] = v.idx; smc[wid] = ((long long)v.ex << 32) | (unsigned)v.nr; }
+  __syncthreads();
+  KeyIdxC r{-INFINITY, LLONG_MAX, 0, 0};
+  if (wid == 0) {
+    if (lane < nw) { r.key = smk[lane]; r.idx = smi[lane]; r.ex = (int)(smc[lane] >> 32); r.nr = (int)(smc[lane] & 0xffffffffLL); }
+    r = warp_argmax_c(r);
+  }
+  return r;
+}
+// tie counts (excluding the winner itself) packed into the low 32 bits of a candidate's `tie` word, saturating at 65535
+__device__ __forceinline__ long long pack_ties(int ex, int nr) {
+  const int e = min(max(ex - 1, 0), 65535), n = min(max(nr - 1, 0), 65535);
+  return ((long long)n << 16) | (long long)e;
+}
+constexpr int RED_CNT_OFF = 2048;  // per-CTA packed counts live in red_i[RED_CNT_OFF + block] (ratio grids are <= 1024 CTAs)
+
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(FULLMASK, v, o));
@@ -741,35 +793,44 @@ __global__ void __launch_bounds__(256) k_ratio_primal_1(const double* __restrict
   }
 }
 // Harris pass 2 (solver.rs:800-823): among rows with slack/|alpha| <= max_step the largest |alpha|;
-// exact ties go to the lowest row (the reference: first in col_coeffs list order).
+// exact ties go to the lowest row (the reference: first in col_coeffs list order) and are COUNTED, so the
+// caller knows whenever the reference's order-dependent rule would have been in play.
 __global__ void __launch_bounds__(256) k_ratio_primal_2(const double* __restrict__ alpha, const double* __restrict__ xB,
                                                          const double* __restrict__ loB, const double* __restrict__ hiB, int m,
                                                          int sign, const double* __restrict__ scal, double* __restrict__ red_f,
                                                          long long* __restrict__ red_i, unsigned* counter, DevRes* res) {
   __shared__ double smk[32];
   __shared__ long long smi[32];
+  __shared__ long long smc[32];
   const double max_step = scal[0];
-  KeyIdx best{-INFINITY, LLONG_MAX};
+  KeyIdxC best{-INFINITY, LLONG_MAX, 0, 0};
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
     const double a = alpha[r], aa = fabs(a);
     if (aa < EPS) continue;
     bool tm;
     const double st = leaving_step(a, sign, xB[r], loB[r], hiB[r], tm);
     const double cur = st / aa;  // 810
-    if (cur <= max_step && better_max(aa, r, best.key, best.idx)) { best.key = aa; best.idx = r; }
+    if (cur <= max_step) kic_merge(best, aa, (long long)r, 1, 1);
   }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
+  best = block_argmax_c(best, smk, smi, smc);
+  if (threadIdx.x == 0) {
+    red_f[blockIdx.x] = best.key;
+    red_i[blockIdx.x] = best.idx;
+    red_i[RED_CNT_OFF + blockIdx.x] = ((long long)best.ex << 32) | (unsigned)best.nr;
+  }
   if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
+  KeyIdxC b{-INFINITY, LLONG_MAX, 0, 0};
   for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
     const double k = __ldcg(red_f + q);
     const long long i = __ldcg(red_i + q);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
+    const long long c = __ldcg(red_i + RED_CNT_OFF + q);
+    kic_merge(b, k, i, (int)(c >> 32), (int)(c & 0xffffffffLL));
   }
-  b = block_argmax(b, smk, smi);
+  b = block_argmax_c(b, smk, smi, smc);
   if (threadIdx.x == 0) {
     *counter = 0;
+    res->i[2] = 0;
+    res->i[3] = 0;
     if (b.idx == LLONG_MAX) res->i[0] = -1;
     else {
       const int r = (int)b.idx;
@@ -781,6 +842,8 @@ __global__ void __launch_bounds__(256) k_ratio_primal_2(const double* __restrict
       res->f[1] = tm ? hiB[r] : loB[r];  // 813-819
       res->f[2] = xB[r];
       res->f[3] = max_step;
+      res->i[2] = b.ex - 1;  // other rows sharing the winning |alpha| exactly: the reference would decide by list order
+      res->i[3] = b.nr - 1;  // ... or within NEAR_TIE of it
     }
   }
 }

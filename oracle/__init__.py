@@ -176,6 +176,11 @@ class _State:
     eta_count = property(lambda s: s._i64(10))
     lu_nnz = property(lambda s: s._i64(11))
     nnz = property(lambda s: s._i64(13))
+    # pass-2 winners of the ratio tests that were contested: exactly (the reference then decides by list order) / within 1e-9
+    tied_pivots = property(lambda s: s._i64(14))
+    near_tie_pivots = property(lambda s: s._i64(15))
+    first_tied_pivot = property(lambda s: s._i64(16))
+    first_near_tie_pivot = property(lambda s: s._i64(17))
 
     def _farr(self, what):
         cap = self.num_vars + 2 * self.num_constraints + 8

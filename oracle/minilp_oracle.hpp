@@ -648,6 +648,15 @@ struct Solver {  // solver.rs:14-58
   SolverOptions opts;
   std::vector<PivotRecord> trace;
   int64_t pivots_done = 0, refactor_count = 0, tie_events = 0;
+  // Ties that MATTER for the pass-2 winner of the two ratio tests (804-823, 982-1002): pivots whose winning |coeff| is
+  // shared exactly by another eligible candidate (tied_pivots: the reference then decides by list order) or approached
+  // within NEAR_TIE relative (near_tie_pivots >= tied_pivots: the decision is within rounding of the summation order).
+  static constexpr double NEAR_TIE = 1e-9;
+  int64_t tied_pivots = 0, near_tie_pivots = 0, first_tied_pivot = -1, first_near_tie_pivot = -1;
+  void note_ties(int64_t exact_cnt, int64_t near_cnt) {  // counts include the winner itself
+    if (exact_cnt > 1) { tied_pivots += 1; if (first_tied_pivot < 0) first_tied_pivot = pivots_done; }
+    if (near_cnt > 1) { near_tie_pivots += 1; if (first_near_tie_pivot < 0) first_near_tie_pivot = pivots_done; }
+  }
   int32_t cur_phase = 1;
   bool last_refactored = false;
 
@@ -870,6 +879,15 @@ struct Solver {  // solver.rs:14-58
     }
 
     if (have_row) {
+      int64_t ex = 0, nr = 0;  // instrumentation only: how contested was the winner
+      for (usize k = 0; k < col_coeffs.len(); ++k) {
+        double coeff = col_coeffs.values[k], coeff_abs = std::fabs(coeff);
+        if (coeff_abs < EPS) continue;
+        if (!(leaving_step(col_coeffs.indices[k], coeff) / coeff_abs <= max_step)) continue;
+        if (coeff_abs == pivot_coeff_abs) ex += 1;
+        if (coeff_abs >= pivot_coeff_abs * (1.0 - NEAR_TIE)) nr += 1;
+      }
+      note_ties(ex, nr);
       calc_row_coeffs(leaving_r);  // 826
       double entering_diff = (basic_var_vals[leaving_r] - leaving_new_val) / pivot_coeff;
       out = PivotInfo{entering_c, entering_cur_val + entering_diff, entering_diff, true, {leaving_r, pivot_coeff, leaving_new_val}};
@@ -944,6 +962,19 @@ struct Solver {  // solver.rs:14-58
       }
     }
     if (!have) throw SolveError(Error::Infeasible, "infeasible");  // 1019
+    {
+      int64_t ex = 0, nr = 0;  // instrumentation only
+      for (usize c : row_coeffs.nonzero) {
+        double coeff = row_coeffs.values[c];
+        const NonBasicVarState& st = nb_var_states[c];
+        if (!eligible(coeff, st)) continue;
+        double oc = clamp_obj(nb_var_obj_coeffs[c], st);
+        if (!(std::fabs(oc) / std::fabs(coeff) <= max_step)) continue;
+        if (std::fabs(coeff) == pivot_coeff_abs) ex += 1;
+        if (std::fabs(coeff) >= pivot_coeff_abs * (1.0 - NEAR_TIE)) nr += 1;
+      }
+      note_ties(ex, nr);
+    }
     double entering_diff = (basic_var_vals[row] - leaving_new_val) / pivot_coeff;
     return PivotInfo{entering_c, nb_var_vals[entering_c] + entering_diff, entering_diff, true, {row, pivot_coeff, leaving_new_val}};
   }

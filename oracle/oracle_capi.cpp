@@ -64,6 +64,10 @@ template <class Sv> int64_t get_i64(const Sv& s, int what) {
     case 11: return (int64_t)s.basis_solver.lu_factors.nnz();
     case 12: return (int64_t)s.nb_vars.size();
     case 13: return (int64_t)s.mat.nnz();
+    case 14: return s.tied_pivots;
+    case 15: return s.near_tie_pivots;
+    case 16: return s.first_tied_pivot;
+    case 17: return s.first_near_tie_pivot;
     default: return -1;
   }
 }

@@ -32,9 +32,10 @@ def main():
         dist.all_gather_object(kinds, s.engine.exchange_kind())
         assert len(set(kinds)) == 1, kinds  # every rank took the same exchange path
         assert s.run()
-        ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+        ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)  # the reference's own tie rule
         assert ref.continue_solve()
         tg, tr = s.trace(), ref.trace()
+        assert ref.near_tie_pivots == 0 and s.tie_stats()["tied_pivots"] == 0
         assert tg.shape == tr.shape and np.array_equal(tg[:, :5], tr[:, :5]), "basis sequence differs from the oracle"
         assert abs(s.cur_obj_val - ref.cur_obj_val) <= 1e-8 * max(1.0, abs(ref.cur_obj_val))
         objs = [None] * world

@@ -12,7 +12,7 @@ import oracle
 CASES = [(3, 1800, 1800, 2, 5000), (1, 1500, 2500, 3, 6000)]
 for kind, m, n, seed, budget in CASES:
     lp = mb.synth_dense(kind, m, n, seed, threads=os.cpu_count() or 1)
-    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
     t0 = time.perf_counter()
     done = ref.continue_solve(budget)
     tr = ref.trace()

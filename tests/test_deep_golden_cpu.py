@@ -17,7 +17,7 @@ def test_oracle_reproduces_the_golden_prefix(path):
     g = np.load(path)
     kind, m, n, seed = (int(g[k]) for k in ("kind", "m", "n", "seed"))
     lp = mb.synth_dense(kind, m, n, seed, threads=os.cpu_count() or 1)
-    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
     ref.continue_solve(300)
     tr = ref.trace()
     assert tr.shape[0] == 300

@@ -76,7 +76,7 @@ def test_hand_over_between_fused_and_separate_paths(kind):
     limit is 512) — the solve must not notice the hand-over, in either direction (K drops to 0 at every refactorization)."""
     lp = mb.synth_dense(kind, 120, 160, 2)
     s = make(lp, MLP_FUSED=1, MLP_FUSED_MAX=6)
-    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
     assert s.run() and ref.continue_solve()
     tg, tr = s.trace(), ref.trace()
     assert tg.shape == tr.shape and np.array_equal(tg[:, :5], tr[:, :5])
@@ -89,7 +89,7 @@ def test_probe_after_fused_pivots_matches_oracle():
     """mlp_ftran_col of an arbitrary variable goes through the fused chain too; its alpha against the oracle's probe."""
     lp = mb.synth_dense(0, 400, 500, 3)
     s = make(lp, MLP_FUSED=1)
-    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
     s.run(45)
     ref.continue_solve(45)
     assert np.array_equal(s.trace()[:, :5], ref.trace()[:, :5])

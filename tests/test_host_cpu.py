@@ -84,3 +84,28 @@ def test_tuning_knobs_match_the_header():
     hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "minilp_b200.h")).read()
     enum = dict((k.lower(), int(v)) for k, v in re.findall(r"MLP_TUNE_([A-Z0-9_]+)\s*=\s*(\d+)", hdr))
     assert enum == Engine.TUNE
+
+
+def test_trivial_solution_has_the_incremental_methods():
+    """lib.rs:368-423 on a problem without constraints (no engine is created: CPU only)."""
+    import numpy as np
+    import pytest
+    import minilp_b200 as mb
+    p = mb.Problem(mb.OptimizationDirection.Maximize)
+    a = p.add_var(1.0, (0.0, 4.0))
+    b = p.add_var(-1.0, (1.0, np.inf))
+    sol = p.solve()
+    assert (sol[a], sol[b], sol.objective()) == (4.0, 1.0, 3.0)
+    assert dict(sol) == {0: 4.0, 1: 1.0}
+    f = sol.fix_var(a, 2.0)
+    assert (f[a], f.objective()) == (2.0, 1.0) and sol[a] == 4.0
+    with pytest.raises(mb.Infeasible):
+        sol.fix_var(a, 5.0)
+    u, was = f.unfix_var(a)
+    assert was and u[a] == 4.0
+    assert sol.unfix_var(b) == (sol, False)
+    assert f.clone()[a] == 2.0
+    with pytest.raises(ValueError):
+        sol.add_gomory_cut(a)
+    with pytest.raises(mb.Infeasible):
+        sol.add_constraint([], mb.ComparisonOp.Ge, 1.0)  # solver.rs:558-570

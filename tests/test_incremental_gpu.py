@@ -127,13 +127,14 @@ def both(kind, m, n, seed, storage="dense"):
         e = [(j, float(lp.a[i, j])) for j in range(n)]
         p.add_constraint(e, int(lp.ops[i]), lp.rhs[i])
         q.add_constraint(e, int(lp.ops[i]), lp.rhs[i])
-    return lp, p.solve(storage=storage), q.solve(tie_lowest_index=True)
+    return lp, p.solve(storage=storage), q.solve()  # the oracle keeps the reference's own tie rule
 
 
 def same(g, r):
     assert close(g.objective(), r.objective()), (g.objective(), r.objective())
     assert close(g.solver.values(), r.values())
     tg, tr = g.solver.trace(), r.trace()
+    assert r.near_tie_pivots == 0, "contested ratio-test winner: the sequence would depend on the tie rule"
     assert tg.shape[0] == tr.shape[0] and np.array_equal(tg[:, [1, 3, 4]], tr[:, [1, 3, 4]]), "basis sequence differs"
 
 
@@ -202,3 +203,50 @@ def test_gomory_cuts_match_oracle_objective(storage):
         r.add_gomory_cut(v)
         g.add_gomory_cut(v)
         assert close(g.objective(), r.objective(), 1e-7), (g.objective(), r.objective())
+
+
+@STORAGES
+def test_many_added_rows_grow_the_row_capacity(storage):
+    """Solution::add_constraint has no limit on the number of rows (lib.rs:368-382); the engine's row arrays are allocated
+    for m + max(64, m/8) rows and must grow beyond that (a cutting-plane loop adds hundreds)."""
+    lp, g, r = both(0, 20, 30, 5, storage)
+    same(g, r)
+    rng = np.random.default_rng(11)
+    n = 30
+    added = 0
+    for t in range(90):
+        x = r.values()
+        idx = np.sort(rng.choice(n, size=5, replace=False))
+        co = np.round(rng.standard_normal(idx.size), 3)
+        act = float(co @ x[idx])
+        e = [(int(j), float(c)) for j, c in zip(idx, co)]
+        op, b = (Le, act - 0.01) if t % 2 == 0 else (Ge, act + 0.01)
+        try:
+            r.add_constraint(e, op, b)
+        except oracle.Infeasible:
+            with pytest.raises(mb.Infeasible):
+                g.add_constraint(e, op, b)
+            break
+        g.add_constraint(e, op, b)
+        added += 1
+        assert close(g.objective(), r.objective()), (t, g.objective(), r.objective())
+    assert added > 70, added  # past the initial reserve of 64 rows
+    assert close(g.solver.values(), r.values())
+    c = g.clone()  # a clone of a grown engine keeps working
+    c.add_constraint([(0, 1.0)], Le, float(r.values()[0]) + 1.0)
+    assert close(c.objective(), g.objective())
+
+
+def test_unconstrained_problem_takes_incremental_constraints():
+    """lib.rs:368: a Solution of a problem without constraints accepts add_constraint / fix_var / unfix_var."""
+    p = mb.Problem(mb.OptimizationDirection.Minimize)
+    x = p.add_var(1.0, (0.0, 10.0))
+    y = p.add_var(2.0, (1.0, 10.0))
+    sol = p.solve()
+    assert (sol[x], sol[y], sol.objective()) == (0.0, 1.0, 2.0)
+    sol = sol.fix_var(x, 3.0)
+    assert sol.objective() == 5.0
+    sol = sol.add_constraint([(x, 1.0), (y, 1.0)], Ge, 6.0)
+    assert close(sol.objective(), 3.0 + 2.0 * 3.0) and close(sol[y], 3.0)
+    sol, was = sol.unfix_var(x)
+    assert was and close(sol.objective(), 5.0 + 2.0 * 1.0) and close(sol[x], 5.0)

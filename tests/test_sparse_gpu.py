@@ -46,11 +46,11 @@ def test_reference_mps_fixture_solves_to_the_reference_answer():
 ])
 def test_sparse_engine_matches_oracle_via_mps(gen, args):
     text, d = gen(*args)
-    ref = oracle.MpsFile.parse(text, d).problem.solve(tie_lowest_index=True)
+    ref = oracle.MpsFile.parse(text, d).problem.solve()  # the reference's own tie rule
     p = mps.MpsFile.parse(text, d).problem
     gpu = solver_from_problem(p, "sparse")
     assert gpu.run()
-    assert_same_trace(gpu.trace(), ref.trace())
+    assert_same_trace(gpu.trace(), ref.trace(), ref, gpu)
     assert close(gpu.cur_obj_val, ref.cur_obj_val)
     assert close(gpu.values(), ref.values())
     assert_same_state(gpu, ref, 1e-7)
@@ -66,10 +66,10 @@ def test_sparse_engine_matches_oracle_via_mps(gen, args):
 def test_sparse_per_operation_probes():
     """FTRAN of a structural column and calc_row_coeffs (BTRAN + CSC price-out) against the oracle mid-solve."""
     text, d = synth.netlib_like(200, 260, 6.0, 4)
-    ref = oracle.MpsFile.parse(text, d).problem.solve(tie_lowest_index=True, max_pivots=40)
+    ref = oracle.MpsFile.parse(text, d).problem.solve(max_pivots=40)
     gpu = solver_from_problem(mps.MpsFile.parse(text, d).problem, "sparse")
     gpu.run(40)
-    assert_same_trace(gpu.trace(), ref.trace())
+    assert_same_trace(gpu.trace(), ref.trace(), ref, gpu)
     nb = ref.nb_vars
     for c in (0, 7, len(nb) - 1):
         gpu.engine.ftran_col(int(nb[c]))
@@ -85,9 +85,9 @@ def test_sparse_per_operation_probes():
 def test_sparse_medium_budgeted():
     """2000 x 2000 netlib-like LP: first 400 pivots in lock-step with the oracle (refactorizations included)."""
     text, d = synth.netlib_like(2000, 2000, 8.0, 3)
-    ref = oracle.MpsFile.parse(text, d).problem.solve(tie_lowest_index=True, max_pivots=400)
+    ref = oracle.MpsFile.parse(text, d).problem.solve(max_pivots=400)
     gpu = solver_from_problem(mps.MpsFile.parse(text, d).problem, "sparse")
     assert not gpu.run(400)
-    assert_same_trace(gpu.trace(), ref.trace())
+    assert_same_trace(gpu.trace(), ref.trace(), ref, gpu)
     assert gpu.engine.counters()["refactors"] > 1
     gpu.close()

@@ -9,7 +9,7 @@ import oracle
 m = n = 1000
 lp = mb.synth_dense(0, m, n, 1)
 gpu = mb.Solver.from_dense(lp)
-ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
 gpu.run(60); ref.continue_solve(60)
 e = gpu.engine
 nb = gpu.nb_vars()

@@ -17,7 +17,7 @@ for kind, m, n, seed, budget in cases:
     dg = s.run(budget)
     s.engine.sync()
     tg = time.perf_counter() - t0
-    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs, tie_lowest_index=True)
+    ref = oracle.DenseSolver(lp.direction, lp.a, lp.obj, lp.mins, lp.maxs, lp.ops, lp.rhs)
     t0 = time.perf_counter()
     dr = ref.continue_solve(budget)
     tc = time.perf_counter() - t0
