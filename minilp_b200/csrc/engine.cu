@@ -271,6 +271,8 @@ struct mlp_engine {
   int32_t *Jpos = nullptr, *Jslot = nullptr, *Rp = nullptr;  // kcap
   int32_t* rowcover = nullptr;                                 // m
   int32_t *lu_aff = nullptr, *lu_perm = nullptr;              // panel row-permutation records (192), in-place permutation (kcap)
+  int32_t* lu_rcnt = nullptr;                                  // kcap (sparse storage): entries per core row, the reference's orig_row2elt_count
+  unsigned long long* d_nnzcnt = nullptr;                      // [0] stored entries of the core before, [1] off-diagonal entries of L\U after the factorization
   double *Bcols = nullptr, *LUc = nullptr, *Cinv = nullptr;   // column cache m x kcap (slot-indexed); LU factors and (LU)^-1, kcap x kcap
   // eta file
   int64_t K = 0, Kcap = 0;
@@ -1647,8 +1649,8 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
   }
   for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
   dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
-  dev_free(e->lu_aff); dev_free(e->lu_perm);
-  ST(dev_alloc(&e->lu_aff, 192)); ST(dev_alloc(&e->lu_perm, cap));
+  dev_free(e->lu_aff); dev_free(e->lu_perm); dev_free(e->lu_rcnt);
+  ST(dev_alloc(&e->lu_aff, 192)); ST(dev_alloc(&e->lu_perm, cap)); ST(dev_alloc(&e->lu_rcnt, cap));
   if (e->sparse) {
     if (e->corevar_k > 0) {  // un-mark with the old list before it is freed
       LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
@@ -1702,6 +1704,17 @@ static mlp_status refactor_impl(mlp_engine* e) {
   }
   for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
   const int64_t k = (int64_t)jpos.size();
+  if (e->sparse && k > 1) {
+    // order_simple (ordering.rs:4-21): columns by ascending entry count, FIFO — i.e. ascending basis position — within a
+    // count.  (For a dense A every column has m entries and the order is the basis-position order built above.)
+    std::vector<int32_t> ord((size_t)k);
+    for (int64_t t = 0; t < k; ++t) ord[(size_t)t] = (int32_t)t;
+    auto cnt = [&](int32_t t) { return e->h_csc_ptr[(size_t)jvar[(size_t)t] + 1] - e->h_csc_ptr[(size_t)jvar[(size_t)t]]; };
+    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return cnt(a) < cnt(b); });
+    std::vector<int32_t> p2((size_t)k), v2((size_t)k), s2((size_t)k);
+    for (int64_t t = 0; t < k; ++t) { p2[(size_t)t] = jpos[(size_t)ord[(size_t)t]]; v2[(size_t)t] = jvar[(size_t)ord[(size_t)t]]; s2[(size_t)t] = jslot[(size_t)ord[(size_t)t]]; }
+    jpos.swap(p2); jvar.swap(v2); jslot.swap(s2);
+  }
   if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
   for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
   e->h_pending_free.clear();
@@ -1752,6 +1765,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
       CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
       LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
              (int)e->ncseg, e->corepos, e->rowcore, e->LUc, e->kcap);
+      CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
+      LAUNCH(e, k_core_row_counts, cdiv(k, 256), 256, 0, e->LUc, e->kcap, (int)k, e->lu_rcnt, e->d_nnzcnt);
     } else
       LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
     int* flags = e->d_res->flags;
@@ -1759,13 +1774,14 @@ static mlp_status refactor_impl(mlp_engine* e) {
       const int rows = (int)k - j0;
       // widest panel whose rows x nb block (+ row ids, permutation) fits in shared memory; else work in place in global memory
       int nb = LU_NB, use_smem = 0;
+      const size_t per_row = e->sparse ? 12 : 8;  // row ids + permutation (+ row entry counts)
       for (int cand = LU_NB; cand >= 4; cand /= 2)
-        if ((size_t)rows * cand * 8 + (size_t)rows * 8 <= e->smem_optin) { nb = cand; use_smem = 1; break; }
+        if ((size_t)rows * cand * 8 + (size_t)rows * per_row <= e->smem_optin) { nb = cand; use_smem = 1; break; }
       nb = std::min(nb, rows);
-      const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * 8 : 0;
+      const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * per_row : 0;
       const int pt = std::max(64, std::min(1024, (rows + 31) / 32 * 32));  // one row per thread
-      LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, flags, e->lu_aff, e->lu_aff + 64, e->lu_aff + 128,
-             e->lu_perm, use_smem);
+      LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, e->sparse ? e->lu_rcnt : (int32_t*)nullptr, flags,
+             e->lu_aff, e->lu_aff + 64, e->lu_aff + 128, e->lu_perm, use_smem);
       if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
                               e->lu_aff + 128, flags);
       const int rem = rows - nb;
@@ -1780,6 +1796,10 @@ static mlp_status refactor_impl(mlp_engine* e) {
       else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
     }
+    if (e->sparse) {
+      LAUNCH(e, k_count_offdiag, dim3(cdiv(k, 256), cdiv(k, 64)), 256, 0, e->LUc, e->kcap, (int)k, e->d_nnzcnt + 1);
+      CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
+    }
     ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
   } else {
@@ -1789,17 +1809,19 @@ static mlp_status refactor_impl(mlp_engine* e) {
     }
     CU(cudaStreamSynchronize(e->stream));
   }
-  // LUFactors::nnz (lu.rs:52-54) of the reference's factors of this basis: every stored entry of the k structural basic
-  // columns lands in L or U except the k pivots, plus the m diagonal entries — nnz(D) - k + m.  Exact when A is fully
-  // dense (L: k(k-1)/2, U: (m-k)k + k(k-1)/2); for a sparse A it leaves out the fill-in of the core (a lower bound: the
-  // engine then refactorizes no later than the reference would).
+  // LUFactors::nnz (lu.rs:52-54): lower.nondiag + upper.nondiag + m.  The entries of the k structural basic columns in
+  // slack-covered rows go to U unchanged; the core contributes the off-diagonal entries of its factors, FILL-IN INCLUDED
+  // (counted on the device; exact zeros are not stored, lu.rs:253-255).  Dense A: no zeros, k(k-1) + (m-k)k + m in closed
+  // form.  The refactor rule (solver.rs:1096-1097) is the reference's, applied to the factors the engine really has: with
+  // the same column order and pivot rule (ties aside) their size tracks the reference's.
   if (e->sparse) {
     int64_t nz = 0;
     for (int64_t p = 0; p < m; ++p) {
       const int64_t v = e->h_bvar[p];
       if (v < ng) nz += e->h_csc_ptr[v + 1] - e->h_csc_ptr[v];
     }
-    e->lu_nnz = nz - k + m;
+    const int64_t core_before = k > 0 ? e->h_res->i[4] : 0, core_offdiag = k > 0 ? e->h_res->i[5] : 0;
+    e->lu_nnz = (nz - core_before) + core_offdiag + m;
   } else e->lu_nnz = k * (k - 1) + (m - k) * k + m;
   e->cnt.refactors += 1;
   e->cnt.k_structural = k;
@@ -2011,7 +2033,7 @@ static void destroy_engine(mlp_engine* e) {
   for (int r = 0; r < 8; ++r) if (e->peer_base[r] && e->peer_base[r] != e->pbuf) cudaIpcCloseMemHandle(e->peer_base[r]);
   dev_free(e->pbuf);
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
-  dev_free(e->lu_aff); dev_free(e->lu_perm);
+  dev_free(e->lu_aff); dev_free(e->lu_perm); dev_free(e->lu_rcnt); dev_free(e->d_nnzcnt);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   dev_free(e->etaLast); dev_free(e->fz_scratch); dev_free(e->fz_cta_cnt); dev_free(e->fz_cta_ss); dev_free(e->fz_bar);
   for (int l = 0; l < 2; ++l) {
@@ -2123,7 +2145,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   A(dev_alloc(&e->work_m, ml)); A(dev_alloc(&e->work_mb, ml)); A(dev_alloc(&e->colq, ml));
   A(dev_alloc(&e->rc, ntc)); A(dev_alloc(&e->helper, ntc));
   A(dev_alloc(&e->list_idx, ml)); A(dev_alloc(&e->list_val, ml)); A(dev_alloc(&e->vlist_idx, ml)); A(dev_alloc(&e->vlist_val, ml));
-  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16));
+  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16)); A(dev_alloc(&e->d_nnzcnt, 2));
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
     A(dev_alloc(&ln.wm, ml));

@@ -555,6 +555,15 @@ __device__ __forceinline__ int warp_argmin_u32(unsigned key, int payload, unsign
   *min_out = mk;
   return __shfl_sync(FULLMASK, payload, __ffs(who) - 1);
 }
+// lexicographic arg-min of (hi, lo) key pairs with distinct lo (UINT_MAX, UINT_MAX: none)
+__device__ __forceinline__ int warp_argmin_u32x2(unsigned hi, unsigned lo, int payload, unsigned* hi_out, unsigned* lo_out) {
+  const unsigned mh = __reduce_min_sync(FULLMASK, hi);
+  const unsigned ml = __reduce_min_sync(FULLMASK, hi == mh ? lo : 0xffffffffu);
+  const unsigned who = __ballot_sync(FULLMASK, hi == mh && lo == ml);
+  *hi_out = mh;
+  *lo_out = ml;
+  return __shfl_sync(FULLMASK, payload, __ffs(who) - 1);
+}
 // The panel factorization is column-sequential — per column: pivot search (two reductions: max |x|, then the lowest
 // original row among the rows within 0.1 of it), row swap, scaling and rank-1 update of the rest of the panel — so it is
 // bound by the LATENCY of one column step, not by throughput.  Per column: 4 CTA barriers (9 in the first version), the
@@ -565,25 +574,33 @@ __device__ __forceinline__ int warp_argmin_u32(unsigned key, int payload, unsign
 // threads as the panel has rows (<= 1024), which keeps the barriers cheap for small cores.
 // Measured per 32-column panel at ~200 rows: 91 us (flat index, 9 barriers) -> 81 us (row per thread, shuffle trees)
 // -> see profiles/ for this form.  The arithmetic and the pivot rule are unchanged: factors are bit-identical.
+// Rcnt (sparse storage; nullptr for a dense A, where every row has the same count): number of entries of each core row in
+// the basis matrix, the reference's orig_row2elt_count (lu.rs:139-144) — among the rows that pass the threshold the one
+// with the FEWEST entries is taken (lu.rs:219-231); equal counts go to the lowest original row.
 __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
-                                                    int32_t* __restrict__ Rp, int* __restrict__ flags,
+                                                    int32_t* __restrict__ Rp, int32_t* __restrict__ Rcnt, int* __restrict__ flags,
                                                     int32_t* __restrict__ aff_pos, int32_t* __restrict__ aff_src,
                                                     int32_t* __restrict__ aff_cnt, int32_t* __restrict__ perm_glob, int use_smem) {
   extern __shared__ __align__(16) unsigned char lu_smem[];
   __shared__ double redk[32];
   __shared__ unsigned redrp[32];
+  __shared__ unsigned redrc[32];
   __shared__ int redr[32];
   __shared__ int s_cnt;
   const int rows = k - j0, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = (blockDim.x + 31) >> 5;
   const int T = blockDim.x;
   double* P;
   int64_t pld;
-  int32_t *rp, *perm;
+  int32_t *rp, *perm, *rc = nullptr;
   if (use_smem) {
     P = reinterpret_cast<double*>(lu_smem);
     pld = rows;
     rp = reinterpret_cast<int32_t*>(P + (size_t)rows * nb);
     perm = rp + rows;
+    if (Rcnt) {
+      rc = perm + rows;
+      for (int r = tid; r < rows; r += T) rc[r] = Rcnt[j0 + r];
+    }
     for (int r = tid; r < rows; r += T) {  // 8 global loads in flight per thread (a plain loop serialises them: ~12 us per panel)
       const double* src = C + (int64_t)j0 * ld + j0 + r;
       for (int c0 = 0; c0 < nb; c0 += 8) {
@@ -601,6 +618,7 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
     pld = ld;
     rp = Rp + j0;
     perm = perm_glob;
+    if (Rcnt) rc = Rcnt + j0;
   }
   for (int r = tid; r < rows; r += T) perm[r] = r;
   if (tid == 0) s_cnt = 0;
@@ -623,21 +641,23 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
       stop = true;
       break;
     }
-    // pivot search 2: lowest original row among the eligible ones (original rows are distinct)
-    unsigned bk = 0xffffffffu;
+    // pivot search 2: among the eligible rows the one with the fewest entries in the basis matrix, then the lowest
+    // original row (original rows are distinct)
+    unsigned bc = 0xffffffffu, bk = 0xffffffffu;
     int br = -1;
     const double thr = 0.1 * max_abs;
     for (int r = c + tid; r < rows; r += T)
       if (fabs(col[r]) >= thr) {
-        const unsigned key = (unsigned)rp[r];
-        if (key < bk) { bk = key; br = r; }
+        const unsigned cnt = rc ? (unsigned)rc[r] : 0u, key = (unsigned)rp[r];
+        if (cnt < bc || (cnt == bc && key < bk)) { bc = cnt; bk = key; br = r; }
       }
-    unsigned wk;
-    const int wr = warp_argmin_u32(bk, br, &wk);
-    if (lane == 0) { redrp[wid] = wk; redr[wid] = wr; }
+    unsigned wc, wk;
+    const int wr = warp_argmin_u32x2(bc, bk, br, &wc, &wk);
+    if (lane == 0) { redrc[wid] = wc; redrp[wid] = wk; redr[wid] = wr; }
     __syncthreads();
-    unsigned dummy;
-    const int p = warp_argmin_u32(lane < nw ? redrp[lane] : 0xffffffffu, lane < nw ? redr[lane] : -1, &dummy);
+    unsigned d0, d1;
+    const int p = warp_argmin_u32x2(lane < nw ? redrc[lane] : 0xffffffffu, lane < nw ? redrp[lane] : 0xffffffffu,
+                                    lane < nw ? redr[lane] : -1, &d0, &d1);
     if (p != c) {
       if (tid < nb) {
         double* q = P + (size_t)tid * pld;
@@ -647,6 +667,7 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
       } else if (tid == nb) {
         const int a = rp[c]; rp[c] = rp[p]; rp[p] = a;
         const int bb = perm[c]; perm[c] = perm[p]; perm[p] = bb;
+        if (rc) { const int cc2 = rc[c]; rc[c] = rc[p]; rc[p] = cc2; }
       }
     }
     __syncthreads();
@@ -691,6 +712,7 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
           if (c0 + u < nb) dst[(int64_t)(c0 + u) * ld] = v[u];
       }
       Rp[j0 + r] = rp[r];
+      if (rc) Rcnt[j0 + r] = rc[r];
     }
   }
   for (int r = tid; r < rows; r += T)
@@ -732,6 +754,30 @@ __global__ void __launch_bounds__(256) k_lu_swap_solve(double* __restrict__ C, i
     if (lane > sc && lane < nb) a -= L11[lane][sc] * us;
   }
   if (lane < nb) colj[j0 + lane] = a;
+}
+// Entries per core row before the factorization (orig_row2elt_count of the reference restricted to the core: the slack of
+// a core row is non-basic, so only structural columns count), and the number of stored entries of the core.
+__global__ void __launch_bounds__(256) k_core_row_counts(const double* __restrict__ C, int64_t ld, int k, int32_t* __restrict__ rcnt,
+                                                          unsigned long long* __restrict__ total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  if (i < k)
+    for (int t = 0; t < k; ++t) c += C[(int64_t)t * ld + i] != 0.0;
+  if (i < k) rcnt[i] = c;
+  unsigned s = __reduce_add_sync(FULLMASK, (unsigned)c);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, (unsigned long long)s);
+}
+// Off-diagonal non-zeros of the finished factors L\U (LUFactors::nnz counts lower.nondiag + upper.nondiag, lu.rs:52-54;
+// exact zeros are not stored, lu.rs:253-255)
+__global__ void __launch_bounds__(256) k_count_offdiag(const double* __restrict__ C, int64_t ld, int k,
+                                                        unsigned long long* __restrict__ total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t0 = blockIdx.y * 64, t1 = min(k, t0 + 64);
+  int c = 0;
+  if (i < k)
+    for (int t = t0; t < t1; ++t) c += (t != i) && C[(int64_t)t * ld + i] != 0.0;
+  unsigned s = __reduce_add_sync(FULLMASK, (unsigned)c);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, (unsigned long long)s);
 }
 constexpr int LU_NC = 16;
 __global__ void __launch_bounds__(256) k_lu_trailing(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
