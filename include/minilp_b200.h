@@ -350,6 +350,24 @@ void mlp_solver_tie_stats(mlp_solver* s, int64_t out4[4]);
 /* seconds of wall clock spent inside mlp_solver_run so far, and of that inside refactorizations */
 void mlp_solver_timers(mlp_solver* s, double* run_seconds, double* refactor_seconds);
 
+/* ===================================================================== MPS ingest (host, no GPU) */
+/* MpsFile::parse (mps.rs:39-329) over one in-memory buffer of free-format MPS text: same sections, same first-vector
+ * rules, same bound defaults, ranged rows doubled (306-321).  Syntax errors: MLP_INVALID, mlp_last_error() = the reference's
+ * "line N: ..." message.  The result is held as flat arrays — variables (objective in the user's sign, bounds as
+ * Problem::add_var gets them, mps.rs:294-303) and every constraint as a CSR row with ascending variable indices
+ * (CsVec::new, lib.rs:279) — ready for Solver::try_new / mlp_solver_create_sparse after the empty-row filter
+ * (solver.rs:201-213). */
+typedef struct mlp_mps mlp_mps;
+mlp_status mlp_mps_parse(const char* text, int64_t len, mlp_mps** out);
+void mlp_mps_free(mlp_mps* f);
+const char* mlp_mps_name(mlp_mps* f); /* MpsFile::problem_name */
+void mlp_mps_sizes(mlp_mps* f, int64_t* num_vars, int64_t* num_constraints, int64_t* nnz, int64_t* names_bytes);
+/* Copies out whatever is non-NULL.  obj/mins/maxs: num_vars; row_ptr: num_constraints + 1; col_idx/vals: nnz; ops (0 Eq,
+ * 1 Le, 2 Ge) / rhs: num_constraints; names_blob: names_bytes (variable names concatenated, MpsFile::variables),
+ * names_off: num_vars + 1. */
+mlp_status mlp_mps_export(mlp_mps* f, double* obj, double* mins, double* maxs, int64_t* row_ptr, int32_t* col_idx, double* vals,
+                          int32_t* ops, double* rhs, char* names_blob, int64_t* names_off);
+
 /* ===================================================================== sharding helpers (host, no GPU) */
 /* Column block [begin, end) of rank `rank` of `world` over n structural columns. */
 void mlp_shard_range(int64_t n, int32_t world, int32_t rank, int64_t* begin, int64_t* end);

@@ -142,6 +142,11 @@ SIGNATURES = {
     "mlp_solver_get_basic_vars": (i32, [vp, pi64]),
     "mlp_solver_timers": (None, [vp, pd, pd]),
     "mlp_solver_tie_stats": (None, [vp, pi64]),
+    "mlp_mps_parse": (i32, [C.c_char_p, i64, C.POINTER(vp)]),
+    "mlp_mps_free": (None, [vp]),
+    "mlp_mps_name": (C.c_char_p, [vp]),
+    "mlp_mps_sizes": (None, [vp, pi64, pi64, pi64, pi64]),
+    "mlp_mps_export": (i32, [vp, pd, pd, pd, pi64, pi32, pd, pi32, pd, C.c_char_p, pi64]),
     "mlp_shard_range": (None, [i64, i32, i32, pi64, pi64]),
     "mlp_reduce_candidates": (i32, [pd, pi64, pi64, i32]),
     "mlp_synth_rows": (None, [i32, i64, i64, C.c_uint64, i64, i64, i32, pd]),

@@ -412,12 +412,42 @@ class Solver:
 
 # ------------------------------------------------------------------------------------------------ public API mirror
 class Problem:
-    """lib.rs:192-305.  Constraints are collected on the host; solve() hands a dense A to the device engine."""
+    """lib.rs:192-305.  Constraints are collected on the host; solve() hands the matrix to the device engine.  A problem that
+    comes out of the native MPS reader holds its constraints as flat CSR arrays (`from_arrays`) — the list-of-tuples view
+    (`constraints`) is only materialised if somebody asks for it."""
 
     def __init__(self, direction):
         self.direction = direction
         self.obj_coeffs, self.var_mins, self.var_maxs = [], [], []
-        self.constraints = []
+        self._constraints = []
+        self._bulk = None  # (row_ptr, col_idx, vals, ops, rhs) over ALL constraints, empty ones included
+
+    @classmethod
+    def from_arrays(cls, direction, obj_user, mins, maxs, row_ptr, col_idx, vals, ops, rhs):
+        """obj_user: objective in the user's sign (add_var applies lib.rs:235-238); rows with ascending variable indices."""
+        p = cls(direction)
+        sign = 1.0 if direction == OptimizationDirection.Minimize else -1.0
+        p.obj_coeffs = (sign * np.asarray(obj_user, dtype=np.float64)).tolist()
+        p.var_mins, p.var_maxs = np.asarray(mins, dtype=np.float64).tolist(), np.asarray(maxs, dtype=np.float64).tolist()
+        p._bulk = (np.ascontiguousarray(row_ptr, dtype=np.int64), np.ascontiguousarray(col_idx, dtype=np.int32),
+                   np.ascontiguousarray(vals, dtype=np.float64), np.ascontiguousarray(ops, dtype=np.int32),
+                   np.ascontiguousarray(rhs, dtype=np.float64))
+        p._constraints = None
+        return p
+
+    @property
+    def constraints(self):
+        if self._constraints is None:
+            rp, ci, va, ops, rhs = self._bulk
+            ci_l, va_l = ci.tolist(), va.tolist()
+            self._constraints = [(list(zip(ci_l[rp[i]:rp[i + 1]], va_l[rp[i]:rp[i + 1]])), int(ops[i]), float(rhs[i]))
+                                 for i in range(len(ops))]
+            self._bulk = None
+        return self._constraints
+
+    @constraints.setter
+    def constraints(self, value):
+        self._constraints, self._bulk = value, None
 
     def add_var(self, obj_coeff, bounds):
         v = len(self.obj_coeffs)
@@ -435,52 +465,60 @@ class Problem:
             raise ValueError("unknown variable")
         self.constraints.append((sorted(expr), cmp_op, float(rhs)))  # CsVec::new sorts by index (lib.rs:279)
 
+    def _all_rows(self):
+        """Every constraint as CSR (row_ptr, col_idx, vals, ops, rhs), empty rows included."""
+        if self._constraints is None:
+            return self._bulk
+        cons = self._constraints
+        row_ptr = np.zeros(len(cons) + 1, dtype=np.int64)
+        for i, (e, _, _) in enumerate(cons):
+            row_ptr[i + 1] = row_ptr[i] + len(e)
+        col_idx = np.fromiter((v for e, _, _ in cons for v, _ in e), dtype=np.int32, count=int(row_ptr[-1]))
+        vals = np.fromiter((c for e, _, _ in cons for _, c in e), dtype=np.float64, count=int(row_ptr[-1]))
+        ops = np.array([op for _, op, _ in cons], dtype=np.int32)
+        rhs = np.array([r for _, _, r in cons], dtype=np.float64)
+        return row_ptr, col_idx, vals, ops, rhs
+
     def to_csr(self):
         """The constraint rows that survive Solver::try_new's empty-row filter (solver.rs:201-213) as CSR, plus ops / rhs."""
-        kept = [(e, op, r) for e, op, r in self.constraints if e]
-        row_ptr = np.zeros(len(kept) + 1, dtype=np.int64)
-        for i, (e, _, _) in enumerate(kept):
-            row_ptr[i + 1] = row_ptr[i] + len(e)
-        col_idx = np.fromiter((v for e, _, _ in kept for v, _ in e), dtype=np.int32, count=int(row_ptr[-1]))
-        vals = np.fromiter((c for e, _, _ in kept for _, c in e), dtype=np.float64, count=int(row_ptr[-1]))
-        ops = np.array([op for _, op, _ in kept], dtype=np.int32)
-        rhs = np.array([r for _, _, r in kept], dtype=np.float64)
-        return row_ptr, col_idx, vals, ops, rhs
+        row_ptr, col_idx, vals, ops, rhs = self._all_rows()
+        lens = np.diff(row_ptr)
+        keep = lens > 0
+        if keep.all():
+            return row_ptr, col_idx, vals, ops, rhs
+        new_ptr = np.zeros(int(keep.sum()) + 1, dtype=np.int64)
+        np.cumsum(lens[keep], out=new_ptr[1:])
+        return new_ptr, col_idx, vals, ops[keep], rhs[keep]  # empty rows own no entries: the entry arrays stay as they are
 
     def solve(self, device=0, max_pivots=-1, storage="auto"):
         """storage: "dense" (row-major f64 A in HBM), "sparse" (CSR + CSC), or "auto" (sparse below 10 % density once A
         has more than 2^20 entries)."""
         n = len(self.obj_coeffs)
-        for mn, mx in zip(self.var_mins, self.var_maxs):
-            if mn > mx:
-                raise Infeasible("min > max")  # solver.rs:138-140
-        kept = []
-        for expr, op, rhs in self.constraints:  # solver.rs:201-213
-            if not expr:
-                ok = (0.0 == rhs) if op == ComparisonOp.Eq else (0.0 <= rhs) if op == ComparisonOp.Le else (0.0 >= rhs)
-                if not ok:
-                    raise Infeasible("empty constraint cannot hold")
-                continue
-            kept.append((expr, op, rhs))
-        if n == 0 or not kept:
+        if np.any(np.asarray(self.var_mins) > np.asarray(self.var_maxs)):
+            raise Infeasible("min > max")  # solver.rs:138-140
+        row_ptr, col_idx, vals, ops, rhs = self._all_rows()
+        lens = np.diff(row_ptr)
+        empty = lens == 0
+        if empty.any():  # solver.rs:201-213
+            o, r = ops[empty], rhs[empty]
+            ok = np.where(o == ComparisonOp.Eq, 0.0 == r, np.where(o == ComparisonOp.Le, 0.0 <= r, 0.0 >= r))
+            if not ok.all():
+                raise Infeasible("empty constraint cannot hold")
+        m = int((~empty).sum())
+        if n == 0 or m == 0:
             return _TrivialSolution(self, n)
-        m = len(kept)
-        nnz = sum(len(e) for e, _, _ in kept)
+        row_ptr, col_idx, vals, ops, rhs = self.to_csr()
+        nnz = int(row_ptr[-1])
         if storage == "auto":
             storage = "sparse" if (m * n > (1 << 20) and nnz < 0.1 * m * n) else "dense"
         if storage == "sparse":
-            row_ptr, col_idx, vals, ops, rhs = self.to_csr()
             s = Solver(m, n, device, csr=(row_ptr, col_idx, vals))
-            s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs), ops, rhs)
         else:
             a = np.zeros((m, n))
-            for i, (expr, _, _) in enumerate(kept):
-                for v, c in expr:
-                    a[i, v] = c
+            a[np.repeat(np.arange(m), np.diff(row_ptr)), col_idx] = vals
             s = Solver(m, n, device)
             s.upload_rows(0, a)
-            s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs),
-                   np.array([op for _, op, _ in kept], dtype=np.int32), np.array([r for _, _, r in kept]))
+        s.init(np.array(self.obj_coeffs), np.array(self.var_mins), np.array(self.var_maxs), ops, rhs)
         s.direction = self.direction
         s.run(max_pivots)
         return Solution(s, self.direction, n)

@@ -24,6 +24,7 @@
 static thread_local std::string g_err;
 static void set_err(const std::string& s) { g_err = s; }
 extern "C" const char* mlp_last_error(void) { return g_err.c_str(); }
+extern "C" void mlp_set_last_error(const char* msg) { g_err = msg ? msg : ""; }  // for the other translation units of the library
 extern "C" const char* mlp_version(void) { return "minilp_b200 0.2 (sm_100a)"; }
 extern "C" int mlp_device_count(void) {
   int n = 0;

@@ -87,6 +87,47 @@ class MpsFile:
 
     @classmethod
     def parse(cls, text, direction):
+        """The product path: the native reader (csrc/mps_reader.cpp behind mlp_mps_parse — one pass over the buffer, flat
+        arrays out; ~100x the pure-Python restatement below, which is kept as `parse_python` and cross-checked in the tests)."""
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib
+        if hasattr(text, "read"):
+            text = text.read()
+        raw = text.encode() if isinstance(text, str) else bytes(text)
+        L = _lib.lib()
+        h = C.c_void_p()
+        st = L.mlp_mps_parse(raw, len(raw), C.byref(h))
+        if st != 0:
+            msg = L.mlp_last_error().decode()
+            if msg.startswith("line "):
+                raise MpsError(msg)
+            raise ValueError(msg)  # CsVec::new's panic on a repeated variable (lib.rs:247-249)
+        try:
+            nv, nc, nnz, nb = (C.c_int64() for _ in range(4))
+            L.mlp_mps_sizes(h, C.byref(nv), C.byref(nc), C.byref(nnz), C.byref(nb))
+            nv, nc, nnz, nb = nv.value, nc.value, nnz.value, nb.value
+            obj, mins, maxs = np.empty(nv), np.empty(nv), np.empty(nv)
+            row_ptr, col_idx, vals = np.empty(nc + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+            ops, rhs = np.empty(nc, dtype=np.int32), np.empty(nc)
+            blob, off = C.create_string_buffer(max(nb, 1)), np.empty(nv + 1, dtype=np.int64)
+            pd, pi64, pi32 = _lib.pd, _lib.pi64, _lib.pi32
+            L.mlp_mps_export(h, obj.ctypes.data_as(pd), mins.ctypes.data_as(pd), maxs.ctypes.data_as(pd),
+                             row_ptr.ctypes.data_as(pi64), col_idx.ctypes.data_as(pi32), vals.ctypes.data_as(pd),
+                             ops.ctypes.data_as(pi32), rhs.ctypes.data_as(pd), blob, off.ctypes.data_as(pi64))
+            name = L.mlp_mps_name(h).decode()
+        finally:
+            L.mlp_mps_free(h)
+        names = blob.raw[:nb]
+        o = off.tolist()
+        variables = {names[o[j]:o[j + 1]].decode(): j for j in range(nv)}
+        return cls(name, variables, Problem.from_arrays(direction, obj, mins, maxs, row_ptr, col_idx, vals, ops, rhs))
+
+    @classmethod
+    def parse_python(cls, text, direction):
+        """Pure-Python restatement of mps.rs:39-329, line by line (reference for the native reader's behaviour)."""
         if hasattr(text, "read"):
             text = text.read()
         lines = _Lines(text)
