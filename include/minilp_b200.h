@@ -62,6 +62,9 @@ mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine*
  * indices.  Every other entry point is storage-agnostic; mlp_engine_upload_rows is rejected. */
 mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
                                     const int32_t* col_idx, const double* vals, mlp_engine** out);
+/* The CSC copy the engine derived on the device (SparseMat::transpose, sparse.rs:230-269: rows ascending within a column);
+ * col_ptr: n+1, row_idx / vals: nnz; NULL pointers are skipped. */
+mlp_status mlp_engine_download_csc(mlp_engine* e, int64_t* col_ptr, int32_t* row_idx, double* vals);
 /* Column-sharded engine: rank `rank` of `world` owns the structural columns
  * mlp_shard_range(n_global, world, rank) of A and all per-variable arrays of those columns; m-sized state and the
  * basis factors are replicated and every rank runs the identical host control loop (SPMD).  All variable indices

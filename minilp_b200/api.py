@@ -211,6 +211,12 @@ class Engine:
         _check(_lib.lib().mlp_download_basic_vars(self._e, _p(out, pi64)))
         return out
 
+    def download_csc(self, nnz):
+        """The CSC copy of a sparse-storage engine as built on the device: (col_ptr, row_idx, vals)."""
+        cp, ri, va = np.empty(self.n + 1, dtype=np.int64), np.empty(nnz, dtype=np.int32), np.empty(nnz)
+        _check(_lib.lib().mlp_engine_download_csc(self._e, _p(cp, pi64), _p(ri, pi32), _p(va)))
+        return cp, ri, va
+
     def var_state(self):
         fl = np.empty(self.n + self.m, dtype=np.uint8)
         pos = np.empty(self.n + self.m, dtype=np.int32)

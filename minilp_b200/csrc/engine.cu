@@ -68,6 +68,7 @@ static_assert(sizeof(Cand) == 64, "Cand must be 64 bytes");
 
 #include "kernels_common.cuh"
 #include "chain_fused.cuh"
+#include "sparse_build.cuh"
 
 // ------------------------------------------------------------------------------------------------ communicators
 // The pivot path has ONE real exchange step per pivot: the arg-reduce of the per-shard pricing
@@ -2232,40 +2233,16 @@ mlp_status mlp_nccl_get_unique_id(void* out128) {
 mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine** out) {
   return create_engine(device, m, n, 0, 1, nullptr, out);
 }
-// (Re)build everything the engine derives from the host CSR copy (h_csr_*): the CSC copy — CsMat::to_csc (solver.rs:253,
-// 610), a counting transpose with rows ascending within a column (sparse.rs:230-269 does the same) —, the segment table
-// of the CSC copy, and the device arrays.  m = number of rows of the CSR copy.
+// (Re)build everything the engine derives from the host CSR copy (h_csr_*): the device CSR arrays, and ON THE DEVICE
+// (sparse_build.cuh) the CSC copy — CsMat::to_csc (solver.rs:253, 610), rows ascending within a column as sparse.rs:230-269
+// produces them — and the segment table of the CSC copy.  m = number of rows of the CSR copy.  MLP_HOST_TRANSPOSE=1 builds
+// the CSC copy with the host counting transpose instead (kept for the equality test).
 static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   const int64_t n = e->n, nnz = (int64_t)e->h_csr_idx.size();
   const int64_t* row_ptr = e->h_csr_ptr.data();
   const int32_t* col_idx = e->h_csr_idx.data();
   const double* vals = e->h_csr_val.data();
-  std::vector<int64_t> cptr((size_t)n + 1, 0);
-  for (int64_t t = 0; t < nnz; ++t) cptr[(size_t)col_idx[t] + 1] += 1;
-  for (int64_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
-  std::vector<int32_t> cidx((size_t)nnz);
-  std::vector<double> cval((size_t)nnz);
-  {
-    std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
-    for (int64_t i = 0; i < m; ++i)
-      for (int64_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
-        const int64_t d = fill[col_idx[t]]++;
-        cidx[d] = (int32_t)i;
-        cval[d] = vals[t];
-      }
-  }
   e->nnz = nnz;
-  e->h_csc_ptr = cptr;
-  std::vector<int32_t> sgc;
-  std::vector<int64_t> sgo, cseg((size_t)n + 1, 0);
-  for (int64_t j = 0; j < n; ++j) {
-    cseg[j] = (int64_t)sgc.size();
-    int64_t b = cptr[j];
-    do { sgc.push_back((int32_t)j); sgo.push_back(b); b += CSC_SEG; } while (b < cptr[j + 1]);  // an empty column keeps one empty segment
-  }
-  cseg[n] = (int64_t)sgc.size();
-  e->nseg = (int64_t)sgc.size();
-  e->h_col_seg = cseg;
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   dev_free(e->csr_ptr); dev_free(e->csr_idx); dev_free(e->csr_val); dev_free(e->csc_ptr); dev_free(e->csc_idx); dev_free(e->csc_val);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum);
@@ -2273,21 +2250,77 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
   A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
   A(dev_alloc(&e->csc_ptr, n + 1)); A(dev_alloc(&e->csc_idx, nnz)); A(dev_alloc(&e->csc_val, nnz));
-  A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg)); A(dev_alloc(&e->col_seg, n + 1));
-  A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
-  if (st == MLP_OK) {
-    A(h2d(e, e->seg_col, sgc.data(), e->nseg * sizeof(int32_t)));
-    A(h2d(e, e->seg_off, sgo.data(), e->nseg * sizeof(int64_t)));
-    A(h2d(e, e->col_seg, cseg.data(), (n + 1) * sizeof(int64_t)));
-    A(h2d(e, e->csr_ptr, row_ptr, (m + 1) * sizeof(int64_t)));
-    A(h2d(e, e->csr_idx, col_idx, nnz * sizeof(int32_t)));
-    A(h2d(e, e->csr_val, vals, nnz * sizeof(double)));
-    A(h2d(e, e->csc_ptr, cptr.data(), (n + 1) * sizeof(int64_t)));
-    A(h2d(e, e->csc_idx, cidx.data(), nnz * sizeof(int32_t)));
-    A(h2d(e, e->csc_val, cval.data(), nnz * sizeof(double)));
+  A(dev_alloc(&e->col_seg, n + 1));
+  if (st != MLP_OK) return st;
+  ST(h2d(e, e->csr_ptr, row_ptr, (m + 1) * sizeof(int64_t)));
+  ST(h2d(e, e->csr_idx, col_idx, nnz * sizeof(int32_t)));
+  ST(h2d(e, e->csr_val, vals, nnz * sizeof(double)));
+  e->h_csc_ptr.assign((size_t)n + 1, 0);
+  e->h_col_seg.assign((size_t)n + 1, 0);
+  bool host_transpose = false;
+  if (const char* v = getenv("MLP_HOST_TRANSPOSE")) host_transpose = atoi(v) != 0;
+  if (host_transpose) {
+    std::vector<int64_t>& cptr = e->h_csc_ptr;
+    for (int64_t t = 0; t < nnz; ++t) cptr[(size_t)col_idx[t] + 1] += 1;
+    for (int64_t j = 0; j < n; ++j) cptr[j + 1] += cptr[j];
+    std::vector<int32_t> cidx((size_t)nnz);
+    std::vector<double> cval((size_t)nnz);
+    std::vector<int64_t> fill(cptr.begin(), cptr.end() - 1);
+    for (int64_t i = 0; i < m; ++i)
+      for (int64_t t = row_ptr[i]; t < row_ptr[i + 1]; ++t) {
+        const int64_t d = fill[col_idx[t]]++;
+        cidx[d] = (int32_t)i;
+        cval[d] = vals[t];
+      }
+    for (int64_t j = 0; j < n; ++j) {
+      const int64_t c = cptr[j + 1] - cptr[j];
+      e->h_col_seg[j + 1] = e->h_col_seg[j] + (c == 0 ? 1 : (c + CSC_SEG - 1) / CSC_SEG);
+    }
+    ST(h2d(e, e->csc_ptr, cptr.data(), (n + 1) * sizeof(int64_t)));
+    ST(h2d(e, e->csc_idx, cidx.data(), nnz * sizeof(int32_t)));
+    ST(h2d(e, e->csc_val, cval.data(), nnz * sizeof(double)));
+    ST(h2d(e, e->col_seg, e->h_col_seg.data(), (n + 1) * sizeof(int64_t)));
+    CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+  } else {
+    // chunks of consecutive rows: about two CTAs per SM for the fill, bounded by 256 MB of per-chunk column counters
+    int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(2 * e->sm_count, m), ((int64_t)256 << 20) / (4 * std::max<int64_t>(n, 1))));
+    const int rpc = (int)((m + chunks - 1) / chunks);
+    chunks = (int)((m + rpc - 1) / rpc);
+    int32_t* hist = nullptr;
+    int64_t *cnt = nullptr, *segs = nullptr;
+    A(dev_alloc(&hist, (size_t)chunks * n)); A(dev_alloc(&cnt, n)); A(dev_alloc(&segs, n));
+    if (st == MLP_OK) {
+      cudaMemsetAsync(hist, 0, (size_t)chunks * n * sizeof(int32_t), e->stream);
+      LAUNCH(e, k_t_hist, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, m, n, rpc, hist);
+      LAUNCH(e, k_t_colscan, cdiv(n, 256), 256, 0, hist, n, chunks, cnt, segs, CSC_SEG);
+      LAUNCH(e, k_scan_excl, 1, 1024, 0, cnt, n, e->csc_ptr);
+      LAUNCH(e, k_scan_excl, 1, 1024, 0, segs, n, e->col_seg);
+      LAUNCH(e, k_t_fill, chunks, 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, n, rpc, hist, e->csc_ptr, e->csc_idx, e->csc_val);
+      // the host keeps the two pointer arrays: column counts for LUFactors::nnz, segment ranges for the core's segment list
+      A(d2h(e, e->h_csc_ptr.data(), e->csc_ptr, (n + 1) * sizeof(int64_t)));
+      A(d2h(e, e->h_col_seg.data(), e->col_seg, (n + 1) * sizeof(int64_t)));
+    }
+    dev_free(hist); dev_free(cnt); dev_free(segs);
+    if (st != MLP_OK) return st;
+    if (e->h_csc_ptr[(size_t)n] != nnz) { set_err("sparse upload: device transpose lost entries"); return MLP_CUDA_ERROR; }
   }
-  if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("sparse upload failed"); st = MLP_CUDA_ERROR; }
-  return st;  // host vectors go out of scope only after the synchronize
+  e->nseg = e->h_col_seg[(size_t)n];
+  A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg));
+  A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
+  if (st != MLP_OK) return st;
+  LAUNCH(e, k_t_segs, cdiv(n, 256), 256, 0, e->csc_ptr, e->col_seg, n, CSC_SEG, e->seg_col, e->seg_off);
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("sparse upload failed"); return MLP_CUDA_ERROR; }
+  return MLP_OK;
+}
+// the CSC copy as the engine holds it (parity tests of the on-device transpose)
+mlp_status mlp_engine_download_csc(mlp_engine* e, int64_t* col_ptr, int32_t* row_idx, double* vals) {
+  if (!e || !e->sparse) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  ST(begin0(e));
+  if (col_ptr) ST(d2h(e, col_ptr, e->csc_ptr, (e->n + 1) * sizeof(int64_t)));
+  if (row_idx) ST(d2h(e, row_idx, e->csc_idx, e->nnz * sizeof(int32_t)));
+  if (vals) ST(d2h(e, vals, e->csc_val, e->nnz * sizeof(double)));
+  return MLP_OK;
 }
 mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
                                     const double* vals, mlp_engine** out) {
@@ -2300,6 +2333,9 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
     if (row_ptr[i + 1] < row_ptr[i]) { set_err("create_sparse: row_ptr not monotone"); return MLP_INVALID; }
   for (int64_t t = 0; t < nnz; ++t)
     if (col_idx[t] < 0 || col_idx[t] >= n) { set_err("create_sparse: column index out of range"); return MLP_INVALID; }
+  for (int64_t i = 0; i < m; ++i)  // CsVec::new (lib.rs:279): sorted, no repeated index — the device transpose relies on it
+    for (int64_t t = row_ptr[i] + 1; t < row_ptr[i + 1]; ++t)
+      if (col_idx[t] <= col_idx[t - 1]) { set_err("create_sparse: columns must be strictly ascending within a row"); return MLP_INVALID; }
   mlp_engine* e = nullptr;
   ST(create_engine(device, m, n, 0, 1, nullptr, &e, true));
   e->h_csr_ptr.assign(row_ptr, row_ptr + m + 1);

@@ -1,0 +1,81 @@
+// On-device CSR -> CSC (second half): CsMat::to_csc (solver.rs:253, 610) / SparseMat::transpose
+// (sparse.rs:230-269) as a segmented counting transpose.  The result must list every column's rows in ASCENDING order —
+// that is the order the reference's transpose produces and the order every column-oriented kernel here sums in — so a
+// scatter with atomics is not enough.  Rows are cut into C chunks of consecutive rows:
+//   1. k_t_hist     hist[c][j] = entries of column j in chunk c (integer atomics: the count does not depend on their order)
+//   2. k_t_colscan  per column, exclusive scan over the chunks (start of chunk c's entries inside column j) + column count
+//   3. k_scan_excl  column counts -> csc_ptr; segment counts -> col_seg  (one CTA, three-phase scan)
+//   4. k_t_fill     one CTA per chunk walks ITS rows in order; the threads take the entries of one row in parallel — a row
+//                   holds a column at most once, so no two threads touch the same counter — and a barrier separates rows.
+//   5. k_t_segs     segment table of the CSC copy (<= CSC_SEG consecutive entries of one column per segment)
+// Deterministic, bit-identical to the host counting transpose (tests/test_sparse_gpu.py compares them).
+#pragma once
+
+__global__ void __launch_bounds__(256) k_t_hist(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t m,
+                                                int64_t n, int rows_per_chunk, int32_t* __restrict__ hist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= m) return;
+  int32_t* h = hist + (r / rows_per_chunk) * n;
+  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) atomicAdd(h + idx[t], 1);
+}
+__global__ void __launch_bounds__(256) k_t_colscan(int32_t* __restrict__ hist, int64_t n, int chunks, int64_t* __restrict__ cnt,
+                                                   int64_t* __restrict__ segs, int seg_len) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int32_t run = 0;
+  for (int c = 0; c < chunks; ++c) {
+    const int32_t t = hist[(int64_t)c * n + j];
+    hist[(int64_t)c * n + j] = run;
+    run += t;
+  }
+  cnt[j] = run;
+  segs[j] = run == 0 ? 1 : (run + seg_len - 1) / seg_len;  // an empty column keeps one empty segment
+}
+// out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total).  One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_scan_excl(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024, b = (int64_t)t * per, e = b + per < n ? b + per : n;
+  int64_t s = 0;
+  for (int64_t i = b; i < e; ++i) s += in[i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    int64_t run = 0;
+    for (int q = 0; q < 1024; ++q) { const int64_t v = part[q]; part[q] = run; run += v; }
+    out[n] = run;
+  }
+  __syncthreads();
+  int64_t run = part[t];
+  for (int64_t i = b; i < e; ++i) { const int64_t v = in[i]; out[i] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                const double* __restrict__ val, int64_t m, int64_t n, int rows_per_chunk,
+                                                int32_t* __restrict__ hist, const int64_t* __restrict__ csc_ptr,
+                                                int32_t* __restrict__ csc_idx, double* __restrict__ csc_val) {
+  const int c = blockIdx.x;
+  int32_t* h = hist + (int64_t)c * n;
+  const int64_t r0 = (int64_t)c * rows_per_chunk, r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
+  for (int64_t r = r0; r < r1; ++r) {
+    for (int64_t t = ptr[r] + threadIdx.x; t < ptr[r + 1]; t += blockDim.x) {
+      const int32_t j = idx[t];
+      const int32_t k = h[j];
+      h[j] = k + 1;
+      const int64_t pos = csc_ptr[j] + k;
+      csc_idx[pos] = (int32_t)r;
+      csc_val[pos] = val[t];
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_t_segs(const int64_t* __restrict__ csc_ptr, const int64_t* __restrict__ col_seg, int64_t n,
+                                                int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t b = csc_ptr[j];
+  for (int64_t sg = col_seg[j]; sg < col_seg[j + 1]; ++sg) {
+    seg_col[sg] = (int32_t)j;
+    seg_off[sg] = b + (sg - col_seg[j]) * seg_len;
+  }
+}

@@ -91,3 +91,29 @@ def test_sparse_medium_budgeted():
     assert_same_trace(gpu.trace(), ref.trace(), ref, gpu)
     assert gpu.engine.counters()["refactors"] > 1
     gpu.close()
+
+
+@pytest.mark.parametrize("gen,args", [(synth.netlib_like, (3000, 2500, 12.0, 7)), (synth.sparse_pos, (700, 5000, 9.0, 1)),
+                                      (synth.netlib_like, (40, 30, 3.0, 2))])
+def test_device_transpose_equals_the_host_counting_transpose(gen, args, monkeypatch):
+    """Row f3: the CSC copy is built on the device (segmented counting transpose) and must equal SparseMat::transpose
+    (sparse.rs:230-269) entry for entry: columns in order, rows ascending within a column, same values."""
+    text, d = gen(*args)
+    p = mps.MpsFile.parse(text, d).problem
+    rp, ci, va, ops, rhs = p.to_csr()
+    m, n = len(ops), len(p.obj_coeffs)
+    rows = np.repeat(np.arange(m), np.diff(rp))
+    order = np.lexsort((rows, ci))  # by column, then by row
+    want_ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(ci, minlength=n), out=want_ptr[1:])
+    dev = solver_from_problem(p, "sparse")
+    cp, ri, cv = dev.engine.download_csc(len(va))
+    assert np.array_equal(cp, want_ptr) and np.array_equal(ri, rows[order]) and np.array_equal(cv, va[order])
+    monkeypatch.setenv("MLP_HOST_TRANSPOSE", "1")
+    host = solver_from_problem(p, "sparse")
+    for a, b in zip(host.engine.download_csc(len(va)), (cp, ri, cv)):
+        assert np.array_equal(a, b)
+    assert dev.run(60) == host.run(60)
+    assert np.array_equal(dev.trace(), host.trace())
+    dev.close()
+    host.close()
