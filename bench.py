@@ -270,105 +270,9 @@ def load_traffic(a, nloc):
     return None
 
 
-def run_ours_sparse(a):
-    """BASELINE config 4 on one GPU: MPS text -> native reader -> CSR -> device (CSC built there) -> dual simplex loop."""
-    import minilp_b200 as mb
-    from minilp_b200 import mps
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("the sparse workloads run on one GPU (bench.py --workload netlib_like --gpus 1)")
-    if mb.device_count() < 1:
-        raise RuntimeError("bench.py needs a CUDA device: minilp_b200 has no CPU fallback")
-    t0 = time.perf_counter()
-    text, d = sparse_text(a)
-    t1 = time.perf_counter()
-    p = mps.MpsFile.parse(text, d).problem
-    t2 = time.perf_counter()
-    rp, ci, va, ops, rhs = p.to_csr()
-    m, n, nnz = len(ops), len(p.obj_coeffs), len(va)
-    s = mb.Solver(m, n, csr=(rp, ci, va))
-    t3 = time.perf_counter()
-    s.init(np.array(p.obj_coeffs), np.array(p.var_mins), np.array(p.var_maxs), ops, rhs)
-    s.engine.sync()
-    t4 = time.perf_counter()
-    setup = {"generate_text_s": round(t1 - t0, 3), "mps_bytes": len(text), "mps_parse_s": round(t2 - t1, 3),
-             "create_upload_transpose_s": round(t3 - t2, 3), "try_new_s": round(t4 - t3, 3),
-             "ingest_s (parse + upload + try_new)": round(t4 - t1, 3)}
-    e = s.engine
-    s.set_record_trace(True)
-    if a.warmup > 0:
-        s.run(a.warmup)
-    c0 = e.counters()
-    p0 = s.pivots_done
-    e.profile_enable(True)
-    sampler = ClockSampler(0)
-    time.sleep(0.3)
-    e.sync()
-    w0 = time.perf_counter()
-    e.event_mark(0)
-    done = s.run(a.steps)
-    e.event_mark(1)
-    e.sync()
-    w1 = time.perf_counter()
-    dev_ms = e.event_elapsed_ms(0, 1)
-    clocks = sampler.stop()
-    e.profile_enable(False)
-    prof = e.profile()
-    c1 = e.counters()
-    steps = s.pivots_done - p0
-    _, refac_s = s.timers()
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    # the dual loop prices out the tableau row (slot rho); the primal loop (sparse_pos) adds the N^T v product (slot v)
-    lau = prof["price_rho_launches"] + prof["price_v_launches"]
-    pms = prof["price_rho_ms"] + prof["price_v_ms"]
-    pby = prof["price_rho_bytes"] + prof["price_v_bytes"]
-    ach = pby / (pms * 1e-3) / 1e9 if pms > 0 else 0.0
-    traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "price_csc_traffic.json")))
-        if t.get("nnz") == nnz:
-            traffic = t.get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    line = {
-        "metric": METRIC, "value": steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": a.warmup,
-        "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": bench_config(a),
-        "run_detail": {"rows": m, "cols": n, "nnz": nnz, "pivots_before_timed_region": p0, "optimal_reached": bool(done),
-                       "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
-                       "refactors_in_region": c1["refactors"] - c0["refactors"], "refactor_wall_s": refac_s, "setup": setup,
-                       "objective_after": s.cur_obj_val, "l2": "the CSC copy (12 nnz bytes) is about the size of the 126 MB L2"},
-        "clocks": clocks,
-        "e2e": {"value": steps / (w1 - w0), "unit": UNIT, "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),
-                "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(steps, 1), "wall_s": w1 - w0},
-        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
-        "roofline": {"bound": "hbm", "kernel": "k_price_csc_seg + k_price_csc_fin: price-out over the CSC copy (calc_row_coeffs "
-                                               "solver.rs:685-692; N^T v 1117-1132 in the primal loop)",
-                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": pby / max(lau, 1), "formula": "12 nnz + 8 m + 8 (n + m)",
-                     "launches_timed": lau, "avg_launch_ms": pms / max(lau, 1), "share_of_step_time": pms / dev_ms if dev_ms else 0,
-                     "note": "12 nnz = 117 MB sits at the edge of the 126 MB L2: a launch that finds the matrix there runs above "
-                             "the HBM figure; traffic (ncu dram bytes per launch, profiles/) says how much really came from HBM"},
-    }
-    if a.cpu_baseline_seconds > 0:
-        piv, sec, tr_cpu, ties, setup_s = cpu_port_run_sparse(a, text, d, a.warmup, 100000, a.cpu_baseline_seconds)
-        line["parity"] = parity_against(s.trace(), tr_cpu, ties, m, m)
-        line["parity"]["engine_ties"] = s.tie_stats()
-        line["cpu_baseline"] = {"value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
-                                "sample": (f"pivots {a.warmup + 1}..{a.warmup + piv} of the same LP from the same MPS text ({sec:.1f}s of "
-                                           f"single-thread CPU work after {a.warmup} untimed pivots; parse + try_new {setup_s:.1f}s excluded)"),
-                                "host_cores_available": os.cpu_count() or 1}
-    emit(line)
-    s.close()
-
-
-def run_ours(a):
-    """One process per GPU.  world > 1 (torchrun): the SAME LP is column-sharded over the ranks (strong scaling); every rank
-    runs the identical host control loop, the one exchange step per pivot goes over NCCL inside the engine."""
+def dist_setup():
+    """One process per GPU (torchrun): NCCL process group for the bench's own barriers / max-over-ranks, and a fresh NCCL
+    unique id for the engine's communicator."""
     import torch
 
     import minilp_b200 as mb
@@ -402,6 +306,118 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    return world, rank, local, dist, comm, barrier, max_over_ranks
+
+
+def run_ours_sparse(a):
+    """BASELINE config 4 on one GPU: MPS text -> native reader -> CSR -> device (CSC built there) -> dual simplex loop."""
+    import minilp_b200 as mb
+    from minilp_b200 import mps
+    world, rank, local, dist, comm, barrier, max_over_ranks = dist_setup()
+    t0 = time.perf_counter()
+    text, d = sparse_text(a)
+    t1 = time.perf_counter()
+    p = mps.MpsFile.parse(text, d).problem
+    t2 = time.perf_counter()
+    rp, ci, va, ops, rhs = p.to_csr()
+    m, n, nnz = len(ops), len(p.obj_coeffs), len(va)
+    s = mb.Solver(m, n, local, rank, world, comm, csr=(rp, ci, va))
+    t3 = time.perf_counter()
+    s.init(np.array(p.obj_coeffs), np.array(p.var_mins), np.array(p.var_maxs), ops, rhs)
+    s.engine.sync()
+    t4 = time.perf_counter()
+    setup = {"generate_text_s": round(t1 - t0, 3), "mps_bytes": len(text), "mps_parse_s": round(t2 - t1, 3),
+             "create_upload_transpose_s": round(t3 - t2, 3), "try_new_s": round(t4 - t3, 3),
+             "ingest_s (parse + upload + try_new)": round(t4 - t1, 3)}
+    e = s.engine
+    s.set_record_trace(True)
+    if a.warmup > 0:
+        s.run(a.warmup)
+    c0 = e.counters()
+    p0 = s.pivots_done
+    e.profile_enable(True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    e.sync()
+    barrier()
+    w0 = time.perf_counter()
+    e.event_mark(0)
+    done = s.run(a.steps)
+    e.event_mark(1)
+    e.sync()
+    barrier()
+    w1 = max_over_ranks(time.perf_counter() - w0) + w0
+    dev_ms = max_over_ranks(e.event_elapsed_ms(0, 1))
+    clocks = sampler.stop() if sampler else None
+    e.profile_enable(False)
+    prof = e.profile()
+    c1 = e.counters()
+    steps = s.pivots_done - p0
+    _, refac_s = s.timers()
+    if rank != 0:
+        s.close()
+        dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    # the dual loop prices out the tableau row (slot rho); the primal loop (sparse_pos) adds the N^T v product (slot v)
+    lau = prof["price_rho_launches"] + prof["price_v_launches"]
+    pms = prof["price_rho_ms"] + prof["price_v_ms"]
+    pby = prof["price_rho_bytes"] + prof["price_v_bytes"]
+    ach = pby / (pms * 1e-3) / 1e9 if pms > 0 else 0.0
+    traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "price_csc_traffic.json")))
+        if t.get("nnz") == nnz:
+            traffic = t.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": steps / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
+        "ms_per_step": dev_ms / max(steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": bench_config(a),
+        "run_detail": {"rows": m, "cols": n, "nnz": nnz,
+                       "parallelism": (f"price-out and per-variable arrays column-sharded over {world} GPUs ({e.n} columns each), "
+                                       f"matrix and basis replicated, one candidate exchange per pivot ({e.exchange_kind()})")
+                       if world > 1 else "single GPU", "pivots_before_timed_region": p0, "optimal_reached": bool(done),
+                       "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
+                       "refactors_in_region": c1["refactors"] - c0["refactors"], "refactor_wall_s": refac_s, "setup": setup,
+                       "objective_after": s.cur_obj_val, "l2": "the CSC copy (12 nnz bytes) is about the size of the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": steps / (w1 - w0), "unit": UNIT, "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),
+                "d2h_bytes_per_step": (c1["d2h_bytes"] - c0["d2h_bytes"]) / max(steps, 1), "wall_s": w1 - w0},
+        "gpu_launches": (c1["kernel_launches"] - c0["kernel_launches"]) * world,
+        "roofline": {"bound": "hbm", "kernel": "k_price_csc_seg + k_price_csc_fin: price-out over the CSC copy (calc_row_coeffs "
+                                               "solver.rs:685-692; N^T v 1117-1132 in the primal loop)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": pby / max(lau, 1), "formula": "12 nnz + 8 m + 8 (n + m)",
+                     "launches_timed": lau, "avg_launch_ms": pms / max(lau, 1), "share_of_step_time": pms / dev_ms if dev_ms else 0,
+                     "note": "12 nnz = 117 MB sits at the edge of the 126 MB L2: a launch that finds the matrix there runs above "
+                             "the HBM figure; traffic (ncu dram bytes per launch, profiles/) says how much really came from HBM"},
+    }
+    if a.cpu_baseline_seconds > 0 and world == 1:
+        piv, sec, tr_cpu, ties, setup_s = cpu_port_run_sparse(a, text, d, a.warmup, 100000, a.cpu_baseline_seconds)
+        line["parity"] = parity_against(s.trace(), tr_cpu, ties, m, m)
+        line["parity"]["engine_ties"] = s.tie_stats()
+        line["cpu_baseline"] = {"value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": (f"pivots {a.warmup + 1}..{a.warmup + piv} of the same LP from the same MPS text ({sec:.1f}s of "
+                                           f"single-thread CPU work after {a.warmup} untimed pivots; parse + try_new {setup_s:.1f}s excluded)"),
+                                "host_cores_available": os.cpu_count() or 1}
+    emit(line)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_ours(a):
+    """One process per GPU.  world > 1 (torchrun): the SAME LP is column-sharded over the ranks (strong scaling); every rank
+    runs the identical host control loop, the one exchange step per pivot goes over NCCL inside the engine."""
+    import minilp_b200 as mb
+    world, rank, local, dist, comm, barrier, max_over_ranks = dist_setup()
     s, setup = build_solver(a, local, rank, world, comm)
     e = s.engine
     nloc = e.n

@@ -78,6 +78,14 @@ mlp_status mlp_engine_download_csc(mlp_engine* e, int64_t* col_ptr, int32_t* row
 #define MLP_COMM_LOCAL 2
 mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
                                            int32_t comm_kind, const void* comm_arg, mlp_engine** out);
+/* Column-sharded SPARSE engine (BASELINE north_star: Netlib-shaped LPs at 1/2/4/8 GPUs).  Every rank passes the WHOLE CSR
+ * matrix and keeps it (12 nnz bytes — small next to HBM; FTRAN / BTRAN / refactorization need the basic columns wherever
+ * they are priced, and with it no column ever crosses NVLink); what is sharded is the work that scales with the matrix and
+ * the variables: the price-out runs over the rank's own column block of the CSC copy only, and the per-variable arrays
+ * (reduced costs, steepest-edge norms, states) hold that block plus the slacks.  Exchange step as in the dense case. */
+mlp_status mlp_engine_create_sparse_sharded(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                            const int32_t* col_idx, const double* vals, int32_t rank, int32_t world,
+                                            int32_t comm_kind, const void* comm_arg, mlp_engine** out);
 mlp_status mlp_nccl_get_unique_id(void* out128);
 mlp_status mlp_local_group_create(int32_t world, void** out);
 void mlp_local_group_destroy(void* group);
@@ -311,6 +319,9 @@ mlp_status mlp_solver_create_dense_sharded(int device, int64_t m, int64_t n_glob
                                            int32_t comm_kind, const void* comm_arg, mlp_solver** out);
 mlp_status mlp_solver_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
                                     const int32_t* col_idx, const double* vals, mlp_solver** out);
+mlp_status mlp_solver_create_sparse_sharded(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                            const int32_t* col_idx, const double* vals, int32_t rank, int32_t world,
+                                            int32_t comm_kind, const void* comm_arg, mlp_solver** out);
 mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local);
 void mlp_solver_destroy(mlp_solver* s);
 mlp_engine* mlp_solver_engine(mlp_solver* s);

@@ -77,6 +77,8 @@ SIGNATURES = {
     "mlp_engine_create_sparse": (i32, [C.c_int, i64, i64, i64, pi64, pi32, pd, C.POINTER(vp)]),
     "mlp_solver_create_sparse": (i32, [C.c_int, i64, i64, i64, pi64, pi32, pd, C.POINTER(vp)]),
     "mlp_engine_download_csc": (i32, [vp, pi64, pi32, pd]),
+    "mlp_engine_create_sparse_sharded": (i32, [C.c_int, i64, i64, i64, pi64, pi32, pd, i32, i32, i32, vp, C.POINTER(vp)]),
+    "mlp_solver_create_sparse_sharded": (i32, [C.c_int, i64, i64, i64, pi64, pi32, pd, i32, i32, i32, vp, C.POINTER(vp)]),
     "mlp_engine_create_dense_sharded": (i32, [C.c_int, i64, i64, i32, i32, i32, vp, C.POINTER(vp)]),
     "mlp_nccl_get_unique_id": (i32, [vp]),
     "mlp_local_group_create": (i32, [i32, C.POINTER(vp)]),

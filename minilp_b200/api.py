@@ -277,13 +277,19 @@ class Solver:
         csr: (row_ptr int64[m+1], col_idx int32[nnz], vals f64[nnz]) selects the sparse-storage engine."""
         h = C.c_void_p()
         if csr is not None:
-            assert world == 1, "the sparse engine is single-shard"
             rp = np.ascontiguousarray(csr[0], dtype=np.int64)
             ci = np.ascontiguousarray(csr[1], dtype=np.int32)
             va = _f64(csr[2])
             assert rp.shape[0] == m + 1 and ci.shape == va.shape
-            _check(_lib.lib().mlp_solver_create_sparse(device, m, n, int(va.shape[0]), _p(rp, pi64), _p(ci, pi32), _p(va),
-                                                       C.byref(h)))
+            if world == 1:
+                kind, arg = 0, None
+            elif isinstance(comm, LocalGroup):
+                kind, arg = 2, comm._g
+            else:
+                buf = C.create_string_buffer(bytes(comm), 128)
+                kind, arg = 1, C.cast(buf, C.c_void_p)
+            _check(_lib.lib().mlp_solver_create_sparse_sharded(device, m, n, int(va.shape[0]), _p(rp, pi64), _p(ci, pi32), _p(va),
+                                                               rank, world, kind, arg, C.byref(h)))
         elif world == 1:
             _check(_lib.lib().mlp_solver_create_dense(device, m, n, C.byref(h)))
         elif isinstance(comm, LocalGroup):

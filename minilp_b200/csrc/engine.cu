@@ -226,7 +226,8 @@ struct mlp_engine {
   // sparse storage (BASELINE config 4): CSR + CSC copies of A with 32-bit indices, as solver.rs:21-22 keeps both
   bool sparse = false;
   int64_t nnz = 0;
-  int64_t *csr_ptr = nullptr, *csc_ptr = nullptr;         // m+1, n+1
+  int64_t nnz_loc = 0, sg0 = 0, sg1 = 0;                  // entries / segment range of this shard's column block [c0, c0+n)
+  int64_t *csr_ptr = nullptr, *csc_ptr = nullptr;         // m+1, ng+1 (every shard holds the whole matrix)
   int32_t *csr_idx = nullptr, *csc_idx = nullptr;         // nnz
   double *csr_val = nullptr, *csc_val = nullptr;          // nnz
   std::vector<int64_t> h_csc_ptr;                         // host copy: column counts for LUFactors::nnz
@@ -815,6 +816,8 @@ __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict_
 // expanded into the dense column cache when they enter, so only three things read the sparse matrix — the column
 // load, the price-out and the set-up passes.
 // rhs.set(column) (solver.rs:672-675): dst is zero-filled by the caller; var < 0 comes from a candidate header.
+// Every shard of a sparse-storage engine holds the WHOLE matrix (12 nnz bytes: small next to HBM; the basis operations
+// need the basic columns wherever they price): n and lv are GLOBAL here.
 __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                                int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst,
                                Cand* __restrict__ win_out) {
@@ -822,7 +825,7 @@ __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* _
   if (cand && win_out && blockIdx.x == 0 && threadIdx.x == 0) *win_out = *cand;
   if (cand) {
     if (cand->var < 0) return;
-    lv = cand->var;  // single shard: local == global
+    lv = cand->var;  // GLOBAL variable index
   }
   if (lv >= n) {
     if (blockIdx.x == 0 && threadIdx.x == 0) dst[lv - n] = 1.0;
@@ -838,18 +841,20 @@ __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* _
 // segment, rows ascending, fixed shuffle tree; pass 2 adds a column's segment sums in order.  Bit-reproducible, no atomics.
 // MODE 0: out[v] = sum_i A[i,v] w[i] (slack v: w[v-n]; basic v: 0)     MODE 1: out[v] = |a_v|^2 + 1
 constexpr int CSC_SEG = 1024;
+// Column-sharded engines price out only the segments [sg0, sg1) of their own column block [c0, c0 + n_loc); vflag is indexed
+// by LOCAL variable (global column - c0).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_price_csc_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                                        const double* __restrict__ val, const int32_t* __restrict__ seg_col,
-                                                       const int64_t* __restrict__ seg_off, int64_t nseg,
+                                                       const int64_t* __restrict__ seg_off, int64_t sg0, int64_t sg1, int64_t c0,
                                                        const double* __restrict__ w, const uint8_t* __restrict__ vflag,
                                                        double* __restrict__ seg_sum) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t sg = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); sg < nseg; sg += warps) {
+  for (int64_t sg = sg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); sg < sg1; sg += warps) {
     const int v = seg_col[sg];
     double acc = 0.0;
-    if (MODE == 1 || !(vflag[v] & MLP_BASIC)) {
+    if (MODE == 1 || !(vflag[v - c0] & MLP_BASIC)) {
       const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
       for (int64_t t = b + lane; t < e; t += 32) {
         const double a = __ldcs(val + t);
@@ -862,26 +867,30 @@ __global__ void __launch_bounds__(256) k_price_csc_seg(const int64_t* __restrict
 }
 template <int MODE>
 __global__ void __launch_bounds__(256) k_price_csc_fin(const int64_t* __restrict__ col_seg, const double* __restrict__ seg_sum,
-                                                       int64_t n, int64_t m, const double* __restrict__ w,
+                                                       int64_t n, int64_t m, int64_t c0, const double* __restrict__ w,
                                                        const uint8_t* __restrict__ vflag, double* __restrict__ out) {
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // LOCAL variable
   if (v < n) {
     double t = 0.0;
-    for (int64_t sg = col_seg[v]; sg < col_seg[v + 1]; ++sg) t += seg_sum[sg];
+    for (int64_t sg = col_seg[c0 + v]; sg < col_seg[c0 + v + 1]; ++sg) t += seg_sum[sg];
     out[v] = (MODE == 1) ? t + 1.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : t);
   } else if (v < n + m) {
     out[v] = (MODE == 1) ? 2.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : w[v - n]);
   }
 }
 // rows of A x_N over the CSR copy (solver.rs:234-238): one warp per row
+// (a shard sums only the entries of its own column block [c0, c0 + n_loc); xnb is indexed by LOCAL variable)
 __global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                     const double* __restrict__ val, int64_t m, const double* __restrict__ xnb,
-                                                     double* __restrict__ out) {
+                                                     const double* __restrict__ val, int64_t m, int64_t c0, int64_t n_loc,
+                                                     const double* __restrict__ xnb, double* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= m) return;
   double acc = 0.0;
-  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) acc += val[t] * xnb[idx[t]];
+  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) {
+    const int64_t j = (int64_t)idx[t] - c0;
+    if (j >= 0 && j < n_loc) acc += val[t] * xnb[j];
+  }
   acc = warp_sum(acc);
   if (lane == 0) out[r] = acc;
 }
@@ -1506,9 +1515,9 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
     double* ssum = &ln == &e->lane[0] ? e->seg_sum : e->seg_sum + e->nseg;
-    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->nseg,
-            slack_vals, e->vflag, ssum);
-    LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, slack_vals, e->vflag, out);
+    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->sg0,
+            e->sg1, e->c0, slack_vals, e->vflag, ssum);
+    LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, e->c0, slack_vals, e->vflag, out);
   } else {
     // Lane 1 (the tableau-row price-out, support <= k+1 rows) runs BESIDE lane 0's dense N^T v price-out.  The bulk-copy
     // kernel holds 194 KB of shared memory per SM, so a second instance cannot become resident until the first one has
@@ -1546,7 +1555,7 @@ static mlp_status collect_profile(mlp_engine* e, int par) {
     CU(cudaEventSynchronize(e->pev[slot][par][1]));
     CU(cudaEventElapsedTime(&ms, e->pev[slot][par][0], e->pev[slot][par][1]));
     const int64_t sz = e->h_mail[par * 4 + slot];
-    const int64_t bytes = e->sparse ? 12 * e->nnz + 8 * e->m + 8 * e->nt : 8 * e->n * sz + 8 * sz + 8 * e->n;
+    const int64_t bytes = e->sparse ? 12 * e->nnz_loc + 8 * e->m + 8 * e->nt : 8 * e->n * sz + 8 * sz + 8 * e->n;
     if (slot == 0) { e->prof.price_rho_ms += ms; e->prof.price_rho_launches += 1; e->prof.price_rho_bytes += bytes; }
     else { e->prof.price_v_ms += ms; e->prof.price_v_launches += 1; e->prof.price_v_bytes += bytes; }
   }
@@ -1848,7 +1857,7 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
   Cand* win = e->world > 1 ? nullptr : e->d_win;
   if (e->sparse) {
     CU(cudaMemsetAsync(dst, 0, (size_t)m * sizeof(double), e->stream));
-    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, (int64_t)-1, (const Cand*)e->xsend, dst, win);
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->ng, (int64_t)-1, (const Cand*)e->xsend, dst, win);
   } else {
     LAUNCH(e, k_cand_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, e->c0, e->ng, m, (const Cand*)e->xsend, dst, win);
   }
@@ -1891,11 +1900,11 @@ static mlp_status fetch_column(mlp_engine* e, int64_t var) {
   if (e->colq_var == var) return MLP_OK;
   const int m = (int)e->m;
   const int64_t lv = to_local(e, var);
-  if (e->sparse) {
+  if (e->sparse) {  // every shard holds the whole matrix: no broadcast
     CU(cudaMemsetAsync(e->colq, 0, (size_t)m * sizeof(double), e->stream));
-    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->n, lv, (const Cand*)nullptr, e->colq, (Cand*)nullptr);
+    LAUNCH(e, k_load_col_csc, 4, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->ng, var, (const Cand*)nullptr, e->colq, (Cand*)nullptr);
   } else if (lv >= 0) LAUNCH(e, k_load_col, cdiv(m, 256), 256, 0, e->A, e->lda, e->n, m, lv, e->colq);
-  if (e->world > 1 && var < e->ng) ST(e->comm->broadcast(e->colq, (size_t)m * sizeof(double), owner_of(e, var), e->stream));
+  if (!e->sparse && e->world > 1 && var < e->ng) ST(e->comm->broadcast(e->colq, (size_t)m * sizeof(double), owner_of(e, var), e->stream));
   e->colq_var = var;
   return MLP_OK;
 }
@@ -2238,7 +2247,7 @@ mlp_status mlp_engine_create_dense(int device, int64_t m, int64_t n, mlp_engine*
 // produces them — and the segment table of the CSC copy.  m = number of rows of the CSR copy.  MLP_HOST_TRANSPOSE=1 builds
 // the CSC copy with the host counting transpose instead (kept for the equality test).
 static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
-  const int64_t n = e->n, nnz = (int64_t)e->h_csr_idx.size();
+  const int64_t n = e->ng, nnz = (int64_t)e->h_csr_idx.size();  // the WHOLE matrix on every shard
   const int64_t* row_ptr = e->h_csr_ptr.data();
   const int32_t* col_idx = e->h_csr_idx.data();
   const double* vals = e->h_csr_val.data();
@@ -2305,6 +2314,9 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
     if (e->h_csc_ptr[(size_t)n] != nnz) { set_err("sparse upload: device transpose lost entries"); return MLP_CUDA_ERROR; }
   }
   e->nseg = e->h_col_seg[(size_t)n];
+  e->sg0 = e->h_col_seg[(size_t)e->c0];
+  e->sg1 = e->h_col_seg[(size_t)(e->c0 + e->n)];
+  e->nnz_loc = e->h_csc_ptr[(size_t)(e->c0 + e->n)] - e->h_csc_ptr[(size_t)e->c0];
   A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg));
   A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
   if (st != MLP_OK) return st;
@@ -2317,13 +2329,35 @@ mlp_status mlp_engine_download_csc(mlp_engine* e, int64_t* col_ptr, int32_t* row
   if (!e || !e->sparse) return MLP_INVALID;
   CU(cudaSetDevice(e->device));
   ST(begin0(e));
-  if (col_ptr) ST(d2h(e, col_ptr, e->csc_ptr, (e->n + 1) * sizeof(int64_t)));
+  if (col_ptr) ST(d2h(e, col_ptr, e->csc_ptr, (e->ng + 1) * sizeof(int64_t)));
   if (row_idx) ST(d2h(e, row_idx, e->csc_idx, e->nnz * sizeof(int32_t)));
   if (vals) ST(d2h(e, vals, e->csc_val, e->nnz * sizeof(double)));
   return MLP_OK;
 }
-mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
-                                    const double* vals, mlp_engine** out) {
+// communicator of a column-sharded engine (nullptr for a single shard)
+static mlp_status make_comm(int device, int32_t rank, int32_t world, int32_t comm_kind, const void* comm_arg, Comm** out) {
+  *out = nullptr;
+  if (world <= 1) return MLP_OK;
+  if (mlp_device_count() <= device) { set_err("no CUDA device: the engine has no CPU fallback"); return MLP_NO_DEVICE; }
+  CU(cudaSetDevice(device));
+  if (comm_kind == MLP_COMM_NCCL) {
+    NcclComm* c = new NcclComm();
+    mlp_status st = c->init(comm_arg, rank, world);
+    if (st != MLP_OK) { delete c; return st; }
+    *out = c;
+  } else if (comm_kind == MLP_COMM_LOCAL) {
+    LocalComm* c = new LocalComm();
+    c->g = (LocalGroup*)comm_arg;
+    c->rank = rank;
+    c->world = world;
+    if (!c->g || c->g->world != world) { delete c; set_err("local group size mismatch"); return MLP_INVALID; }
+    *out = c;
+  } else { set_err("unknown comm kind"); return MLP_INVALID; }
+  return MLP_OK;
+}
+mlp_status mlp_engine_create_sparse_sharded(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                            const int32_t* col_idx, const double* vals, int32_t rank, int32_t world,
+                                            int32_t comm_kind, const void* comm_arg, mlp_engine** out) {
   *out = nullptr;
   if (!row_ptr || !col_idx || !vals || nnz < 0 || m <= 0 || n <= 0 || row_ptr[0] != 0 || row_ptr[m] != nnz) {
     set_err("create_sparse: bad CSR");
@@ -2336,8 +2370,10 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
   for (int64_t i = 0; i < m; ++i)  // CsVec::new (lib.rs:279): sorted, no repeated index — the device transpose relies on it
     for (int64_t t = row_ptr[i] + 1; t < row_ptr[i + 1]; ++t)
       if (col_idx[t] <= col_idx[t - 1]) { set_err("create_sparse: columns must be strictly ascending within a row"); return MLP_INVALID; }
+  Comm* comm = nullptr;
+  ST(make_comm(device, rank, world, comm_kind, comm_arg, &comm));
   mlp_engine* e = nullptr;
-  ST(create_engine(device, m, n, 0, 1, nullptr, &e, true));
+  ST(create_engine(device, m, n, rank, world, comm, &e, true));
   e->h_csr_ptr.assign(row_ptr, row_ptr + m + 1);
   e->h_csr_idx.assign(col_idx, col_idx + nnz);
   e->h_csr_val.assign(vals, vals + nnz);
@@ -2347,30 +2383,19 @@ mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nn
   if (st == MLP_OK && cudaMemsetAsync(e->corepos, 0xff, n * sizeof(int32_t), e->stream) != cudaSuccess) st = MLP_CUDA_ERROR;
   A(sparse_upload(e, m));
   if (st != MLP_OK) { destroy_engine(e); return st; }
+  if (world > 1 && comm_kind == MLP_COMM_NCCL) setup_p2p(e, (NcclComm*)comm);  // best effort: falls back to the all-gather
   *out = e;
   return MLP_OK;
+}
+mlp_status mlp_engine_create_sparse(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr, const int32_t* col_idx,
+                                    const double* vals, mlp_engine** out) {
+  return mlp_engine_create_sparse_sharded(device, m, n, nnz, row_ptr, col_idx, vals, 0, 1, MLP_COMM_NONE, nullptr, out);
 }
 mlp_status mlp_engine_create_dense_sharded(int device, int64_t m, int64_t n_global, int32_t rank, int32_t world,
                                            int32_t comm_kind, const void* comm_arg, mlp_engine** out) {
   *out = nullptr;
   Comm* comm = nullptr;
-  if (world > 1) {
-    if (mlp_device_count() <= device) { set_err("no CUDA device: the engine has no CPU fallback"); return MLP_NO_DEVICE; }
-    CU(cudaSetDevice(device));
-    if (comm_kind == MLP_COMM_NCCL) {
-      NcclComm* c = new NcclComm();
-      mlp_status st = c->init(comm_arg, rank, world);
-      if (st != MLP_OK) { delete c; return st; }
-      comm = c;
-    } else if (comm_kind == MLP_COMM_LOCAL) {
-      LocalComm* c = new LocalComm();
-      c->g = (LocalGroup*)comm_arg;
-      c->rank = rank;
-      c->world = world;
-      if (!c->g || c->g->world != world) { delete c; set_err("local group size mismatch"); return MLP_INVALID; }
-      comm = c;
-    } else { set_err("unknown comm kind"); return MLP_INVALID; }
-  }
+  ST(make_comm(device, rank, world, comm_kind, comm_arg, &comm));
   ST(create_engine(device, m, n_global, rank, world, comm, out));
   if (world > 1 && comm_kind == MLP_COMM_NCCL) setup_p2p(*out, (NcclComm*)comm);  // best effort: falls back to the all-gather
   return MLP_OK;
@@ -2460,7 +2485,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   e->dual_row_host = -1;
   if (!st->basic_var_vals) {
     double* part = e->world > 1 ? e->work_m : e->xred;
-    if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->xnb, part);
+    if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->c0, n, e->xnb, part);
     else LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->xnb, part);
     if (e->world > 1) ST(e->comm->allgather(part, e->xred, (size_t)m * sizeof(double), e->stream));
     LAUNCH(e, k_init_basic_vals, cdiv(m, 256), 256, 0, e->xred, e->world, (int)m, e->rhs, e->xB);
@@ -2470,9 +2495,9 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
     if (e->sparse)
     {
-      LAUNCH(e, k_price_csc_seg<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->nseg,
-             (const double*)nullptr, e->vflag, e->seg_sum);
-      LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, (const double*)nullptr, e->vflag, e->gam);
+      LAUNCH(e, k_price_csc_seg<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->sg0, e->sg1,
+             e->c0, (const double*)nullptr, e->vflag, e->seg_sum);
+      LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, e->c0, (const double*)nullptr, e->vflag, e->gam);
     }
     else {
     LAUNCH(e, k_price_partial<1>, price_grid(e), PR_THREADS, 0, e->A, e->lda, (const int32_t*)nullptr, (const double*)nullptr,
@@ -3074,7 +3099,7 @@ mlp_status mlp_recalc_basic_vals(mlp_engine* e) {
   if (e->K > 0) ST(refactor_impl(e));  // 1188-1191
   LAUNCH(e, k_masked_xnb, cdiv(nt, 256), 256, 0, e->xnb, e->vflag, nt, e->helper);
   double* part = e->world > 1 ? e->work_m : e->xred;
-  if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->helper, part);
+  if (e->sparse) LAUNCH(e, k_row_dot_csr, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, e->c0, n, e->helper, part);
   else LAUNCH(e, k_row_dot, (unsigned)m, 256, 0, e->A, e->lda, n, e->helper, part);
   if (e->world > 1) ST(e->comm->allgather(part, e->xred, (size_t)m * sizeof(double), e->stream));
   LAUNCH(e, k_init_basic_vals, cdiv(m, 256), 256, 0, e->xred, e->world, (int)m, e->rhs, e->work_mb);  // rhs - A x_N (structural part)
@@ -3274,7 +3299,7 @@ mlp_status mlp_bench_price_dense(mlp_engine* e, int32_t iters, double* ms_per_la
   cudaEventDestroy(b);
   *ms_per_launch = (double)ms / iters;
   // algorithmic bytes: 8 n s + 8 s + 8 n  with s = m, n = this shard's columns
-  *bytes_per_launch = e->sparse ? 12 * e->nnz + 8 * (int64_t)m + 8 * e->nt : 8 * e->n * (int64_t)m + 8 * (int64_t)m + 8 * e->n;
+  *bytes_per_launch = e->sparse ? 12 * e->nnz_loc + 8 * (int64_t)m + 8 * e->nt : 8 * e->n * (int64_t)m + 8 * (int64_t)m + 8 * e->n;
   return MLP_OK;
 }
 

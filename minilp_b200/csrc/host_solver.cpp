@@ -214,6 +214,19 @@ mlp_status mlp_solver_create_sparse(int device, int64_t m, int64_t n, int64_t nn
   *out = s;
   return MLP_OK;
 }
+mlp_status mlp_solver_create_sparse_sharded(int device, int64_t m, int64_t n, int64_t nnz, const int64_t* row_ptr,
+                                            const int32_t* col_idx, const double* vals, int32_t rank, int32_t world,
+                                            int32_t comm_kind, const void* comm_arg, mlp_solver** out) {
+  *out = nullptr;
+  mlp_engine* e = nullptr;
+  ST(mlp_engine_create_sparse_sharded(device, m, n, nnz, row_ptr, col_idx, vals, rank, world, comm_kind, comm_arg, &e));
+  mlp_solver* s = new mlp_solver();
+  s->eng = e;
+  s->m = m;
+  s->n = n;  // GLOBAL indices in the control loop
+  *out = s;
+  return MLP_OK;
+}
 mlp_status mlp_solver_upload_local_rows(mlp_solver* s, int64_t row0, int64_t nrows, const double* rows_local) {
   return mlp_engine_upload_local_rows(s->eng, row0, nrows, rows_local);
 }

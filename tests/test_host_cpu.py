@@ -109,3 +109,20 @@ def test_trivial_solution_has_the_incremental_methods():
         sol.add_gomory_cut(a)
     with pytest.raises(mb.Infeasible):
         sol.add_constraint([], mb.ComparisonOp.Ge, 1.0)  # solver.rs:558-570
+
+
+def test_rust_binding_is_generated_from_the_header():
+    """bindings/minilp_b200.rs (INTEGRATION.md section 2) is regenerated from include/minilp_b200.h and must be current;
+    it names every symbol the ctypes table — and with it the .so — knows."""
+    import importlib.util
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_bindings", os.path.join(root, "scripts", "gen_rust_bindings.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, names = gen.generate()
+    assert open(os.path.join(root, "bindings", "minilp_b200.rs")).read() == text, "run python scripts/gen_rust_bindings.py"
+    from minilp_b200 import _lib
+    assert set(names) == set(_lib.SIGNATURES)
+    assert set(re.findall(r"pub fn (\w+)\(", text)) == set(_lib.SIGNATURES)

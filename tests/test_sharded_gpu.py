@@ -111,5 +111,78 @@ def test_nccl_two_processes_match_oracle(p2p):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "_nccl_worker.py")],
                          capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, MLP_P2P=p2p))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("NCCL_OK") == 6, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("NCCL_OK") == 10, out.stdout[-3000:] + out.stderr[-3000:]  # (3 dense + 2 sparse LPs) x 2 ranks
+    log = os.path.join(root, "gpurun_out", f"nccl_two_process_p2p{p2p}.log")  # evidence for profiles/: which path ran, on what
+    os.makedirs(os.path.dirname(log), exist_ok=True)
+    with open(log, "w") as f:
+        f.write(out.stdout[-6000:])
     assert ("via nvlink_peer_memory" if p2p == "1" else "via nccl_allgather") in out.stdout, out.stdout[-2000:]
+
+
+# ---------------------------------------------------------------- column-sharded SPARSE engine (north_star: Netlib-shaped LPs at 1/2/4/8)
+def run_sharded_sparse(p, world, max_pivots=-1):
+    rp, ci, va, ops, rhs = p.to_csr()
+    m, n = len(ops), len(p.obj_coeffs)
+    group = mb.LocalGroup(world)
+    out = [None] * world
+    errs = []
+
+    def work(rank):
+        try:
+            s = mb.Solver(m, n, rank=rank, world=world, comm=group, csr=(rp, ci, va))
+            s.init(np.array(p.obj_coeffs), np.array(p.var_mins), np.array(p.var_maxs), ops, rhs)
+            done = s.run(max_pivots)
+            e = s.engine
+            out[rank] = dict(done=done, trace=s.trace(), ties=s.tie_stats(), obj=s.cur_obj_val, values=s.values(),
+                             basic=s.basic_vars(), d=e.download(0), xb=e.download(3), w=e.download(4), ids=e.global_ids(),
+                             flags=e.var_state()[0], range=(e.col_begin, e.col_end))
+            s.close()
+        except Exception as exc:  # noqa: BLE001
+            errs.append((rank, repr(exc)))
+            raise
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    assert all(o is not None for o in out), "a shard thread did not finish"
+    return out
+
+
+@pytest.mark.parametrize("family,args,world", [
+    ("netlib_like", (300, 300, 6.0, 1), 2), ("sparse_pos", (200, 300, 6.0, 2), 4), ("netlib_like", (500, 350, 7.0, 5), 3),
+    ("sparse_pos", (400, 900, 8.0, 3), 8), ("netlib_like", (60, 80, 4.0, 1), 2),
+])
+def test_sharded_sparse_matches_single_and_oracle(family, args, world):
+    """Sparse storage, columns sharded: same pivot sequence as the single-shard sparse engine and as the oracle's faithful
+    sparse solver on the same MPS text; every float the single-shard run produces, bit for bit where x_N starts at 0."""
+    from minilp_b200 import mps, synth
+    from test_sparse_gpu import solver_from_problem
+    text, d = getattr(synth, family)(*args)
+    ref = oracle.MpsFile.parse(text, d).problem.solve()
+    p = mps.MpsFile.parse(text, d).problem
+    single = solver_from_problem(p, "sparse")
+    assert single.run()
+    assert not assert_sequence_parity(single.trace(), ref.trace(), ref, single)
+    shards = run_sharded_sparse(p, world)
+    t1 = single.trace()
+    d1, f1 = single.engine.download(0), single.engine.var_state()[0]
+    covered = 0
+    for o in shards:
+        assert o["done"]
+        assert np.array_equal(o["trace"][:, :5], t1[:, :5]), "sharded basis sequence differs from the single-shard one"
+        assert np.all(np.abs(o["trace"][:, 5:8] - t1[:, 5:8]) <= 1e-9 * np.maximum(1.0, np.abs(t1[:, 5:8])))
+        assert abs(o["obj"] - single.cur_obj_val) <= 1e-9 * max(1.0, abs(single.cur_obj_val))
+        assert np.array_equal(o["basic"], single.basic_vars())
+        assert np.all(np.abs(o["values"] - single.values()) <= 1e-9 * np.maximum(1.0, np.abs(single.values())))
+        assert np.array_equal(o["trace"], shards[0]["trace"]), "shards disagree with each other"
+        assert o["ties"] == single.tie_stats()
+        assert np.array_equal(o["flags"], f1[o["ids"]])
+        nb = (o["flags"] & 4) == 0
+        assert np.all(np.abs(o["d"][nb] - d1[o["ids"]][nb]) <= 1e-9 * np.maximum(1.0, np.abs(d1[o["ids"]][nb])))
+        covered += o["range"][1] - o["range"][0]
+    assert covered == len(p.obj_coeffs)
+    assert abs(single.cur_obj_val - ref.cur_obj_val) <= 1e-8 * max(1.0, abs(ref.cur_obj_val))
+    single.close()
