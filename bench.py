@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--workload", default="dense", choices=["dense", "netlib_like", "sparse_pos"],
                     help="dense: BASELINE config 3 / 5 (the default, what the driver runs); netlib_like / sparse_pos: BASELINE "
                          "config 4, a sparse LP that enters as free-format MPS text (use with --rows 100000 --cols 100000)")
+    ap.add_argument("--refactor-factor", type=float, default=1.0,
+                    help="refactorize when eta nnz >= factor * lu nnz; 1 = the reference's rule (solver.rs:1096-1097)")
     ap.add_argument("--col-nnz", type=float, default=100.0, help="mean entries per column of the sparse workloads (0.1 % of 100k)")
     return ap.parse_args()
 
@@ -331,6 +333,7 @@ def run_ours_sparse(a):
              "ingest_s (parse + upload + try_new)": round(t4 - t1, 3)}
     e = s.engine
     s.set_record_trace(True)
+    s.set_refactor_factor(a.refactor_factor)
     if a.warmup > 0:
         s.run(a.warmup)
     c0 = e.counters()
@@ -385,7 +388,9 @@ def run_ours_sparse(a):
                                        f"matrix and basis replicated, one candidate exchange per pivot ({e.exchange_kind()})")
                        if world > 1 else "single GPU", "pivots_before_timed_region": p0, "optimal_reached": bool(done),
                        "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
-                       "refactors_in_region": c1["refactors"] - c0["refactors"], "refactor_wall_s": refac_s, "setup": setup,
+                       "refactor_rule": f"eta nnz >= {a.refactor_factor:g} * lu nnz (1 = the reference's, solver.rs:1096-1097)",
+                       "refactors_in_region": c1["refactors"] - c0["refactors"], "refactor_wall_s": refac_s,
+                       "refactor_share_of_wall": refac_s / max(w1 - w0, 1e-9), "setup": setup,
                        "objective_after": s.cur_obj_val, "l2": "the CSC copy (12 nnz bytes) is about the size of the 126 MB L2"},
         "clocks": clocks,
         "e2e": {"value": steps / (w1 - w0), "unit": UNIT, "h2d_bytes_per_step": (c1["h2d_bytes"] - c0["h2d_bytes"]) / max(steps, 1),

@@ -353,6 +353,9 @@ mlp_status mlp_solver_clone(mlp_solver* s, mlp_solver** out);
 /* host mirrors of nb_vars (n) and basic_vars (m) */
 mlp_status mlp_solver_get_nb_vars(mlp_solver* s, int64_t* out);
 mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out);
+/* The refactor rule of solver.rs:1096-1097 is `eta nnz >= lu nnz`; here `eta nnz >= factor * lu nnz`.  factor = 1 (default):
+ * the reference's rule.  factor > 1 keeps the eta file longer (fewer refactorizations); results change in rounding only. */
+void mlp_solver_set_refactor_factor(mlp_solver* s, double factor);
 /* Row f4: every `period` pivots (0, the default = never = the reference's behaviour) recompute x_B and — unless the
  * artificial objective of solver.rs:261 is in place — d and the objective from scratch. */
 void mlp_solver_set_recalc_period(mlp_solver* s, int64_t period);

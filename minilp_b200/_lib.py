@@ -102,6 +102,7 @@ SIGNATURES = {
     "mlp_recalc_obj_coeffs": (i32, [vp, pd]),
     "mlp_recalc_basic_vals": (i32, [vp]),
     "mlp_solver_set_recalc_period": (None, [vp, i64]),
+    "mlp_solver_set_refactor_factor": (None, [vp, f64]),
     "mlp_solver_recalcs_done": (i64, [vp]),
     "mlp_engine_clone": (i32, [vp, C.POINTER(vp)]),
     "mlp_solver_clone": (i32, [vp, C.POINTER(vp)]),

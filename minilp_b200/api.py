@@ -376,6 +376,10 @@ class Solver:
     def set_record_trace(self, on):
         _lib.lib().mlp_solver_set_record_trace(self._s, int(on))
 
+    def set_refactor_factor(self, factor):
+        """Refactorize when eta nnz >= factor * lu nnz (solver.rs:1096-1097 is factor = 1, the default)."""
+        _lib.lib().mlp_solver_set_refactor_factor(self._s, float(factor))
+
     def set_recalc_period(self, period):
         """Row f4: recompute x_B and d from scratch every `period` pivots (0 = never, the reference's behaviour)."""
         _lib.lib().mlp_solver_set_recalc_period(self._s, int(period))

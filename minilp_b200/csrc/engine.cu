@@ -238,6 +238,7 @@ struct mlp_engine {
   int64_t corevar_k = 0;                                  // entries of corevar currently marked in corepos
   // segment table of the CSC copy (<= CSC_SEG entries of one column per segment) and the core's slice of it
   int64_t nseg = 0;
+  struct SegDesc* seg_desc = nullptr;  // nseg: (first entry, length, column) of every segment, one 16-byte load
   int32_t* seg_col = nullptr;      // nseg
   int64_t* seg_off = nullptr;      // nseg
   int64_t* col_seg = nullptr;      // n+1
@@ -298,6 +299,7 @@ struct mlp_engine {
   int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE; default: choose_price_tiling)
   int price_split = 1;  // column slices per item of the last, partial round (MLP_PRICE_SPLIT)
   int lane1_ldg = 1;    // lane 1 prices out with the LDG kernel while lane 0 runs the bulk-copy one (MLP_LANE1_LDG=0: both bulk-copy)
+  int csc_grid = 148 * 5;  // CSC price-out: one full wave of resident CTAs (occupancy query at creation)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
   cudaEvent_t s0_mark = nullptr, s1_mark = nullptr, ev_vbtran = nullptr, ev_win = nullptr;
@@ -841,28 +843,70 @@ __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* _
 // segment, rows ascending, fixed shuffle tree; pass 2 adds a column's segment sums in order.  Bit-reproducible, no atomics.
 // MODE 0: out[v] = sum_i A[i,v] w[i] (slack v: w[v-n]; basic v: 0)     MODE 1: out[v] = |a_v|^2 + 1
 constexpr int CSC_SEG = 1024;
-// Column-sharded engines price out only the segments [sg0, sg1) of their own column block [c0, c0 + n_loc); vflag is indexed
-// by LOCAL variable (global column - c0).
+// Column-sharded engines price out only the segments [sg0, sg1) of their own column block.
+//
+// Latency, not bandwidth, bounds this kernel: a column of the config-4 LP holds ~100 entries, so a warp spends its time in
+// the dependent chain descriptor -> (row index, value) -> multiplier[row] -> shuffle tree, three global round trips per
+// segment (first version: five — segment column, its offset and end, the basic flag, then the entries — 89 us per launch
+// = 1.3 TB/s, profiles/r02_price_csc_full.md).  Here a segment is ONE 16-byte descriptor, the basic flag is left to
+// k_price_csc_fin, and a warp works on PR_CSC_U segments at once with the first two strides of each in flight together.
+// Per segment the sum is unchanged: lane-strided partial sums in ascending entry order, then the fixed shuffle tree.
+struct SegDesc {
+  int64_t begin;
+  int32_t len, col;
+};
+static_assert(sizeof(SegDesc) == 16, "SegDesc is one 16-byte load");
+constexpr int PR_CSC_U = 4;
 template <int MODE>
-__global__ void __launch_bounds__(256) k_price_csc_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                       const double* __restrict__ val, const int32_t* __restrict__ seg_col,
-                                                       const int64_t* __restrict__ seg_off, int64_t sg0, int64_t sg1, int64_t c0,
-                                                       const double* __restrict__ w, const uint8_t* __restrict__ vflag,
-                                                       double* __restrict__ seg_sum) {
+__global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict__ desc, const int32_t* __restrict__ idx,
+                                                       const double* __restrict__ val, int64_t sg0, int64_t sg1,
+                                                       const double* __restrict__ w, double* __restrict__ seg_sum) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t sg = sg0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5); sg < sg1; sg += warps) {
-    const int v = seg_col[sg];
-    double acc = 0.0;
-    if (MODE == 1 || !(vflag[v - c0] & MLP_BASIC)) {
-      const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
-      for (int64_t t = b + lane; t < e; t += 32) {
-        const double a = __ldcs(val + t);
-        acc += (MODE == 0) ? a * w[__ldcs(idx + t)] : a * a;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int64_t base = sg0 + wid; base < sg1; base += warps * PR_CSC_U) {
+    int64_t b[PR_CSC_U];
+    int len[PR_CSC_U];
+#pragma unroll
+    for (int q = 0; q < PR_CSC_U; ++q) {
+      const int64_t sg = base + q * warps;
+      b[q] = 0;
+      len[q] = 0;
+      if (sg < sg1) {
+        const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sg));
+        b[q] = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
+        len[q] = d.z;
       }
-      acc = warp_sum(acc);
     }
-    if (lane == 0) seg_sum[sg] = acc;
+    double a[PR_CSC_U][2];
+    int r[PR_CSC_U][2];
+#pragma unroll
+    for (int q = 0; q < PR_CSC_U; ++q)
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int o = lane + 32 * it;
+        const bool ok = o < len[q];
+        a[q][it] = ok ? __ldcs(val + b[q] + o) : 0.0;
+        r[q][it] = (MODE == 0 && ok) ? __ldcs(idx + b[q] + o) : 0;
+      }
+    double acc[PR_CSC_U];
+#pragma unroll
+    for (int q = 0; q < PR_CSC_U; ++q) {
+      acc[q] = 0.0;
+#pragma unroll
+      for (int it = 0; it < 2; ++it)
+        if (lane + 32 * it < len[q]) acc[q] += (MODE == 0) ? a[q][it] * w[r[q][it]] : a[q][it] * a[q][it];
+    }
+#pragma unroll
+    for (int q = 0; q < PR_CSC_U; ++q) {
+      for (int o = lane + 64; o < len[q]; o += 32) {  // long segments (up to CSC_SEG entries)
+        const double av = __ldcs(val + b[q] + o);
+        acc[q] += (MODE == 0) ? av * w[__ldcs(idx + b[q] + o)] : av * av;
+      }
+      const double tot = warp_sum(acc[q]);
+      const int64_t sg = base + q * warps;
+      if (lane == 0 && sg < sg1) seg_sum[sg] = tot;
+    }
   }
 }
 template <int MODE>
@@ -1174,13 +1218,17 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
                                                        const double* __restrict__ xnb, int64_t nt, int64_t n, int64_t c0,
                                                        int64_t ng, int lds, const double* __restrict__ scal,
                                                        double* __restrict__ red_f, long long* __restrict__ red_i,
-                                                       unsigned* counter, const int* __restrict__ flags, Cand* out) {
+                                                       unsigned* counter, const int* __restrict__ flags, Cand* out,
+                                                       int scan_slacks) {
   __shared__ double smk[32];
   __shared__ long long smi[32];
   __shared__ long long smc[32];
   const double max_step = scal[0];
   KeyIdxC best{-INFINITY, LLONG_MAX, 0, 0};
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
+  // The slack variables are replicated on every shard: only ONE shard (rank 0) proposes and counts them, so that every
+  // variable is scanned exactly once across the shards and the tie counts add up to the single-shard ones.
+  const int64_t vend = scan_slacks ? nt : n;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vend; v += (int64_t)gridDim.x * blockDim.x) {
     const unsigned f = vflag[v];
     if (f & MLP_BASIC) continue;
     const double coeff = rc[v];
@@ -1515,8 +1563,7 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
     double* ssum = &ln == &e->lane[0] ? e->seg_sum : e->seg_sum + e->nseg;
-    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->sg0,
-            e->sg1, e->c0, slack_vals, e->vflag, ssum);
+    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->sg0, e->sg1, slack_vals, ssum);
     LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, e->c0, slack_vals, e->vflag, out);
   } else {
     // Lane 1 (the tableau-row price-out, support <= k+1 rows) runs BESIDE lane 0's dense N^T v price-out.  The bulk-copy
@@ -2034,6 +2081,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->csr_ptr); dev_free(e->csc_ptr); dev_free(e->csr_idx); dev_free(e->csc_idx); dev_free(e->csr_val); dev_free(e->csc_val);
   dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
+  dev_free(e->seg_desc);
   dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
@@ -2114,6 +2162,11 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
       cudaGetLastError();
       e->fused = 0;
     }
+  }
+  {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_price_csc_seg<0>, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
+    e->csc_grid = e->sm_count * nb;
   }
   choose_price_tiling(e->lda, m, e->sm_count, &e->price_tile, &e->price_split);
   if (const char* v = getenv("MLP_PRICE_TILE")) {
@@ -2254,7 +2307,7 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   e->nnz = nnz;
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   dev_free(e->csr_ptr); dev_free(e->csr_idx); dev_free(e->csr_val); dev_free(e->csc_ptr); dev_free(e->csc_idx); dev_free(e->csc_val);
-  dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum);
+  dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->seg_desc);
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
   A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
@@ -2317,10 +2370,10 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   e->sg0 = e->h_col_seg[(size_t)e->c0];
   e->sg1 = e->h_col_seg[(size_t)(e->c0 + e->n)];
   e->nnz_loc = e->h_csc_ptr[(size_t)(e->c0 + e->n)] - e->h_csc_ptr[(size_t)e->c0];
-  A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg));
+  A(dev_alloc(&e->seg_col, e->nseg)); A(dev_alloc(&e->seg_off, e->nseg)); A(dev_alloc(&e->seg_desc, e->nseg));
   A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
   if (st != MLP_OK) return st;
-  LAUNCH(e, k_t_segs, cdiv(n, 256), 256, 0, e->csc_ptr, e->col_seg, n, CSC_SEG, e->seg_col, e->seg_off);
+  LAUNCH(e, k_t_segs, cdiv(n, 256), 256, 0, e->csc_ptr, e->col_seg, n, CSC_SEG, e->seg_col, e->seg_off, (int4*)e->seg_desc);
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("sparse upload failed"); return MLP_CUDA_ERROR; }
   return MLP_OK;
 }
@@ -2495,8 +2548,8 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
     if (e->sparse)
     {
-      LAUNCH(e, k_price_csc_seg<1>, e->sm_count * 8, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->sg0, e->sg1,
-             e->c0, (const double*)nullptr, e->vflag, e->seg_sum);
+      LAUNCH(e, k_price_csc_seg<1>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->sg0, e->sg1, (const double*)nullptr,
+             e->seg_sum);
       LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, e->c0, (const double*)nullptr, e->vflag, e->gam);
     }
     else {
@@ -2676,7 +2729,7 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
     LAUNCH(e, k_min_small, 1, 1, 0, e->xred, e->world, e->scal);
   }
   LAUNCH(e, k_ratio_dual_2, grid, 256, 0, e->rc, e->d, e->vflag, e->vpos, e->xnb, e->nt, e->n, e->c0, e->ng, lds, e->scal,
-         l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend);
+         l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend, e->rank == 0 ? 1 : 0);
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w));

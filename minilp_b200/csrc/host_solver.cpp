@@ -48,6 +48,12 @@ struct mlp_solver {
   // f4: every recalc_period pivots (0 = never, the reference's behaviour) recompute x_B and d from scratch — the TODO at
   // solver.rs:1024-1025 — with recalc_basic_var_vals (1177-1197) and recalc_obj_coeffs (1199-1231)
   int64_t recalc_period = 0, recalcs_done = 0;
+  // Refactor rule.  The reference refactorizes when the eta file holds as many entries as the LU factors (solver.rs:1096-1097:
+  // the point where ITS solves cost twice a fresh factorization's).  refactor_factor scales the right-hand side: 1 (default) is
+  // the reference's rule; a larger value lets the eta file grow longer — on the device an eta column is one more column
+  // of a coalesced m x K pass, while a refactorization is O(k) sequential pivot steps plus O(k^3) work, so the balance
+  // point lies elsewhere.  Only the rounding of later pivots depends on it.
+  double refactor_factor = 1.0;
   bool artificial_obj = false;  // solver.rs:261: while the artificial objective is in place d must not be recomputed from c
   bool initialized = false;
 };
@@ -78,7 +84,9 @@ static mlp_status do_pivot(mlp_solver* s, int phase, int64_t entering_var, int64
   pi.row = row;
   pi.coeff = coeff;
   pi.leaving_new_val = leaving_new_val;
-  pi.refactor = (has_elem && !(s->eta_nnz < s->lu_nnz)) ? 1 : 0;  // 1096-1103
+  const bool keep_etas = s->refactor_factor == 1.0 ? s->eta_nnz < s->lu_nnz  // 1096-1103
+                                                   : (double)s->eta_nnz < s->refactor_factor * (double)s->lu_nnz;
+  pi.refactor = (has_elem && !keep_etas) ? 1 : 0;
   mlp_pivot_result pr;
   auto t0 = Clock::now();
   ST(mlp_pivot(s->eng, &pi, &pr));
@@ -591,6 +599,7 @@ mlp_status mlp_solver_get_basic_vars(mlp_solver* s, int64_t* out) {
   std::memcpy(out, s->basic_vars.data(), s->m * sizeof(int64_t));
   return MLP_OK;
 }
+void mlp_solver_set_refactor_factor(mlp_solver* s, double factor) { s->refactor_factor = factor > 0.0 ? factor : 1.0; }
 void mlp_solver_set_recalc_period(mlp_solver* s, int64_t period) { s->recalc_period = period > 0 ? period : 0; }
 int64_t mlp_solver_recalcs_done(mlp_solver* s) { return s->recalcs_done; }
 void mlp_solver_tie_stats(mlp_solver* s, int64_t out4[4]) {

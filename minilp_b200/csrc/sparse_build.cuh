@@ -70,12 +70,16 @@ __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr,
   }
 }
 __global__ void __launch_bounds__(256) k_t_segs(const int64_t* __restrict__ csc_ptr, const int64_t* __restrict__ col_seg, int64_t n,
-                                                int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off) {
+                                                int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off,
+                                                int4* __restrict__ seg_desc) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  const int64_t b = csc_ptr[j];
+  const int64_t b = csc_ptr[j], e = csc_ptr[j + 1];
   for (int64_t sg = col_seg[j]; sg < col_seg[j + 1]; ++sg) {
+    const int64_t o = b + (sg - col_seg[j]) * seg_len;
     seg_col[sg] = (int32_t)j;
-    seg_off[sg] = b + (sg - col_seg[j]) * seg_len;
+    seg_off[sg] = o;
+    const int64_t len = e - o < seg_len ? e - o : seg_len;
+    seg_desc[sg] = make_int4((int)(unsigned)(o & 0xffffffffLL), (int)(o >> 32), (int)(len > 0 ? len : 0), (int)j);  // SegDesc
   }
 }

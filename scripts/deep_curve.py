@@ -12,6 +12,7 @@ ap.add_argument("--kind", type=int, default=0); ap.add_argument("--seed", type=i
 ap.add_argument("--segment", type=int, default=500); ap.add_argument("--max-pivots", type=int, default=40000)
 ap.add_argument("--max-seconds", type=float, default=400.0)
 a = ap.parse_args()
+a.workload = "dense"
 s, setup = bench.build_solver(a, 0)
 e = s.engine
 s.set_record_trace(True)
