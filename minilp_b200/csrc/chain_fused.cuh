@@ -22,8 +22,9 @@
 
 constexpr int FZ_T = 512;     // threads per CTA
 constexpr int FZ_WARPS = FZ_T / 32;
-constexpr int FZ_MAX = 512;   // largest k and K handled here; beyond, the basis passes are bandwidth-bound (>= 200 MB each)
-                              // and the separate kernels with their column-group splits take over
+constexpr int FZ_MAX = 1024;  // largest k and K handled here (shared-memory staging of x / t); MLP_FUSED_MAX lowers it.  Config 3
+                              // peaks at k = 855, K = 656 on its way to the optimum (profiles/r02_deep_curve_config3.jsonl): the whole
+                              // solve stays inside the fused chain; beyond, the separate kernels with their column-group splits run
 constexpr int FZ_G = 32;      // column groups of the small mat-vecs
 constexpr int FZ_MAXS = 64;   // row slices of the transposed tall-skinny products
 constexpr int FZ_SEG = 1024;  // compaction segment (= CP_SEG)

@@ -11,11 +11,14 @@ ap.add_argument("--m", type=int, default=50000); ap.add_argument("--n", type=int
 ap.add_argument("--kind", type=int, default=0); ap.add_argument("--seed", type=int, default=1)
 ap.add_argument("--segment", type=int, default=500); ap.add_argument("--max-pivots", type=int, default=40000)
 ap.add_argument("--max-seconds", type=float, default=400.0)
+ap.add_argument("--skip", type=int, default=0, help="pivots to run before the first measured segment")
 a = ap.parse_args()
 a.workload = "dense"
 s, setup = bench.build_solver(a, 0)
 e = s.engine
 s.set_record_trace(True)
+if a.skip > 0:
+    s.run(a.skip)
 t_start = time.perf_counter()
 tot_ms = 0.0
 done = False

@@ -16,8 +16,13 @@ pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deep_trace_*.npz")))
 
 
+@pytest.mark.parametrize("fused_max", [None, 256], ids=["fused<=1024", "fused<=256"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
-def test_deep_run_follows_the_oracle_trace(path):
+def test_deep_run_follows_the_oracle_trace(path, fused_max, monkeypatch):
+    """fused_max=None: the fused FTRAN -> BTRAN chain serves k, K up to 1024 (the whole run); 256: beyond 256 the separate
+    kernels with their column-group splits run — both regimes must follow the oracle."""
+    if fused_max is not None:
+        monkeypatch.setenv("MLP_FUSED_MAX", str(fused_max))
     g = np.load(path)
     kind, m, n, seed, budget = (int(g[k]) for k in ("kind", "m", "n", "seed", "budget"))
     assert int(g["tie_events"]) == 0  # the sequence is well-defined: the oracle met no exact tie
