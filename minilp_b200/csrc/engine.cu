@@ -1852,6 +1852,8 @@ static mlp_status refactor_impl(mlp_engine* e) {
       if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      else if (k <= 2048) LAUNCH(e, k_core_inverse_pf<8>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      else if (k <= 4096) LAUNCH(e, k_core_inverse_pf<16>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
     }
     if (e->sparse) {
