@@ -1897,7 +1897,9 @@ static mlp_status chain_fused(mlp_engine* e, int64_t var);
 static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq);
 static constexpr int64_t VAR_PENDING = -2;
 
-static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
+// want_alpha_nnz (dual loop): the host also waits for nnz(alpha_q) of the winner's FTRAN, so that mlp_pivot can return
+// without a device round trip of its own (the primal loop gets that count with the ratio test's read-back).
+static mlp_status exchange_candidates(mlp_engine* e, Cand* winner, bool want_alpha_nnz = false) {
   const int m = (int)e->m;
   Lane& l0 = e->lane[0];
   // single shard: the candidate's column goes straight into colq and its header is the winner
@@ -1930,13 +1932,19 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner) {
     ST(ftran(e, l0, e->colq, e->alpha));
     compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
     ST(mark0(e));
+    if (want_alpha_nnz && e->async_pivot) {  // header + nnz(alpha_q) in one wait, still ahead of the steepest-edge tail
+      CU(cudaMemcpyAsync(e->h_mail + 6, e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+      CU(cudaEventRecord(e->ev_win, e->stream));
+    } else want_alpha_nnz = false;
     if (e->enable_pse && e->overlap) ST(se_helper(e, VAR_PENDING));
   }
+  if (chain_fusable(e)) want_alpha_nnz = false;
   e->alpha_nnz_host = -1;
-  CU(cudaEventSynchronize(e->ev_win));  // the header only, not the chain queued behind it
+  CU(cudaEventSynchronize(e->ev_win));  // the header only (dual loop: and the FTRAN), not the chain queued behind it
   if (e->prof_on) ST(collect_profile(e, (int)((e->pivot_seq & 1) ^ 1)));  // the previous pivot is complete by now
   e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
   *winner = e->h_cands[0];
+  if (want_alpha_nnz && winner->var >= 0) { e->alpha_nnz_host = e->h_mail[6]; e->cnt.d2h_bytes += 4; }
   if (winner->f[4] == 2.0) { set_err("device-side rendezvous timed out (peer-memory exchange: a rank stopped participating; or a grid barrier of the fused chain)"); return MLP_CUDA_ERROR; }
   if (winner->f[4] != 0.0) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   e->colq_var = e->ftran_var = winner->var;
@@ -2734,7 +2742,7 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
          l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend, e->rank == 0 ? 1 : 0);
   Cand w;
   w.var = -1;
-  ST(exchange_candidates(e, &w));
+  ST(exchange_candidates(e, &w, true));
   out->var = w.var;
   if (w.var < 0) { out->pos = -1; return MLP_OK; }
   out->coeff = w.f[0];
