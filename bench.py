@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--workload", default="dense", choices=["dense", "netlib_like", "sparse_pos"],
                     help="dense: BASELINE config 3 / 5 (the default, what the driver runs); netlib_like / sparse_pos: BASELINE "
                          "config 4, a sparse LP that enters as free-format MPS text (use with --rows 100000 --cols 100000)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="default run only: skip the short config-5 and config-4 runs reported under `extra`")
     ap.add_argument("--refactor-factor", type=float, default=1.0,
                     help="refactorize when eta nnz >= factor * lu nnz; 1 = the reference's rule (solver.rs:1096-1097)")
     ap.add_argument("--col-nnz", type=float, default=100.0, help="mean entries per column of the sparse workloads (0.1 % of 100k)")
@@ -272,50 +274,62 @@ def load_traffic(a, nloc):
     return None
 
 
-def dist_setup():
+class Ctx:
     """One process per GPU (torchrun): NCCL process group for the bench's own barriers / max-over-ranks, and a fresh NCCL
-    unique id for the engine's communicator."""
-    import torch
+    unique id per engine (an id serves one ncclCommInitRank round)."""
 
-    import minilp_b200 as mb
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if mb.device_count() < 1:
-        raise RuntimeError("bench.py needs a CUDA device: minilp_b200 has no CPU fallback")
-    dist = None
-    comm = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    def __init__(self):
+        import torch
+
+        import minilp_b200 as mb
+        self.torch, self.mb = torch, mb
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if mb.device_count() < 1:
+            raise RuntimeError("bench.py needs a CUDA device: minilp_b200 has no CPU fallback")
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def fresh_comm(self):
+        if self.dist is None:
+            return None
+        torch = self.torch
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.tensor(list(mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(idt, 0)
-        comm = bytes(idt.cpu().tolist())
+        if self.rank == 0:
+            idt = torch.tensor(list(self.mb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        self.dist.broadcast(idt, 0)
+        return bytes(idt.cpu().tolist())
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    def max_over_ranks(x):
-        if dist is None:
+    def max_over_ranks(self, x):
+        if self.dist is None:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    return world, rank, local, dist, comm, barrier, max_over_ranks
+    def close(self):
+        if self.dist is not None:
+            self.dist.destroy_process_group()
 
 
-def run_ours_sparse(a):
-    """BASELINE config 4 on one GPU: MPS text -> native reader -> CSR -> device (CSC built there) -> dual simplex loop."""
+def measure_sparse(a, ctx):
+    """BASELINE config 4: MPS text -> native reader -> CSR -> device (CSC built there) -> dual simplex loop.  Returns the JSON
+    line on rank 0, None elsewhere."""
     import minilp_b200 as mb
     from minilp_b200 import mps
-    world, rank, local, dist, comm, barrier, max_over_ranks = dist_setup()
+    world, rank, local, barrier, max_over_ranks = ctx.world, ctx.rank, ctx.local, ctx.barrier, ctx.max_over_ranks
+    comm = ctx.fresh_comm()
     t0 = time.perf_counter()
     text, d = sparse_text(a)
     t1 = time.perf_counter()
@@ -359,8 +373,7 @@ def run_ours_sparse(a):
     _, refac_s = s.timers()
     if rank != 0:
         s.close()
-        dist.destroy_process_group()
-        return
+        return None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -412,18 +425,16 @@ def run_ours_sparse(a):
                                 "sample": (f"pivots {a.warmup + 1}..{a.warmup + piv} of the same LP from the same MPS text ({sec:.1f}s of "
                                            f"single-thread CPU work after {a.warmup} untimed pivots; parse + try_new {setup_s:.1f}s excluded)"),
                                 "host_cores_available": os.cpu_count() or 1}
-    emit(line)
     s.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return line
 
 
-def run_ours(a):
+def measure_dense(a, ctx):
     """One process per GPU.  world > 1 (torchrun): the SAME LP is column-sharded over the ranks (strong scaling); every rank
-    runs the identical host control loop, the one exchange step per pivot goes over NCCL inside the engine."""
-    import minilp_b200 as mb
-    world, rank, local, dist, comm, barrier, max_over_ranks = dist_setup()
-    s, setup = build_solver(a, local, rank, world, comm)
+    runs the identical host control loop, the one exchange step per pivot goes over NVLink inside the engine.  Returns the
+    JSON line on rank 0, None elsewhere."""
+    world, rank, local, barrier, max_over_ranks = ctx.world, ctx.rank, ctx.local, ctx.barrier, ctx.max_over_ranks
+    s, setup = build_solver(a, local, rank, world, ctx.fresh_comm())
     e = s.engine
     nloc = e.n
     s.set_record_trace(True)
@@ -468,12 +479,13 @@ def run_ours(a):
     barrier()
     if rank != 0:
         s.close()
-        dist.destroy_process_group()
-        return
+        return None
     roofline = {
         "bound": "hbm", "kernel": "k_price_partial_tma (bulk-copy ring; chunk partials reduced inside k_update_select): N^T v of "
                                    "update_primal_sq_norms, solver.rs:1117-1132",
         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic(a, nloc),
+        "traffic_source": "static: DRAM bytes per launch from the committed ncu --set full capture (profiles/price_traffic.json), "
+                          "reported when its shape equals this run's; not measured in this run",
         "peak_source": peak_src, "launches_timed": prof["price_v_launches"],
         "avg_launch_ms": prof["price_v_ms"] / nv, "algorithmic_bytes_per_launch": prof["price_v_bytes"] / nv,
         "share_of_step_time": prof["price_v_ms"] / dev_ms,
@@ -519,10 +531,53 @@ def run_ours(a):
             "value": piv / sec if sec > 0 else 0.0, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"pivots 2..{piv + 1} of the same {m_used}x{a.n} LP after one untimed pivot ({sec:.1f}s of single-thread "
                        f"CPU work; the reference is single-threaded){note}"), "host_cores_available": cores}
-    emit(line)
     s.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return line
+
+
+def compact_line(line):
+    """What an `extra` entry keeps of a full bench line."""
+    keep = ("value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "e2e", "gpu_launches", "parity", "cpu_baseline")
+    out = {k: line[k] for k in keep if k in line}
+    r = line.get("roofline", {})
+    out["roofline"] = {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "algorithmic_bytes_per_launch",
+                                             "share_of_step_time", "launches_timed")}
+    d = line.get("run_detail", {})
+    out["run_detail"] = {k: d[k] for k in ("parallelism", "k_structural_end", "eta_count_end", "refactors_in_region", "refactor_share_of_wall",
+                                           "setup", "objective_after", "nnz") if k in d}
+    return out
+
+
+def run_ours(a):
+    """The driver's line is BASELINE config 3 (or whatever --workload / --rows / --cols / --kind name).  With the default
+    workload it also carries `extra`: short runs of the other two benchmark configurations on the same GPUs, so that they are
+    measured wherever the headline is — config 5 (dense 50k x 200k, the column-sharding config) and config 4 (netlib_like
+    100k x 100k through MPS)."""
+    import copy
+    ctx = Ctx()
+    line = measure_dense(a, ctx) if a.workload == "dense" else measure_sparse(a, ctx)
+    default_run = a.workload == "dense" and (a.m, a.n, a.kind, a.seed) == (50000, 50000, 0, 1)
+    if a.extras and default_run:
+        extra = {}
+        c5 = copy.copy(a)
+        c5.n, c5.steps, c5.warmup, c5.cpu_baseline_seconds = 200000, min(a.steps, 20), 3, 0.0
+        c4 = copy.copy(a)
+        c4.workload, c4.m, c4.n, c4.steps, c4.warmup = "netlib_like", 100000, 100000, 2000, 20
+        c4.cpu_baseline_seconds = min(a.cpu_baseline_seconds, 8.0)
+        for name, args, fn in (("config5_dense_50000x200000", c5, measure_dense), ("config4_netlib_like_100000x100000", c4, measure_sparse)):
+            try:
+                t0 = time.perf_counter()
+                got = fn(args, ctx)
+                if got is not None:
+                    extra[name] = compact_line(got)
+                    extra[name]["bench_seconds"] = round(time.perf_counter() - t0, 1)
+            except Exception as exc:  # an extra must never cost the headline line
+                extra[name] = {"error": repr(exc)}
+        if line is not None:
+            line["extra"] = extra
+    if line is not None:
+        emit(line)
+    ctx.close()
 
 
 def emit(line):
@@ -542,8 +597,6 @@ def main():
     os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
-    elif a.workload != "dense":
-        run_ours_sparse(a)
     else:
         run_ours(a)
 

@@ -22,9 +22,10 @@
 
 constexpr int FZ_T = 512;     // threads per CTA
 constexpr int FZ_WARPS = FZ_T / 32;
-constexpr int FZ_MAX = 1024;  // largest k and K handled here (shared-memory staging of x / t); MLP_FUSED_MAX lowers it.  Config 3
-                              // peaks at k = 855, K = 656 on its way to the optimum (profiles/r02_deep_curve_config3.jsonl): the whole
-                              // solve stays inside the fused chain; beyond, the separate kernels with their column-group splits run
+constexpr int FZ_MAX = 512;   // largest k and K handled here; beyond, the basis passes are bandwidth-bound (>= 200 MB each) and the
+                              // separate kernels with their column-group splits take over.  A/B at 1024 (r02s3, config 3 pivots
+                              // 2500-4500, k 710-844, K up to 756): 3.36-3.46 ms/pivot fused vs 3.35-3.42 separate — no gain, the deep
+                              // regime is bandwidth-bound as a whole (profiles/r02_deep_curve_config3.md)
 constexpr int FZ_G = 32;      // column groups of the small mat-vecs
 constexpr int FZ_MAXS = 64;   // row slices of the transposed tall-skinny products
 constexpr int FZ_SEG = 1024;  // compaction segment (= CP_SEG)
@@ -47,6 +48,8 @@ struct ChainArgs {
   double* scal;   // [2] |alpha|^2  [3] |v|^2
   unsigned* bar;
   int* flags;     // [2]: a grid barrier timed out
+  const uint8_t* touched;  // stored positions of the newest eta (k_touch_mark in kernels_common.cuh)
+  uint8_t* touched_new;    // touched U nz(alpha0): the stored size of col_coeffs is its population count -> icnt[1]
 };
 
 // Grid-wide barrier (the cooperative-groups scheme: CTA 0 adds the complement, the top bit flips when all have arrived).
@@ -209,13 +212,20 @@ __global__ void __launch_bounds__(FZ_T, 1) k_chain_primal(ChainArgs a) {
     if (cv < 0) continue;
     const double acc = fz_row_sub(a.colq[i], a.Bcols + i, a.mld, k, xs, sl);
     a.alpha[cv] = acc;
-    if (K == 0) { st_cnt += acc != 0.0; st_ss += acc * acc; }
+    const int tch = (acc != 0.0) | (a.touched[cv] != 0);  // structural size of col_coeffs: see k_touch_mark
+    a.touched_new[cv] = (uint8_t)tch;
+    st_cnt += tch;
+    if (K == 0) st_ss += acc * acc;
   }
   if (blockIdx.x == 0)
     for (int t = tid; t < k; t += FZ_T) {
       const double xv = xs[t];
-      a.alpha[a.Jpos[t]] = xv;
-      if (K == 0) { st_cnt += xv != 0.0; st_ss += xv * xv; }
+      const int p = a.Jpos[t];
+      a.alpha[p] = xv;
+      const int tch = (xv != 0.0) | (a.touched[p] != 0);
+      a.touched_new[p] = (uint8_t)tch;
+      st_cnt += tch;
+      if (K == 0) st_ss += xv * xv;
     }
   FZ_BAR();
   if (K > 0) {
@@ -232,7 +242,6 @@ __global__ void __launch_bounds__(FZ_T, 1) k_chain_primal(ChainArgs a) {
     for (int i = blockIdx.x * FZ_T + tid; i < m; i += gridDim.x * FZ_T) {
       const double acc = fz_row_sub(__ldcg(a.alpha + i), a.E + i, a.mld, K, xs, nullptr);
       a.alpha[i] = acc;
-      st_cnt += acc != 0.0;
       st_ss += acc * acc;
     }
   }

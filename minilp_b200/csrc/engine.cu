@@ -239,6 +239,8 @@ struct mlp_engine {
   // segment table of the CSC copy (<= CSC_SEG entries of one column per segment) and the core's slice of it
   int64_t nseg = 0;
   struct SegDesc* seg_desc = nullptr;  // nseg: (first entry, length, column) of every segment, one 16-byte load
+  int32_t *seg_long = nullptr, *seg_short = nullptr;  // this shard's segments with more than / at most PR_CSC_LONG entries
+  int64_t nseg_long = 0, nseg_short = 0;
   int32_t* seg_col = nullptr;      // nseg
   int64_t* seg_off = nullptr;      // nseg
   int64_t* col_seg = nullptr;      // n+1
@@ -283,6 +285,7 @@ struct mlp_engine {
   double *E = nullptr, *Ginv = nullptr, *gK = nullptr;  // eta columns m x Kcap; (I+G)^-1 Kcap x Kcap; coupling row of the newest eta
   int32_t *etaR = nullptr, *etaPrev = nullptr, *etaHead = nullptr;
   int32_t* etaLast = nullptr;  // mld: index of the newest eta whose leaving row is r, -1 if none (head of k_eta_scatter's chain)
+  uint8_t *touched = nullptr, *touched_new = nullptr;  // mld each: stored positions of the newest eta / of the column being priced in (k_touch_mark)
   // fused FTRAN -> BTRAN chain (chain_fused.cuh)
   int fused = 1;               // MLP_FUSED=0: separate kernels
   int fused_max = FZ_MAX;      // largest k / K that takes the fused chain (MLP_FUSED_MAX lowers it: tests of the hand-over)
@@ -856,24 +859,57 @@ struct SegDesc {
   int32_t len, col;
 };
 static_assert(sizeof(SegDesc) == 16, "SegDesc is one 16-byte load");
-constexpr int PR_CSC_U = 4;
+constexpr int PR_CSC_U = 4;      // short segments (<= 64 entries) in flight per warp
+constexpr int PR_CSC_LONG = 64;  // a segment with more entries is "long": one per warp, eight strides in flight
+// Where the entries are: the column counts are power-law distributed, so on config 4 ~8 % of the segments (the full
+// 1024-entry pieces of the ~1 % longest columns) hold ~85 % of the entries, while ~90 % of the segments are short columns of a
+// few dozen entries.  Two work lists (built with the segment table): a LONG segment goes to one warp that keeps eight
+// strides (256 entries: values, row indices, then the gathers) in flight — bandwidth; SHORT ones are taken four at a time
+// with both strides of each issued together — latency.  Per segment the summation order is the same in both: lane-strided
+// partial sums in ascending entry order, then the fixed shuffle tree (bit-identical to the first version of the kernel).
 template <int MODE>
 __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict__ desc, const int32_t* __restrict__ idx,
-                                                       const double* __restrict__ val, int64_t sg0, int64_t sg1,
+                                                       const double* __restrict__ val, const int32_t* __restrict__ long_ids,
+                                                       int nlong, const int32_t* __restrict__ short_ids, int nshort,
                                                        const double* __restrict__ w, double* __restrict__ seg_sum) {
   const int lane = threadIdx.x & 31;
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  for (int64_t base = sg0 + wid; base < sg1; base += warps * PR_CSC_U) {
+  const int warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
+  const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  for (int i = wid; i < nlong; i += warps) {
+    const int sg = long_ids[i];
+    const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sg));
+    const int64_t b = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
+    const int len = d.z;
+    double acc = 0.0;
+    for (int o0 = lane; o0 < len; o0 += 256) {
+      double a[8];
+      int r[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int o = o0 + 32 * u;
+        const bool ok = o < len;
+        a[u] = ok ? __ldcs(val + b + o) : 0.0;
+        r[u] = (MODE == 0 && ok) ? __ldcs(idx + b + o) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (o0 + 32 * u < len) acc += (MODE == 0) ? a[u] * w[r[u]] : a[u] * a[u];
+    }
+    const double tot = warp_sum(acc);
+    if (lane == 0) seg_sum[sg] = tot;
+  }
+  for (int base = wid; base < nshort; base += warps * PR_CSC_U) {
     int64_t b[PR_CSC_U];
-    int len[PR_CSC_U];
+    int len[PR_CSC_U], sgq[PR_CSC_U];
 #pragma unroll
     for (int q = 0; q < PR_CSC_U; ++q) {
-      const int64_t sg = base + q * warps;
+      const int i = base + q * warps;
       b[q] = 0;
       len[q] = 0;
-      if (sg < sg1) {
-        const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sg));
+      sgq[q] = -1;
+      if (i < nshort) {
+        sgq[q] = short_ids[i];
+        const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sgq[q]));
         b[q] = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
         len[q] = d.z;
       }
@@ -889,23 +925,14 @@ __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict
         a[q][it] = ok ? __ldcs(val + b[q] + o) : 0.0;
         r[q][it] = (MODE == 0 && ok) ? __ldcs(idx + b[q] + o) : 0;
       }
-    double acc[PR_CSC_U];
 #pragma unroll
     for (int q = 0; q < PR_CSC_U; ++q) {
-      acc[q] = 0.0;
+      double acc = 0.0;
 #pragma unroll
       for (int it = 0; it < 2; ++it)
-        if (lane + 32 * it < len[q]) acc[q] += (MODE == 0) ? a[q][it] * w[r[q][it]] : a[q][it] * a[q][it];
-    }
-#pragma unroll
-    for (int q = 0; q < PR_CSC_U; ++q) {
-      for (int o = lane + 64; o < len[q]; o += 32) {  // long segments (up to CSC_SEG entries)
-        const double av = __ldcs(val + b[q] + o);
-        acc[q] += (MODE == 0) ? av * w[__ldcs(idx + b[q] + o)] : av * av;
-      }
-      const double tot = warp_sum(acc[q]);
-      const int64_t sg = base + q * warps;
-      if (lane == 0 && sg < sg1) seg_sum[sg] = tot;
+        if (lane + 32 * it < len[q]) acc += (MODE == 0) ? a[q][it] * w[r[q][it]] : a[q][it] * a[q][it];
+      const double tot = warp_sum(acc);
+      if (lane == 0 && sgq[q] >= 0) seg_sum[sgq[q]] = tot;
     }
   }
 }
@@ -1278,9 +1305,11 @@ __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ a
                                                      double* __restrict__ xB, double* __restrict__ w, int m, int row,
                                                      double entering_new_val, double entering_diff, double coeff, int has_elem,
                                                      int dse, const double* __restrict__ scal, double* __restrict__ eta_col,
-                                                     int* __restrict__ flags) {
+                                                     int* __restrict__ flags, uint8_t* __restrict__ touched,
+                                                     const uint8_t* __restrict__ touched_new) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
+  if (eta_col) touched[r] = touched_new[r];  // the pushed eta stores every listed position of col_coeffs (solver.rs:1274-1284)
   const double a = alpha[r];
   if (!has_elem) {  // bound flip, solver.rs:1035-1037
     if (a != 0.0) xB[r] -= entering_diff * a;
@@ -1563,7 +1592,8 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
     double* ssum = &ln == &e->lane[0] ? e->seg_sum : e->seg_sum + e->nseg;
-    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->sg0, e->sg1, slack_vals, ssum);
+    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
+            e->seg_short, (int)e->nseg_short, slack_vals, ssum);
     LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, e->c0, slack_vals, e->vflag, out);
   } else {
     // Lane 1 (the tableau-row price-out, support <= k+1 rows) runs BESIDE lane 0's dense N^T v price-out.  The bulk-copy
@@ -1610,9 +1640,10 @@ static mlp_status collect_profile(mlp_engine* e, int par) {
 }
 
 // list / stats of a dense m-vector (see k_compact_count). idx == nullptr: stats only.
-static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq) {
+static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq,
+                    const uint8_t* mask = nullptr) {
   const int m = (int)e->m, nseg = cdiv(m, CP_SEG);
-  LAUNCHS(e, ln.st, k_compact_count, nseg, CP_SEG, 0, x, m, ln.seg_cnt, ln.seg_ss, ln.red_counter, count, sumsq);
+  LAUNCHS(e, ln.st, k_compact_count, nseg, CP_SEG, 0, x, m, ln.seg_cnt, ln.seg_ss, ln.red_counter, count, sumsq, mask);
   if (idx) LAUNCHS(e, ln.st, k_compact_write, nseg, CP_SEG, 0, x, m, ln.seg_cnt, idx, val);
 }
 static int gemv_split(const mlp_engine* e, int rows, int cols) {
@@ -1635,7 +1666,8 @@ static void gemv_t(mlp_engine* e, Lane& ln, const double* M, int64_t ld, int row
 }
 
 // BasisSolver::solve (solver.rs:1305-1319). rhs0: dense m-vector by constraint row (device). out: by basis position.
-static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out) {
+// mark: this is the FTRAN of an entering column — record the structural pattern of its result (k_touch_mark)
+static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out, bool mark = false) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
@@ -1650,6 +1682,7 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   } else
     LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
             e->Jslot, out);
+  if (mark) LAUNCHS(e, ln.st, k_touch_mark, cdiv(m, 256), 256, 0, out, e->touched, m, e->touched_new);
   if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
     LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
     const int GK = tall_groups(e, m, K);
@@ -1786,6 +1819,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
   e->K = 0;
   CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
   CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)e->mld * sizeof(int32_t), e->stream));  // eta file is empty: no chains
+  CU(cudaMemsetAsync(e->touched, 0, (size_t)e->mld, e->stream));
   std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
   ST(h2d(e, e->rowcover, rowcover.data(), m * sizeof(int32_t)));
   if (k > 0) {
@@ -1890,11 +1924,12 @@ static mlp_status refactor_impl(mlp_engine* e) {
 
 // The exchange step: every shard's candidate header + candidate column are all-gathered, the winner is chosen with the
 // reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
-static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out);
+static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out, bool mark);
 static mlp_status se_helper(mlp_engine* e, int64_t var);
 static bool chain_fusable(const mlp_engine* e);
 static mlp_status chain_fused(mlp_engine* e, int64_t var);
-static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq);
+static void compact(mlp_engine* e, Lane& ln, const double* x, int32_t* idx, double* val, int32_t* count, double* sumsq,
+                    const uint8_t* mask);
 static constexpr int64_t VAR_PENDING = -2;
 
 // want_alpha_nnz (dual loop): the host also waits for nnz(alpha_q) of the winner's FTRAN, so that mlp_pivot can return
@@ -1929,8 +1964,8 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner, bool want_alp
   e->spec_var = -1;
   if (chain_fusable(e)) ST(chain_fused(e, VAR_PENDING));
   else {
-    ST(ftran(e, l0, e->colq, e->alpha));
-    compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+    ST(ftran(e, l0, e->colq, e->alpha, true));
+    compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2, e->touched_new);
     ST(mark0(e));
     if (want_alpha_nnz && e->async_pivot) {  // header + nnz(alpha_q) in one wait, still ahead of the steepest-edge tail
       CU(cudaMemcpyAsync(e->h_mail + 6, e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -2014,6 +2049,7 @@ static mlp_status chain_fused(mlp_engine* e, int64_t var) {
   a.vidx = e->vlist_idx; a.vval = e->vlist_val;
   a.icnt = e->icnt; a.scal = e->scal;
   a.bar = e->fz_bar; a.flags = e->d_res->flags;
+  a.touched = e->touched; a.touched_new = e->touched_new;
   void* args[] = {&a};
   CU(cudaLaunchCooperativeKernel((const void*)k_chain_primal, dim3((unsigned)e->sm_count), dim3(FZ_T), args, 0, l0.st));
   e->cnt.kernel_launches += 1;
@@ -2091,7 +2127,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->csr_ptr); dev_free(e->csc_ptr); dev_free(e->csr_idx); dev_free(e->csc_idx); dev_free(e->csr_val); dev_free(e->csc_val);
   dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
-  dev_free(e->seg_desc);
+  dev_free(e->seg_desc); dev_free(e->seg_long); dev_free(e->seg_short);
   dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
@@ -2104,7 +2140,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->rowcover); dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
   dev_free(e->lu_aff); dev_free(e->lu_perm); dev_free(e->lu_rcnt); dev_free(e->d_nnzcnt);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
-  dev_free(e->etaLast); dev_free(e->fz_scratch); dev_free(e->fz_cta_cnt); dev_free(e->fz_cta_ss); dev_free(e->fz_bar);
+  dev_free(e->etaLast); dev_free(e->touched); dev_free(e->touched_new); dev_free(e->fz_scratch); dev_free(e->fz_cta_cnt); dev_free(e->fz_cta_ss); dev_free(e->fz_bar);
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
     dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.wm); dev_free(ln.gpart); dev_free(ln.gt_part_k);
@@ -2232,7 +2268,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   }
   e->d_res = e->lane[0].d_res;
   A(dev_alloc(&e->rowcover, ml));
-  A(dev_alloc(&e->etaLast, ml));
+  A(dev_alloc(&e->etaLast, ml)); A(dev_alloc(&e->touched, ml)); A(dev_alloc(&e->touched_new, ml));
   A(dev_alloc(&e->fz_scratch, (size_t)(2 * FZ_G + 2 * FZ_MAXS + 3) * FZ_MAX));
   A(dev_alloc(&e->fz_cta_cnt, (size_t)e->sm_count)); A(dev_alloc(&e->fz_cta_ss, (size_t)e->sm_count)); A(dev_alloc(&e->fz_bar, 4));
   e->xbytes = sizeof(Cand) + (size_t)ml * sizeof(double);
@@ -2256,6 +2292,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
     CU(cudaMemsetAsync(e->lane[l].d_res, 0, sizeof(DevRes), e->stream));
   }
   CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)ml * sizeof(int32_t), e->stream));
+  CU(cudaMemsetAsync(e->touched, 0, (size_t)ml, e->stream));
+  CU(cudaMemsetAsync(e->touched_new, 0, (size_t)ml, e->stream));
   CU(cudaMemsetAsync(e->fz_bar, 0, 4 * sizeof(unsigned), e->stream));
   CU(cudaMemsetAsync(e->gam, 0, ntc * sizeof(double), e->stream));
   CU(cudaMemsetAsync(e->helper, 0, ntc * sizeof(double), e->stream));
@@ -2318,6 +2356,7 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   dev_free(e->csr_ptr); dev_free(e->csr_idx); dev_free(e->csr_val); dev_free(e->csc_ptr); dev_free(e->csc_idx); dev_free(e->csc_val);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->seg_desc);
+  dev_free(e->seg_long); dev_free(e->seg_short);
   mlp_status st = MLP_OK;
   auto A = [&](mlp_status s2) { if (st == MLP_OK) st = s2; };
   A(dev_alloc(&e->csr_ptr, m + 1)); A(dev_alloc(&e->csr_idx, nnz)); A(dev_alloc(&e->csr_val, nnz));
@@ -2384,6 +2423,23 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
   A(dev_alloc(&e->seg_sum, 2 * e->nseg));  // one set per lane
   if (st != MLP_OK) return st;
   LAUNCH(e, k_t_segs, cdiv(n, 256), 256, 0, e->csc_ptr, e->col_seg, n, CSC_SEG, e->seg_col, e->seg_off, (int4*)e->seg_desc);
+  {  // work lists of the price-out over this shard's column block (host: O(segments))
+    std::vector<int32_t> lg, sh;
+    for (int64_t j = e->c0; j < e->c0 + e->n; ++j) {
+      const int64_t cnt = e->h_csc_ptr[(size_t)j + 1] - e->h_csc_ptr[(size_t)j];
+      for (int64_t sg = e->h_col_seg[(size_t)j], t = 0; sg < e->h_col_seg[(size_t)j + 1]; ++sg, ++t) {
+        const int64_t len = std::min<int64_t>(CSC_SEG, cnt - t * CSC_SEG);
+        (len > PR_CSC_LONG ? lg : sh).push_back((int32_t)sg);
+      }
+    }
+    e->nseg_long = (int64_t)lg.size();
+    e->nseg_short = (int64_t)sh.size();
+    A(dev_alloc(&e->seg_long, lg.size())); A(dev_alloc(&e->seg_short, sh.size()));
+    if (st != MLP_OK) return st;
+    if (!lg.empty()) ST(h2d(e, e->seg_long, lg.data(), lg.size() * sizeof(int32_t)));
+    if (!sh.empty()) ST(h2d(e, e->seg_short, sh.data(), sh.size() * sizeof(int32_t)));
+    CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+  }
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("sparse upload failed"); return MLP_CUDA_ERROR; }
   return MLP_OK;
 }
@@ -2558,8 +2614,8 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
     if (e->sparse)
     {
-      LAUNCH(e, k_price_csc_seg<1>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->sg0, e->sg1, (const double*)nullptr,
-             e->seg_sum);
+      LAUNCH(e, k_price_csc_seg<1>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
+             e->seg_short, (int)e->nseg_short, (const double*)nullptr, e->seg_sum);
       LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, e->c0, (const double*)nullptr, e->vflag, e->gam);
     }
     else {
@@ -2644,9 +2700,9 @@ mlp_status mlp_ftran_col(mlp_engine* e, int64_t var) {
   ST(fetch_column(e, var));
   e->spec_var = -1;
   if (chain_fusable(e)) return chain_fused(e, var);
-  ST(ftran(e, l0, e->colq, e->alpha));
-  // |alpha|^2 and nnz(alpha) for update_primal_sq_norms (1136) and the eta bookkeeping
-  compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2);
+  ST(ftran(e, l0, e->colq, e->alpha, true));
+  // |alpha|^2 (update_primal_sq_norms, 1136) and the stored size of col_coeffs (eta bookkeeping, 1096-1099)
+  compact(e, l0, e->alpha, nullptr, nullptr, e->icnt + 1, e->scal + 2, e->touched_new);
   ST(mark0(e));
   if (e->enable_pse && e->overlap) ST(se_helper(e, var));  // runs ahead of the ratio test on lane 0
   return MLP_OK;
@@ -2777,7 +2833,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     ST(begin0(e));
     e->sel_valid = false;
     LAUNCH(e, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, -1, pi->entering_new_val, pi->entering_diff,
-           1.0, 0, 0, e->scal, (double*)nullptr, e->d_res->flags);
+           1.0, 0, 0, e->scal, (double*)nullptr, e->d_res->flags, e->touched, e->touched_new);
     if (ql >= 0) LAUNCH(e, k_flip_var, 1, 1, 0, e->xnb, e->vflag, e->lo, e->hi, q, ql, pi->entering_new_val);
     ST(mark0(e));
     out->eta_count = e->K;
@@ -2803,7 +2859,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   // lane 1: row half of the pivot, eta push
   double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->mld;
   LAUNCHS(e, l1.st, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val,
-          pi->entering_diff, pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags);
+          pi->entering_diff, pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags, e->touched, e->touched_new);
   if (!do_refactor) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
@@ -3110,6 +3166,7 @@ static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** ou
     cp(e->etaR, src->etaR, Kc * 4); cp(e->etaPrev, src->etaPrev, Kc * 4); cp(e->etaHead, src->etaHead, Kc * 4);
     cp(e->etaLast, src->etaLast, ml * 4);
   }
+  cp(e->touched, src->touched, ml); cp(e->touched_new, src->touched_new, ml);
   if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("clone: copy failed"); st = MLP_CUDA_ERROR; }
   if (st != MLP_OK) { destroy_engine(e); return st; }
   e->nt = src->nt;

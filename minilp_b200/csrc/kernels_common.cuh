@@ -139,15 +139,18 @@ __device__ __forceinline__ bool last_block(unsigned* counter) {
 // finish adds the per-segment results in segment order (deterministic).  Pass 2 (only when the list is
 // needed): each CTA derives its output offset from the segment counts and writes its entries in order.
 constexpr int CP_SEG = 1024;
+// mask != nullptr: the count is the number of set mask bytes instead (the STRUCTURAL size of col_coeffs, see k_touch_mark);
+// the sum of squares is always the numeric one.
 __global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restrict__ x, int m, int32_t* __restrict__ seg_cnt,
                                                            double* __restrict__ seg_ss, unsigned* counter,
-                                                           int32_t* __restrict__ count, double* __restrict__ sumsq) {
+                                                           int32_t* __restrict__ count, double* __restrict__ sumsq,
+                                                           const uint8_t* __restrict__ mask) {
   __shared__ double sm[32];
   __shared__ int smi[32];
   const int i = blockIdx.x * CP_SEG + threadIdx.x;
   const double v = i < m ? x[i] : 0.0;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(FULLMASK, v != 0.0);
+  const unsigned bal = __ballot_sync(FULLMASK, mask ? (i < m && mask[i] != 0) : (v != 0.0));
   if (lane == 0) smi[wid] = __popc(bal);
   const double ss = block_sum(v * v, sm);  // has the barriers that publish smi
   if (threadIdx.x == 0) {
@@ -196,6 +199,20 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restri
     idx[p] = i;
     val[p] = v;
   }
+}
+
+// Structural size of col_coeffs.  The reference's FTRAN keeps a position in the result's non-zero list once it has been
+// TOUCHED, whatever its value: BasisSolver::solve (solver.rs:1305-1319) applies every eta to all of that eta's stored
+// positions (`*rhs.get_mut(r) -= coeff * val`, sparse.rs:75-80 marks r) even when coeff is 0, and push_eta_matrix
+// (1274-1284) stores every listed position of col_coeffs, zeros included.  So the stored size of eta K is
+// |pattern(LU solve of a_q) U stored positions of eta K-1|, and THAT is what the refactor rule (1096-1097) adds up — on
+// sparse LPs several times the numeric count.  `touched` holds the stored positions of the newest eta (cleared at a
+// refactorization), `touched_new` = touched U nz(alpha0) is written by the FTRAN of an entering column (alpha0: the result
+// of the LU part, before the etas) and becomes `touched` when that column is pushed (k_pivot_rows).
+__global__ void k_touch_mark(const double* __restrict__ alpha0, const uint8_t* __restrict__ touched, int m,
+                             uint8_t* __restrict__ touched_new) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) touched_new[i] = (uint8_t)((alpha0[i] != 0.0) | (touched[i] != 0));
 }
 
 // ------------------------------------------------------------------------------------------------ explicit inverses

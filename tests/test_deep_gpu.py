@@ -16,11 +16,11 @@ pytestmark = pytest.mark.gpu
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "deep_trace_*.npz")))
 
 
-@pytest.mark.parametrize("fused_max", [None, 256], ids=["fused<=1024", "fused<=256"])
+@pytest.mark.parametrize("fused_max", [None, 128], ids=["fused<=512", "fused<=128"])
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_deep_run_follows_the_oracle_trace(path, fused_max, monkeypatch):
-    """fused_max=None: the fused FTRAN -> BTRAN chain serves k, K up to 1024 (the whole run); 256: beyond 256 the separate
-    kernels with their column-group splits run — both regimes must follow the oracle."""
+    """fused_max=None: the fused FTRAN -> BTRAN chain serves k, K up to 512; 128: the separate kernels with their
+    column-group splits take over from 128 on — both hand-over points must follow the oracle."""
     if fused_max is not None:
         monkeypatch.setenv("MLP_FUSED_MAX", str(fused_max))
     g = np.load(path)

@@ -117,3 +117,21 @@ def test_device_transpose_equals_the_host_counting_transpose(gen, args, monkeypa
     assert np.array_equal(dev.trace(), host.trace())
     dev.close()
     host.close()
+
+
+def test_refactor_factor_changes_the_cadence_not_the_result():
+    """mlp_solver_set_refactor_factor: `eta nnz >= f * lu nnz` with f = 1 the reference's rule (solver.rs:1096-1097).  A larger f
+    means fewer refactorizations and longer eta files; the optimum is the same (only rounding depends on the cadence)."""
+    text, d = synth.netlib_like(600, 600, 7.0, 2)
+    p = mps.MpsFile.parse(text, d).problem
+    a, b = solver_from_problem(p, "sparse"), solver_from_problem(p, "sparse")
+    b.set_refactor_factor(8.0)
+    assert a.run() and b.run()
+    ra, rb = a.engine.counters()["refactors"], b.engine.counters()["refactors"]
+    assert rb < ra, (ra, rb)
+    assert close(a.cur_obj_val, b.cur_obj_val) and close(a.values(), b.values(), 1e-7)
+    ref = oracle.MpsFile.parse(text, d).problem.solve()
+    assert_same_trace(a.trace(), ref.trace(), ref, a)  # f = 1: the oracle's sequence
+    assert close(b.cur_obj_val, ref.cur_obj_val)
+    a.close()
+    b.close()
