@@ -69,6 +69,7 @@ static_assert(sizeof(Cand) == 64, "Cand must be 64 bytes");
 #include "kernels_common.cuh"
 #include "chain_fused.cuh"
 #include "sparse_build.cuh"
+#include "dense_block.cuh"
 
 // ------------------------------------------------------------------------------------------------ communicators
 // The pivot path has ONE real exchange step per pivot: the arg-reduce of the per-shard pricing
@@ -296,12 +297,14 @@ struct mlp_engine {
   int64_t lu_nnz = 0;
 
   // lane synchronisation (see "host side")
+  int pdl = 1;          // MLP_PDL=0: ordinary launches (no programmatic dependent launch)
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
   int async_pivot = 1;  // MLP_ASYNC_PIVOT=0: mlp_pivot always waits for the device
   int price_tma = 1;    // bulk-copy price-out kernel (MLP_PRICE_TMA=0: LDG kernel)
   int price_tile = 512; // its tile width in columns (MLP_PRICE_TILE; default: choose_price_tiling)
   int price_split = 1;  // column slices per item of the last, partial round (MLP_PRICE_SPLIT)
   int lane1_ldg = 1;    // lane 1 prices out with the LDG kernel while lane 0 runs the bulk-copy one (MLP_LANE1_LDG=0: both bulk-copy)
+  int64_t inv_blocked_min = 2048;  // cores at least this large get their inverse by blocked substitution (MLP_INV_BLOCKED_MIN)
   int csc_grid = 148 * 5;  // CSC price-out: one full wave of resident CTAs (occupancy query at creation)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
@@ -339,10 +342,29 @@ struct mlp_engine {
   mlp_counters cnt{};
 };
 
-#define LAUNCHS(e, st, kern, grid, block, smem, ...)        \
-  do {                                                      \
-    kern<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);   \
-    (e)->cnt.kernel_launches += 1;                          \
+// Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait in kernels_common.cuh).
+template <class... KArgs, class... Args>
+static inline void launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (!pdl) {
+    kern<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define LAUNCHS(e, st, kern, grid, block, smem, ...)                                        \
+  do {                                                                                      \
+    launch_kernel((e)->pdl != 0, kern, dim3(grid), dim3(block), (size_t)(smem), (st), __VA_ARGS__); \
+    (e)->cnt.kernel_launches += 1;                                                          \
   } while (0)
 #define LAUNCH(e, kern, grid, block, smem, ...) LAUNCHS(e, (e)->stream, kern, grid, block, smem, __VA_ARGS__)
 
@@ -410,6 +432,7 @@ __global__ void __launch_bounds__(PR_THREADS)
 k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
                 const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
                 double* __restrict__ partial) {
+  pdl_wait();
   __shared__ int32_t srow[PR_BATCH];
   __shared__ double sw[PR_BATCH];
   const int s = count_ptr ? *count_ptr : fixed_count;
@@ -574,6 +597,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1)
 k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
                     const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
                     double* __restrict__ partial, int tile_cols, int split) {
+  pdl_wait();
   extern __shared__ __align__(128) unsigned char tp_smem[];
   double* sw = reinterpret_cast<double*>(tp_smem + (size_t)TP_STAGES * TP_STAGE_BYTES);   // [stage][row] weights
   uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_MAXROWS);
@@ -695,6 +719,7 @@ k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __
 __global__ void k_price_finish(const double* __restrict__ partial, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
                                int64_t lda, int64_t n, int64_t m, const double* __restrict__ slack_vals,
                                const uint8_t* __restrict__ vflag, double* __restrict__ out, int mode) {
+  pdl_wait();
   int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= n + m) return;
   const int C = price_chunks_for(count_ptr ? *count_ptr : fixed_count);
@@ -713,6 +738,7 @@ __global__ void k_price_finish(const double* __restrict__ partial, const int32_t
 // ------------------------------------------------------------------------------------------------ columns
 // rhs.set(column of var) (solver.rs:672-675, sparse.rs:103): column of [A|I] of LOCAL variable lv as a dense m-vector
 __global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int m, int64_t lv, double* __restrict__ dst) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   dst[i] = lv < n ? A[(int64_t)i * lda + lv] : ((int64_t)i == lv - n ? 1.0 : 0.0);
@@ -720,6 +746,7 @@ __global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n,
 // same, for the variable named by a candidate header that is still on the device (no host round trip)
 __global__ void k_cand_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int64_t c0, int64_t ng, int m,
                                 const Cand* __restrict__ cand, double* __restrict__ dst, Cand* __restrict__ win_out) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && win_out) *win_out = *cand;  // single shard: the candidate IS the winner
   if (i >= m) return;
@@ -735,6 +762,7 @@ __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__
                                                        const double* __restrict__ xk, const double* __restrict__ rhs0,
                                                        const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
                                                        const int32_t* __restrict__ Jslot, double* __restrict__ out) {
+  pdl_wait();
   __shared__ double ts[512];
   __shared__ int32_t sl[512];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -773,6 +801,7 @@ __global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int
                                      const double* __restrict__ xk, const double* __restrict__ rhs0,
                                      const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
                                      double* __restrict__ out) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) {
     const int cov = rowcover[i];
@@ -787,6 +816,7 @@ __global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int
 // core C = D[R,:] (k x k, column-major) from the column cache
 __global__ void k_extract_core(const double* __restrict__ Bcols, int64_t ldb, int k, const int32_t* __restrict__ Rp,
                                const int32_t* __restrict__ Jslot, double* __restrict__ C, int64_t ld) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (i < k && t < k) C[(int64_t)t * ld + i] = Bcols[(int64_t)Jslot[t] * ldb + Rp[i]];
@@ -796,6 +826,7 @@ __global__ void k_extract_core(const double* __restrict__ Bcols, int64_t ldb, in
 __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict__ Bcols, int64_t ldb, int rows, int k,
                                                         const int32_t* __restrict__ Jslot, const double* __restrict__ x,
                                                         double* __restrict__ part) {
+  pdl_wait();
   __shared__ double sm[32];
   const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
   const int L = (rows + S - 1) / S;
@@ -826,6 +857,7 @@ __global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict_
 __global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
                                int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst,
                                Cand* __restrict__ win_out) {
+  pdl_wait();
   int64_t lv = lv_arg;
   if (cand && win_out && blockIdx.x == 0 && threadIdx.x == 0) *win_out = *cand;
   if (cand) {
@@ -872,6 +904,7 @@ __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict
                                                        const double* __restrict__ val, const int32_t* __restrict__ long_ids,
                                                        int nlong, const int32_t* __restrict__ short_ids, int nshort,
                                                        const double* __restrict__ w, double* __restrict__ seg_sum) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
   const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -940,6 +973,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_price_csc_fin(const int64_t* __restrict__ col_seg, const double* __restrict__ seg_sum,
                                                        int64_t n, int64_t m, int64_t c0, const double* __restrict__ w,
                                                        const uint8_t* __restrict__ vflag, double* __restrict__ out) {
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // LOCAL variable
   if (v < n) {
     double t = 0.0;
@@ -954,6 +988,7 @@ __global__ void __launch_bounds__(256) k_price_csc_fin(const int64_t* __restrict
 __global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                                      const double* __restrict__ val, int64_t m, int64_t c0, int64_t n_loc,
                                                      const double* __restrict__ xnb, double* __restrict__ out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= m) return;
@@ -976,6 +1011,7 @@ __global__ void __launch_bounds__(256) k_ftran_finish_csr(const int64_t* __restr
                                                           const double* __restrict__ xk, const double* __restrict__ rhs0,
                                                           const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
                                                           const int32_t* __restrict__ corepos, double* __restrict__ out) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gt < k) out[Jpos[gt]] = xk[gt];
@@ -997,6 +1033,7 @@ __global__ void __launch_bounds__(256) k_core_rhs_seg(const int64_t* __restrict_
                                                       const double* __restrict__ val, const int32_t* __restrict__ seg_col,
                                                       const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
                                                       int ncseg, const double* __restrict__ cov, double* __restrict__ csum) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= ncseg) return;
@@ -1010,6 +1047,7 @@ __global__ void __launch_bounds__(256) k_core_rhs_seg(const int64_t* __restrict_
 }
 __global__ void k_core_rhs_fin(const double* __restrict__ csum, const int32_t* __restrict__ cseg_first, int k,
                                const double* __restrict__ c, const int32_t* __restrict__ Jpos, double* __restrict__ x) {
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= k) return;
   double tsum = 0.0;
@@ -1022,6 +1060,7 @@ __global__ void __launch_bounds__(256) k_extract_core_seg(const int64_t* __restr
                                                           const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
                                                           int ncseg, const int32_t* __restrict__ corepos,
                                                           const int32_t* __restrict__ rowcore, double* __restrict__ C, int64_t ld) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= ncseg) return;
@@ -1035,6 +1074,7 @@ __global__ void __launch_bounds__(256) k_extract_core_seg(const int64_t* __restr
   }
 }
 __global__ void k_set_corepos(int32_t* __restrict__ corepos, const int32_t* __restrict__ corevar, int k, int clear) {
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < k) corepos[corevar[t]] = clear ? -1 : t;
 }
@@ -1048,6 +1088,7 @@ __global__ void __launch_bounds__(256) k_select_primal(const double* __restrict_
                                                         double* __restrict__ red_f, long long* __restrict__ red_i,
                                                         unsigned* counter, const double* __restrict__ xnb,
                                                         const int* __restrict__ flags, Cand* out) {
+  pdl_wait();
   __shared__ double smk[32];
   __shared__ long long smi[32];
   KeyIdx best{-INFINITY, LLONG_MAX};
@@ -1100,6 +1141,7 @@ __host__ __device__ __forceinline__ long long merge_ties(long long wt, double wk
 // queued behind the selection without a host round trip.  Every thread repeats the <= 8-way comparison.
 __global__ void __launch_bounds__(256) k_pick_winner(const char* __restrict__ recv, size_t xbytes, int world, int m,
                                                       double* __restrict__ colq, Cand* __restrict__ win) {
+  pdl_wait();
   int best = -1;
   double err = 0.0;
   for (int r = 0; r < world; ++r) {
@@ -1137,6 +1179,7 @@ constexpr int P2P_SLOT = 128;  // 64 B header + flag, padded
 __global__ void __launch_bounds__(256) k_exchange_p2p(PeerTable pt, int rank, int world, unsigned long long seq, int parity,
                                                        const Cand* __restrict__ mine, int m, size_t col_bytes, size_t box_off,
                                                        double* __restrict__ colq, Cand* __restrict__ win) {
+  pdl_wait();
   __shared__ Cand hdr[8];
   __shared__ int s_best;
   __shared__ int s_bad;
@@ -1211,6 +1254,7 @@ __device__ __forceinline__ double clamp_obj(double oc, unsigned f) {
 __global__ void __launch_bounds__(256) k_ratio_dual_1(const double* __restrict__ rc, const double* __restrict__ d,
                                                        const uint8_t* __restrict__ vflag, int64_t nt, int lds,
                                                        double* __restrict__ red_f, unsigned* counter, double* __restrict__ scal) {
+  pdl_wait();
   __shared__ double sm[32];
   double best = INFINITY;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
@@ -1234,6 +1278,7 @@ __global__ void __launch_bounds__(256) k_ratio_dual_1(const double* __restrict__
   }
 }
 __global__ void k_min_small(const double* __restrict__ vals, int cnt, double* __restrict__ out) {
+  pdl_wait();
   double b = INFINITY;
   for (int q = 0; q < cnt; ++q) b = fmin(b, vals[q]);
   *out = b;
@@ -1247,6 +1292,7 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
                                                        double* __restrict__ red_f, long long* __restrict__ red_i,
                                                        unsigned* counter, const int* __restrict__ flags, Cand* out,
                                                        int scan_slacks) {
+  pdl_wait();
   __shared__ double smk[32];
   __shared__ long long smi[32];
   __shared__ long long smc[32];
@@ -1307,6 +1353,7 @@ __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ a
                                                      int dse, const double* __restrict__ scal, double* __restrict__ eta_col,
                                                      int* __restrict__ flags, uint8_t* __restrict__ touched,
                                                      const uint8_t* __restrict__ touched_new) {
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
   if (eta_col) touched[r] = touched_new[r];  // the pushed eta stores every listed position of col_coeffs (solver.rs:1274-1284)
@@ -1332,6 +1379,7 @@ __global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ a
   if (eta_col) eta_col[r] = (r == row) ? 1.0 - 1.0 / coeff : a / coeff;  // 1276-1280
 }
 __global__ void k_flip_var(double* xnb, uint8_t* vflag, const double* lo, const double* hi, int64_t q, int64_t ql, double new_val) {
+  pdl_wait();
   xnb[ql] = new_val;
   unsigned f = vflag[ql] & MLP_FIXED;
   if (new_val == lo[q]) f |= MLP_AT_MIN;
@@ -1359,6 +1407,7 @@ __global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restr
                                                         int64_t c0, int64_t ng, const double* __restrict__ scal,
                                                         int* __restrict__ flags, double* __restrict__ red_f,
                                                         long long* __restrict__ red_i, unsigned* counter, DevRes* res, Cand* out) {
+  pdl_wait();
   __shared__ double smk[32];
   __shared__ long long smi[32];
   KeyIdx best{-INFINITY, LLONG_MAX};
@@ -1452,6 +1501,7 @@ __global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restr
 // partial of A x_N over this shard's columns (solver.rs:234-238). One CTA per row.
 __global__ void __launch_bounds__(256) k_row_dot(const double* __restrict__ A, int64_t lda, int64_t n,
                                                   const double* __restrict__ xnb, double* __restrict__ out) {
+  pdl_wait();
   __shared__ double sm[32];
   const int r = blockIdx.x;
   const double* row = A + (int64_t)r * lda;
@@ -1463,6 +1513,7 @@ __global__ void __launch_bounds__(256) k_row_dot(const double* __restrict__ A, i
 // basic_var_vals = rhs - sum over shards (in rank order) of the partial products
 __global__ void k_init_basic_vals(const double* __restrict__ parts, int world, int m, const double* __restrict__ rhs,
                                   double* __restrict__ xB) {
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= m) return;
   double tot = 0.0;
@@ -1472,6 +1523,7 @@ __global__ void k_init_basic_vals(const double* __restrict__ parts, int world, i
 // d_N = c_N - N^T y (recalc_obj_coeffs, solver.rs:1216-1222)
 __global__ void k_recalc_d(const double* __restrict__ cobj, const double* __restrict__ rc, const uint8_t* __restrict__ vflag,
                            int64_t nt, int64_t n, int64_t c0, int64_t ng, double* __restrict__ d) {
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= nt || (vflag[v] & MLP_BASIC)) return;
   const int64_t g = v < n ? c0 + v : ng + (v - n);
@@ -1483,6 +1535,7 @@ __global__ void __launch_bounds__(1024) k_recalc_obj(const double* __restrict__ 
                                                       const double* __restrict__ xB, int m, const double* __restrict__ xnb,
                                                       const uint8_t* __restrict__ vflag, int64_t n, int64_t c0, int64_t ng,
                                                       double* __restrict__ out3) {
+  pdl_wait();
   __shared__ double sm[32];
   double a = 0.0, b = 0.0, c = 0.0;
   for (int r = threadIdx.x; r < m; r += blockDim.x) a += cobj[bvar[r]] * xB[r];
@@ -1496,6 +1549,7 @@ __global__ void __launch_bounds__(1024) k_recalc_obj(const double* __restrict__ 
   if (threadIdx.x == 0) { out3[0] = ta; out3[1] = tb; out3[2] = tc; }
 }
 __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __restrict__ bvar, int m, double* __restrict__ out) {
+  pdl_wait();
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < m) out[r] = cobj[bvar[r]];
 }
@@ -1506,6 +1560,7 @@ __global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __re
 // row' = c - A^T g, rhs' = rhs - g . rhs_old (the same constraint; see DESIGN.md §8 for what that changes).
 __global__ void k_row_combine(double* __restrict__ row, const double* __restrict__ partial, const int32_t* __restrict__ count_ptr,
                               int64_t lda, int64_t n) {
+  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int C = price_chunks_for(*count_ptr);
@@ -1516,6 +1571,7 @@ __global__ void k_row_combine(double* __restrict__ row, const double* __restrict
 // out[0] = base - sum_i a_i b_i (single CTA, deterministic); used for rhs' and for the new basic value rhs - a . x
 __global__ void __launch_bounds__(1024) k_sub_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t cnt, double base,
                                                    const double* __restrict__ base_ptr, double* __restrict__ out) {
+  pdl_wait();
   __shared__ double sm[32];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += a[i] * b[i];
@@ -1525,6 +1581,7 @@ __global__ void __launch_bounds__(1024) k_sub_dot(const double* __restrict__ a, 
 // current value of every structural variable (Solver::get_value, 371-376) as a dense vector
 __global__ void k_struct_values(const double* __restrict__ xnb, const double* __restrict__ xB, const uint8_t* __restrict__ vflag,
                                 const int32_t* __restrict__ vpos, int64_t n, double* __restrict__ out) {
+  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) out[j] = (vflag[j] & MLP_BASIC) ? xB[vpos[j]] : xnb[j];
 }
@@ -1533,6 +1590,7 @@ __global__ void k_new_row_state(int64_t r, int64_t lv, int64_t gv, double smin, 
                                 const double* __restrict__ rhs_new, double* lo, double* hi, double* cobj, double* d, double* gam,
                                 double* xnb, uint8_t* vflag, int32_t* vpos, int32_t* bvar, double* xB, double* loB, double* hiB,
                                 double* w, double* rhs, int32_t* rowcover) {
+  pdl_wait();
   lo[gv] = smin; hi[gv] = smax; cobj[gv] = 0.0;
   d[lv] = 0.0; gam[lv] = 0.0; xnb[lv] = 0.0;
   vflag[lv] = MLP_BASIC; vpos[lv] = (int32_t)r;
@@ -1542,16 +1600,20 @@ __global__ void k_new_row_state(int64_t r, int64_t lv, int64_t gv, double smin, 
 // the cached basis columns get their entry of the new row
 __global__ void k_bcols_new_row(const double* __restrict__ rowA, const int32_t* __restrict__ slots, const int32_t* __restrict__ vars,
                                 int cnt, int64_t ldb, int64_t r, double* __restrict__ Bcols) {
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) Bcols[(int64_t)slots[t] * ldb + r] = rowA[vars[t]];
 }
 // primal_edge_sq_norms[c] += coeff^2 over the new tableau row (618-622)
 __global__ void k_add_sq(double* __restrict__ gam, const double* __restrict__ rc, const uint8_t* __restrict__ vflag, int64_t nt) {
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v < nt && !(vflag[v] & MLP_BASIC)) gam[v] += rc[v] * rc[v];
 }
-__global__ void k_copy1(double* dst, const double* src) { *dst = *src; }
-__global__ void k_set_var_state(uint8_t* vflag, int64_t lv, unsigned f) { vflag[lv] = (uint8_t)f; }
+__global__ void k_copy1(double* dst, const double* src) {
+  pdl_wait(); *dst = *src; }
+__global__ void k_set_var_state(uint8_t* vflag, int64_t lv, unsigned f) {
+  pdl_wait(); vflag[lv] = (uint8_t)f; }
 
 // ================================================================================================ host side
 // Two lanes (streams).  API calls keep sequential semantics through two marks: s0_mark is recorded on lane 0 at the end of
@@ -1814,7 +1876,11 @@ static mlp_status refactor_impl(mlp_engine* e) {
   e->ftran_var = -1;
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
-  ST(ensure_eta_capacity(e, 2 * k + 32));
+  {
+    // (the arena is dense, m doubles per eta: bounded at 16 GB — a full arena just forces the next refactorization)
+    const int64_t by_mem = std::max<int64_t>(1024, ((int64_t)16 << 30) / (8 * e->mld));
+    ST(ensure_eta_capacity(e, std::min<int64_t>(2 * k + 32, by_mem)));
+  }
   e->k = k;
   e->K = 0;
   CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
@@ -1883,7 +1949,25 @@ static mlp_status refactor_impl(mlp_engine* e) {
     {  // (L U)^-1, one CTA per column
       const size_t need = (size_t)k * sizeof(double);
       const int use_smem = need <= e->smem_optin ? 1 : 0;
-      if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+      if (k >= e->inv_blocked_min) {
+        // blocked substitution on all columns at once (dense_block.cuh): X = I; forward through L, backward through U
+        const int nbk = cdiv(k, 32);
+        LAUNCH(e, k_set_identity, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Cinv, e->kcap, (int)k);
+        for (int b = 0; b < nbk; ++b) {  // L y = e: X stays lower triangular, only columns < (b+1)*32 are non-zero
+          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0), nc = std::min<int>((int)k, r0 + nb), below = (int)k - (r0 + nb);
+          LAUNCH(e, k_tri_block<true>, cdiv(nc, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, nc);
+          if (below > 0)
+            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(below, GB_T), cdiv(nc, GB_T)), 256, 0, below, nc, nb, e->LUc + (size_t)r0 * e->kcap + r0 + nb,
+                   e->kcap, e->Cinv + r0, e->kcap, e->Cinv + r0 + nb, e->kcap);
+        }
+        for (int b = nbk - 1; b >= 0; --b) {  // U x = y over all k columns
+          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0);
+          LAUNCH(e, k_tri_block<false>, cdiv(k, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, (int)k);
+          if (r0 > 0)
+            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(r0, GB_T), cdiv(k, GB_T)), 256, 0, r0, (int)k, nb, e->LUc + (size_t)r0 * e->kcap, e->kcap,
+                   e->Cinv + r0, e->kcap, e->Cinv, e->kcap);
+        }
+      } else if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else if (k <= 2048) LAUNCH(e, k_core_inverse_pf<8>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
@@ -2196,6 +2280,8 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   CU(cudaGetDeviceProperties(&prop, device));
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
+  if (const char* v = getenv("MLP_PDL")) e->pdl = atoi(v) != 0;
+  if (const char* v = getenv("MLP_INV_BLOCKED_MIN")) e->inv_blocked_min = std::max<int64_t>(1, atoll(v));
   if (const char* v = getenv("MLP_ASYNC_PIVOT")) e->async_pivot = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
   if (const char* v = getenv("MLP_PRICE_TMA")) e->price_tma = atoi(v) != 0;
@@ -3201,10 +3287,12 @@ static mlp_status grow_rows(mlp_engine* e) {
 // f4: recalc_basic_var_vals (solver.rs:1177-1197; dead code there, the TODO at 1024-1025 asks for it every ~1000
 // pivots): x_B = B^-1 (rhs - N x_N) from scratch.  Off unless the caller asks (mlp_solver_set_recalc_period).
 __global__ void k_masked_xnb(const double* __restrict__ xnb, const uint8_t* __restrict__ vflag, int64_t nt, double* __restrict__ out) {
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (v < nt) out[v] = (vflag[v] & MLP_BASIC) ? 0.0 : xnb[v];
 }
 __global__ void k_sub_vec(double* __restrict__ y, const double* __restrict__ x, int64_t cnt) {
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cnt) y[i] -= x[i];
 }

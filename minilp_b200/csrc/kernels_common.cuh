@@ -1,6 +1,14 @@
 // Kernels of the pivot engine that do not depend on how the variables are sharded.  Included by engine.cu only.
 #pragma once
 // ------------------------------------------------------------------------------------------------ device helpers
+// Programmatic dependent launch: every kernel of the pivot path is launched with programmaticStreamSerializationAllowed, so
+// that its CTAs are scheduled while the previous kernel of the stream is still draining, and parks here until that kernel
+// has completed and its writes are visible (griddepcontrol.wait = cudaGridDependencySynchronize).  First statement of every
+// kernel: nothing before it touches memory, so the semantics are those of plain stream order.  Between the 25-40 short
+// dependent kernels of a pivot this hides most of the launch gap (MLP_PDL=0 launches the ordinary way; the cooperative
+// chain kernel is always launched the ordinary way).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restri
                                                            double* __restrict__ seg_ss, unsigned* counter,
                                                            int32_t* __restrict__ count, double* __restrict__ sumsq,
                                                            const uint8_t* __restrict__ mask) {
+  pdl_wait();
   __shared__ double sm[32];
   __shared__ int smi[32];
   const int i = blockIdx.x * CP_SEG + threadIdx.x;
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_count(const double* __restri
 }
 __global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restrict__ x, int m, const int32_t* __restrict__ seg_cnt,
                                                            int32_t* __restrict__ idx, double* __restrict__ val) {
+  pdl_wait();
   __shared__ int warp_cnt[32];
   __shared__ int base;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -211,6 +221,7 @@ __global__ void __launch_bounds__(CP_SEG) k_compact_write(const double* __restri
 // of the LU part, before the etas) and becomes `touched` when that column is pushed (k_pivot_rows).
 __global__ void k_touch_mark(const double* __restrict__ alpha0, const uint8_t* __restrict__ touched, int m,
                              uint8_t* __restrict__ touched_new) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) touched_new[i] = (uint8_t)((alpha0[i] != 0.0) | (touched[i] != 0));
 }
@@ -225,6 +236,7 @@ __global__ void k_touch_mark(const double* __restrict__ alpha0, const uint8_t* _
 template <bool TRI>
 __global__ void __launch_bounds__(256) k_mv_n(const double* __restrict__ M, int64_t ld, int n, const double* __restrict__ xin,
                                               const int32_t* __restrict__ gidx, double* __restrict__ y) {
+  pdl_wait();
   __shared__ double part[8][33];
   const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane;
@@ -257,6 +269,7 @@ __global__ void __launch_bounds__(256) k_mv_n(const double* __restrict__ M, int6
 template <bool TRI>
 __global__ void __launch_bounds__(256) k_mv_t(const double* __restrict__ M, int64_t ld, int n, const double* __restrict__ xin,
                                               const int32_t* __restrict__ sidx, double* __restrict__ y) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= n) return;
   const double* col = M + (int64_t)j * ld;
@@ -269,6 +282,7 @@ __global__ void __launch_bounds__(256) k_mv_t(const double* __restrict__ M, int6
 // column; the work vector lives in shared memory when it fits (use_smem), else in the output column itself.
 __global__ void __launch_bounds__(256) k_core_inverse(const double* __restrict__ LU, int64_t ld, int k, double* __restrict__ Cinv,
                                                        const int* __restrict__ flags, int use_smem) {
+  pdl_wait();
   extern __shared__ double smem_v[];
   if (flags[1]) return;
   const int j = blockIdx.x, tid = threadIdx.x;
@@ -301,6 +315,7 @@ __global__ void __launch_bounds__(256) k_core_inverse(const double* __restrict__
 template <int RPT>
 __global__ void __launch_bounds__(256) k_core_inverse_pf(const double* __restrict__ LU, int64_t ld, int k, double* __restrict__ Cinv,
                                                           const int* __restrict__ flags) {
+  pdl_wait();
   extern __shared__ double smem_v[];
   if (flags[1]) return;
   const int j = blockIdx.x, tid = threadIdx.x;
@@ -369,6 +384,7 @@ __global__ void __launch_bounds__(256) k_core_inverse_pf(const double* __restric
 // New row K of (I+G)^-1 when eta K with coupling row g (g[i] = E_i[r_K], i < K) is appended:
 // [[T,0],[g^T,1]]^-1 = [[T^-1,0],[-g^T T^-1,1]].  One warp per column.
 __global__ void __launch_bounds__(256) k_eta_inv_row(const double* __restrict__ g, double* __restrict__ Ginv, int64_t ld, int K) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j > K) return;
   double* col = Ginv + (int64_t)j * ld;
@@ -384,6 +400,7 @@ __global__ void __launch_bounds__(256) k_eta_inv_row(const double* __restrict__ 
 // the basis solve alpha_S = a_S - D1 x.
 __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M, int64_t ld, int rows, int cols,
                                                      const double* __restrict__ t, double* __restrict__ y) {
+  pdl_wait();
   __shared__ double ts[512];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double acc = i < rows ? y[i] : 0.0;
@@ -422,6 +439,7 @@ __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M
 __global__ void __launch_bounds__(256) k_tall_part(const double* __restrict__ M, int64_t ld, int rows, int cols,
                                                     const double* __restrict__ t, const int32_t* __restrict__ slots,
                                                     const int32_t* __restrict__ rowmask, double* __restrict__ part, int64_t pld) {
+  pdl_wait();
   __shared__ double ts[512];
   __shared__ int32_t sl[512];
   const int G = gridDim.y, g = blockIdx.y;
@@ -452,6 +470,7 @@ __global__ void __launch_bounds__(256) k_tall_part(const double* __restrict__ M,
 }
 // y[i] -= sum_g part[g][i]
 __global__ void k_sub_parts(const double* __restrict__ part, int G, int64_t pld, int rows, double* __restrict__ y) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows) return;
   double tsum = 0.0;
@@ -465,6 +484,7 @@ __global__ void k_sub_parts(const double* __restrict__ part, int G, int64_t pld,
 constexpr int GT_MAXSPLIT = 16;
 __global__ void __launch_bounds__(256) k_gemv_t_part(const double* __restrict__ M, int64_t ld, int rows, int cols,
                                                       const double* __restrict__ x, double* __restrict__ part) {
+  pdl_wait();
   __shared__ double sm[32];
   const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
   const int L = (rows + S - 1) / S;
@@ -486,6 +506,7 @@ __global__ void __launch_bounds__(256) k_gemv_t_part(const double* __restrict__ 
 }
 __global__ void k_gemv_t_fin(const double* __restrict__ part, int S, int cols, const double* __restrict__ base,
                              const int32_t* __restrict__ base_idx, double* __restrict__ out, int negate) {
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= cols) return;
   double tot = 0.0;
@@ -495,23 +516,28 @@ __global__ void k_gemv_t_fin(const double* __restrict__ part, int S, int cols, c
 }
 
 __global__ void k_gather_idx(const double* __restrict__ src, const int32_t* __restrict__ idx, int cnt, double* __restrict__ dst) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) dst[t] = src[idx[t]];
 }
 __global__ void k_scatter_idx(const double* __restrict__ src, const int32_t* __restrict__ idx, int cnt, double* __restrict__ dst) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) dst[idx[t]] = src[t];
 }
 // strided gather of one row of a column-major matrix: dst[j] = M[row + j*ld]
 __global__ void k_gather_row(const double* __restrict__ M, int64_t ld, int row, int cnt, double* __restrict__ dst) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) dst[t] = M[(int64_t)t * ld + row];
 }
 __global__ void k_fill(double* p, int64_t cnt, double v) {
+  pdl_wait();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) p[t] = v;
 }
 __global__ void k_set_unit(double* p, int64_t cnt, int64_t at) {
+  pdl_wait();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) p[t] = (t == at) ? 1.0 : 0.0;
 }
@@ -521,6 +547,7 @@ __global__ void k_set_unit(double* p, int64_t cnt, int64_t at) {
 __global__ void k_eta_scatter(const double* __restrict__ s, const int32_t* __restrict__ etaR,
                               const int32_t* __restrict__ etaPrev, const int32_t* __restrict__ etaHead, int K,
                               double* __restrict__ rhs) {
+  pdl_wait();
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= K || !etaHead[j]) return;
   double v = rhs[etaR[j]];
@@ -531,6 +558,7 @@ __global__ void k_eta_scatter(const double* __restrict__ s, const int32_t* __res
 // BTRAN head: rho_i = c[pos of slack i] on covered rows (U^T solve over the identity block); cov copy with zeros elsewhere
 __global__ void k_btran_start(const double* __restrict__ c, const int32_t* __restrict__ rowcover, int m,
                               double* __restrict__ out, double* __restrict__ cov) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const int p = rowcover[i];
@@ -598,6 +626,7 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
                                                     int32_t* __restrict__ Rp, int32_t* __restrict__ Rcnt, int* __restrict__ flags,
                                                     int32_t* __restrict__ aff_pos, int32_t* __restrict__ aff_src,
                                                     int32_t* __restrict__ aff_cnt, int32_t* __restrict__ perm_glob, int use_smem) {
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char lu_smem[];
   __shared__ double redk[32];
   __shared__ unsigned redrp[32];
@@ -744,6 +773,7 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double* __restrict__ C, int64
 __global__ void __launch_bounds__(256) k_lu_swap_solve(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
                                                         const int32_t* __restrict__ aff_pos, const int32_t* __restrict__ aff_src,
                                                         const int32_t* __restrict__ aff_cnt, const int* __restrict__ flags) {
+  pdl_wait();
   __shared__ double L11[LU_NB][LU_NB + 1];
   if (flags[1]) return;
   for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
@@ -776,6 +806,7 @@ __global__ void __launch_bounds__(256) k_lu_swap_solve(double* __restrict__ C, i
 // a core row is non-basic, so only structural columns count), and the number of stored entries of the core.
 __global__ void __launch_bounds__(256) k_core_row_counts(const double* __restrict__ C, int64_t ld, int k, int32_t* __restrict__ rcnt,
                                                           unsigned long long* __restrict__ total) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int c = 0;
   if (i < k)
@@ -788,6 +819,7 @@ __global__ void __launch_bounds__(256) k_core_row_counts(const double* __restric
 // exact zeros are not stored, lu.rs:253-255)
 __global__ void __launch_bounds__(256) k_count_offdiag(const double* __restrict__ C, int64_t ld, int k,
                                                         unsigned long long* __restrict__ total) {
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int t0 = blockIdx.y * 64, t1 = min(k, t0 + 64);
   int c = 0;
@@ -799,6 +831,7 @@ __global__ void __launch_bounds__(256) k_count_offdiag(const double* __restrict_
 constexpr int LU_NC = 16;
 __global__ void __launch_bounds__(256) k_lu_trailing(double* __restrict__ C, int64_t ld, int k, int j0, int nb,
                                                       const int* __restrict__ flags) {
+  pdl_wait();
   __shared__ double U[LU_NB][LU_NC];
   if (flags[1]) return;
   const int r0 = j0 + nb;
@@ -834,6 +867,7 @@ __global__ void __launch_bounds__(256) k_ratio_primal_1(const double* __restrict
                                                          const double* __restrict__ loB, const double* __restrict__ hiB, int m,
                                                          int sign, double max_step0, double* __restrict__ red_f,
                                                          unsigned* counter, double* __restrict__ scal) {
+  pdl_wait();
   __shared__ double sm[32];
   double best = INFINITY;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
@@ -862,6 +896,7 @@ __global__ void __launch_bounds__(256) k_ratio_primal_2(const double* __restrict
                                                          const double* __restrict__ loB, const double* __restrict__ hiB, int m,
                                                          int sign, const double* __restrict__ scal, double* __restrict__ red_f,
                                                          long long* __restrict__ red_i, unsigned* counter, DevRes* res) {
+  pdl_wait();
   __shared__ double smk[32];
   __shared__ long long smi[32];
   __shared__ long long smc[32];
@@ -917,6 +952,7 @@ __global__ void __launch_bounds__(256) k_select_row_dual(const double* __restric
                                                           const double* __restrict__ hiB, const double* __restrict__ w, int m,
                                                           int use_se, double* __restrict__ red_f, long long* __restrict__ red_i,
                                                           unsigned* counter, DevRes* res) {
+  pdl_wait();
   __shared__ double smk[32];
   __shared__ long long smi[32];
   KeyIdx best{-INFINITY, LLONG_MAX};
@@ -956,6 +992,7 @@ __global__ void __launch_bounds__(256) k_select_row_dual(const double* __restric
 // k_eta_scatter — see DESIGN.md "eta chain in closed form".
 __global__ void k_eta_grow(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ g,
                            int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int32_t* etaLast, int prev) {
+  pdl_wait();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < K) g[j] = E[(int64_t)j * lde + rK];
   if (j == 0) {

@@ -13,6 +13,7 @@
 
 __global__ void __launch_bounds__(256) k_t_hist(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t m,
                                                 int64_t n, int rows_per_chunk, int32_t* __restrict__ hist) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= m) return;
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(256) k_t_hist(const int64_t* __restrict__ ptr,
 }
 __global__ void __launch_bounds__(256) k_t_colscan(int32_t* __restrict__ hist, int64_t n, int chunks, int64_t* __restrict__ cnt,
                                                    int64_t* __restrict__ segs, int seg_len) {
+  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   int32_t run = 0;
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(256) k_t_colscan(int32_t* __restrict__ hist, i
 }
 // out[0..n] = exclusive prefix sums of in[0..n-1] (out[n] = total).  One CTA of 1024 threads.
 __global__ void __launch_bounds__(1024) k_scan_excl(const int64_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  pdl_wait();
   __shared__ int64_t part[1024];
   const int t = threadIdx.x;
   const int64_t per = (n + 1023) / 1024, b = (int64_t)t * per, e = b + per < n ? b + per : n;
@@ -54,6 +57,7 @@ __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr,
                                                 const double* __restrict__ val, int64_t m, int64_t n, int rows_per_chunk,
                                                 int32_t* __restrict__ hist, const int64_t* __restrict__ csc_ptr,
                                                 int32_t* __restrict__ csc_idx, double* __restrict__ csc_val) {
+  pdl_wait();
   const int c = blockIdx.x;
   int32_t* h = hist + (int64_t)c * n;
   const int64_t r0 = (int64_t)c * rows_per_chunk, r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
@@ -72,6 +76,7 @@ __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr,
 __global__ void __launch_bounds__(256) k_t_segs(const int64_t* __restrict__ csc_ptr, const int64_t* __restrict__ col_seg, int64_t n,
                                                 int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off,
                                                 int4* __restrict__ seg_desc) {
+  pdl_wait();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int64_t b = csc_ptr[j], e = csc_ptr[j + 1];

@@ -44,5 +44,39 @@ def test_deep_run_follows_the_oracle_trace(path, fused_max, monkeypatch):
     s.close()
 
 
+def test_deep_run_with_the_blocked_inverse(monkeypatch):
+    """Cores of 2048+ columns get their explicit inverse by blocked substitution (dense_block.cuh) instead of the
+    per-column kernels; MLP_INV_BLOCKED_MIN=48 forces that path on a golden run whose core grows past 700 columns:
+    the pivot sequence must not notice."""
+    monkeypatch.setenv("MLP_INV_BLOCKED_MIN", "48")
+    path = [p for p in GOLDEN if "k3_1800x1800" in p][0]
+    g = np.load(path)
+    kind, m, n, seed = (int(g[k]) for k in ("kind", "m", "n", "seed"))
+    lp = mb.synth_dense(kind, m, n, seed, threads=os.cpu_count() or 1)
+    s = mb.Solver.from_dense(lp)
+    budget = 2500
+    s.run(budget)
+    tr = s.trace()
+    want = g["seq"][:budget]
+    same = np.all(tr[:, :5].astype(np.int64) == want, axis=1)
+    assert same.all(), f"leaves the oracle's sequence at pivot {int(np.argmin(same))}"
+    assert s.engine.counters()["k_structural"] > 300
+    # the two inverse algorithms agree on B^-1 a_q to rounding
+    var = int(s.nb_vars()[5])
+    s.engine.refactor()
+    s.engine.ftran_col(var)
+    a_blocked = s.engine.download(5)
+    s.close()
+    monkeypatch.setenv("MLP_INV_BLOCKED_MIN", "1000000")
+    s2 = mb.Solver.from_dense(lp)
+    s2.run(budget)
+    assert np.array_equal(s2.trace()[:, :5], tr[:, :5])
+    s2.engine.refactor()
+    s2.engine.ftran_col(var)
+    a_col = s2.engine.download(5)
+    assert np.all(np.abs(a_blocked - a_col) <= 1e-9 * np.maximum(1.0, np.abs(a_col)))
+    s2.close()
+
+
 def test_golden_traces_exist():
     assert len(GOLDEN) >= 2
