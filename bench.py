@@ -66,8 +66,9 @@ def workload_name(a):
     if a.workload != "dense":
         return (f"{a.workload} {a.m}x{a.n}, {a.col_nnz:g} entries per column, seed {a.seed}, through free-format MPS text "
                 f"(BASELINE config 4: sparse price-out)")
+    which = "config 5: pricing column-sharded across the GPUs" if a.n == 4 * a.m else "config 3: full pivot loop with eta updates"
     fam = {0: "dense_pos", 1: "dense_box", 2: "dense_cover", 3: "dense_mixed"}[a.kind]
-    return f"{fam} {a.m}x{a.n} seed {a.seed} (BASELINE config 3: full pivot loop with eta updates)"
+    return f"{fam} {a.m}x{a.n} seed {a.seed} (BASELINE {which})"
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -138,7 +139,8 @@ def cpu_port_run(a, warmup, steps, budget_s, threads_for_gen):
         done_p += 1
         if fin:
             break
-    ties = {"tied_pivots": s.tied_pivots, "near_tie_pivots": s.near_tie_pivots, "tie_events": s.tie_events}
+    ties = {"tied_pivots": s.tied_pivots, "near_tie_pivots": s.near_tie_pivots, "tie_events": s.tie_events,
+            "sel_near_tie_pivots": s.sel_near_tie_pivots}
     return done_p, sec, m, note, s.trace().copy(), ties
 
 
@@ -157,6 +159,7 @@ def parity_against(trace_gpu, trace_cpu, ties, m_used, m):
     rel = float(np.max(np.abs(og - oc) / np.maximum(1.0, np.abs(oc)))) if upto else None
     return {"pivots_compared": k, "first_divergence": first, "oracle_tie_events": ties["tie_events"],
             "oracle_tied_pivots": ties["tied_pivots"], "oracle_near_tie_pivots": ties["near_tie_pivots"],
+            "oracle_selection_near_ties": ties.get("sel_near_tie_pivots"),
             "obj_rel_diff": rel, "tolerance": 1e-8, "oracle": "oracle/ C++ port, reference tie rule, same LP from the slack basis"}
 
 
@@ -182,7 +185,8 @@ def cpu_port_run_sparse(a, text, d, warmup, steps, budget_s):
         done_p = ref.pivots_done - warmup
         if fin:
             break
-    ties = {"tied_pivots": ref.tied_pivots, "near_tie_pivots": ref.near_tie_pivots, "tie_events": ref.tie_events}
+    ties = {"tied_pivots": ref.tied_pivots, "near_tie_pivots": ref.near_tie_pivots, "tie_events": ref.tie_events,
+            "sel_near_tie_pivots": ref.sel_near_tie_pivots}
     return done_p, sec, ref.trace().copy(), ties, setup
 
 

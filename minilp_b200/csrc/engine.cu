@@ -236,6 +236,13 @@ struct mlp_engine {
   std::vector<int32_t> h_csr_idx;                         // rebuilds the CSC copy and the segment table from it, as the reference
   std::vector<double> h_csr_val;                          // rebuilds its CSR and CSC (solver.rs:598-610)
   int32_t *corevar = nullptr, *corepos = nullptr, *rowcore = nullptr;  // kcap, n, m: see k_ftran_finish_csr
+  // compact row-major copy of the basic structural columns (rebuilt at every refactorization, k_ftran_finish_dcsr)
+  int64_t* dcsr_ptr = nullptr;     // mld + 1
+  int32_t* dcsr_idx = nullptr;     // dcsr_cap: core column of the entry
+  double* dcsr_val = nullptr;      // dcsr_cap
+  int64_t dcsr_cap = 0;
+  int32_t* dcsr_hist = nullptr;    // DCSR_CHUNKS x mld
+  int64_t* dcsr_cnt = nullptr;     // mld
   int64_t corevar_k = 0;                                  // entries of corevar currently marked in corepos
   // segment table of the CSC copy (<= CSC_SEG entries of one column per segment) and the core's slice of it
   int64_t nseg = 0;
@@ -305,6 +312,7 @@ struct mlp_engine {
   int price_split = 1;  // column slices per item of the last, partial round (MLP_PRICE_SPLIT)
   int lane1_ldg = 1;    // lane 1 prices out with the LDG kernel while lane 0 runs the bulk-copy one (MLP_LANE1_LDG=0: both bulk-copy)
   int64_t inv_blocked_min = 2048;  // cores at least this large get their inverse by blocked substitution (MLP_INV_BLOCKED_MIN)
+  int csc_stream = 1;      // CSC price-out loads the matrix evict-first (MLP_CSC_STREAM=0: default cache policy)
   int csc_grid = 148 * 5;  // CSC price-out: one full wave of resident CTAs (occupancy query at creation)
   int price_ctas = 6;   // resident price-out CTAs per SM (MLP_PRICE_CTAS); 6 = register-limited occupancy, measured 6.8 TB/s
                         // (4: 6.7, 3: 6.0, 2: 4.7 TB/s)
@@ -899,7 +907,9 @@ constexpr int PR_CSC_LONG = 64;  // a segment with more entries is "long": one p
 // strides (256 entries: values, row indices, then the gathers) in flight — bandwidth; SHORT ones are taken four at a time
 // with both strides of each issued together — latency.  Per segment the summation order is the same in both: lane-strided
 // partial sums in ascending entry order, then the fixed shuffle tree (bit-identical to the first version of the kernel).
-template <int MODE>
+// STREAM: matrix entries are loaded with the evict-first policy (__ldcs: a matrix larger than L2 is streamed once per pivot) or
+// with the default policy (the 117 MB of config 4 can stay partly L2-resident between two price-outs; MLP_CSC_STREAM picks).
+template <int MODE, bool STREAM>
 __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict__ desc, const int32_t* __restrict__ idx,
                                                        const double* __restrict__ val, const int32_t* __restrict__ long_ids,
                                                        int nlong, const int32_t* __restrict__ short_ids, int nshort,
@@ -921,8 +931,8 @@ __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict
       for (int u = 0; u < 8; ++u) {
         const int o = o0 + 32 * u;
         const bool ok = o < len;
-        a[u] = ok ? __ldcs(val + b + o) : 0.0;
-        r[u] = (MODE == 0 && ok) ? __ldcs(idx + b + o) : 0;
+        a[u] = ok ? (STREAM ? __ldcs(val + b + o) : __ldg(val + b + o)) : 0.0;
+        r[u] = (MODE == 0 && ok) ? (STREAM ? __ldcs(idx + b + o) : __ldg(idx + b + o)) : 0;
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u)
@@ -955,8 +965,8 @@ __global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict
       for (int it = 0; it < 2; ++it) {
         const int o = lane + 32 * it;
         const bool ok = o < len[q];
-        a[q][it] = ok ? __ldcs(val + b[q] + o) : 0.0;
-        r[q][it] = (MODE == 0 && ok) ? __ldcs(idx + b[q] + o) : 0;
+        a[q][it] = ok ? (STREAM ? __ldcs(val + b[q] + o) : __ldg(val + b[q] + o)) : 0.0;
+        r[q][it] = (MODE == 0 && ok) ? (STREAM ? __ldcs(idx + b[q] + o) : __ldg(idx + b[q] + o)) : 0;
       }
 #pragma unroll
     for (int q = 0; q < PR_CSC_U; ++q) {
@@ -1654,8 +1664,12 @@ static mlp_status price_list(mlp_engine* e, Lane& ln, const int32_t* rows, const
   if (e->sparse) {
     // slack_vals is the dense multiplier vector the list was compacted from
     double* ssum = &ln == &e->lane[0] ? e->seg_sum : e->seg_sum + e->nseg;
-    LAUNCHS(e, ln.st, k_price_csc_seg<0>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
-            e->seg_short, (int)e->nseg_short, slack_vals, ssum);
+    if (e->csc_stream)
+      LAUNCHS(e, ln.st, (k_price_csc_seg<0, true>), e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
+              e->seg_short, (int)e->nseg_short, slack_vals, ssum);
+    else
+      LAUNCHS(e, ln.st, (k_price_csc_seg<0, false>), e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
+              e->seg_short, (int)e->nseg_short, slack_vals, ssum);
     LAUNCHS(e, ln.st, k_price_csc_fin<0>, cdiv(e->nt, 256), 256, 0, e->col_seg, ssum, e->n, e->m, e->c0, slack_vals, e->vflag, out);
   } else {
     // Lane 1 (the tableau-row price-out, support <= k+1 rows) runs BESIDE lane 0's dense N^T v price-out.  The bulk-copy
@@ -1735,8 +1749,8 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
   const int Gk = tall_groups(e, m, k);
   if (e->sparse) {
-    LAUNCHS(e, ln.st, k_ftran_finish_csr, cdiv(std::max<int64_t>((int64_t)m * 32, k), 256), 256, 0, e->csr_ptr, e->csr_idx, e->csr_val,
-            m, k, ln.xk, rhs0, e->rowcover, e->Jpos, e->corepos, out);
+    LAUNCHS(e, ln.st, k_ftran_finish_dcsr, cdiv(std::max(m, k), 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, m, k, ln.xk, rhs0,
+            e->rowcover, e->Jpos, out);
   } else if (Gk > 1) {
     LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), Gk), 256, 0, e->Bcols, e->mld, m, k, ln.xk, e->Jslot, e->rowcover, ln.gpart, e->mld);
     LAUNCHS(e, ln.st, k_ftran_finish_parts, cdiv(std::max(m, k), 256), 256, 0, ln.gpart, Gk, e->mld, m, k, ln.xk, rhs0, e->rowcover,
@@ -1842,6 +1856,42 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = fal
   return MLP_OK;
 }
 
+// Compact row-major copy of the k basic structural columns (core column ids), built on the device from the CSC copy with the
+// same segmented counting transpose as the CSC copy itself (sparse_build.cuh; input "rows" = the core columns in core
+// order, so every row of the copy lists its entries in ascending core column).  jvar: the core columns' variables, already
+// uploaded to e->corevar.
+constexpr int DCSR_CHUNKS = 64;
+static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jvar) {
+  const int64_t m = e->m, k = (int64_t)jvar.size();
+  if (!e->dcsr_ptr) {
+    ST(dev_alloc(&e->dcsr_ptr, (size_t)e->mld + 1));
+    ST(dev_alloc(&e->dcsr_hist, (size_t)DCSR_CHUNKS * e->mld));
+    ST(dev_alloc(&e->dcsr_cnt, (size_t)e->mld));
+  }
+  if (k == 0) {
+    CU(cudaMemsetAsync(e->dcsr_ptr, 0, (size_t)(m + 1) * sizeof(int64_t), e->stream));
+    return MLP_OK;
+  }
+  int64_t nz = 0;
+  for (int32_t v : jvar) nz += e->h_csc_ptr[(size_t)v + 1] - e->h_csc_ptr[(size_t)v];
+  if (nz > e->dcsr_cap) {
+    CU(cudaStreamSynchronize(e->lane[1].st));
+    dev_free(e->dcsr_idx); dev_free(e->dcsr_val);
+    e->dcsr_cap = std::max<int64_t>(2 * nz, 1 << 16);
+    ST(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); ST(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap));
+  }
+  const int cpc = (int)((k + DCSR_CHUNKS - 1) / DCSR_CHUNKS);   // core columns per chunk
+  const int chunks = (int)((k + cpc - 1) / cpc);
+  CU(cudaMemsetAsync(e->dcsr_hist, 0, (size_t)chunks * m * sizeof(int32_t), e->stream));
+  LAUNCH(e, k_t_hist, cdiv(k * 32, 256), 256, 0, e->csc_ptr, e->csc_idx, k, m, cpc, e->dcsr_hist, (const int32_t*)e->corevar);
+  // per constraint row: scan over the chunks, row counts (the segment output of k_t_colscan is not needed: reuse dcsr_cnt twice)
+  LAUNCH(e, k_t_colscan, cdiv(m, 256), 256, 0, e->dcsr_hist, m, chunks, e->dcsr_cnt, (int64_t*)e->lane[0].wm, CSC_SEG);
+  LAUNCH(e, k_scan_excl, 1, 1024, 0, e->dcsr_cnt, m, e->dcsr_ptr);
+  LAUNCH(e, k_t_fill, chunks, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, k, m, cpc, e->dcsr_hist, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val,
+         (const int32_t*)e->corevar);
+  return MLP_OK;
+}
+
 // BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.
 static mlp_status refactor_impl(mlp_engine* e) {
   const int64_t m = e->m, ng = e->ng;
@@ -1919,6 +1969,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
       CU(cudaStreamSynchronize(e->stream));
     }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+    if (e->sparse) ST(build_core_rows(e, jvar));
     if (e->sparse) {
       CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
       LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
@@ -1981,6 +2032,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
     ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
   } else {
+    if (e->sparse) ST(build_core_rows(e, jvar));  // empty
     if (e->sparse && e->corevar_k > 0) {
       LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
       e->corevar_k = 0;
@@ -2212,6 +2264,7 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
   dev_free(e->seg_desc); dev_free(e->seg_long); dev_free(e->seg_short);
+  dev_free(e->dcsr_ptr); dev_free(e->dcsr_idx); dev_free(e->dcsr_val); dev_free(e->dcsr_hist); dev_free(e->dcsr_cnt);
   dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
   dev_free(e->vflag); dev_free(e->vpos); dev_free(e->bvar); dev_free(e->xB); dev_free(e->loB); dev_free(e->hiB); dev_free(e->w);
@@ -2281,6 +2334,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
   if (const char* v = getenv("MLP_PDL")) e->pdl = atoi(v) != 0;
+  if (const char* v = getenv("MLP_CSC_STREAM")) e->csc_stream = atoi(v) != 0;
   if (const char* v = getenv("MLP_INV_BLOCKED_MIN")) e->inv_blocked_min = std::max<int64_t>(1, atoll(v));
   if (const char* v = getenv("MLP_ASYNC_PIVOT")) e->async_pivot = atoi(v) != 0;
   if (const char* v = getenv("MLP_PRICE_CTAS")) e->price_ctas = std::max(1, std::min(8, atoi(v)));
@@ -2297,7 +2351,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   }
   {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_price_csc_seg<0>, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_price_csc_seg<0, true>, 256, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 4; }
     e->csc_grid = e->sm_count * nb;
   }
   choose_price_tiling(e->lda, m, e->sm_count, &e->price_tile, &e->price_split);
@@ -2488,11 +2542,12 @@ static mlp_status sparse_upload(mlp_engine* e, int64_t m) {
     A(dev_alloc(&hist, (size_t)chunks * n)); A(dev_alloc(&cnt, n)); A(dev_alloc(&segs, n));
     if (st == MLP_OK) {
       cudaMemsetAsync(hist, 0, (size_t)chunks * n * sizeof(int32_t), e->stream);
-      LAUNCH(e, k_t_hist, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, m, n, rpc, hist);
+      LAUNCH(e, k_t_hist, cdiv(m * 32, 256), 256, 0, e->csr_ptr, e->csr_idx, m, n, rpc, hist, (const int32_t*)nullptr);
       LAUNCH(e, k_t_colscan, cdiv(n, 256), 256, 0, hist, n, chunks, cnt, segs, CSC_SEG);
       LAUNCH(e, k_scan_excl, 1, 1024, 0, cnt, n, e->csc_ptr);
       LAUNCH(e, k_scan_excl, 1, 1024, 0, segs, n, e->col_seg);
-      LAUNCH(e, k_t_fill, chunks, 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, n, rpc, hist, e->csc_ptr, e->csc_idx, e->csc_val);
+      LAUNCH(e, k_t_fill, chunks, 256, 0, e->csr_ptr, e->csr_idx, e->csr_val, m, n, rpc, hist, e->csc_ptr, e->csc_idx, e->csc_val,
+             (const int32_t*)nullptr);
       // the host keeps the two pointer arrays: column counts for LUFactors::nnz, segment ranges for the core's segment list
       A(d2h(e, e->h_csc_ptr.data(), e->csc_ptr, (n + 1) * sizeof(int64_t)));
       A(d2h(e, e->h_col_seg.data(), e->col_seg, (n + 1) * sizeof(int64_t)));
@@ -2700,7 +2755,7 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
     // |a_j|^2 + 1 (solver.rs:297-299): all m rows, unit weights
     if (e->sparse)
     {
-      LAUNCH(e, k_price_csc_seg<1>, e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
+      LAUNCH(e, (k_price_csc_seg<1, true>), e->csc_grid, 256, 0, e->seg_desc, e->csc_idx, e->csc_val, e->seg_long, (int)e->nseg_long,
              e->seg_short, (int)e->nseg_short, (const double*)nullptr, e->seg_sum);
       LAUNCH(e, k_price_csc_fin<1>, cdiv(nt, 256), 256, 0, e->col_seg, e->seg_sum, n, m, e->c0, (const double*)nullptr, e->vflag, e->gam);
     }
@@ -3253,6 +3308,13 @@ static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** ou
     cp(e->etaLast, src->etaLast, ml * 4);
   }
   cp(e->touched, src->touched, ml); cp(e->touched_new, src->touched_new, ml);
+  if (st == MLP_OK && src->sparse && src->dcsr_ptr) {
+    A(dev_alloc(&e->dcsr_ptr, (size_t)e->mld + 1)); A(dev_alloc(&e->dcsr_hist, (size_t)DCSR_CHUNKS * e->mld)); A(dev_alloc(&e->dcsr_cnt, (size_t)e->mld));
+    e->dcsr_cap = src->dcsr_cap;
+    if (e->dcsr_cap > 0) { A(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); A(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap)); }
+    cp(e->dcsr_ptr, src->dcsr_ptr, (ml + 1) * 8);
+    if (e->dcsr_cap > 0) { cp(e->dcsr_idx, src->dcsr_idx, (size_t)e->dcsr_cap * 4); cp(e->dcsr_val, src->dcsr_val, (size_t)e->dcsr_cap * 8); }
+  }
   if (st == MLP_OK && cudaStreamSynchronize(e->stream) != cudaSuccess) { set_err("clone: copy failed"); st = MLP_CUDA_ERROR; }
   if (st != MLP_OK) { destroy_engine(e); return st; }
   e->nt = src->nt;

@@ -11,14 +11,19 @@
 // Deterministic, bit-identical to the host counting transpose (tests/test_sparse_gpu.py compares them).
 #pragma once
 
+// `list` (optional): the input rows are list[0..m) instead of 0..m — used to transpose a SUBSET of the columns of the CSC
+// copy (the basic structural columns, at every refactorization) into a compact row-major copy whose column ids are the
+// positions in the list.
 __global__ void __launch_bounds__(256) k_t_hist(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t m,
-                                                int64_t n, int rows_per_chunk, int32_t* __restrict__ hist) {
+                                                int64_t n, int rows_per_chunk, int32_t* __restrict__ hist,
+                                                const int32_t* __restrict__ list) {
   pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= m) return;
+  const int64_t src = list ? list[r] : r;
   int32_t* h = hist + (r / rows_per_chunk) * n;
-  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) atomicAdd(h + idx[t], 1);
+  for (int64_t t = ptr[src] + lane; t < ptr[src + 1]; t += 32) atomicAdd(h + idx[t], 1);
 }
 __global__ void __launch_bounds__(256) k_t_colscan(int32_t* __restrict__ hist, int64_t n, int chunks, int64_t* __restrict__ cnt,
                                                    int64_t* __restrict__ segs, int seg_len) {
@@ -56,13 +61,15 @@ __global__ void __launch_bounds__(1024) k_scan_excl(const int64_t* __restrict__ 
 __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                                 const double* __restrict__ val, int64_t m, int64_t n, int rows_per_chunk,
                                                 int32_t* __restrict__ hist, const int64_t* __restrict__ csc_ptr,
-                                                int32_t* __restrict__ csc_idx, double* __restrict__ csc_val) {
+                                                int32_t* __restrict__ csc_idx, double* __restrict__ csc_val,
+                                                const int32_t* __restrict__ list) {
   pdl_wait();
   const int c = blockIdx.x;
   int32_t* h = hist + (int64_t)c * n;
   const int64_t r0 = (int64_t)c * rows_per_chunk, r1 = r0 + rows_per_chunk < m ? r0 + rows_per_chunk : m;
   for (int64_t r = r0; r < r1; ++r) {
-    for (int64_t t = ptr[r] + threadIdx.x; t < ptr[r + 1]; t += blockDim.x) {
+    const int64_t src = list ? list[r] : r;
+    for (int64_t t = ptr[src] + threadIdx.x; t < ptr[src + 1]; t += blockDim.x) {
       const int32_t j = idx[t];
       const int32_t k = h[j];
       h[j] = k + 1;
@@ -72,6 +79,25 @@ __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr,
     }
     __syncthreads();
   }
+}
+// FTRAN tail over the compact row-major copy of the basic structural columns (dptr / didx / dval, column ids = core
+// columns): alpha[cov_i] = a_i - sum_q dval[q] x[didx[q]], entries of a row in ascending core-column order.  A row holds
+// nnz(D) / m entries on average (2 at k = 2000 on config 4, 15 at k = 15 000): one thread per row.  Replaces the pass over
+// the WHOLE CSR copy (12 nnz bytes = 117 MB per FTRAN on config 4, two FTRANs per pivot) by 12 nnz(D) bytes.
+__global__ void __launch_bounds__(256) k_ftran_finish_dcsr(const int64_t* __restrict__ dptr, const int32_t* __restrict__ didx,
+                                                           const double* __restrict__ dval, int m, int k,
+                                                           const double* __restrict__ xk, const double* __restrict__ rhs0,
+                                                           const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
+                                                           double* __restrict__ out) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k) out[Jpos[i]] = xk[i];
+  if (i >= m) return;
+  const int cov = rowcover[i];
+  if (cov < 0) return;
+  double acc = 0.0;
+  for (int64_t q = dptr[i]; q < dptr[i + 1]; ++q) acc += dval[q] * xk[didx[q]];
+  out[cov] = rhs0[i] - acc;
 }
 __global__ void __launch_bounds__(256) k_t_segs(const int64_t* __restrict__ csc_ptr, const int64_t* __restrict__ col_seg, int64_t n,
                                                 int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off,

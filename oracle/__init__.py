@@ -181,6 +181,9 @@ class _State:
     near_tie_pivots = property(lambda s: s._i64(15))
     first_tied_pivot = property(lambda s: s._i64(16))
     first_near_tie_pivot = property(lambda s: s._i64(17))
+    # selections (pricing, dual row) whose runner-up scored within 1e-9 of the winner: same rule on both sides, rounding decides
+    sel_near_tie_pivots = property(lambda s: s._i64(18))
+    first_sel_near_tie_pivot = property(lambda s: s._i64(19))
 
     def _farr(self, what):
         cap = self.num_vars + 2 * self.num_constraints + 8

@@ -653,6 +653,16 @@ struct Solver {  // solver.rs:14-58
   // within NEAR_TIE relative (near_tie_pivots >= tied_pivots: the decision is within rounding of the summation order).
   static constexpr double NEAR_TIE = 1e-9;
   int64_t tied_pivots = 0, near_tie_pivots = 0, first_tied_pivot = -1, first_near_tie_pivot = -1;
+  // The two SELECTIONS (pricing 696-739, dual row 855-917) use the same rule on both sides — strict '>', lowest index on exact
+  // ties — so only rounding can make them differ: a pivot is recorded here when the runner-up's score is within NEAR_TIE of the
+  // winner's (the order of two such scores is not defined beyond the rounding of the sums that produced them).
+  int64_t sel_near_tie_pivots = 0, first_sel_near_tie_pivot = -1;
+  void note_selection(double best, double second) {
+    if (second >= best * (1.0 - NEAR_TIE) && best > 0.0) {
+      sel_near_tie_pivots += 1;
+      if (first_sel_near_tie_pivot < 0) first_sel_near_tie_pivot = pivots_done;
+    }
+  }
   void note_ties(int64_t exact_cnt, int64_t near_cnt) {  // counts include the winner itself
     if (exact_cnt > 1) { tied_pivots += 1; if (first_tied_pivot < 0) first_tied_pivot = pivots_done; }
     if (near_cnt > 1) { near_tie_pivots += 1; if (first_near_tie_pivot < 0) first_near_tie_pivot = pivots_done; }
@@ -825,15 +835,17 @@ struct Solver {  // solver.rs:14-58
   bool choose_pivot(PivotInfo& out) {
     bool have_col = false;
     usize entering_c = 0;
-    double best_score = -INF;
+    double best_score = -INF, second_score = -INF;
     for (usize col = 0; col < nb_var_obj_coeffs.size(); ++col) {
       double obj_coeff = nb_var_obj_coeffs[col];
       const NonBasicVarState& st = nb_var_states[col];
       if ((st.at_min && obj_coeff > -EPS) || (st.at_max && obj_coeff < EPS)) continue;  // 705-708
       double score = enable_primal_steepest_edge ? obj_coeff * obj_coeff / primal_edge_sq_norms[col] : std::fabs(obj_coeff);
-      if (score > best_score) { have_col = true; entering_c = col; best_score = score; }
+      if (score > best_score) { have_col = true; entering_c = col; second_score = best_score; best_score = score; }
+      else if (score > second_score) second_score = score;  // instrumentation only
     }
     if (!have_col) return false;
+    note_selection(best_score, second_score);
 
     double entering_cur_val = nb_var_vals[entering_c];
     bool entering_diff_sign = nb_var_obj_coeffs[entering_c] < 0.0;  // 743
@@ -902,7 +914,7 @@ struct Solver {  // solver.rs:14-58
   bool choose_pivot_row_dual(usize& row_out, double& new_val_out) const {
     bool have = false;
     usize leaving_r = 0;
-    double max_score = -INF;
+    double max_score = -INF, second = -INF;
     for (usize r = 0; r < basic_var_vals.size(); ++r) {
       double val = basic_var_vals[r], mn = basic_var_mins[r], mx = basic_var_maxs[r];
       double infeas;
@@ -910,9 +922,11 @@ struct Solver {  // solver.rs:14-58
       else if (val > mx + EPS) infeas = val - mx;
       else continue;
       double score = enable_dual_steepest_edge ? infeas * infeas / dual_edge_sq_norms[r] : infeas;
-      if (score > max_score) { have = true; leaving_r = r; max_score = score; }
+      if (score > max_score) { have = true; leaving_r = r; second = max_score; max_score = score; }
+      else if (score > second) second = score;  // instrumentation only
     }
     if (!have) return false;
+    const_cast<Solver*>(this)->note_selection(max_score, second);
     double val = basic_var_vals[leaving_r];
     if (val < basic_var_mins[leaving_r]) new_val_out = basic_var_mins[leaving_r];
     else if (val > basic_var_maxs[leaving_r]) new_val_out = basic_var_maxs[leaving_r];

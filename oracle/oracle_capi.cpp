@@ -68,6 +68,8 @@ template <class Sv> int64_t get_i64(const Sv& s, int what) {
     case 15: return s.near_tie_pivots;
     case 16: return s.first_tied_pivot;
     case 17: return s.first_near_tie_pivot;
+    case 18: return s.sel_near_tie_pivots;
+    case 19: return s.first_sel_near_tie_pivot;
     default: return -1;
   }
 }

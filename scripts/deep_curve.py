@@ -32,6 +32,13 @@ else:  # BASELINE config 4: through MPS text
 s.set_refactor_factor(a.refactor_factor)
 e = s.engine
 s.set_record_trace(True)
+def infeasible_rows(e):
+    """rows whose basic variable is outside its bounds by more than EPS (what choose_pivot_row_dual still has to repair)"""
+    import numpy as np
+    xb, lo, hi = e.download(3), e.download(8), e.download(9)
+    return int(np.sum((xb < lo - 1e-8) | (xb > hi + 1e-8)))
+
+
 if a.skip > 0:
     s.run(a.skip)
 t_start = time.perf_counter()
@@ -57,7 +64,7 @@ while not done and s.pivots_done < a.max_pivots and time.perf_counter() - t_star
                       "other_ms_per_pivot": (ms - pr["price_v_ms"]) / max(piv, 1),
                       "launches_per_pivot": (c1["kernel_launches"] - c0["kernel_launches"]) / max(piv, 1),
                       "refactors": c1["refactors"] - c0["refactors"], "refactor_wall_ms_per_pivot": (s.timers()[1] - rf0) * 1e3 / max(piv, 1),
-                      "lu_nnz": c1["lu_nnz"], "obj": s.cur_obj_val, "done": bool(done)}), flush=True)
+                      "lu_nnz": c1["lu_nnz"], "obj": s.cur_obj_val, "primal_infeasible_rows": infeasible_rows(e), "done": bool(done)}), flush=True)
 print(json.dumps({"summary": True, "workload": bench.workload_name(a), "pivots": s.pivots_done, "optimal": bool(done),
                   "device_seconds": tot_ms / 1e3, "objective": s.cur_obj_val, "ties": s.tie_stats(), "setup": setup}), flush=True)
 s.close()

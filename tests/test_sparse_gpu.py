@@ -9,6 +9,7 @@ import minilp_b200 as mb
 import oracle
 from minilp_b200 import mps, synth
 
+from parity_util import assert_sequence_parity
 from test_parity_gpu import assert_same_state, assert_same_trace, close
 
 pytestmark = pytest.mark.gpu
@@ -50,10 +51,15 @@ def test_sparse_engine_matches_oracle_via_mps(gen, args):
     p = mps.MpsFile.parse(text, d).problem
     gpu = solver_from_problem(p, "sparse")
     assert gpu.run()
-    assert_same_trace(gpu.trace(), ref.trace(), ref, gpu)
+    # (500, 350, seed 5) has ONE contested decision — at pivot 232 two dual rows score infeas^2 / w = 0.0309497963942317 and
+    # ...2321, 1.4e-14 apart: the oracle records it (first_sel_near_tie_pivot) and the sequences must agree up to there;
+    # every other case is uncontested and must agree to the end.  The optimum is the same either way.
+    contested = assert_sequence_parity(gpu.trace(), ref.trace(), ref, gpu)
+    assert contested == (args == (500, 350, 7.0, 5))
     assert close(gpu.cur_obj_val, ref.cur_obj_val)
-    assert close(gpu.values(), ref.values())
-    assert_same_state(gpu, ref, 1e-7)
+    if not contested:
+        assert close(gpu.values(), ref.values())
+        assert_same_state(gpu, ref, 1e-7)
     # the same LP in dense storage reaches the same optimum (its refactorization cadence differs — LUFactors::nnz counts
     # stored entries — so near-ties may resolve differently along the way: only the end state is compared)
     dense = solver_from_problem(p, "dense")
