@@ -1860,7 +1860,7 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = fal
 // same segmented counting transpose as the CSC copy itself (sparse_build.cuh; input "rows" = the core columns in core
 // order, so every row of the copy lists its entries in ascending core column).  jvar: the core columns' variables, already
 // uploaded to e->corevar.
-constexpr int DCSR_CHUNKS = 64;
+constexpr int DCSR_CHUNKS = 128;
 static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jvar) {
   const int64_t m = e->m, k = (int64_t)jvar.size();
   if (!e->dcsr_ptr) {
@@ -1880,15 +1880,16 @@ static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jva
     e->dcsr_cap = std::max<int64_t>(2 * nz, 1 << 16);
     ST(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); ST(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap));
   }
-  const int cpc = (int)((k + DCSR_CHUNKS - 1) / DCSR_CHUNKS);   // core columns per chunk
-  const int chunks = (int)((k + cpc - 1) / cpc);
+  const int ncseg = (int)e->ncseg;                                   // the core's segments (e->cseg_id), in core-column order
+  const int spc = (ncseg + DCSR_CHUNKS - 1) / DCSR_CHUNKS;          // segments per chunk
+  const int chunks = (ncseg + spc - 1) / spc;
   CU(cudaMemsetAsync(e->dcsr_hist, 0, (size_t)chunks * m * sizeof(int32_t), e->stream));
-  LAUNCH(e, k_t_hist, cdiv(k * 32, 256), 256, 0, e->csc_ptr, e->csc_idx, k, m, cpc, e->dcsr_hist, (const int32_t*)e->corevar);
-  // per constraint row: scan over the chunks, row counts (the segment output of k_t_colscan is not needed: reuse dcsr_cnt twice)
+  LAUNCH(e, k_d_hist, cdiv((int64_t)ncseg * 32, 256), 256, 0, (const int4*)e->seg_desc, e->cseg_id, ncseg, e->csc_idx, m, spc, e->dcsr_hist);
+  // per constraint row: scan over the chunks + row counts (k_t_colscan's segment output is not needed: lane scratch)
   LAUNCH(e, k_t_colscan, cdiv(m, 256), 256, 0, e->dcsr_hist, m, chunks, e->dcsr_cnt, (int64_t*)e->lane[0].wm, CSC_SEG);
   LAUNCH(e, k_scan_excl, 1, 1024, 0, e->dcsr_cnt, m, e->dcsr_ptr);
-  LAUNCH(e, k_t_fill, chunks, 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, k, m, cpc, e->dcsr_hist, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val,
-         (const int32_t*)e->corevar);
+  LAUNCH(e, k_d_fill, chunks, 256, 0, (const int4*)e->seg_desc, e->cseg_id, ncseg, e->csc_idx, e->csc_val, m, spc, e->corepos, e->dcsr_hist,
+         e->dcsr_ptr, e->dcsr_idx, e->dcsr_val);
   return MLP_OK;
 }
 

@@ -80,6 +80,46 @@ __global__ void __launch_bounds__(256) k_t_fill(const int64_t* __restrict__ ptr,
     __syncthreads();
   }
 }
+// Compact row-major copy of the basic structural columns, built from their SEGMENTS (<= CSC_SEG entries each; the basis of a
+// netlib-like LP holds columns of 10^4..10^5 entries next to columns of two, so the unit of work must not be a column).
+// cseg_id[j]: j-th segment of the core in core-column order; chunk = j / segs_per_chunk.  Splitting a column over chunks is
+// harmless: a (row, column) pair occurs once, so the order of a row's entries — ascending core column — only depends on the
+// order of the segments.
+__global__ void __launch_bounds__(256) k_d_hist(const int4* __restrict__ seg_desc, const int32_t* __restrict__ cseg_id, int ncseg,
+                                                const int32_t* __restrict__ idx, int64_t m, int segs_per_chunk,
+                                                int32_t* __restrict__ hist) {
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int j = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (j >= ncseg) return;
+  const int4 d = seg_desc[cseg_id[j]];
+  const int64_t b = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
+  int32_t* h = hist + (int64_t)(j / segs_per_chunk) * m;
+  for (int o = lane; o < d.z; o += 32) atomicAdd(h + idx[b + o], 1);
+}
+__global__ void __launch_bounds__(256) k_d_fill(const int4* __restrict__ seg_desc, const int32_t* __restrict__ cseg_id, int ncseg,
+                                                const int32_t* __restrict__ idx, const double* __restrict__ val, int64_t m,
+                                                int segs_per_chunk, const int32_t* __restrict__ corepos, int32_t* __restrict__ hist,
+                                                const int64_t* __restrict__ dptr, int32_t* __restrict__ didx, double* __restrict__ dval) {
+  pdl_wait();
+  const int c = blockIdx.x;
+  int32_t* h = hist + (int64_t)c * m;
+  const int j0 = c * segs_per_chunk, j1 = min(ncseg, j0 + segs_per_chunk);
+  for (int j = j0; j < j1; ++j) {
+    const int4 d = seg_desc[cseg_id[j]];
+    const int64_t b = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
+    const int t = corepos[d.w];  // core column of this segment's variable
+    for (int o = threadIdx.x; o < d.z; o += blockDim.x) {
+      const int32_t r = idx[b + o];
+      const int32_t q = h[r];
+      h[r] = q + 1;
+      const int64_t pos = dptr[r] + q;
+      didx[pos] = t;
+      dval[pos] = val[b + o];
+    }
+    __syncthreads();
+  }
+}
 // FTRAN tail over the compact row-major copy of the basic structural columns (dptr / didx / dval, column ids = core
 // columns): alpha[cov_i] = a_i - sum_q dval[q] x[didx[q]], entries of a row in ascending core-column order.  A row holds
 // nnz(D) / m entries on average (2 at k = 2000 on config 4, 15 at k = 15 000): one thread per row.  Replaces the pass over
