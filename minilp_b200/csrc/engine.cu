@@ -769,7 +769,8 @@ __global__ void k_cand_load_col(const double* __restrict__ A, int64_t lda, int64
 __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__ Bcols, int64_t ldb, int m, int k,
                                                        const double* __restrict__ xk, const double* __restrict__ rhs0,
                                                        const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                                       const int32_t* __restrict__ Jslot, double* __restrict__ out) {
+                                                       const int32_t* __restrict__ Jslot, double* __restrict__ out,
+                                                       const uint8_t* __restrict__ touched, uint8_t* __restrict__ touched_new) {
   pdl_wait();
   __shared__ double ts[512];
   __shared__ int32_t sl[512];
@@ -801,14 +802,20 @@ __global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__
       for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)sl[j] * ldb];
     }
   }
-  if (cov >= 0) out[cov] = acc;
-  if (i < k) out[Jpos[i]] = xk[i];
+  if (cov >= 0) { out[cov] = acc; if (touched_new) touched_new[cov] = (uint8_t)((acc != 0.0) | (touched[cov] != 0)); }
+  if (i < k) {
+    const int p = Jpos[i];
+    const double xv = xk[i];
+    out[p] = xv;
+    if (touched_new) touched_new[p] = (uint8_t)((xv != 0.0) | (touched[p] != 0));  // k_touch_mark, folded in
+  }
 }
 // FTRAN tail after a column-group split (k_tall_part): alpha_slack = a_S - sum_g part[g], alpha[Jpos[t]] = x[t]
 __global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int64_t pld, int m, int k,
                                      const double* __restrict__ xk, const double* __restrict__ rhs0,
                                      const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                     double* __restrict__ out) {
+                                     double* __restrict__ out, const uint8_t* __restrict__ touched,
+                                     uint8_t* __restrict__ touched_new) {
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) {
@@ -816,10 +823,17 @@ __global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int
     if (cov >= 0) {
       double tsum = 0.0;
       for (int g = 0; g < G; ++g) tsum += part[(int64_t)g * pld + i];
-      out[cov] = rhs0[i] - tsum;
+      const double v = rhs0[i] - tsum;
+      out[cov] = v;
+      if (touched_new) touched_new[cov] = (uint8_t)((v != 0.0) | (touched[cov] != 0));
     }
   }
-  if (i < k) out[Jpos[i]] = xk[i];
+  if (i < k) {
+    const int p = Jpos[i];
+    const double xv = xk[i];
+    out[p] = xv;
+    if (touched_new) touched_new[p] = (uint8_t)((xv != 0.0) | (touched[p] != 0));
+  }
 }
 // core C = D[R,:] (k x k, column-major) from the column cache
 __global__ void k_extract_core(const double* __restrict__ Bcols, int64_t ldb, int k, const int32_t* __restrict__ Rp,
@@ -1748,17 +1762,17 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
   const int Gk = tall_groups(e, m, k);
+  uint8_t* tn = mark ? e->touched_new : (uint8_t*)nullptr;  // structural pattern of an entering column's result (k_touch_mark)
   if (e->sparse) {
     LAUNCHS(e, ln.st, k_ftran_finish_dcsr, cdiv(std::max(m, k), 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, m, k, ln.xk, rhs0,
-            e->rowcover, e->Jpos, out);
+            e->rowcover, e->Jpos, out, (const uint8_t*)e->touched, tn);
   } else if (Gk > 1) {
     LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), Gk), 256, 0, e->Bcols, e->mld, m, k, ln.xk, e->Jslot, e->rowcover, ln.gpart, e->mld);
     LAUNCHS(e, ln.st, k_ftran_finish_parts, cdiv(std::max(m, k), 256), 256, 0, ln.gpart, Gk, e->mld, m, k, ln.xk, rhs0, e->rowcover,
-            e->Jpos, out);
+            e->Jpos, out, (const uint8_t*)e->touched, tn);
   } else
     LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
-            e->Jslot, out);
-  if (mark) LAUNCHS(e, ln.st, k_touch_mark, cdiv(m, 256), 256, 0, out, e->touched, m, e->touched_new);
+            e->Jslot, out, (const uint8_t*)e->touched, tn);
   if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
     LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
     const int GK = tall_groups(e, m, K);
@@ -1774,10 +1788,12 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
 
 // BasisSolver::solve_transp (solver.rs:1322-1338). c: dense m-vector by basis position (device, DESTROYED).
 // unit_row >= 0 tells that c == e_unit_row (the eta dot products degenerate to a row gather). out: by constraint row.
-static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out) {
+// gathered: tK already holds row unit_row of E (k_unit_and_gather)
+static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out, bool gathered = false) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   if (K > 0) {  // etas in reverse, 1325-1333: u = E^T c, s = (I+G)^-T u, c[r_j] -= s_j
-    if (unit_row >= 0) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->mld, unit_row, K, ln.tK);
+    if (unit_row >= 0 && !gathered) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->mld, unit_row, K, ln.tK);
+    else if (unit_row >= 0) {}
     else gemv_t(e, ln, e->E, e->mld, m, K, c, ln.gt_part_K, nullptr, nullptr, ln.tK, 0);
     LAUNCHS(e, ln.st, k_mv_t<true>, cdiv(K, 8), 256, 0, e->Ginv, e->Kcap, K, ln.tK, (const int32_t*)nullptr, ln.tK2);
     LAUNCHS(e, ln.st, k_eta_scatter, cdiv(K, 256), 256, 0, ln.tK2, e->etaR, e->etaPrev, e->etaHead, K, c);
@@ -1928,9 +1944,13 @@ static mlp_status refactor_impl(mlp_engine* e) {
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
   {
-    // (the arena is dense, m doubles per eta: bounded at 16 GB — a full arena just forces the next refactorization)
+    // The arena is dense, m doubles per eta, and bounded at 16 GB — a full arena just forces the next refactorization.  Dense
+    // A: lu nnz ~ m k and an eta has m entries, so the file holds up to ~k etas: reserve 2k + 32.  Sparse A: the file is
+    // short (lu nnz / nnz(alpha): tens to hundreds of etas) — reserving 2k + 32 columns would re-allocate gigabytes every
+    // time k doubles (measured: 0.8 s per growth with peer mappings in place); follow the file's own length instead.
     const int64_t by_mem = std::max<int64_t>(1024, ((int64_t)16 << 30) / (8 * e->mld));
-    ST(ensure_eta_capacity(e, std::min<int64_t>(2 * k + 32, by_mem)));
+    const int64_t want = e->sparse ? std::min<int64_t>(2 * k + 32, 4 * e->K + 128) : 2 * k + 32;
+    ST(ensure_eta_capacity(e, std::min<int64_t>(want, by_mem)));
   }
   e->k = k;
   e->K = 0;
@@ -2880,8 +2900,9 @@ mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
   CU(cudaSetDevice(e->device));
   Lane& l1 = e->lane[1];
   ST(begin1(e));
-  LAUNCHS(e, l1.st, k_set_unit, cdiv(e->m, 256), 256, 0, e->work_mb, e->m, row);
-  ST(btran(e, l1, e->work_mb, (int)row, e->rho));
+  // c = e_row and, with etas, u = row `row` of E (solver.rs:1326-1330 for a unit vector) in one launch
+  LAUNCHS(e, l1.st, k_unit_and_gather, cdiv(std::max<int64_t>(e->m, e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, (int)e->K, l1.tK);
+  ST(btran(e, l1, e->work_mb, (int)row, e->rho, true));
   // inv_basis_row_coeffs as a sparse list + |rho|^2 (solver.rs:683, 1160)
   compact(e, l1, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
   ST(mark1(e));

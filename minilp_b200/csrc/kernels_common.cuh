@@ -531,6 +531,14 @@ __global__ void k_gather_row(const double* __restrict__ M, int64_t ld, int row, 
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) dst[t] = M[(int64_t)t * ld + row];
 }
+// c = e_at (cnt entries) and dst[j] = M[at + j ld] for j < ncols, in one launch (BTRAN of a unit vector with an eta file)
+__global__ void k_unit_and_gather(double* __restrict__ c, int64_t cnt, int64_t at, const double* __restrict__ M, int64_t ld,
+                                  int ncols, double* __restrict__ dst) {
+  pdl_wait();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) c[t] = (t == at) ? 1.0 : 0.0;
+  if (t < ncols) dst[t] = M[t * ld + at];
+}
 __global__ void k_fill(double* p, int64_t cnt, double v) {
   pdl_wait();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

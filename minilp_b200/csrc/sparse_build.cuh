@@ -128,16 +128,24 @@ __global__ void __launch_bounds__(256) k_ftran_finish_dcsr(const int64_t* __rest
                                                            const double* __restrict__ dval, int m, int k,
                                                            const double* __restrict__ xk, const double* __restrict__ rhs0,
                                                            const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                                           double* __restrict__ out) {
+                                                           double* __restrict__ out, const uint8_t* __restrict__ touched,
+                                                           uint8_t* __restrict__ touched_new) {
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < k) out[Jpos[i]] = xk[i];
+  if (i < k) {
+    const int p = Jpos[i];
+    const double xv = xk[i];
+    out[p] = xv;
+    if (touched_new) touched_new[p] = (uint8_t)((xv != 0.0) | (touched[p] != 0));  // k_touch_mark, folded in
+  }
   if (i >= m) return;
   const int cov = rowcover[i];
   if (cov < 0) return;
   double acc = 0.0;
   for (int64_t q = dptr[i]; q < dptr[i + 1]; ++q) acc += dval[q] * xk[didx[q]];
-  out[cov] = rhs0[i] - acc;
+  const double v = rhs0[i] - acc;
+  out[cov] = v;
+  if (touched_new) touched_new[cov] = (uint8_t)((v != 0.0) | (touched[cov] != 0));
 }
 __global__ void __launch_bounds__(256) k_t_segs(const int64_t* __restrict__ csc_ptr, const int64_t* __restrict__ col_seg, int64_t n,
                                                 int seg_len, int32_t* __restrict__ seg_col, int64_t* __restrict__ seg_off,

@@ -29,3 +29,32 @@ def work(r):
 th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
 [t.start() for t in th]; [t.join() for t in th]
 print("sharded", outs)
+# round 2 paths: blocked inverse (forced at small k), periodic recomputation, a sparse LP with refactorizations and the compact
+# core rows, sharded sparse, row-capacity growth
+os.environ["MLP_INV_BLOCKED_MIN"] = "8"
+lp = mb.synth_dense(3, 64, 80, 4)
+s = mb.Solver.from_dense(lp)
+s.set_recalc_period(25)
+assert s.run()
+print("blocked inverse + recalc", s.pivots_done, s.recalcs_done, s.cur_obj_val, s.tie_stats())
+s.close()
+del os.environ["MLP_INV_BLOCKED_MIN"]
+text, d = synth.netlib_like(160, 200, 6.0, 3)
+p = mps.MpsFile.parse(text, d).problem
+rp, ci, va, ops, rhs = p.to_csr()
+g2 = mb.LocalGroup(2)
+res = [None, None]
+def work2(r):
+    s = mb.Solver(len(ops), len(p.obj_coeffs), rank=r, world=2, comm=g2, csr=(rp, ci, va))
+    s.init(np.array(p.obj_coeffs), np.array(p.var_mins), np.array(p.var_maxs), ops, rhs)
+    s.run(); res[r] = (s.pivots_done, s.cur_obj_val, s.engine.counters()["refactors"]); s.close()
+th = [threading.Thread(target=work2, args=(r,)) for r in range(2)]
+[t.start() for t in th]; [t.join() for t in th]
+print("sharded sparse", res)
+q = mb.Problem(mb.OptimizationDirection.Maximize)
+xs = [q.add_var(1.0, (0.0, 10.0)) for _ in range(6)]
+q.add_constraint([(x, 1.0) for x in xs], 1, 30.0)
+sol = q.solve()
+for t in range(70):
+    sol = sol.add_constraint([(xs[t % 6], 1.0), (xs[(t + 1) % 6], 0.5)], 1, 14.0 - 0.01 * t)
+print("row growth", sol.objective())

@@ -6,6 +6,7 @@ those sizes without running minutes of oracle on the GPU box.  The oracle runs w
 
   cfg3  dense_pos 50 000 x 50 000 seed 1 (the bench.py workload), first 24 pivots                      ~4 min
   cfg4  netlib_like 100 000 x 100 000, 0.1 % non-zeros, seed 1, through MPS text, first 3 000 pivots    ~6 min
+  cfg4opt  netlib_like 8 000 x 8 000 (the same 0.1 % density), seed 1, through MPS text, TO THE OPTIMUM: 18 058 pivots   ~3 min
   cfg5  dense_pos 30 000 x 120 000 seed 1 — config 5's 1:4 shape at the largest size this host (62 GB) holds in the
         oracle's dense storage; first 12 pivots                                                         ~5 min
 """
@@ -43,6 +44,16 @@ if "cfg3" in which:
     dense("fullsize_cfg3_dense_pos_50000x50000_s1.npz", 0, 50000, 50000, 1, 24)
 if "cfg5" in which:
     dense("fullsize_cfg5_dense_pos_30000x120000_s1.npz", 0, 30000, 120000, 1, 12)
+if "cfg4opt" in which:
+    # the same family, same 0.1 % density, at a size the oracle SOLVES: 8 000 x 8 000 to the optimum (18 058 pivots, ~3 min)
+    from minilp_b200 import synth
+    m = n = 8000
+    text, d = synth.netlib_like(m, n, 8.0, 1)
+    ref = oracle.MpsFile.parse(text, d).problem.init_only()
+    t0 = time.perf_counter()
+    done = ref.continue_solve(-1)
+    assert done and ref.sel_near_tie_pivots == 0
+    save("fullsize_cfg4opt_netlib_like_8000x8000_s1.npz", dict(m=m, n=n, seed=1, col_nnz=8.0), ref, -1, done, time.perf_counter() - t0)
 if "cfg4" in which:
     from minilp_b200 import synth
     m = n = 100000
