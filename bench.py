@@ -78,9 +78,13 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        ms = os.environ.get("MLP_BENCH_CLOCK_SAMPLE_MS", "100")  # 0: no sampling (A/B of the sampler's own interference)
+        if ms == "0":
+            self.p = None
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", ms], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None

@@ -267,6 +267,9 @@ typedef struct mlp_counters {
   int64_t eta_count;    /* eta_matrices.len() */
   int64_t ratio_ties;      /* ratio tests (primal or dual) whose pass-2 winner was tied exactly */
   int64_t ratio_near_ties; /* ... or within 1e-9 relative (includes the exact ones) */
+  int64_t refreshes;       /* of `refactors`: those done as a product-form refresh of the core inverse (MLP_TUNE_LU_EVERY) */
+  int64_t refresh_rejects; /* refreshes whose accuracy probe (max |C C^-1 - I| over sampled columns) exceeded the tolerance: the
+                              next refactorization was a true one */
 } mlp_counters;
 mlp_status mlp_get_counters(mlp_engine* e, mlp_counters* out);
 /* cudaStream_t of the engine (as void*), for CUDA-event timing by the caller. */
@@ -303,7 +306,11 @@ enum {
   MLP_TUNE_LANE1_LDG = 1,  /* 1: the tableau-row price-out runs as the LDG kernel beside lane 0's bulk-copy kernel */
   MLP_TUNE_FUSED = 2,      /* 1: FTRAN -> BTRAN chain of a primal pivot as one cooperative kernel */
   MLP_TUNE_FUSED_MAX = 3,  /* largest k / K that takes the fused chain (<= 512) */
-  MLP_TUNE_PRICE_SPLIT = 4 /* column slices (1, 2, 4) per work item of the price-out's last, partial round */
+  MLP_TUNE_PRICE_SPLIT = 4, /* column slices (1, 2, 4) per work item of the price-out's last, partial round */
+  MLP_TUNE_LU_EVERY = 5     /* sparse storage: pivots between two TRUE factorizations (lu.rs:118-304).  The refactorizations the
+                               refactor rule asks for in between (solver.rs:1096-1103) fold the eta file into the explicit inverse
+                               of the core instead (product form, O(k^2 K); csrc/refresh_inverse.cuh).  0: every refactorization
+                               is a true factorization (BasisSolver::reset as the reference does it). */
 };
 mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value);
 mlp_status mlp_engine_get_tuning(mlp_engine* e, int32_t knob, int32_t* value);

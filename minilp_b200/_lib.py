@@ -59,7 +59,7 @@ class AddRowResult(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("kernel_launches", i64), ("h2d_bytes", i64), ("d2h_bytes", i64), ("refactors", i64), ("etas_pushed", i64),
-                ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64), ("ratio_ties", i64), ("ratio_near_ties", i64)]
+                ("k_structural", i64), ("lu_nnz", i64), ("eta_count", i64), ("ratio_ties", i64), ("ratio_near_ties", i64), ("refreshes", i64), ("refresh_rejects", i64)]
 
 
 class Profile(C.Structure):

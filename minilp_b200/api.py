@@ -247,7 +247,7 @@ class Engine:
         _check(_lib.lib().mlp_profile_get(self._e, C.byref(p)))
         return {k: getattr(p, k) for k, _ in Profile._fields_}
 
-    TUNE = {"price_tile": 0, "lane1_ldg": 1, "fused": 2, "fused_max": 3, "price_split": 4}
+    TUNE = {"price_tile": 0, "lane1_ldg": 1, "fused": 2, "fused_max": 3, "price_split": 4, "lu_every": 5}
 
     def set_tuning(self, knob, value):
         _check(_lib.lib().mlp_engine_set_tuning(self._e, self.TUNE[knob], int(value)))

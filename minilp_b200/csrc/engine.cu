@@ -10,6 +10,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <condition_variable>
@@ -70,6 +71,7 @@ static_assert(sizeof(Cand) == 64, "Cand must be 64 bytes");
 #include "chain_fused.cuh"
 #include "sparse_build.cuh"
 #include "dense_block.cuh"
+#include "refresh_inverse.cuh"
 
 // ------------------------------------------------------------------------------------------------ communicators
 // The pivot path has ONE real exchange step per pivot: the arg-reduce of the per-shard pricing
@@ -302,8 +304,22 @@ struct mlp_engine {
   double* fz_cta_ss = nullptr;
   unsigned* fz_bar = nullptr;
   int64_t lu_nnz = 0;
+  // product-form refresh of the core inverse (refresh_inverse.cuh; sparse storage): between two TRUE factorizations the
+  // refactorizations the host asks for fold the eta file into C^-1 instead
+  int64_t lu_every = 1 << 30;   // pivots between true factorizations (MLP_TUNE_LU_EVERY / MLP_LU_EVERY); 0 or 1: every refactorization is a true
+                                // one.  Default: no count limit — the accuracy probe of every refresh (rf_tol) decides
+  int64_t pivots_since_lu = 0;  // basis changes since the last true factorization
+  std::vector<int32_t> h_Jpos_f, h_R_f;                       // core columns' positions / core rows of the factorized basis
+  std::vector<int32_t> h_pos_core, h_row_core, h_rowcover_f;  // m each: position -> core column, row -> core row, row -> position of its basic slack (-1: none)
+  std::vector<int32_t> h_eta_pos;    // leaving position of every eta pushed since
+  std::vector<int64_t> h_eta_leave;  // ... and the variable that left it
+  int32_t* rf_map = nullptr;         // 3 kcap + 2 RF_MAXK: rowsrc | colsrc | jposn | etasrc | wrow
+  double *rf_W = nullptr, *rf_T = nullptr, *rf_Ep = nullptr;  // RF_MAXK x kcap each
+  double rf_tol = 1e-10, rf_worst = 0.0;    // a refresh whose accuracy probe (k_rf_probe) exceeds rf_tol is redone as a true factorization
+  double fill_true = 1.0;                   // off-diagonal entries of L\U per entry of the core, at the last true factorization
 
   // lane synchronisation (see "host side")
+  int use_pool = 1;     // MLP_POOL=0: growing arenas re-allocated with cudaMalloc / cudaFree instead of the stream-ordered pool
   int pdl = 1;          // MLP_PDL=0: ordinary launches (no programmatic dependent launch)
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
   int async_pivot = 1;  // MLP_ASYNC_PIVOT=0: mlp_pivot always waits for the device
@@ -348,6 +364,13 @@ struct mlp_engine {
                                          // the refactor-time basis still read them (U = [D1; U2]), so they are recycled only then
   std::vector<int32_t> h_last_eta_of_row;
   mlp_counters cnt{};
+  // MLP_REFACTOR_TRACE=1: wall time of every stage of refactor_impl, with a device sync after each (a diagnosis mode: the
+  // syncs serialise what normally overlaps); printed to stderr when the engine is destroyed
+  int refac_trace = 0;
+  bool refac_in_pivot = false;
+  std::vector<std::pair<const char*, double>> refac_stage;
+  std::chrono::steady_clock::time_point refac_t;
+  double refac_k_sum = 0.0;
 };
 
 // Kernel launch with the programmatic-dependent-launch attribute (see pdl_wait in kernels_common.cuh).
@@ -376,10 +399,21 @@ static inline void launch_kernel(bool pdl, void (*kern)(KArgs...), dim3 grid, di
   } while (0)
 #define LAUNCH(e, kern, grid, block, smem, ...) LAUNCHS(e, (e)->stream, kern, grid, block, smem, __VA_ARGS__)
 
+// Arenas that grow DURING a solve (LU / eta / compact-row / core-segment arenas) are re-allocated from the device's
+// stream-ordered pool (cudaMallocAsync / cudaFreeAsync, release threshold = keep everything): cudaFree synchronises the
+// device and returns the pages to the driver — measured 7 to 130 ms per growth event on config 4, varying from run to run
+// (profiles/r02e_refactor_trace.md) — while a pool free is just a stream operation and the next growth reuses the memory.
+// PoolScope switches dev_alloc / dev_free of the calling thread to the pool for its lifetime.
+static thread_local cudaStream_t g_pool_stream = nullptr;
+struct PoolScope {
+  cudaStream_t prev;
+  explicit PoolScope(cudaStream_t st) : prev(g_pool_stream) { g_pool_stream = st; }
+  ~PoolScope() { g_pool_stream = prev; }
+};
 template <class T> static mlp_status dev_alloc(T** p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  cudaError_t err = cudaMalloc((void**)p, count * sizeof(T));
+  cudaError_t err = g_pool_stream ? cudaMallocAsync((void**)p, count * sizeof(T), g_pool_stream) : cudaMalloc((void**)p, count * sizeof(T));
   if (err != cudaSuccess) {
     set_err(std::string("cudaMalloc: ") + cudaGetErrorString(err));
     return err == cudaErrorMemoryAllocation ? MLP_NOMEM : MLP_CUDA_ERROR;
@@ -387,7 +421,10 @@ template <class T> static mlp_status dev_alloc(T** p, size_t count) {
   return MLP_OK;
 }
 template <class T> static void dev_free(T*& p) {
-  if (p) cudaFree(p);
+  if (p) {
+    if (g_pool_stream) cudaFreeAsync(p, g_pool_stream);
+    else cudaFree(p);
+  }
   p = nullptr;
 }
 static mlp_status h2d(mlp_engine* e, void* dst, const void* src, size_t bytes) {
@@ -1824,6 +1861,7 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
   while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
   if (exact) cap = k;        // clone: same leading dimensions as the source
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  PoolScope pool(e->use_pool ? e->stream : nullptr);
   double* nb = nullptr;
   ST(dev_alloc(&nb, e->sparse ? 1 : (size_t)e->mld * cap));  // sparse storage reads the basic columns from the matrix itself
   if (!e->sparse && e->Bcols && e->kcap > 0) {
@@ -1842,6 +1880,10 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
     }
     dev_free(e->corevar); dev_free(e->cseg_first);
     ST(dev_alloc(&e->corevar, cap)); ST(dev_alloc(&e->cseg_first, cap + 1));
+    dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep);
+    ST(dev_alloc(&e->rf_map, 3 * (size_t)cap + 2 * RF_MAXK));
+    ST(dev_alloc(&e->rf_W, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_T, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_Ep, (size_t)RF_MAXK * cap));
+    e->h_Jpos_f.clear(); e->h_R_f.clear();  // C^-1 does not survive the re-allocation: the next refactorization is a true one
   }
   e->Bcols = nb;
   e->kcap = cap;
@@ -1860,6 +1902,7 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = fal
   while (cap < K) cap *= 2;
   if (exact) cap = K;
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
+  PoolScope pool(e->use_pool ? e->stream : nullptr);
   dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
   e->Kcap = cap;
   ST(dev_alloc(&e->E, (size_t)e->mld * cap)); ST(dev_alloc(&e->Ginv, (size_t)cap * cap)); ST(dev_alloc(&e->gK, cap));
@@ -1879,6 +1922,7 @@ static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = fal
 constexpr int DCSR_CHUNKS = 128;
 static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jvar) {
   const int64_t m = e->m, k = (int64_t)jvar.size();
+  PoolScope pool(e->use_pool ? e->stream : nullptr);
   if (!e->dcsr_ptr) {
     ST(dev_alloc(&e->dcsr_ptr, (size_t)e->mld + 1));
     ST(dev_alloc(&e->dcsr_hist, (size_t)DCSR_CHUNKS * e->mld));
@@ -1893,7 +1937,7 @@ static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jva
   if (nz > e->dcsr_cap) {
     CU(cudaStreamSynchronize(e->lane[1].st));
     dev_free(e->dcsr_idx); dev_free(e->dcsr_val);
-    e->dcsr_cap = std::max<int64_t>(2 * nz, 1 << 16);
+    e->dcsr_cap = std::max<int64_t>(4 * nz, 1 << 20);  // 12 bytes per entry: grow rarely
     ST(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); ST(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap));
   }
   const int ncseg = (int)e->ncseg;                                   // the core's segments (e->cseg_id), in core-column order
@@ -1909,9 +1953,110 @@ static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jva
   return MLP_OK;
 }
 
-// BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.
-static mlp_status refactor_impl(mlp_engine* e) {
+static void refac_stage(mlp_engine* e, const char* name) {
+  if (!e->refac_trace) return;
+  if (e->refac_trace == 1) for (int l = 0; l < 2; ++l) cudaStreamSynchronize(e->lane[l].st);  // 2: host-side times only, no extra syncs
+  const auto now = std::chrono::steady_clock::now();
+  if (name) {
+    const double ms = std::chrono::duration<double, std::milli>(now - e->refac_t).count();
+    if (e->refac_trace == 2 && ms > 0.5)
+      fprintf(stderr, "[refactor event] #%lld since-lu %lld k %lld K %lld: %.3f ms in '%s'\n", (long long)e->cnt.refactors,
+              (long long)e->pivots_since_lu, (long long)e->k, (long long)e->K, ms, name);
+    bool found = false;
+    for (auto& st : e->refac_stage) if (st.first == name) { st.second += ms; found = true; break; }
+    if (!found) e->refac_stage.emplace_back(name, ms);
+  }
+  e->refac_t = std::chrono::steady_clock::now();
+}
+static void refac_report(mlp_engine* e) {
+  if (!e->refac_trace || e->cnt.refactors == 0) return;
+  double tot = 0.0;
+  for (auto& st : e->refac_stage) tot += st.second;
+  fprintf(stderr, "[refactor trace] %lld refactorizations (%lld of them product-form refreshes), mean k %.0f, %.3f ms each\n",
+          (long long)e->cnt.refactors, (long long)e->cnt.refreshes, e->refac_k_sum / e->cnt.refactors, tot / e->cnt.refactors);
+  for (auto& st : e->refac_stage) fprintf(stderr, "[refactor trace]   %-28s %9.3f ms each  %5.1f %%\n", st.first, st.second / e->cnt.refactors, 100.0 * st.second / tot);
+}
+
+// Product-form refresh (refresh_inverse.cuh): C_new^-1 from C_old^-1 and the eta file, written into the LUc buffer, which
+// then becomes Cinv.  jpos / R: the NEW core's positions and rows.  Runs before anything of the old factor state (index maps,
+// compact core rows, eta file) is touched; both lanes are drained.
+static bool can_refresh(const mlp_engine* e) {
+  return e->sparse && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_MAXK) &&
+         (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_eta_pos.size() == e->K && (int64_t)e->h_pos_core.size() == e->m &&
+         e->rf_map != nullptr;
+}
+// mlp_pivot asks before it has pushed the eta of the triggering pivot (e->K already counts it, the host list does not)
+static bool can_refresh_after_push(mlp_engine* e) {
+  e->h_eta_pos.push_back(0);
+  const bool ok = can_refresh(e);
+  e->h_eta_pos.pop_back();
+  return ok;
+}
+static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpos, const std::vector<int32_t>& R) {
+  const int k_old = (int)e->k, K = (int)e->K, k_new = (int)jpos.size();
+  const int64_t ld = e->kcap;
+  std::vector<int32_t> qpos, wrow;  // old slack positions whose row of B_old^-1 is needed, and the rows of those slacks
+  auto q_of = [&](int32_t p) -> int {
+    for (size_t q = 0; q < qpos.size(); ++q) if (qpos[q] == p) return (int)q;
+    return -1;
+  };
+  std::vector<int32_t> map((size_t)3 * k_new + K + RF_MAXK, 0);
+  int32_t *rowsrc = map.data(), *colsrc = rowsrc + k_new, *jposn = colsrc + k_new, *etasrc = jposn + k_new, *wr = etasrc + K;
+  for (int j = 0; j < K; ++j) {
+    const int32_t p = e->h_eta_pos[(size_t)j];
+    if (e->h_pos_core[(size_t)p] >= 0) { etasrc[j] = e->h_pos_core[(size_t)p]; continue; }
+    int q = q_of(p);
+    if (q < 0) {  // the FIRST eta at a position tells which variable the factorized basis held there
+      const int64_t v = e->h_eta_leave[(size_t)j];
+      if (v < e->ng) { set_err("refresh: basis bookkeeping inconsistent (structural variable at a slack position)"); return MLP_INVALID; }
+      q = (int)qpos.size();
+      qpos.push_back(p);
+      wrow.push_back((int32_t)(v - e->ng));
+    }
+    etasrc[j] = -1 - q;
+  }
+  for (int t = 0; t < k_new; ++t) {
+    const int32_t p = jpos[(size_t)t];
+    jposn[t] = p;
+    if (e->h_pos_core[(size_t)p] >= 0) { rowsrc[t] = e->h_pos_core[(size_t)p]; continue; }
+    const int q = q_of(p);
+    if (q < 0) { set_err("refresh: basis bookkeeping inconsistent (new core column without an eta)"); return MLP_INVALID; }
+    rowsrc[t] = -1 - q;
+  }
+  for (int c = 0; c < k_new; ++c) {
+    const int32_t r = R[(size_t)c];
+    if (e->h_row_core[(size_t)r] >= 0) { colsrc[c] = e->h_row_core[(size_t)r]; continue; }
+    const int32_t p = e->h_rowcover_f[(size_t)r];
+    if (p < 0) { set_err("refresh: basis bookkeeping inconsistent (new core row without a basic slack)"); return MLP_INVALID; }
+    colsrc[c] = -1 - p;
+  }
+  const int nq = (int)wrow.size();
+  for (int q = 0; q < nq; ++q) wr[q] = wrow[(size_t)q];
+  ST(h2d(e, e->rf_map, map.data(), ((size_t)3 * k_new + K + nq) * sizeof(int32_t)));
+  const int32_t *d_rowsrc = e->rf_map, *d_colsrc = d_rowsrc + k_new, *d_jposn = d_colsrc + k_new, *d_etasrc = d_jposn + k_new,
+                *d_wrow = d_etasrc + K;
+  if (nq > 0)
+    LAUNCH(e, k_rf_w, dim3(cdiv(k_old, 256), (unsigned)nq), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, d_wrow, k_old, e->Cinv, ld, e->rf_W, ld);
+  LAUNCH(e, k_rf_t, cdiv(k_new, 32), 256, 0, e->Ginv, e->Kcap, K, d_etasrc, e->etaR, d_colsrc, k_new, e->Cinv, ld, e->rf_W, ld, e->rf_T);
+  double* Cn = e->LUc;
+  LAUNCH(e, k_rf_x0, dim3(cdiv(k_new, 256), (unsigned)std::min(k_new, 16384)), 256, 0, d_rowsrc, d_jposn, d_colsrc, k_new, e->Cinv, ld, e->rf_W, ld, Cn);
+  LAUNCH(e, k_rf_ep, dim3(cdiv(k_new, 256), (unsigned)K), 256, 0, e->E, e->mld, d_jposn, k_new, e->rf_Ep, ld);
+  for (int j0 = 0; j0 < K; j0 += GB_K)
+    LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(k_new, GB_T), cdiv(k_new, GB_T)), 256, 0, k_new, k_new, std::min(GB_K, K - j0),
+           e->rf_Ep + (size_t)j0 * ld, ld, e->rf_T + j0, (int64_t)RF_MAXK, Cn, ld);
+  CU(cudaStreamSynchronize(e->stream));  // the host map goes out of scope
+  std::swap(e->Cinv, e->LUc);
+  e->cnt.refreshes += 1;
+  return MLP_OK;
+}
+
+// BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.  allow_refresh: the caller (mlp_pivot) has
+// pushed the eta of the pivot that triggers the refactorization, so the eta file describes the whole change of the basis
+// since the factors were made and may be folded into C^-1 instead of factorizing (refresh_inverse above).
+static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   const int64_t m = e->m, ng = e->ng;
+  refac_stage(e, allow_refresh || e->refac_in_pivot ? "pivot: read-back, enter" : nullptr);
+  e->refac_in_pivot = false;
   std::vector<int32_t> jpos, jslot, jvar, rowcover(m, -1), R;
   for (int64_t p = 0; p < m; ++p) {
     const int64_t v = e->h_bvar[p];
@@ -1936,11 +2081,20 @@ static mlp_status refactor_impl(mlp_engine* e) {
     jpos.swap(p2); jvar.swap(v2); jslot.swap(s2);
   }
   if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
+  refac_stage(e, "host: index sets + column order");
   for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
   e->h_pending_free.clear();
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
   e->spec_var = -1;
   e->ftran_var = -1;
+  refac_stage(e, "drain both lanes");
+  bool refreshed = false;
+  int64_t rf_core_before = 0;
+  if (allow_refresh && k > 0 && k <= e->kcap && can_refresh(e)) {
+    ST(refresh_inverse(e, jpos, R));
+    refreshed = true;
+    refac_stage(e, "refresh: C^-1 from the eta file");
+  }
   ST(ensure_lu_capacity(e, k));
   // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
   {
@@ -1952,6 +2106,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
     const int64_t want = e->sparse ? std::min<int64_t>(2 * k + 32, 4 * e->K + 128) : 2 * k + 32;
     ST(ensure_eta_capacity(e, std::min<int64_t>(want, by_mem)));
   }
+  refac_stage(e, "capacity (LU, eta arena)");
   e->k = k;
   e->K = 0;
   CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
@@ -1981,8 +2136,9 @@ static mlp_status refactor_impl(mlp_engine* e) {
       cfirst[k] = (int32_t)cid.size();
       e->ncseg = (int64_t)cid.size();
       if (e->ncseg > e->cseg_cap) {
+        PoolScope pool(e->use_pool ? e->stream : nullptr);
         dev_free(e->cseg_id); dev_free(e->csum[0]); dev_free(e->csum[1]);
-        e->cseg_cap = std::max<int64_t>(2 * e->ncseg, 4096);
+        e->cseg_cap = std::max<int64_t>(4 * e->ncseg, 1 << 15);
         ST(dev_alloc(&e->cseg_id, e->cseg_cap)); ST(dev_alloc(&e->csum[0], e->cseg_cap)); ST(dev_alloc(&e->csum[1], e->cseg_cap));
       }
       ST(h2d(e, e->cseg_id, cid.data(), cid.size() * sizeof(int32_t)));
@@ -1990,7 +2146,27 @@ static mlp_status refactor_impl(mlp_engine* e) {
       CU(cudaStreamSynchronize(e->stream));
     }
     CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+  refac_stage(e, "uploads: index maps, core segments");
     if (e->sparse) ST(build_core_rows(e, jvar));
+  refac_stage(e, "compact core rows (DCSR)");
+    if (refreshed) {
+      // C^-1 is already the new core's.  Probe it against the new core (max |C C^-1 - I| over sampled columns) and count the
+      // core's entries for the estimate of LUFactors::nnz below — one read-back; a failed probe falls through to the true
+      // factorization (LUc, the old inverse's buffer, is scratch again).
+      CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
+      const int ncol = (int)std::min<int64_t>(4, k);
+      LAUNCH(e, k_rf_probe, cdiv(k, 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, e->Rp, (int)k, e->Cinv, e->kcap,
+             (int)((e->cnt.refactors * 2654435761ull) % (unsigned long long)k), (int)std::max<int64_t>(1, k / 4), ncol, e->d_nnzcnt);
+      CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
+      ST(fetch_res(e, e->lane[0]));
+      rf_core_before = e->h_res->i[4];
+      double r;
+      std::memcpy(&r, &e->h_res->i[5], sizeof(double));
+      e->rf_worst = std::max(e->rf_worst, r);
+      if (!(r <= e->rf_tol)) { refreshed = false; e->cnt.refresh_rejects += 1; e->cnt.refreshes -= 1; }
+  refac_stage(e, "refresh: accuracy probe + read back");
+    }
+    if (!refreshed) {
     if (e->sparse) {
       CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
       LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
@@ -1999,6 +2175,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
       LAUNCH(e, k_core_row_counts, cdiv(k, 256), 256, 0, e->LUc, e->kcap, (int)k, e->lu_rcnt, e->d_nnzcnt);
     } else
       LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
+  refac_stage(e, "extract core + row counts");
     int* flags = e->d_res->flags;
     for (int j0 = 0; j0 < (int)k;) {
       const int rows = (int)k - j0;
@@ -2018,6 +2195,7 @@ static mlp_status refactor_impl(mlp_engine* e) {
       if (rem > 0) LAUNCH(e, k_lu_trailing, dim3(cdiv(rem, LU_NC), cdiv(rem, 256)), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, flags);
       j0 += nb;
     }
+  refac_stage(e, "LU panels / swap-solve / trailing");
     {  // (L U)^-1, one CTA per column
       const size_t need = (size_t)k * sizeof(double);
       const int use_smem = need <= e->smem_optin ? 1 : 0;
@@ -2046,12 +2224,17 @@ static mlp_status refactor_impl(mlp_engine* e) {
       else if (k <= 4096) LAUNCH(e, k_core_inverse_pf<16>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
       else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
     }
+  refac_stage(e, "explicit inverse");
     if (e->sparse) {
       LAUNCH(e, k_count_offdiag, dim3(cdiv(k, 256), cdiv(k, 64)), 256, 0, e->LUc, e->kcap, (int)k, e->d_nnzcnt + 1);
       CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
     }
     ST(fetch_res(e, e->lane[0]));
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
+    // the factorization permuted the core's rows (Rp): column c of C^-1 belongs to row Rp[c] — the next refresh needs that order
+    if (e->sparse) ST(d2h(e, R.data(), e->Rp, (size_t)k * sizeof(int32_t)));
+    }
+  refac_stage(e, "count off-diagonal + read back");
   } else {
     if (e->sparse) ST(build_core_rows(e, jvar));  // empty
     if (e->sparse && e->corevar_k > 0) {
@@ -2071,11 +2254,31 @@ static mlp_status refactor_impl(mlp_engine* e) {
       const int64_t v = e->h_bvar[p];
       if (v < ng) nz += e->h_csc_ptr[v + 1] - e->h_csc_ptr[v];
     }
-    const int64_t core_before = k > 0 ? e->h_res->i[4] : 0, core_offdiag = k > 0 ? e->h_res->i[5] : 0;
-    e->lu_nnz = (nz - core_before) + core_offdiag + m;
+    if (refreshed) {
+      // no factors to count: the part outside the core is exact, the core's L\U is taken to fill as it did at the last true
+      // factorization (off-diagonal entries of the factors per entry of the core)
+      e->lu_nnz = (nz - rf_core_before) + (int64_t)((double)rf_core_before * e->fill_true) + m;
+    } else {
+      const int64_t core_before = k > 0 ? e->h_res->i[4] : 0, core_offdiag = k > 0 ? e->h_res->i[5] : 0;
+      e->lu_nnz = (nz - core_before) + core_offdiag + m;
+      e->fill_true = core_before > 0 ? (double)core_offdiag / (double)core_before : 1.0;
+      e->pivots_since_lu = 0;
+    }
   } else e->lu_nnz = k * (k - 1) + (m - k) * k + m;
+  if (e->sparse) {  // the sets of the factorized basis, for the next refresh
+    e->h_pos_core.assign((size_t)m, -1);
+    e->h_row_core.assign((size_t)m, -1);
+    for (int64_t t = 0; t < k; ++t) { e->h_pos_core[(size_t)jpos[(size_t)t]] = (int32_t)t; e->h_row_core[(size_t)R[(size_t)t]] = (int32_t)t; }
+    e->h_Jpos_f = jpos;
+    e->h_R_f = R;
+    e->h_rowcover_f.swap(rowcover);
+    e->h_eta_pos.clear();
+    e->h_eta_leave.clear();
+  }
   e->cnt.refactors += 1;
   e->cnt.k_structural = k;
+  e->refac_k_sum += (double)k;
+  refac_stage(e, "host: lu nnz");
   return MLP_OK;
 }
 
@@ -2281,10 +2484,12 @@ static void destroy_engine(mlp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (int l = 0; l < 2; ++l) if (e->lane[l].st) cudaStreamSynchronize(e->lane[l].st);
+  refac_report(e);
   dev_free(e->csr_ptr); dev_free(e->csc_ptr); dev_free(e->csr_idx); dev_free(e->csc_idx); dev_free(e->csr_val); dev_free(e->csc_val);
   dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
   dev_free(e->seg_desc); dev_free(e->seg_long); dev_free(e->seg_short);
+  dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep); 
   dev_free(e->dcsr_ptr); dev_free(e->dcsr_idx); dev_free(e->dcsr_val); dev_free(e->dcsr_hist); dev_free(e->dcsr_cnt);
   dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
@@ -2355,6 +2560,18 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   e->sm_count = prop.multiProcessorCount;
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
   if (const char* v = getenv("MLP_PDL")) e->pdl = atoi(v) != 0;
+  if (const char* v = getenv("MLP_POOL")) e->use_pool = atoi(v) != 0;
+  if (const char* v = getenv("MLP_REFRESH_TOL")) e->rf_tol = atof(v);
+  if (e->use_pool) {  // keep what the growing arenas free (see PoolScope)
+    cudaMemPool_t mp = nullptr;
+    unsigned long long keep = ~0ull;
+    if (cudaDeviceGetDefaultMemPool(&mp, device) != cudaSuccess || cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+      cudaGetLastError();
+      e->use_pool = 0;
+    }
+  }
+  if (const char* v = getenv("MLP_REFACTOR_TRACE")) e->refac_trace = atoi(v);
+  if (const char* v = getenv("MLP_LU_EVERY")) e->lu_every = std::max<int64_t>(0, atoll(v));
   if (const char* v = getenv("MLP_CSC_STREAM")) e->csc_stream = atoi(v) != 0;
   if (const char* v = getenv("MLP_INV_BLOCKED_MIN")) e->inv_blocked_min = std::max<int64_t>(1, atoll(v));
   if (const char* v = getenv("MLP_ASYNC_PIVOT")) e->async_pivot = atoi(v) != 0;
@@ -3009,6 +3226,12 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   const double pivot_obj = pi->entering_obj_coeff / pi->coeff;  // solver.rs:1073
   bool do_refactor = pi->refactor != 0;
   if (!do_refactor && e->K >= e->Kcap) do_refactor = true;  // arena full
+  if (do_refactor && e->refac_trace) { refac_stage(e, nullptr); e->refac_in_pivot = true; }
+  // A refactorization between two true factorizations folds the eta file into C^-1 (refresh_inverse.cuh): then the eta of
+  // THIS pivot is pushed like any other, so that the file describes the whole change of the basis.
+  e->K += 1;  // as can_refresh will see it
+  bool refresh = do_refactor && e->K <= e->Kcap && e->pivots_since_lu + 1 < e->lu_every && can_refresh_after_push(e);
+  e->K -= 1;
   // lane 1: tau = B^-1 rho (solver.rs:1157)
   ST(begin1(e));
   if (e->enable_dse) ST(ftran(e, l1, e->rho, e->tau));
@@ -3020,12 +3243,15 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   e->spec_var = -1;
   e->ftran_var = -1;
   // lane 1: row half of the pivot, eta push
-  double* eta_col = do_refactor ? nullptr : e->E + (size_t)e->K * e->mld;
+  const bool push_eta = !do_refactor || refresh;
+  double* eta_col = push_eta ? e->E + (size_t)e->K * e->mld : nullptr;
   LAUNCHS(e, l1.st, k_pivot_rows, cdiv(m, 256), 256, 0, e->alpha, e->tau, e->xB, e->w, m, row, pi->entering_new_val,
           pi->entering_diff, pi->coeff, 1, e->enable_dse, e->scal, eta_col, e->d_res->flags, e->touched, e->touched_new);
-  if (!do_refactor) {
+  e->pivots_since_lu += 1;
+  if (push_eta) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
+    if (e->sparse) { e->h_eta_pos.push_back((int32_t)row); e->h_eta_leave.push_back(lv); }
     LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
     LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
     e->h_last_eta_of_row[row] = K;
@@ -3053,6 +3279,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
       // doubles the cache; its content and slot numbers survive, the LU arrays do not: refactor in this pivot
       ST(ensure_lu_capacity(e, e->kcap + 1));
       do_refactor = true;
+      refresh = false;
     }
     const int32_t slot = e->h_free_slots.back();
     e->h_free_slots.pop_back();
@@ -3075,6 +3302,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
     return MLP_OK;
   }
   // one device->host read: status flags, leaving var, nnz(alpha)
+  if (e->refac_in_pivot) refac_stage(e, "pivot: its own kernels (both lanes)");
   CU(cudaMemcpyAsync(&e->d_res->i[1], e->icnt + 1, sizeof(int32_t), cudaMemcpyDeviceToDevice, e->stream));
   ST(mark0(e));
   ST(fetch_res(e, l0));
@@ -3084,7 +3312,7 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (out->leaving_var != lv) { set_err("pivot: host/device basis mirrors diverged"); return MLP_INVALID; }
   if (e->h_res->flags[0] && e->world == 1) { set_err("non-finite steepest-edge norm"); return MLP_NONFINITE; }
   if (do_refactor) {
-    ST(refactor_impl(e));
+    ST(refactor_impl(e, refresh));
     ST(mark0(e));
     out->refactored = 1;
     out->lu_nnz = e->lu_nnz;
@@ -3348,6 +3576,10 @@ static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** ou
   e->async_pivot = src->async_pivot;
   e->h_bvar = src->h_bvar; e->h_slot_of_row = src->h_slot_of_row; e->h_free_slots = src->h_free_slots;
   e->h_pending_free = src->h_pending_free; e->h_last_eta_of_row = src->h_last_eta_of_row;
+  e->lu_every = src->lu_every; e->pivots_since_lu = src->pivots_since_lu; e->fill_true = src->fill_true; e->rf_tol = src->rf_tol;
+  e->h_Jpos_f = src->h_Jpos_f; e->h_R_f = src->h_R_f; e->h_pos_core = src->h_pos_core; e->h_row_core = src->h_row_core;
+  e->h_rowcover_f = src->h_rowcover_f; e->h_eta_pos = src->h_eta_pos; e->h_eta_leave = src->h_eta_leave;
+  if (new_mld != src->mld) { e->h_Jpos_f.clear(); e->h_R_f.clear(); }  // grow_rows refactorizes anyway
   e->cnt = src->cnt;
   e->initialized = true;
   ST(mark0(e));
@@ -3549,6 +3781,7 @@ mlp_status mlp_engine_set_tuning(mlp_engine* e, int32_t knob, int32_t value) {
       break;
     }
     case MLP_TUNE_FUSED_MAX: e->fused_max = std::max(0, std::min(FZ_MAX, (int)value)); break;
+    case MLP_TUNE_LU_EVERY: e->lu_every = std::max(0, (int)value); break;
     default: set_err("set_tuning: unknown knob"); return MLP_INVALID;
   }
   e->spec_var = -1;
@@ -3563,6 +3796,7 @@ mlp_status mlp_engine_get_tuning(mlp_engine* e, int32_t knob, int32_t* value) {
     case MLP_TUNE_LANE1_LDG: *value = e->lane1_ldg; break;
     case MLP_TUNE_FUSED: *value = e->fused; break;
     case MLP_TUNE_FUSED_MAX: *value = e->fused_max; break;
+    case MLP_TUNE_LU_EVERY: *value = (int32_t)e->lu_every; break;
     default: set_err("get_tuning: unknown knob"); return MLP_INVALID;
   }
   return MLP_OK;
