@@ -410,7 +410,10 @@ def measure_sparse(a, ctx):
                        if world > 1 else "single GPU", "pivots_before_timed_region": p0, "optimal_reached": bool(done),
                        "k_structural_end": c1["k_structural"], "eta_count_end": c1["eta_count"],
                        "refactor_rule": f"eta nnz >= {a.refactor_factor:g} * lu nnz (1 = the reference's, solver.rs:1096-1097)",
-                       "refactors_in_region": c1["refactors"] - c0["refactors"], "refactor_wall_s": refac_s,
+                       "refactors_in_region": c1["refactors"] - c0["refactors"],
+                       "of_them_product_form_refreshes": c1["refreshes"] - c0["refreshes"],
+                       "refreshes_redone_as_true_factorizations (accuracy probe)": c1["refresh_rejects"] - c0["refresh_rejects"],
+                       "refactor_wall_s": refac_s,
                        "refactor_share_of_wall": refac_s / max(w1 - w0, 1e-9), "setup": setup,
                        "objective_after": s.cur_obj_val, "l2": "the CSC copy (12 nnz bytes) is about the size of the 126 MB L2"},
         "clocks": clocks,
@@ -551,7 +554,7 @@ def compact_line(line):
     out["roofline"] = {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "algorithmic_bytes_per_launch",
                                              "share_of_step_time", "launches_timed")}
     d = line.get("run_detail", {})
-    out["run_detail"] = {k: d[k] for k in ("parallelism", "k_structural_end", "eta_count_end", "refactors_in_region", "refactor_share_of_wall",
+    out["run_detail"] = {k: d[k] for k in ("parallelism", "k_structural_end", "eta_count_end", "refactors_in_region", "of_them_product_form_refreshes", "refactor_share_of_wall",
                                            "setup", "objective_after", "nnz") if k in d}
     return out
 

@@ -315,6 +315,7 @@ struct mlp_engine {
   std::vector<int64_t> h_eta_leave;  // ... and the variable that left it
   int32_t* rf_map = nullptr;         // 3 kcap + 2 RF_MAXK: rowsrc | colsrc | jposn | etasrc | wrow
   double *rf_W = nullptr, *rf_T = nullptr, *rf_Ep = nullptr;  // RF_MAXK x kcap each
+  double rf_worst_true = 0.0;               // (trace mode) the same probe right after true factorizations
   double rf_tol = 1e-10, rf_worst = 0.0;    // a refresh whose accuracy probe (k_rf_probe) exceeds rf_tol is redone as a true factorization
   double fill_true = 1.0;                   // off-diagonal entries of L\U per entry of the core, at the last true factorization
 
@@ -368,6 +369,8 @@ struct mlp_engine {
   // syncs serialise what normally overlaps); printed to stderr when the engine is destroyed
   int refac_trace = 0;
   bool refac_in_pivot = false;
+  double wait_ms = 0.0;  // (trace mode) host time blocked in the per-pivot device waits (fetch_res, winner header)
+  int64_t waits = 0;
   std::vector<std::pair<const char*, double>> refac_stage;
   std::chrono::steady_clock::time_point refac_t;
   double refac_k_sum = 0.0;
@@ -1688,7 +1691,9 @@ static mlp_status begin0(mlp_engine* e) { if (e->overlap) CU(cudaStreamWaitEvent
 static mlp_status begin1(mlp_engine* e) { if (e->overlap) CU(cudaStreamWaitEvent(e->lane[1].st, e->s0_mark, 0)); return MLP_OK; }
 static mlp_status fetch_res(mlp_engine* e, Lane& ln) {
   CU(cudaMemcpyAsync(ln.h_res, ln.d_res, sizeof(DevRes), cudaMemcpyDeviceToHost, ln.st));
+  const auto t0 = std::chrono::steady_clock::now();
   CU(cudaStreamSynchronize(ln.st));
+  if (e->refac_trace) { e->wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); e->waits += 1; }
   e->cnt.d2h_bytes += (int64_t)sizeof(DevRes);
   return MLP_OK;
 }
@@ -1974,12 +1979,39 @@ static void refac_report(mlp_engine* e) {
   for (auto& st : e->refac_stage) tot += st.second;
   fprintf(stderr, "[refactor trace] %lld refactorizations (%lld of them product-form refreshes), mean k %.0f, %.3f ms each\n",
           (long long)e->cnt.refactors, (long long)e->cnt.refreshes, e->refac_k_sum / e->cnt.refactors, tot / e->cnt.refactors);
+  fprintf(stderr, "[refactor trace] host blocked in %lld per-pivot device waits: %.1f ms in total (%.1f us each) over %lld basis changes, %lld launches\n",
+          (long long)e->waits, e->wait_ms, e->waits ? 1e3 * e->wait_ms / e->waits : 0.0, (long long)e->pivot_seq, (long long)e->cnt.kernel_launches);
+  fprintf(stderr, "[refactor trace] accuracy probe (normwise backward error of sampled columns of C^-1): worst accepted refresh %.3g, "
+                  "worst after a true factorization %.3g, tolerance %.3g, rejected refreshes %lld\n", e->rf_worst, e->rf_worst_true, e->rf_tol,
+          (long long)e->cnt.refresh_rejects);
   for (auto& st : e->refac_stage) fprintf(stderr, "[refactor trace]   %-28s %9.3f ms each  %5.1f %%\n", st.first, st.second / e->cnt.refactors, 100.0 * st.second / tot);
 }
 
 // Product-form refresh (refresh_inverse.cuh): C_new^-1 from C_old^-1 and the eta file, written into the LUc buffer, which
 // then becomes Cinv.  jpos / R: the NEW core's positions and rows.  Runs before anything of the old factor state (index maps,
 // compact core rows, eta file) is touched; both lanes are drained.
+// k_rf_probe on the current C^-1 against the compact rows of the current basic columns; one read-back.  *err: the largest
+// normwise backward error over the sampled columns, *core_entries: entries of the core.
+static mlp_status probe_inverse(mlp_engine* e, int64_t k, double* err, int64_t* core_entries) {
+  unsigned long long* out = e->d_nnzcnt;
+  CU(cudaMemsetAsync(out, 0, (1 + 2 * RF_PROBE) * sizeof(unsigned long long), e->stream));
+  const int ncol = (int)std::min<int64_t>(RF_PROBE, k);
+  LAUNCH(e, k_rf_probe, cdiv(k, 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, e->Rp, (int)k, e->Cinv, e->kcap,
+         (int)((e->cnt.refactors * 2654435761ull) % (unsigned long long)k), (int)std::max<int64_t>(1, k / RF_PROBE), ncol, out);
+  unsigned long long h[1 + 2 * RF_PROBE];
+  ST(d2h(e, h, out, sizeof(h)));
+  *core_entries = (int64_t)h[0];
+  double worst = 0.0;
+  for (int q = 0; q < ncol; ++q) {
+    double num, den;
+    std::memcpy(&num, &h[1 + q], 8);
+    std::memcpy(&den, &h[1 + RF_PROBE + q], 8);
+    const double r = den > 0.0 ? num / den : num;
+    if (!(r <= worst)) worst = r;
+  }
+  *err = worst;
+  return MLP_OK;
+}
 static bool can_refresh(const mlp_engine* e) {
   return e->sparse && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_MAXK) &&
          (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_eta_pos.size() == e->K && (int64_t)e->h_pos_core.size() == e->m &&
@@ -2153,16 +2185,9 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
       // C^-1 is already the new core's.  Probe it against the new core (max |C C^-1 - I| over sampled columns) and count the
       // core's entries for the estimate of LUFactors::nnz below — one read-back; a failed probe falls through to the true
       // factorization (LUc, the old inverse's buffer, is scratch again).
-      CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
-      const int ncol = (int)std::min<int64_t>(4, k);
-      LAUNCH(e, k_rf_probe, cdiv(k, 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, e->Rp, (int)k, e->Cinv, e->kcap,
-             (int)((e->cnt.refactors * 2654435761ull) % (unsigned long long)k), (int)std::max<int64_t>(1, k / 4), ncol, e->d_nnzcnt);
-      CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
-      ST(fetch_res(e, e->lane[0]));
-      rf_core_before = e->h_res->i[4];
       double r;
-      std::memcpy(&r, &e->h_res->i[5], sizeof(double));
-      e->rf_worst = std::max(e->rf_worst, r);
+      ST(probe_inverse(e, k, &r, &rf_core_before));
+      if (r <= e->rf_tol) e->rf_worst = std::max(e->rf_worst, r);
       if (!(r <= e->rf_tol)) { refreshed = false; e->cnt.refresh_rejects += 1; e->cnt.refreshes -= 1; }
   refac_stage(e, "refresh: accuracy probe + read back");
     }
@@ -2233,6 +2258,12 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
     if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
     // the factorization permuted the core's rows (Rp): column c of C^-1 belongs to row Rp[c] — the next refresh needs that order
     if (e->sparse) ST(d2h(e, R.data(), e->Rp, (size_t)k * sizeof(int32_t)));
+    if (e->sparse && e->refac_trace) {  // calibration of the refresh probe: the same measure on a freshly factorized inverse
+      double r;
+      int64_t ce;
+      ST(probe_inverse(e, k, &r, &ce));
+      e->rf_worst_true = std::max(e->rf_worst_true, r);
+    }
     }
   refac_stage(e, "count off-diagonal + read back");
   } else {
@@ -2335,7 +2366,11 @@ static mlp_status exchange_candidates(mlp_engine* e, Cand* winner, bool want_alp
   }
   if (chain_fusable(e)) want_alpha_nnz = false;
   e->alpha_nnz_host = -1;
-  CU(cudaEventSynchronize(e->ev_win));  // the header only (dual loop: and the FTRAN), not the chain queued behind it
+  {
+    const auto t0 = std::chrono::steady_clock::now();
+    CU(cudaEventSynchronize(e->ev_win));  // the header only (dual loop: and the FTRAN), not the chain queued behind it
+    if (e->refac_trace) { e->wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); e->waits += 1; }
+  }
   if (e->prof_on) ST(collect_profile(e, (int)((e->pivot_seq & 1) ^ 1)));  // the previous pivot is complete by now
   e->cnt.d2h_bytes += (int64_t)sizeof(Cand);
   *winner = e->h_cands[0];
@@ -2633,7 +2668,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   A(dev_alloc(&e->work_m, ml)); A(dev_alloc(&e->work_mb, ml)); A(dev_alloc(&e->colq, ml));
   A(dev_alloc(&e->rc, ntc)); A(dev_alloc(&e->helper, ntc));
   A(dev_alloc(&e->list_idx, ml)); A(dev_alloc(&e->list_val, ml)); A(dev_alloc(&e->vlist_idx, ml)); A(dev_alloc(&e->vlist_val, ml));
-  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16)); A(dev_alloc(&e->d_nnzcnt, 2));
+  A(dev_alloc(&e->scal, 16)); A(dev_alloc(&e->icnt, 16)); A(dev_alloc(&e->d_nnzcnt, 2 + 2 * RF_PROBE));
   for (int l = 0; l < 2; ++l) {
     Lane& ln = e->lane[l];
     A(dev_alloc(&ln.wm, ml));

@@ -87,35 +87,57 @@ __global__ void __launch_bounds__(256) k_rf_ep(const double* __restrict__ E, int
   if (t < k_new) Ep[(int64_t)j * ld + t] = E[(int64_t)j * mld + jposn[t]];
 }
 
-// Accuracy probe of a refreshed inverse: out[1] = bits of max |C_new C_new^-1[:, c] - e_c| over a few columns c, with C_new
-// read from the compact row-major copy of the NEW basic columns (row Rp[i] of it is row i of the core); out[0] = entries of
-// the core (for the estimate of LUFactors::nnz).  Above the tolerance the refresh is redone as a true factorization.
+// Accuracy probe of a refreshed inverse.  For RF_PROBE sampled columns c, x = C_new^-1[:, c] is checked against the new core
+// itself (read from the compact row-major copy of the NEW basic columns; row Rp[i] of it is row i of the core):
+//   out[1 + q] = bits of max_i |C x - e_c|_i          out[1 + RF_PROBE + q] = bits of max_i (|C||x| + |e_c|)_i
+// and the host takes the largest quotient: a normwise backward error (a componentwise one is useless here — where the exact
+// x_t is 0 a refresh leaves 1e-17 and a row with that single entry reports 100 %).  A fresh factorization sits at 1e-16..1e-12
+// (MLP_REFACTOR_TRACE prints both); above the tolerance the refresh is redone as a true factorization.
+// out[0] = entries of the core (for the estimate of LUFactors::nnz).
+constexpr int RF_PROBE = 4;
 __global__ void __launch_bounds__(256) k_rf_probe(const int64_t* __restrict__ dptr, const int32_t* __restrict__ didx,
                                                    const double* __restrict__ dval, const int32_t* __restrict__ Rp, int k,
                                                    const double* __restrict__ Cinv, int64_t ld, int c0, int cstep, int ncol,
                                                    unsigned long long* __restrict__ out) {
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double worst = 0.0;
+  double num[RF_PROBE], den[RF_PROBE];
+#pragma unroll
+  for (int q = 0; q < RF_PROBE; ++q) num[q] = den[q] = 0.0;
   unsigned len = 0;
   if (i < k) {
     const int r = Rp[i];
     len = (unsigned)(dptr[r + 1] - dptr[r]);
-    for (int q = 0; q < ncol; ++q) {
+#pragma unroll
+    for (int q = 0; q < RF_PROBE; ++q) {
+      if (q >= ncol) break;
       const int c = (c0 + q * cstep) % k;
       const double* col = Cinv + (int64_t)c * ld;
-      double acc = i == c ? -1.0 : 0.0;
-      for (int64_t e = dptr[r]; e < dptr[r + 1]; ++e) acc += dval[e] * col[didx[e]];
-      acc = fabs(acc);
-      if (!(acc <= worst)) worst = acc;  // a NaN sticks
+      double acc = i == c ? -1.0 : 0.0, mag = i == c ? 1.0 : 0.0;
+      for (int64_t e = dptr[r]; e < dptr[r + 1]; ++e) {
+        const double t = dval[e] * col[didx[e]];
+        acc += t;
+        mag += fabs(t);
+      }
+      num[q] = acc == acc ? fabs(acc) : 1e300;  // a NaN counts as a failure
+      den[q] = mag == mag ? mag : 0.0;
     }
   }
-  if (!(worst == worst)) worst = 1e300;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_down_sync(0xffffffffu, worst, o));
+  for (int q = 0; q < RF_PROBE; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      num[q] = fmax(num[q], __shfl_down_sync(0xffffffffu, num[q], o));
+      den[q] = fmax(den[q], __shfl_down_sync(0xffffffffu, den[q], o));
+    }
+  }
   len = __reduce_add_sync(0xffffffffu, len);
   if ((threadIdx.x & 31) == 0) {
-    if (worst > 0.0) atomicMax(out + 1, (unsigned long long)__double_as_longlong(worst));
+#pragma unroll
+    for (int q = 0; q < RF_PROBE; ++q) {
+      if (num[q] > 0.0) atomicMax(out + 1 + q, (unsigned long long)__double_as_longlong(num[q]));
+      if (den[q] > 0.0) atomicMax(out + 1 + RF_PROBE + q, (unsigned long long)__double_as_longlong(den[q]));
+    }
     if (len) atomicAdd(out, (unsigned long long)len);
   }
 }
