@@ -311,8 +311,19 @@ struct mlp_engine {
   int64_t pivots_since_lu = 0;  // basis changes since the last true factorization
   std::vector<int32_t> h_Jpos_f, h_R_f;                       // core columns' positions / core rows of the factorized basis
   std::vector<int32_t> h_pos_core, h_row_core, h_rowcover_f;  // m each: position -> core column, row -> core row, row -> position of its basic slack (-1: none)
-  std::vector<int32_t> h_eta_pos;    // leaving position of every eta pushed since
+  std::vector<int32_t> h_eta_pos;    // position of every basis change since (= leaving position of every eta pushed since)
   std::vector<int64_t> h_eta_leave;  // ... and the variable that left it
+  std::vector<int32_t> h_rc_old_rows, h_rc_old_vals;  // slack rows touched by incremental_sets and their rowcover values BEFORE it
+  std::vector<int32_t> h_R_sorted;   // core rows of the factorized basis, ascending (h_R_f is in the factors' row order)
+  bool inv_valid = false;            // Cinv holds the inverse of the core described by h_Jpos_f / h_R_f (false after a re-allocation)
+  bool chg_complete = false;         // h_eta_pos / h_eta_leave list EVERY basis change since the last refactorization: the next one
+                                     // may derive its index sets from the previous ones in O(k + K) instead of O(m)
+  // pinned staging for the index arrays a refactorization uploads (two buffers, reused alternately behind an event)
+  int32_t* stg_h[2] = {nullptr, nullptr};
+  size_t stg_cap[2] = {0, 0};
+  cudaEvent_t stg_ev[2] = {nullptr, nullptr};
+  int stg_cur = 0;
+  size_t stg_off = 0;
   int32_t* rf_map = nullptr;         // 3 kcap + 2 RF_MAXK: rowsrc | colsrc | jposn | etasrc | wrow
   double *rf_W = nullptr, *rf_T = nullptr, *rf_Ep = nullptr;  // RF_MAXK x kcap each
   double rf_worst_true = 0.0;               // (trace mode) the same probe right after true factorizations
@@ -1888,7 +1899,7 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
     dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep);
     ST(dev_alloc(&e->rf_map, 3 * (size_t)cap + 2 * RF_MAXK));
     ST(dev_alloc(&e->rf_W, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_T, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_Ep, (size_t)RF_MAXK * cap));
-    e->h_Jpos_f.clear(); e->h_R_f.clear();  // C^-1 does not survive the re-allocation: the next refactorization is a true one
+    e->inv_valid = false;  // C^-1 does not survive the re-allocation: the next refactorization is a true one
   }
   e->Bcols = nb;
   e->kcap = cap;
@@ -1990,6 +2001,110 @@ static void refac_report(mlp_engine* e) {
 // Product-form refresh (refresh_inverse.cuh): C_new^-1 from C_old^-1 and the eta file, written into the LUc buffer, which
 // then becomes Cinv.  jpos / R: the NEW core's positions and rows.  Runs before anything of the old factor state (index maps,
 // compact core rows, eta file) is touched; both lanes are drained.
+// Pinned staging: every index array of a refactorization goes through ONE pinned buffer (a cudaMemcpyAsync from pageable memory
+// first waits for the stream and then copies synchronously: eight of them serialised the host with the device).
+static mlp_status stage_begin(mlp_engine* e, size_t ints_needed) {
+  e->stg_cur ^= 1;
+  const int c = e->stg_cur;
+  if (!e->stg_ev[c]) CU(cudaEventCreateWithFlags(&e->stg_ev[c], cudaEventDisableTiming));
+  else CU(cudaEventSynchronize(e->stg_ev[c]));  // the copies that last used this buffer (two refactorizations ago) are long done
+  if (ints_needed > e->stg_cap[c]) {
+    if (e->stg_h[c]) cudaFreeHost(e->stg_h[c]);
+    e->stg_h[c] = nullptr;
+    e->stg_cap[c] = std::max<size_t>(2 * ints_needed, (size_t)1 << 16);
+    CU(cudaHostAlloc((void**)&e->stg_h[c], e->stg_cap[c] * sizeof(int32_t), cudaHostAllocDefault));
+  }
+  e->stg_off = 0;
+  return MLP_OK;
+}
+static mlp_status stage_put(mlp_engine* e, void* dst_dev, const int32_t* src, size_t n) {
+  if (n == 0) return MLP_OK;
+  const int c = e->stg_cur;
+  if (e->stg_off + n > e->stg_cap[c]) { set_err("refactor: staging buffer too small"); return MLP_INVALID; }
+  int32_t* h = e->stg_h[c] + e->stg_off;
+  std::memcpy(h, src, n * sizeof(int32_t));
+  e->stg_off += n;
+  CU(cudaMemcpyAsync(dst_dev, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  e->cnt.h2d_bytes += (int64_t)(n * sizeof(int32_t));
+  return MLP_OK;
+}
+static mlp_status stage_end(mlp_engine* e) {
+  CU(cudaEventRecord(e->stg_ev[e->stg_cur], e->stream));
+  return MLP_OK;
+}
+
+// dst[idx[i]] = val[i]
+__global__ void k_patch_i32(int32_t* __restrict__ dst, const int32_t* __restrict__ idx, const int32_t* __restrict__ val, int n) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = val[i];
+}
+// rowcore[Rp[c]] = c
+__global__ void k_set_rowcore(int32_t* __restrict__ rowcore, const int32_t* __restrict__ Rp, int k) {
+  pdl_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < k) rowcore[Rp[c]] = c;
+}
+
+// The index sets of the new basis derived from those of the factorized one and the list of basis changes since
+// (sparse storage, every change recorded): O(k + K log k) instead of three passes over all m positions / rows.
+//   jpos   core columns' positions in order_simple's order (ordering.rs:4-21: ascending entry count, ascending position within a count)
+//   R      core rows, ascending
+//   prow / pval   rows whose rowcover entry changes and the new values (device patch)
+//   gone   rows that left the core (rowcore <- -1)
+// e->h_rowcover_f is updated in place.
+static mlp_status incremental_sets(mlp_engine* e, std::vector<int32_t>& jpos, std::vector<int32_t>& R, std::vector<int32_t>& prow,
+                                   std::vector<int32_t>& pval, std::vector<int32_t>& gone) {
+  const int64_t ng = e->ng;
+  std::vector<int32_t> P;       // distinct changed positions
+  std::vector<int64_t> oldv;    // variable the factorized basis held there
+  for (size_t j = 0; j < e->h_eta_pos.size(); ++j) {
+    const int32_t p = e->h_eta_pos[j];
+    if (std::find(P.begin(), P.end(), p) == P.end()) { P.push_back(p); oldv.push_back(e->h_eta_leave[j]); }
+  }
+  std::vector<int32_t>& rc = e->h_rowcover_f;
+  std::vector<int32_t> T;  // slack rows involved
+  e->h_rc_old_rows.clear();
+  e->h_rc_old_vals.clear();
+  auto touch = [&](int32_t i) {
+    if (std::find(T.begin(), T.end(), i) != T.end()) return;
+    T.push_back(i);
+    e->h_rc_old_rows.push_back(i);
+    e->h_rc_old_vals.push_back(rc[(size_t)i]);  // the factorized basis' value: the refresh needs it
+  };
+  for (size_t q = 0; q < P.size(); ++q) if (oldv[q] >= ng) touch((int32_t)(oldv[q] - ng));
+  for (size_t q = 0; q < P.size(); ++q) { const int64_t nv = e->h_bvar[(size_t)P[q]]; if (nv >= ng) touch((int32_t)(nv - ng)); }
+  for (size_t q = 0; q < P.size(); ++q) if (oldv[q] >= ng) rc[(size_t)(oldv[q] - ng)] = -1;
+  for (size_t q = 0; q < P.size(); ++q) { const int64_t nv = e->h_bvar[(size_t)P[q]]; if (nv >= ng) rc[(size_t)(nv - ng)] = P[q]; }
+  auto key_less = [&](int32_t pa, int32_t pb) {  // order_simple's key of the column at a position
+    const int64_t va = e->h_bvar[(size_t)pa], vb = e->h_bvar[(size_t)pb];
+    const int64_t ca = e->h_csc_ptr[(size_t)va + 1] - e->h_csc_ptr[(size_t)va], cb = e->h_csc_ptr[(size_t)vb + 1] - e->h_csc_ptr[(size_t)vb];
+    return ca != cb ? ca < cb : pa < pb;
+  };
+  jpos.clear();
+  jpos.reserve(e->h_Jpos_f.size() + P.size());
+  std::vector<int32_t> Ps(P);
+  std::sort(Ps.begin(), Ps.end());
+  for (int32_t p : e->h_Jpos_f)
+    if (!std::binary_search(Ps.begin(), Ps.end(), p)) jpos.push_back(p);  // unchanged columns keep their relative order
+  for (size_t q = 0; q < P.size(); ++q) {
+    if (e->h_bvar[(size_t)P[q]] >= ng) continue;
+    jpos.insert(std::lower_bound(jpos.begin(), jpos.end(), P[q], key_less), P[q]);
+  }
+  R = e->h_R_sorted;
+  prow.clear(); pval.clear(); gone.clear();
+  for (int32_t i : T) {
+    prow.push_back(i);
+    pval.push_back(rc[(size_t)i]);
+    auto it = std::lower_bound(R.begin(), R.end(), i);
+    const bool in_old = it != R.end() && *it == i;
+    const bool in_new = rc[(size_t)i] < 0;
+    if (in_old && !in_new) { R.erase(it); gone.push_back(i); }
+    else if (!in_old && in_new) R.insert(it, i);
+  }
+  return MLP_OK;
+}
+
 // k_rf_probe on the current C^-1 against the compact rows of the current basic columns; one read-back.  *err: the largest
 // normwise backward error over the sampled columns, *core_entries: entries of the core.
 static mlp_status probe_inverse(mlp_engine* e, int64_t k, double* err, int64_t* core_entries) {
@@ -2013,16 +2128,9 @@ static mlp_status probe_inverse(mlp_engine* e, int64_t k, double* err, int64_t* 
   return MLP_OK;
 }
 static bool can_refresh(const mlp_engine* e) {
-  return e->sparse && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_MAXK) &&
+  return e->sparse && e->inv_valid && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_MAXK) &&
          (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_eta_pos.size() == e->K && (int64_t)e->h_pos_core.size() == e->m &&
          e->rf_map != nullptr;
-}
-// mlp_pivot asks before it has pushed the eta of the triggering pivot (e->K already counts it, the host list does not)
-static bool can_refresh_after_push(mlp_engine* e) {
-  e->h_eta_pos.push_back(0);
-  const bool ok = can_refresh(e);
-  e->h_eta_pos.pop_back();
-  return ok;
 }
 static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpos, const std::vector<int32_t>& R) {
   const int k_old = (int)e->k, K = (int)e->K, k_new = (int)jpos.size();
@@ -2058,13 +2166,15 @@ static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpo
   for (int c = 0; c < k_new; ++c) {
     const int32_t r = R[(size_t)c];
     if (e->h_row_core[(size_t)r] >= 0) { colsrc[c] = e->h_row_core[(size_t)r]; continue; }
-    const int32_t p = e->h_rowcover_f[(size_t)r];
+    int32_t p = e->h_rowcover_f[(size_t)r];  // position of the row's slack in the FACTORIZED basis: incremental_sets may have
+    for (size_t q = 0; q < e->h_rc_old_rows.size(); ++q)  // moved h_rowcover_f on to the new basis already
+      if (e->h_rc_old_rows[q] == r) { p = e->h_rc_old_vals[q]; break; }
     if (p < 0) { set_err("refresh: basis bookkeeping inconsistent (new core row without a basic slack)"); return MLP_INVALID; }
     colsrc[c] = -1 - p;
   }
   const int nq = (int)wrow.size();
   for (int q = 0; q < nq; ++q) wr[q] = wrow[(size_t)q];
-  ST(h2d(e, e->rf_map, map.data(), ((size_t)3 * k_new + K + nq) * sizeof(int32_t)));
+  ST(stage_put(e, e->rf_map, map.data(), (size_t)3 * k_new + K + nq));
   const int32_t *d_rowsrc = e->rf_map, *d_colsrc = d_rowsrc + k_new, *d_jposn = d_colsrc + k_new, *d_etasrc = d_jposn + k_new,
                 *d_wrow = d_etasrc + K;
   if (nq > 0)
@@ -2076,7 +2186,6 @@ static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpo
   for (int j0 = 0; j0 < K; j0 += GB_K)
     LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(k_new, GB_T), cdiv(k_new, GB_T)), 256, 0, k_new, k_new, std::min(GB_K, K - j0),
            e->rf_Ep + (size_t)j0 * ld, ld, e->rf_T + j0, (int64_t)RF_MAXK, Cn, ld);
-  CU(cudaStreamSynchronize(e->stream));  // the host map goes out of scope
   std::swap(e->Cinv, e->LUc);
   e->cnt.refreshes += 1;
   return MLP_OK;
@@ -2089,19 +2198,28 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   const int64_t m = e->m, ng = e->ng;
   refac_stage(e, allow_refresh || e->refac_in_pivot ? "pivot: read-back, enter" : nullptr);
   e->refac_in_pivot = false;
-  std::vector<int32_t> jpos, jslot, jvar, rowcover(m, -1), R;
-  for (int64_t p = 0; p < m; ++p) {
-    const int64_t v = e->h_bvar[p];
-    if (v < ng) {
-      jpos.push_back((int32_t)p);
-      jvar.push_back((int32_t)v);
-      if (!e->sparse && e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
-      jslot.push_back(e->h_slot_of_row[p]);
-    } else rowcover[v - ng] = (int32_t)p;
+  std::vector<int32_t> jpos, jslot, jvar, rowcover, R, prow, pval, gone;
+  // Sparse storage, every basis change since the last refactorization on record: the new sets follow from the old ones.
+  const bool incremental = e->sparse && e->chg_complete && (int64_t)e->h_pos_core.size() == m && (int64_t)e->h_rowcover_f.size() == m &&
+                           (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_R_sorted.size() == e->k;
+  if (incremental) {
+    ST(incremental_sets(e, jpos, R, prow, pval, gone));
+    for (int32_t p : jpos) { jvar.push_back((int32_t)e->h_bvar[(size_t)p]); jslot.push_back(e->h_slot_of_row[(size_t)p]); }
+  } else {
+    rowcover.assign((size_t)m, -1);
+    for (int64_t p = 0; p < m; ++p) {
+      const int64_t v = e->h_bvar[p];
+      if (v < ng) {
+        jpos.push_back((int32_t)p);
+        jvar.push_back((int32_t)v);
+        if (!e->sparse && e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
+        jslot.push_back(e->h_slot_of_row[p]);
+      } else rowcover[v - ng] = (int32_t)p;
+    }
+    for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
   }
-  for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
   const int64_t k = (int64_t)jpos.size();
-  if (e->sparse && k > 1) {
+  if (!incremental && e->sparse && k > 1) {
     // order_simple (ordering.rs:4-21): columns by ascending entry count, FIFO — i.e. ascending basis position — within a
     // count.  (For a dense A every column has m entries and the order is the basis-position order built above.)
     std::vector<int32_t> ord((size_t)k);
@@ -2113,6 +2231,7 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
     jpos.swap(p2); jvar.swap(v2); jslot.swap(s2);
   }
   if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
+  std::vector<int32_t> Rsorted(R);  // R itself is overwritten with the factors' row order after a true factorization
   refac_stage(e, "host: index sets + column order");
   for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
   e->h_pending_free.clear();
@@ -2120,6 +2239,11 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   e->spec_var = -1;
   e->ftran_var = -1;
   refac_stage(e, "drain both lanes");
+  {
+    size_t segs = 0;
+    if (e->sparse) for (int32_t v : jvar) segs += (size_t)(e->h_col_seg[(size_t)v + 1] - e->h_col_seg[(size_t)v]);
+    ST(stage_begin(e, 2 * (size_t)m + 10 * (size_t)k + segs + 4 * RF_MAXK + 4 * prow.size() + 256));
+  }
   bool refreshed = false;
   int64_t rf_core_before = 0;
   if (allow_refresh && k > 0 && k <= e->kcap && can_refresh(e)) {
@@ -2144,21 +2268,43 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
   CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)e->mld * sizeof(int32_t), e->stream));  // eta file is empty: no chains
   CU(cudaMemsetAsync(e->touched, 0, (size_t)e->mld, e->stream));
-  std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
-  ST(h2d(e, e->rowcover, rowcover.data(), m * sizeof(int32_t)));
+  // device maps by patches (the touched slack rows fit the scratch behind the refresh's maps) or in full
+  const bool patch_maps = incremental && prow.size() <= (size_t)RF_MAXK && e->rf_map != nullptr;
+  if (incremental) for (int32_t p : e->h_eta_pos) e->h_last_eta_of_row[(size_t)p] = -1;
+  else std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
+  if (patch_maps) {
+    int32_t* d_patch = e->rf_map + 3 * e->kcap;  // 2 RF_MAXK entries; stream-ordered behind the refresh kernels that read this area
+    if (!prow.empty()) {  // rowcover: only the slack rows the basis changes touched
+      ST(stage_put(e, d_patch, prow.data(), prow.size()));
+      ST(stage_put(e, d_patch + RF_MAXK, pval.data(), pval.size()));
+      LAUNCH(e, k_patch_i32, cdiv((int64_t)prow.size(), 256), 256, 0, e->rowcover, (const int32_t*)d_patch, (const int32_t*)(d_patch + RF_MAXK), (int)prow.size());
+    }
+    if (!gone.empty()) {  // rowcore: rows that left the core (a subset of the touched rows); the rows of the new core are set below
+      std::vector<int32_t> minus((size_t)gone.size(), -1);
+      ST(stage_put(e, d_patch, gone.data(), gone.size()));
+      ST(stage_put(e, d_patch + RF_MAXK, minus.data(), minus.size()));
+      LAUNCH(e, k_patch_i32, cdiv((int64_t)gone.size(), 256), 256, 0, e->rowcore, (const int32_t*)d_patch, (const int32_t*)(d_patch + RF_MAXK), (int)gone.size());
+    }
+  } else if (incremental) {
+    ST(stage_put(e, e->rowcover, e->h_rowcover_f.data(), (size_t)m));
+  } else {
+    ST(stage_put(e, e->rowcover, rowcover.data(), (size_t)m));
+  }
+  if (e->sparse && !patch_maps) {  // also for an empty core: later refactorizations patch this map
+    std::vector<int32_t> rowcore((size_t)m, -1);
+    for (int64_t i = 0; i < k; ++i) rowcore[R[i]] = (int32_t)i;
+    ST(stage_put(e, e->rowcore, rowcore.data(), (size_t)m));
+  }
   if (k > 0) {
-    ST(h2d(e, e->Jpos, jpos.data(), k * sizeof(int32_t)));
-    ST(h2d(e, e->Jslot, jslot.data(), k * sizeof(int32_t)));
-    ST(h2d(e, e->Rp, R.data(), k * sizeof(int32_t)));
-    std::vector<int32_t> rowcore;
+    ST(stage_put(e, e->Jpos, jpos.data(), (size_t)k));
+    ST(stage_put(e, e->Jslot, jslot.data(), (size_t)k));
+    ST(stage_put(e, e->Rp, R.data(), (size_t)k));
     if (e->sparse) {
       if (e->corevar_k > 0) LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
-      ST(h2d(e, e->corevar, jvar.data(), k * sizeof(int32_t)));
+      ST(stage_put(e, e->corevar, jvar.data(), (size_t)k));
       LAUNCH(e, k_set_corepos, cdiv(k, 256), 256, 0, e->corepos, e->corevar, (int)k, 0);
       e->corevar_k = k;
-      rowcore.assign(m, -1);
-      for (int64_t i = 0; i < k; ++i) rowcore[R[i]] = (int32_t)i;
-      ST(h2d(e, e->rowcore, rowcore.data(), m * sizeof(int32_t)));
+      if (patch_maps) LAUNCH(e, k_set_rowcore, cdiv(k, 256), 256, 0, e->rowcore, (const int32_t*)e->Rp, (int)k);
       // the core's segments
       std::vector<int32_t> cid, cfirst((size_t)k + 1, 0);
       for (int64_t t = 0; t < k; ++t) {
@@ -2173,11 +2319,9 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
         e->cseg_cap = std::max<int64_t>(4 * e->ncseg, 1 << 15);
         ST(dev_alloc(&e->cseg_id, e->cseg_cap)); ST(dev_alloc(&e->csum[0], e->cseg_cap)); ST(dev_alloc(&e->csum[1], e->cseg_cap));
       }
-      ST(h2d(e, e->cseg_id, cid.data(), cid.size() * sizeof(int32_t)));
-      ST(h2d(e, e->cseg_first, cfirst.data(), cfirst.size() * sizeof(int32_t)));
-      CU(cudaStreamSynchronize(e->stream));
+      ST(stage_put(e, e->cseg_id, cid.data(), cid.size()));
+      ST(stage_put(e, e->cseg_first, cfirst.data(), cfirst.size()));
     }
-    CU(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
   refac_stage(e, "uploads: index maps, core segments");
     if (e->sparse) ST(build_core_rows(e, jvar));
   refac_stage(e, "compact core rows (DCSR)");
@@ -2281,10 +2425,7 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   // the same column order and pivot rule (ties aside) their size tracks the reference's.
   if (e->sparse) {
     int64_t nz = 0;
-    for (int64_t p = 0; p < m; ++p) {
-      const int64_t v = e->h_bvar[p];
-      if (v < ng) nz += e->h_csc_ptr[v + 1] - e->h_csc_ptr[v];
-    }
+    for (int32_t v : jvar) nz += e->h_csc_ptr[(size_t)v + 1] - e->h_csc_ptr[(size_t)v];
     if (refreshed) {
       // no factors to count: the part outside the core is exact, the core's L\U is taken to fill as it did at the last true
       // factorization (off-diagonal entries of the factors per entry of the core)
@@ -2296,16 +2437,27 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
       e->pivots_since_lu = 0;
     }
   } else e->lu_nnz = k * (k - 1) + (m - k) * k + m;
-  if (e->sparse) {  // the sets of the factorized basis, for the next refresh
-    e->h_pos_core.assign((size_t)m, -1);
-    e->h_row_core.assign((size_t)m, -1);
+  if (e->sparse) {  // the sets of the factorized basis, for the next refresh / the next incremental set-up
+    if (incremental) {
+      for (int32_t p : e->h_Jpos_f) e->h_pos_core[(size_t)p] = -1;
+      for (int32_t r : e->h_R_f) e->h_row_core[(size_t)r] = -1;
+    } else {
+      e->h_pos_core.assign((size_t)m, -1);
+      e->h_row_core.assign((size_t)m, -1);
+      e->h_rowcover_f.swap(rowcover);
+    }
     for (int64_t t = 0; t < k; ++t) { e->h_pos_core[(size_t)jpos[(size_t)t]] = (int32_t)t; e->h_row_core[(size_t)R[(size_t)t]] = (int32_t)t; }
-    e->h_Jpos_f = jpos;
-    e->h_R_f = R;
-    e->h_rowcover_f.swap(rowcover);
+    e->h_Jpos_f.swap(jpos);
+    e->h_R_f.swap(R);          // the factors' row order (permuted by a true factorization)
+    e->h_R_sorted.swap(Rsorted);
     e->h_eta_pos.clear();
     e->h_eta_leave.clear();
+    e->h_rc_old_rows.clear();
+    e->h_rc_old_vals.clear();
+    e->chg_complete = true;
+    e->inv_valid = true;
   }
+  ST(stage_end(e));
   e->cnt.refactors += 1;
   e->cnt.k_structural = k;
   e->refac_k_sum += (double)k;
@@ -2524,7 +2676,11 @@ static void destroy_engine(mlp_engine* e) {
   dev_free(e->corevar); dev_free(e->corepos); dev_free(e->rowcore);
   dev_free(e->seg_col); dev_free(e->seg_off); dev_free(e->col_seg); dev_free(e->seg_sum); dev_free(e->cseg_id); dev_free(e->cseg_first);
   dev_free(e->seg_desc); dev_free(e->seg_long); dev_free(e->seg_short);
-  dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep); 
+  dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep);
+  for (int c = 0; c < 2; ++c) {
+    if (e->stg_h[c]) cudaFreeHost(e->stg_h[c]);
+    if (e->stg_ev[c]) cudaEventDestroy(e->stg_ev[c]);
+  }
   dev_free(e->dcsr_ptr); dev_free(e->dcsr_idx); dev_free(e->dcsr_val); dev_free(e->dcsr_hist); dev_free(e->dcsr_cnt);
   dev_free(e->csum[0]); dev_free(e->csum[1]);
   dev_free(e->A); dev_free(e->lo); dev_free(e->hi); dev_free(e->cobj); dev_free(e->d); dev_free(e->gam); dev_free(e->xnb);
@@ -3002,6 +3158,8 @@ mlp_status mlp_engine_init_state(mlp_engine* e, const mlp_init_state* st) {
   }
   e->enable_pse = st->enable_primal_steepest_edge;
   e->enable_dse = st->enable_dual_steepest_edge;
+  e->chg_complete = false;  // a whole new basis: the next refactorization builds its index sets from scratch
+  e->h_Jpos_f.clear();
   ST(h2d(e, e->d, d.data(), nt * 8));
   ST(h2d(e, e->xnb, xnb.data(), nt * 8));
   ST(h2d(e, e->gam, gam.data(), nt * 8));
@@ -3264,8 +3422,9 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (do_refactor && e->refac_trace) { refac_stage(e, nullptr); e->refac_in_pivot = true; }
   // A refactorization between two true factorizations folds the eta file into C^-1 (refresh_inverse.cuh): then the eta of
   // THIS pivot is pushed like any other, so that the file describes the whole change of the basis.
+  if (e->sparse) { e->h_eta_pos.push_back((int32_t)row); e->h_eta_leave.push_back(lv); }  // every basis change is on record
   e->K += 1;  // as can_refresh will see it
-  bool refresh = do_refactor && e->K <= e->Kcap && e->pivots_since_lu + 1 < e->lu_every && can_refresh_after_push(e);
+  bool refresh = do_refactor && e->K <= e->Kcap && e->pivots_since_lu + 1 < e->lu_every && can_refresh(e);
   e->K -= 1;
   // lane 1: tau = B^-1 rho (solver.rs:1157)
   ST(begin1(e));
@@ -3286,7 +3445,6 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (push_eta) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
-    if (e->sparse) { e->h_eta_pos.push_back((int32_t)row); e->h_eta_leave.push_back(lv); }
     LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
     LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
     e->h_last_eta_of_row[row] = K;
@@ -3614,7 +3772,8 @@ static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** ou
   e->lu_every = src->lu_every; e->pivots_since_lu = src->pivots_since_lu; e->fill_true = src->fill_true; e->rf_tol = src->rf_tol;
   e->h_Jpos_f = src->h_Jpos_f; e->h_R_f = src->h_R_f; e->h_pos_core = src->h_pos_core; e->h_row_core = src->h_row_core;
   e->h_rowcover_f = src->h_rowcover_f; e->h_eta_pos = src->h_eta_pos; e->h_eta_leave = src->h_eta_leave;
-  if (new_mld != src->mld) { e->h_Jpos_f.clear(); e->h_R_f.clear(); }  // grow_rows refactorizes anyway
+  e->h_R_sorted = src->h_R_sorted; e->chg_complete = src->chg_complete && new_mld == src->mld;
+  e->inv_valid = src->inv_valid && new_mld == src->mld;  // grow_rows refactorizes anyway
   e->cnt = src->cnt;
   e->initialized = true;
   ST(mark0(e));
