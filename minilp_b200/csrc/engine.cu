@@ -331,6 +331,7 @@ struct mlp_engine {
   double fill_true = 1.0;                   // off-diagonal entries of L\U per entry of the core, at the last true factorization
 
   // lane synchronisation (see "host side")
+  int merge_small = 1;  // MLP_MERGE_SMALL=0: short eta files take the separate kernels too (A/B of k_eta_apply / k_unit_eta_t / k_eta_push)
   int use_pool = 1;     // MLP_POOL=0: growing arenas re-allocated with cudaMalloc / cudaFree instead of the stream-ordered pool
   int pdl = 1;          // MLP_PDL=0: ordinary launches (no programmatic dependent launch)
   int overlap = 1;      // MLP_OVERLAP=0: both lanes on one stream
@@ -1815,20 +1816,25 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
   // x = U^-1 L^-1 P a_R (lu.rs:92-93) as one product with the explicit inverse of the core
   if (k > 0) LAUNCHS(e, ln.st, k_mv_n<false>, cdiv(k, 32), 256, 0, e->Cinv, e->kcap, k, rhs0, e->Rp, ln.xk);
   const int Gk = tall_groups(e, m, k);
+  const int GK = K > 0 ? tall_groups(e, m, K) : 1;
+  // short eta file: its whole application is one launch (k_eta_apply) reading the LU part's result from lane scratch
+  const bool eta_one = e->merge_small && K > 0 && K <= FE_MAXK && GK == 1 && rhs0 != ln.wm && out != ln.wm;
+  double* mid = eta_one ? ln.wm : out;
   uint8_t* tn = mark ? e->touched_new : (uint8_t*)nullptr;  // structural pattern of an entering column's result (k_touch_mark)
   if (e->sparse) {
     LAUNCHS(e, ln.st, k_ftran_finish_dcsr, cdiv(std::max(m, k), 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, m, k, ln.xk, rhs0,
-            e->rowcover, e->Jpos, out, (const uint8_t*)e->touched, tn);
+            e->rowcover, e->Jpos, mid, (const uint8_t*)e->touched, tn);
   } else if (Gk > 1) {
     LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), Gk), 256, 0, e->Bcols, e->mld, m, k, ln.xk, e->Jslot, e->rowcover, ln.gpart, e->mld);
     LAUNCHS(e, ln.st, k_ftran_finish_parts, cdiv(std::max(m, k), 256), 256, 0, ln.gpart, Gk, e->mld, m, k, ln.xk, rhs0, e->rowcover,
-            e->Jpos, out, (const uint8_t*)e->touched, tn);
+            e->Jpos, mid, (const uint8_t*)e->touched, tn);
   } else
     LAUNCHS(e, ln.st, k_ftran_finish, cdiv(std::max(m, k), 256), 256, 0, e->Bcols, e->mld, m, k, ln.xk, rhs0, e->rowcover, e->Jpos,
-            e->Jslot, out, (const uint8_t*)e->touched, tn);
-  if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
+            e->Jslot, mid, (const uint8_t*)e->touched, tn);
+  if (eta_one) {
+    LAUNCHS(e, ln.st, k_eta_apply, cdiv(m, 256), 256, 0, e->E, e->mld, m, K, e->Ginv, e->Kcap, e->etaR, (const double*)mid, out);
+  } else if (K > 0) {  // eta file, solver.rs:1310-1316 in closed form: t = (I+G)^-1 alpha0[r], alpha -= E t
     LAUNCHS(e, ln.st, k_mv_n<true>, cdiv(K, 32), 256, 0, e->Ginv, e->Kcap, K, out, e->etaR, ln.tK);
-    const int GK = tall_groups(e, m, K);
     if (GK > 1) {
       LAUNCHS(e, ln.st, k_tall_part, dim3(cdiv(m, 256), GK), 256, 0, e->E, e->mld, m, K, ln.tK, (const int32_t*)nullptr,
               (const int32_t*)nullptr, ln.gpart, e->mld);
@@ -1842,13 +1848,14 @@ static mlp_status ftran(mlp_engine* e, Lane& ln, const double* rhs0, double* out
 // BasisSolver::solve_transp (solver.rs:1322-1338). c: dense m-vector by basis position (device, DESTROYED).
 // unit_row >= 0 tells that c == e_unit_row (the eta dot products degenerate to a row gather). out: by constraint row.
 // gathered: tK already holds row unit_row of E (k_unit_and_gather)
-static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out, bool gathered = false) {
+static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double* out, bool gathered = false, bool s_ready = false) {
   const int m = (int)e->m, k = (int)e->k, K = (int)e->K;
   if (K > 0) {  // etas in reverse, 1325-1333: u = E^T c, s = (I+G)^-T u, c[r_j] -= s_j
-    if (unit_row >= 0 && !gathered) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->mld, unit_row, K, ln.tK);
+    if (s_ready) {}  // k_unit_eta_t left s in tK2
+    else if (unit_row >= 0 && !gathered) LAUNCHS(e, ln.st, k_gather_row, cdiv(K, 256), 256, 0, e->E, e->mld, unit_row, K, ln.tK);
     else if (unit_row >= 0) {}
     else gemv_t(e, ln, e->E, e->mld, m, K, c, ln.gt_part_K, nullptr, nullptr, ln.tK, 0);
-    LAUNCHS(e, ln.st, k_mv_t<true>, cdiv(K, 8), 256, 0, e->Ginv, e->Kcap, K, ln.tK, (const int32_t*)nullptr, ln.tK2);
+    if (!s_ready) LAUNCHS(e, ln.st, k_mv_t<true>, cdiv(K, 8), 256, 0, e->Ginv, e->Kcap, K, ln.tK, (const int32_t*)nullptr, ln.tK2);
     LAUNCHS(e, ln.st, k_eta_scatter, cdiv(K, 256), 256, 0, ln.tK2, e->etaR, e->etaPrev, e->etaHead, K, c);
   }
   LAUNCHS(e, ln.st, k_btran_start, cdiv(m, 256), 256, 0, c, e->rowcover, m, out, ln.wm);
@@ -1874,6 +1881,9 @@ static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double
 static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = false) {
   if (k <= e->kcap && e->Bcols) return MLP_OK;
   int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->mld)))));
+  // sparse storage keeps no column cache: the arenas are kcap^2 (factors, inverse) — start at 4096 columns (0.27 GB) so that the
+  // first thousands of pivots meet no growth (each growth is a re-allocation AND a true factorization: 5 - 20 ms on config 4)
+  if (e->sparse) cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, 4096));
   while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
   if (exact) cap = k;        // clone: same leading dimensions as the source
   for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
@@ -1897,8 +1907,8 @@ static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = fals
     dev_free(e->corevar); dev_free(e->cseg_first);
     ST(dev_alloc(&e->corevar, cap)); ST(dev_alloc(&e->cseg_first, cap + 1));
     dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep);
-    ST(dev_alloc(&e->rf_map, 3 * (size_t)cap + 2 * RF_MAXK));
-    ST(dev_alloc(&e->rf_W, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_T, (size_t)RF_MAXK * cap)); ST(dev_alloc(&e->rf_Ep, (size_t)RF_MAXK * cap));
+    ST(dev_alloc(&e->rf_map, 3 * (size_t)cap + 2 * RF_CAP));
+    ST(dev_alloc(&e->rf_W, (size_t)RF_CAP * cap)); ST(dev_alloc(&e->rf_T, (size_t)RF_CAP * cap)); ST(dev_alloc(&e->rf_Ep, (size_t)RF_CAP * cap));
     e->inv_valid = false;  // C^-1 does not survive the re-allocation: the next refactorization is a true one
   }
   e->Bcols = nb;
@@ -1953,7 +1963,7 @@ static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jva
   if (nz > e->dcsr_cap) {
     CU(cudaStreamSynchronize(e->lane[1].st));
     dev_free(e->dcsr_idx); dev_free(e->dcsr_val);
-    e->dcsr_cap = std::max<int64_t>(4 * nz, 1 << 20);  // 12 bytes per entry: grow rarely
+    e->dcsr_cap = std::max<int64_t>(4 * nz, 1 << 22);  // 12 bytes per entry: grow rarely
     ST(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); ST(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap));
   }
   const int ncseg = (int)e->ncseg;                                   // the core's segments (e->cseg_id), in core-column order
@@ -2128,7 +2138,9 @@ static mlp_status probe_inverse(mlp_engine* e, int64_t k, double* err, int64_t* 
   return MLP_OK;
 }
 static bool can_refresh(const mlp_engine* e) {
-  return e->sparse && e->inv_valid && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_MAXK) &&
+  // the rank-K product costs 2 k^2 K flops: worth it while the eta file is short next to the core (a factorization is ~2 k^3)
+  return e->sparse && e->inv_valid && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_CAP) &&
+         e->K <= std::max<int64_t>(RF_MAXK, e->k / 2) &&
          (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_eta_pos.size() == e->K && (int64_t)e->h_pos_core.size() == e->m &&
          e->rf_map != nullptr;
 }
@@ -2140,7 +2152,7 @@ static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpo
     for (size_t q = 0; q < qpos.size(); ++q) if (qpos[q] == p) return (int)q;
     return -1;
   };
-  std::vector<int32_t> map((size_t)3 * k_new + K + RF_MAXK, 0);
+  std::vector<int32_t> map((size_t)3 * k_new + 2 * (size_t)K + 8, 0);
   int32_t *rowsrc = map.data(), *colsrc = rowsrc + k_new, *jposn = colsrc + k_new, *etasrc = jposn + k_new, *wr = etasrc + K;
   for (int j = 0; j < K; ++j) {
     const int32_t p = e->h_eta_pos[(size_t)j];
@@ -2185,7 +2197,7 @@ static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpo
   LAUNCH(e, k_rf_ep, dim3(cdiv(k_new, 256), (unsigned)K), 256, 0, e->E, e->mld, d_jposn, k_new, e->rf_Ep, ld);
   for (int j0 = 0; j0 < K; j0 += GB_K)
     LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(k_new, GB_T), cdiv(k_new, GB_T)), 256, 0, k_new, k_new, std::min(GB_K, K - j0),
-           e->rf_Ep + (size_t)j0 * ld, ld, e->rf_T + j0, (int64_t)RF_MAXK, Cn, ld);
+           e->rf_Ep + (size_t)j0 * ld, ld, e->rf_T + j0, (int64_t)RF_CAP, Cn, ld);
   std::swap(e->Cinv, e->LUc);
   e->cnt.refreshes += 1;
   return MLP_OK;
@@ -2242,7 +2254,7 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
   {
     size_t segs = 0;
     if (e->sparse) for (int32_t v : jvar) segs += (size_t)(e->h_col_seg[(size_t)v + 1] - e->h_col_seg[(size_t)v]);
-    ST(stage_begin(e, 2 * (size_t)m + 10 * (size_t)k + segs + 4 * RF_MAXK + 4 * prow.size() + 256));
+    ST(stage_begin(e, 2 * (size_t)m + 10 * (size_t)k + segs + 2 * (size_t)e->K + 4 * RF_MAXK + 4 * prow.size() + 256));
   }
   bool refreshed = false;
   int64_t rf_core_before = 0;
@@ -2752,6 +2764,7 @@ static mlp_status create_engine(int device, int64_t m, int64_t ng, int rank, int
   if (const char* v = getenv("MLP_OVERLAP")) e->overlap = atoi(v) != 0;
   if (const char* v = getenv("MLP_PDL")) e->pdl = atoi(v) != 0;
   if (const char* v = getenv("MLP_POOL")) e->use_pool = atoi(v) != 0;
+  if (const char* v = getenv("MLP_MERGE_SMALL")) e->merge_small = atoi(v) != 0;
   if (const char* v = getenv("MLP_REFRESH_TOL")) e->rf_tol = atof(v);
   if (e->use_pool) {  // keep what the growing arenas free (see PoolScope)
     cudaMemPool_t mp = nullptr;
@@ -3311,8 +3324,14 @@ mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
   Lane& l1 = e->lane[1];
   ST(begin1(e));
   // c = e_row and, with etas, u = row `row` of E (solver.rs:1326-1330 for a unit vector) in one launch
-  LAUNCHS(e, l1.st, k_unit_and_gather, cdiv(std::max<int64_t>(e->m, e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, (int)e->K, l1.tK);
-  ST(btran(e, l1, e->work_mb, (int)row, e->rho, true));
+  if (e->merge_small && e->K > 0 && e->K <= FE_MAXK) {  // short eta file: ... and s = (I+G)^-T u as well
+    LAUNCHS(e, l1.st, k_unit_eta_t, cdiv(std::max<int64_t>(e->m, 32 * e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, e->Ginv, e->Kcap,
+            (int)e->K, l1.tK2);
+    ST(btran(e, l1, e->work_mb, (int)row, e->rho, true, true));
+  } else {
+    LAUNCHS(e, l1.st, k_unit_and_gather, cdiv(std::max<int64_t>(e->m, e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, (int)e->K, l1.tK);
+    ST(btran(e, l1, e->work_mb, (int)row, e->rho, true));
+  }
   // inv_basis_row_coeffs as a sparse list + |rho|^2 (solver.rs:683, 1160)
   compact(e, l1, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
   ST(mark1(e));
@@ -3445,8 +3464,12 @@ mlp_status mlp_pivot(mlp_engine* e, const mlp_pivot_info* pi, mlp_pivot_result* 
   if (push_eta) {
     const int prev = e->h_last_eta_of_row[row];
     const int K = (int)e->K;
-    LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
-    LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
+    if (e->merge_small && K <= FE_MAXK)
+      LAUNCHS(e, l1.st, k_eta_push, cdiv(K + 1, 8), 256, 0, e->E, e->mld, K, row, e->Ginv, e->Kcap, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
+    else {
+      LAUNCHS(e, l1.st, k_eta_grow, cdiv(std::max(K, 1), 256), 256, 0, e->E, e->mld, K, row, e->gK, e->etaR, e->etaPrev, e->etaHead, e->etaLast, prev);
+      LAUNCHS(e, l1.st, k_eta_inv_row, cdiv(K + 1, 8), 256, 0, e->gK, e->Ginv, e->Kcap, K);
+    }
     e->h_last_eta_of_row[row] = K;
     e->K += 1;
     e->cnt.etas_pushed += 1;
@@ -3766,7 +3789,7 @@ static mlp_status clone_engine(mlp_engine* src, int64_t new_mld, mlp_engine** ou
   // the tuning state decides how reductions are tiled: the copy must round exactly like its source
   e->price_tma = src->price_tma; e->price_tile = src->price_tile; e->price_split = src->price_split;
   e->lane1_ldg = src->lane1_ldg; e->price_ctas = src->price_ctas; e->fused = src->fused; e->fused_max = src->fused_max;
-  e->async_pivot = src->async_pivot;
+  e->async_pivot = src->async_pivot; e->merge_small = src->merge_small;
   e->h_bvar = src->h_bvar; e->h_slot_of_row = src->h_slot_of_row; e->h_free_slots = src->h_free_slots;
   e->h_pending_free = src->h_pending_free; e->h_last_eta_of_row = src->h_last_eta_of_row;
   e->lu_every = src->lu_every; e->pivots_since_lu = src->pivots_since_lu; e->fill_true = src->fill_true; e->rf_tol = src->rf_tol;

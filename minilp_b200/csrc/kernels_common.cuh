@@ -432,6 +432,99 @@ __global__ void __launch_bounds__(256) k_gemv_n_sub(const double* __restrict__ M
   if (i < rows) y[i] = acc;
 }
 
+// The eta part of an FTRAN in ONE launch for short eta files (K <= FE_MAXK): every CTA first forms the K scalars
+// t = (I+G)^-1 in[etaR] itself — K^2/2 multiply-adds, nothing next to a launch — and then applies out[i] = in[i] - sum_j t_j E[i,j]
+// to its rows.  Same operations in the same order as k_mv_n<true> followed by k_gemv_n_sub (eight column groups per row of the
+// triangular product, added in group order; columns subtracted in ascending order): bit-identical results.  `in` and `out`
+// are different buffers (every CTA reads in[etaR[*]], which other CTAs would be overwriting in place).
+constexpr int FE_MAXK = 128;
+__global__ void __launch_bounds__(256) k_eta_apply(const double* __restrict__ E, int64_t ld, int rows, int K,
+                                                    const double* __restrict__ Ginv, int64_t Kld, const int32_t* __restrict__ etaR,
+                                                    const double* __restrict__ in, double* __restrict__ out) {
+  pdl_wait();
+  __shared__ double xs[FE_MAXK];
+  __shared__ double ts[FE_MAXK];
+  __shared__ double part[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < K; j += 256) xs[j] = in[etaR[j]];
+  __syncthreads();
+  for (int i0 = 0; i0 < K; i0 += 32) {
+    const int i = i0 + lane;
+    double acc = 0.0;
+    if (i < K) {
+      const double* p = Ginv + i;
+      for (int j = g; j <= i; j += 8) acc += p[(int64_t)j * Kld] * xs[j];
+    }
+    part[g][lane] = acc;
+    __syncthreads();
+    if (g == 0 && i < K) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += part[q][lane];
+      ts[i] = t;
+    }
+    __syncthreads();
+  }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  double acc = in[i];
+  const double* p = E + i;
+  int j = 0;
+  for (; j + 16 <= K; j += 16) {
+    double v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = p[(int64_t)(j + u) * ld];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc -= ts[j + u] * v[u];
+  }
+  for (; j + 4 <= K; j += 4) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = p[(int64_t)(j + u) * ld];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc -= ts[j + u] * v[u];
+  }
+  for (; j < K; ++j) acc -= ts[j] * p[(int64_t)j * ld];
+  out[i] = acc;
+}
+// BTRAN of a unit vector e_r through a short eta file, first half in ONE launch: c = e_r (cnt entries) and
+// s = (I+G)^-T u with u = row r of E read in place (k_unit_and_gather + k_mv_t<true>; one warp per column, same order).
+__global__ void __launch_bounds__(256) k_unit_eta_t(double* __restrict__ c, int64_t cnt, int64_t at, const double* __restrict__ E,
+                                                     int64_t lde, const double* __restrict__ Ginv, int64_t Kld, int K,
+                                                     double* __restrict__ s) {
+  pdl_wait();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cnt) c[t] = (t == at) ? 1.0 : 0.0;
+  const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j >= K) return;
+  const double* col = Ginv + (int64_t)j * Kld;
+  double acc = 0.0;
+  for (int i = j + lane; i < K; i += 32) acc += col[i] * E[(int64_t)i * lde + at];
+  acc = warp_sum(acc);
+  if (lane == 0) s[j] = acc;
+}
+// Eta push in ONE launch for short eta files: the bookkeeping of k_eta_grow and the new row K of (I+G)^-1 (k_eta_inv_row) with
+// the coupling row g[i] = E_i[r_K] read in place.  Same order of operations: bit-identical.
+__global__ void __launch_bounds__(256) k_eta_push(const double* __restrict__ E, int64_t lde, int K, int rK, double* __restrict__ Ginv,
+                                                   int64_t ld, int32_t* etaR, int32_t* etaPrev, int32_t* etaHead, int32_t* etaLast, int prev) {
+  pdl_wait();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    etaR[K] = rK;
+    etaPrev[K] = prev;
+    etaHead[K] = 1;
+    etaLast[rK] = K;
+    if (prev >= 0) etaHead[prev] = 0;
+  }
+  const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (j > K) return;
+  double* col = Ginv + (int64_t)j * ld;
+  if (j == K) { if (lane == 0) col[K] = 1.0; return; }
+  double acc = 0.0;
+  for (int i = j + lane; i < K; i += 32) acc += E[(int64_t)i * lde + rK] * col[i];
+  acc = warp_sum(acc);
+  if (lane == 0) col[K] = -acc;
+}
+
 // Column-group split of the same tall-skinny products for wide basis blocks: with one thread per row a 50k-row pass
 // has only ~340 threads per SM, too few loads in flight to saturate HBM once cols grows into the hundreds.  Grid
 // (row tiles, G): CTA (x, g) accumulates column group g into part[g][i]; the finishing kernels add the G partials in

@@ -21,7 +21,8 @@
 // quantity (the reference solves with L and U), so the rank-K product may contract a*b+c.
 #pragma once
 
-constexpr int RF_MAXK = 128;  // etas folded by one refresh; a longer file takes the true factorization
+constexpr int RF_MAXK = 128;  // chunk of etas held in shared memory by k_rf_t; also the length of the device-map patch lists
+constexpr int RF_CAP = 1024;  // etas folded by one refresh at most (rows of rf_W / rf_T / rf_Ep); a longer file takes the true factorization
 
 // entry of B_old^-1: row descriptor rs (>= 0: old core column; < 0: row -1-rs of W) at basis position pos, column descriptor
 // cs (>= 0: old core row; < 0: the unit vector at position -1-cs)
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(256) k_rf_w(const int64_t* __restrict__ dptr, 
 }
 
 // T[:, c'] = (I+G)^-1 X0[etaR, c'] for 32 columns c' per CTA (lower-triangular product, as k_mv_n<true>).  T is K x k_new,
-// leading dimension RF_MAXK.
+// leading dimension RF_CAP.  The eta index j is walked in chunks of RF_MAXK held in shared memory; a chunk contributes to
+// every row i at or below it, accumulated in T itself (each (i, c') is touched by one thread per chunk, chunks are
+// separated by CTA barriers).  K <= RF_MAXK: one chunk, no accumulation through memory.
 __global__ void __launch_bounds__(256) k_rf_t(const double* __restrict__ Ginv, int64_t Kld, int K, const int32_t* __restrict__ etasrc,
                                                const int32_t* __restrict__ etapos, const int32_t* __restrict__ colsrc, int k_new,
                                                const double* __restrict__ Cinv, int64_t ld, const double* __restrict__ W, int64_t wld,
@@ -54,17 +57,24 @@ __global__ void __launch_bounds__(256) k_rf_t(const double* __restrict__ Ginv, i
   pdl_wait();
   __shared__ double Us[RF_MAXK][33];
   const int c0 = blockIdx.x * 32;
-  for (int q = threadIdx.x; q < K * 32; q += 256) {
-    const int j = q >> 5, cc = q & 31;
-    Us[j][cc] = c0 + cc < k_new ? rf_x0(etasrc[j], etapos[j], colsrc[c0 + cc], Cinv, ld, W, wld) : 0.0;
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < K * 32; q += 256) {
-    const int i = q % K, cc = q / K;
-    if (c0 + cc >= k_new) continue;
-    double acc = 0.0;
-    for (int j = 0; j <= i; ++j) acc += Ginv[(int64_t)j * Kld + i] * Us[j][cc];
-    T[(int64_t)(c0 + cc) * RF_MAXK + i] = acc;
+  for (int jc = 0; jc < K; jc += RF_MAXK) {
+    const int nj = min(RF_MAXK, K - jc);
+    __syncthreads();  // the previous chunk's readers of Us are done (and its updates of T are visible)
+    for (int q = threadIdx.x; q < nj * 32; q += 256) {
+      const int j = q >> 5, cc = q & 31;
+      Us[j][cc] = c0 + cc < k_new ? rf_x0(etasrc[jc + j], etapos[jc + j], colsrc[c0 + cc], Cinv, ld, W, wld) : 0.0;
+    }
+    __syncthreads();
+    const int ni = K - jc;  // rows jc .. K-1 see this chunk
+    for (int q = threadIdx.x; q < ni * 32; q += 256) {
+      const int i = jc + q % ni, cc = q / ni;
+      if (c0 + cc >= k_new) continue;
+      const int jend = min(nj, i - jc + 1);  // j <= i
+      double acc = 0.0;
+      for (int j = 0; j < jend; ++j) acc += Ginv[(int64_t)(jc + j) * Kld + i] * Us[j][cc];
+      double* dst = T + (int64_t)(c0 + cc) * RF_CAP + i;
+      *dst = jc == 0 ? acc : *dst + acc;
+    }
   }
 }
 
