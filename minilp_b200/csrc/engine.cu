@@ -469,1227 +469,8 @@ static inline int owner_of(const mlp_engine* e, int64_t g) {
   return -1;
 }
 
-// ------------------------------------------------------------------------------------------------ K5 price-out
-// calc_row_coeffs price-out (solver.rs:685-692), the N^T v product of update_primal_sq_norms (1117-1132), the full
-// c_N - N^T y of recalc_obj_coeffs (1216-1222) and the column norms of try_new (297-299).  Row-gather GEMV^T over
-// row-major A: a CTA owns a 512-column tile and one chunk of the multiplier's support; each thread accumulates two
-// adjacent columns with 128-bit streaming loads, 8 rows in flight; rows of a chunk are taken in list order;
-// (row, weight) pairs are staged through shared memory.  The chunking depends ONLY on the support size s
-// (C = clamp(ceil(s/128), 1, 64)), never on the grid or the shard width, so a column's sum is bit-identical however
-// the columns are sharded.  Chunk partials are reduced in chunk order by k_price_finish — no atomics.
-constexpr int PR_THREADS = 256;
-constexpr int PR_TILE = PR_THREADS * 2;
-constexpr int PR_BATCH = 256;
-constexpr int PR_UNROLL = 8;
-constexpr int PR_MAXC = 64;
-__host__ __device__ __forceinline__ int price_chunks_for(int s) {
-  int c = (s + 127) / 128;
-  return c < 1 ? 1 : (c > PR_MAXC ? PR_MAXC : c);
-}
-
-template <int MODE>  // 0: sum_r w_r * A[r,j]   1: sum_r A[r,j]^2
-__global__ void __launch_bounds__(PR_THREADS)
-k_price_partial(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
-                const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
-                double* __restrict__ partial) {
-  pdl_wait();
-  __shared__ int32_t srow[PR_BATCH];
-  __shared__ double sw[PR_BATCH];
-  const int s = count_ptr ? *count_ptr : fixed_count;
-  const int C = price_chunks_for(s);
-  const int L = (s + C - 1) / C;
-  const int tiles = (int)((lda + PR_TILE - 1) / PR_TILE);
-  // Persistent CTAs: the grid is sized to a fixed number of CTAs per SM (not to the work), so that the rest of each SM stays
-  // free for the latency-bound kernels of the other lane; work item = (column tile, support chunk).
-  for (int item = blockIdx.x; item < tiles * C; item += gridDim.x) {
-    const int tile = item % tiles, chunk = item / tiles;
-    const int k0 = chunk * L;
-    const int k1 = min(s, k0 + L);
-    const int64_t col = ((int64_t)tile * PR_THREADS + threadIdx.x) * 2;
-    const bool active = col < lda;
-    double acc0 = 0.0, acc1 = 0.0;
-    const double* base = A + col;
-    for (int kb = k0; kb < k1; kb += PR_BATCH) {
-      const int nb = min(PR_BATCH, k1 - kb);
-      __syncthreads();
-      for (int t = threadIdx.x; t < nb; t += PR_THREADS) {
-        srow[t] = rows ? rows[kb + t] : kb + t;
-        sw[t] = (MODE == 0) ? wts[kb + t] : 1.0;
-      }
-      __syncthreads();
-      if (active) {
-        int i = 0;
-        for (; i + PR_UNROLL <= nb; i += PR_UNROLL) {
-          double2 v[PR_UNROLL];
-#pragma unroll
-          for (int u = 0; u < PR_UNROLL; ++u)
-            v[u] = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i + u] * lda));
-#pragma unroll
-          for (int u = 0; u < PR_UNROLL; ++u) {
-            if (MODE == 0) {
-              const double wv = sw[i + u];
-              acc0 += wv * v[u].x;
-              acc1 += wv * v[u].y;
-            } else {
-              acc0 += v[u].x * v[u].x;
-              acc1 += v[u].y * v[u].y;
-            }
-          }
-        }
-        for (; i < nb; ++i) {
-          const double2 v = __ldcs(reinterpret_cast<const double2*>(base + (int64_t)srow[i] * lda));
-          if (MODE == 0) {
-            const double wv = sw[i];
-            acc0 += wv * v.x;
-            acc1 += wv * v.y;
-          } else {
-            acc0 += v.x * v.x;
-            acc1 += v.y * v.y;
-          }
-        }
-      }
-    }
-    if (active) {
-      double2 o;
-      o.x = acc0;
-      o.y = acc1;
-      *reinterpret_cast<double2*>(partial + (int64_t)chunk * lda + col) = o;
-    }
-  }
-}
-
-// ---- bulk-copy (TMA) form of the same price-out --------------------------------------------------------------
-// The LDG kernel above needs 6 resident CTAs per SM (all registers) to keep enough bytes in flight; that starves the
-// latency-bound kernels of lane 1 that should run beside it.  Here the bytes in flight live in SHARED memory instead:
-// one CTA per SM, a producer warp gathers the listed rows with 1-D bulk copies (cp.async.bulk, 4 KB row segments,
-// L2 evict-first) into a TP_STAGES-deep ring guarded by mbarriers, eight consumer warps accumulate.  Work items,
-// chunking and the per-column accumulation order (list order within a chunk, thread t owns columns 2t, 2t+1 of the
-// tile) are those of k_price_partial, so the partial sums are bit-identical.
-constexpr int TP_STAGE_BYTES = 32768;             // one stage: R rows x tile_cols x 8 B, R = 32768 / (tile_cols * 8) <= 32
-constexpr int TP_STAGES = 6;                      // ring depth: 6 x 32 KB = 192 KB in flight per SM
-constexpr int TP_MAXROWS = 32;                    // one row per producer lane
-constexpr int TP_CONSUMERS = PR_THREADS;          // 8 warps
-constexpr int TP_THREADS = TP_CONSUMERS + 32;     // + producer warp
-constexpr size_t TP_SMEM = (size_t)TP_STAGES * TP_STAGE_BYTES + TP_STAGES * TP_MAXROWS * 8 + 2 * TP_STAGES * 8 + 16;
-// Tile width: 512 columns (4 KB row segments).  Narrower tiles were measured and lose: 6.77 TB/s at 512, 6.19 at 256,
-// 4.30 at 128 columns (more, smaller bulk copies per byte); a narrow column block of a sharded engine has fewer work
-// items per SM, but the tail still has enough SMs active to saturate HBM.  MLP_PRICE_TILE overrides for experiments.
-// Choice of the tiling (host), from the measured sweeps in profiles/r01d_price_sweep.md (B200, isolated dense N^T v,
-// m = 50k; GB/s at 512-column tiles -> at the width chosen here):  n_loc 50 000: 6760 -> 7068 (1280);  25 000: 6735 -> 7070
-// (1280);  12 500: 6668 -> 7102 (4096);  6 250: 6125 -> 6998 (4096).  Wider row segments mean fewer, larger bulk copies and
-// longer contiguous DRAM bursts, and that matters more the shorter the rows of the local block are; widths whose rows fill
-// a 32 KB stage badly (2560 columns = 20 KB: one row per stage) lose the bytes in flight again.  The kernel is HBM-bound
-// with ~28 MB in flight, so a partly filled last round of work items costs little (a round model that predicted gains
-// from balancing it did not survive the measurement; the tail split stays available as a knob, default 1).
-static void choose_price_tiling(int64_t lda, int64_t /*m*/, int /*G*/, int* tile, int* split) {
-  *split = 1;
-  const int w = lda < 20000 ? 4096 : 1280;
-  const int need = (int)std::min<int64_t>(4096, (lda + 63) / 64 * 64);  // never wider than the block itself
-  *tile = std::max(128, std::min(w, need));
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(b)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::"r"(
-          smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)  // L2 evict-first: A is streamed once per pivot
-      : "memory");
-}
-
-// NV = column pairs per consumer thread: a tile is up to NV * 512 columns wide (NV * 4 KB row segments).  Thread t owns
-// column pairs t, t + 256, ... of the tile; every column still accumulates its rows in list order, so the partial sums
-// do not depend on the tiling.
-//
-// Work items and load balance.  An item is (column tile, support chunk); CTA b takes items b, b + G, ... (G CTAs).  With
-// tiles * C items the last round is only partly filled — at 50k columns and 1024-column tiles 3136 items are 21.2
-// rounds, i.e. 4 % of the kernel runs with 80 % of the SMs idle.  So only the items of the FULL rounds keep the whole tile
-// width; the items of the last, partial round are cut into `split` column slices each, which spreads that round over
-// all CTAs again (narrower row segments are less efficient, but only the tail pays that).
-struct PriceItem {
-  int chunk;
-  int64_t col0;
-  int cols;   // columns actually present (0: the slice lies beyond the matrix)
-  int width;  // nominal width: row stride of the stage in shared memory
-};
-__device__ __forceinline__ PriceItem price_item(int idx, int main_items, int tiles, int tile_cols, int split, int64_t lda) {
-  PriceItem it;
-  int item, sub = 0;
-  it.width = tile_cols;
-  if (idx < main_items) item = idx;
-  else {
-    const int j = idx - main_items;
-    item = main_items + j / split;
-    sub = j % split;
-    it.width = tile_cols / split;
-  }
-  it.chunk = item / tiles;
-  it.col0 = (int64_t)(item % tiles) * tile_cols + (int64_t)sub * it.width;
-  const int64_t tile_end = min(lda, (int64_t)(item % tiles + 1) * tile_cols);
-  const int64_t c = min((int64_t)it.width, tile_end - it.col0);
-  it.cols = c > 0 ? (int)c : 0;
-  return it;
-}
-template <int NV>
-__global__ void __launch_bounds__(TP_THREADS, 1)
-k_price_partial_tma(const double* __restrict__ A, int64_t lda, const int32_t* __restrict__ rows,
-                    const double* __restrict__ wts, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
-                    double* __restrict__ partial, int tile_cols, int split) {
-  pdl_wait();
-  extern __shared__ __align__(128) unsigned char tp_smem[];
-  double* sw = reinterpret_cast<double*>(tp_smem + (size_t)TP_STAGES * TP_STAGE_BYTES);   // [stage][row] weights
-  uint64_t* full = reinterpret_cast<uint64_t*>(sw + TP_STAGES * TP_MAXROWS);
-  uint64_t* empty = full + TP_STAGES;
-  const int s = count_ptr ? *count_ptr : fixed_count;
-  const int C = price_chunks_for(s);
-  const int L = (s + C - 1) / C;
-  const int tiles = (int)((lda + tile_cols - 1) / tile_cols);
-  const int items = tiles * C;
-  const int main_items = items / (int)gridDim.x * (int)gridDim.x;
-  const int total = main_items + (items - main_items) * split;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int q = 0; q < TP_STAGES; ++q) { mbar_init(full + q, 1); mbar_init(empty + q, TP_CONSUMERS / 32); }
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-  }
-  __syncthreads();
-  uint32_t it = 0;  // stages handled so far by this role: slot = it % TP_STAGES, phase = (it / TP_STAGES) & 1
-  if (warp == TP_CONSUMERS / 32) {
-    // ---------------- producer warp: lane r < R fetches row r of the stage
-    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
-      const PriceItem pi = price_item(idx, main_items, tiles, tile_cols, split, lda);
-      if (pi.cols == 0) continue;
-      const int k0 = pi.chunk * L, k1 = min(s, k0 + L);
-      const int tile_bytes = pi.width * 8;
-      const int R = min(TP_MAXROWS, TP_STAGE_BYTES / tile_bytes);  // rows per stage
-      const uint32_t tbytes = (uint32_t)pi.cols * 8u;
-      for (int kb = k0; kb < k1; kb += R, ++it) {
-        const int nr = min(R, k1 - kb);
-        const int slot = it % TP_STAGES;
-        int32_t r = 0;
-        double wv = 0.0;
-        if (lane < nr) { r = rows[kb + lane]; wv = wts[kb + lane]; }  // issued before the wait: latency overlaps
-        mbar_wait(empty + slot, ((it / TP_STAGES) & 1) ^ 1);
-        if (lane < nr) sw[slot * TP_MAXROWS + lane] = wv;
-        __syncwarp();
-        if (lane == 0) mbar_arrive_expect_tx(full + slot, tbytes * nr);
-        __syncwarp();
-        if (lane < nr)
-          bulk_g2s(tp_smem + (size_t)slot * TP_STAGE_BYTES + (size_t)lane * tile_bytes, A + (int64_t)r * lda + pi.col0, tbytes,
-                   full + slot);
-      }
-    }
-  } else {
-    // ---------------- consumers: thread t owns column pairs t + 256 v (v < NV) of the tile
-    const int t = threadIdx.x;
-    constexpr int RU = 8 / NV;            // rows per unrolled batch: 8 loads in flight per thread
-    for (int idx = blockIdx.x; idx < total; idx += gridDim.x) {
-      const PriceItem pi = price_item(idx, main_items, tiles, tile_cols, split, lda);
-      if (pi.cols == 0) continue;
-      const int k0 = pi.chunk * L, k1 = min(s, k0 + L);
-      const int tile_bytes = pi.width * 8;
-      const int R = min(TP_MAXROWS, TP_STAGE_BYTES / tile_bytes);
-      const int rstride = tile_bytes / 16;  // double2 per row
-      const int64_t col = pi.col0 + 2 * t;
-      bool active[NV];
-      double acc0[NV], acc1[NV];
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        active[v] = 2 * (t + TP_CONSUMERS * v) < pi.cols;
-        acc0[v] = 0.0;
-        acc1[v] = 0.0;
-      }
-      for (int kb = k0; kb < k1; kb += R, ++it) {
-        const int nr = min(R, k1 - kb);
-        const int slot = it % TP_STAGES;
-        mbar_wait(full + slot, (it / TP_STAGES) & 1);
-        if (active[0]) {
-          const double2* p = reinterpret_cast<const double2*>(tp_smem + (size_t)slot * TP_STAGE_BYTES) + t;
-          const double* w = sw + slot * TP_MAXROWS;
-          int u0 = 0;
-          for (; u0 + RU <= nr; u0 += RU) {
-            double2 x[RU][NV];
-#pragma unroll
-            for (int u = 0; u < RU; ++u)
-#pragma unroll
-              for (int v = 0; v < NV; ++v)
-                if (NV == 1 || active[v]) x[u][v] = p[(u0 + u) * rstride + TP_CONSUMERS * v];
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-              const double wv = w[u0 + u];
-#pragma unroll
-              for (int v = 0; v < NV; ++v)
-                if (NV == 1 || active[v]) {
-                  acc0[v] += wv * x[u][v].x;
-                  acc1[v] += wv * x[u][v].y;
-                }
-            }
-          }
-          for (; u0 < nr; ++u0) {
-            const double wv = w[u0];
-#pragma unroll
-            for (int v = 0; v < NV; ++v)
-              if (NV == 1 || active[v]) {
-                const double2 x = p[u0 * rstride + TP_CONSUMERS * v];
-                acc0[v] += wv * x.x;
-                acc1[v] += wv * x.y;
-              }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + slot);
-      }
-#pragma unroll
-      for (int v = 0; v < NV; ++v)
-        if (active[v]) {
-          double2 o;
-          o.x = acc0[v];
-          o.y = acc1[v];
-          *reinterpret_cast<double2*>(partial + (int64_t)pi.chunk * lda + col + 2 * TP_CONSUMERS * v) = o;
-        }
-    }
-  }
-}
-
-// Reduce chunk partials in chunk order; slack columns of [A|I] contribute rho_i (the `I` part of the CSR row,
-// solver.rs:250); basic variables are not part of row_coeffs (solver.rs:688).
-// mode 0: out = sum   mode 1: out = sum + 1 (primal edge norms, solver.rs:298)
-__global__ void k_price_finish(const double* __restrict__ partial, const int32_t* __restrict__ count_ptr, int32_t fixed_count,
-                               int64_t lda, int64_t n, int64_t m, const double* __restrict__ slack_vals,
-                               const uint8_t* __restrict__ vflag, double* __restrict__ out, int mode) {
-  pdl_wait();
-  int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n + m) return;
-  const int C = price_chunks_for(count_ptr ? *count_ptr : fixed_count);
-  double r;
-  if (v < n) {
-    r = 0.0;
-    for (int c = 0; c < C; ++c) r += partial[(int64_t)c * lda + v];
-    if (mode == 1) r += 1.0;
-  } else {
-    r = (mode == 1) ? 2.0 : slack_vals[v - n];  // |e_i|^2 + 1
-  }
-  if (mode == 0 && (vflag[v] & MLP_BASIC)) r = 0.0;
-  out[v] = r;
-}
-
-// ------------------------------------------------------------------------------------------------ columns
-// rhs.set(column of var) (solver.rs:672-675, sparse.rs:103): column of [A|I] of LOCAL variable lv as a dense m-vector
-__global__ void k_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int m, int64_t lv, double* __restrict__ dst) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  dst[i] = lv < n ? A[(int64_t)i * lda + lv] : ((int64_t)i == lv - n ? 1.0 : 0.0);
-}
-// same, for the variable named by a candidate header that is still on the device (no host round trip)
-__global__ void k_cand_load_col(const double* __restrict__ A, int64_t lda, int64_t n, int64_t c0, int64_t ng, int m,
-                                const Cand* __restrict__ cand, double* __restrict__ dst, Cand* __restrict__ win_out) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0 && win_out) *win_out = *cand;  // single shard: the candidate IS the winner
-  if (i >= m) return;
-  const long long g = cand->var;
-  if (g < 0) { dst[i] = 0.0; return; }
-  const int64_t lv = g >= ng ? n + (g - ng) : g - c0;
-  dst[i] = lv < n ? A[(int64_t)i * lda + lv] : ((int64_t)i == lv - n ? 1.0 : 0.0);
-}
-
-// FTRAN tail: alpha[pos] for slack positions = a_i - (D1 x)_i ; alpha[Jpos[t]] = x[t]   (U-solve of the
-// identity-bordered basis, lu.rs:93 with B = [D | E_S]).  The t-th dense column lives in cache slot Jslot[t].
-__global__ void __launch_bounds__(256) k_ftran_finish(const double* __restrict__ Bcols, int64_t ldb, int m, int k,
-                                                       const double* __restrict__ xk, const double* __restrict__ rhs0,
-                                                       const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                                       const int32_t* __restrict__ Jslot, double* __restrict__ out,
-                                                       const uint8_t* __restrict__ touched, uint8_t* __restrict__ touched_new) {
-  pdl_wait();
-  __shared__ double ts[512];
-  __shared__ int32_t sl[512];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double acc = i < m ? rhs0[i] : 0.0;
-  const int cov = i < m ? rowcover[i] : -1;
-  for (int j0 = 0; j0 < k; j0 += 512) {
-    const int nj = min(512, k - j0);
-    __syncthreads();
-    for (int q = threadIdx.x; q < nj; q += blockDim.x) { ts[q] = xk[j0 + q]; sl[q] = Jslot[j0 + q]; }
-    __syncthreads();
-    if (cov >= 0) {
-      const double* p = Bcols + i;
-      int j = 0;
-      for (; j + 16 <= nj; j += 16) {  // 16 loads in flight, subtraction still in column order
-        double v[16];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
-#pragma unroll
-        for (int u = 0; u < 16; ++u) acc -= ts[j + u] * v[u];
-      }
-      for (; j + 4 <= nj; j += 4) {
-        double v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = p[(int64_t)sl[j + u] * ldb];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc -= ts[j + u] * v[u];
-      }
-      for (; j < nj; ++j) acc -= ts[j] * p[(int64_t)sl[j] * ldb];
-    }
-  }
-  if (cov >= 0) { out[cov] = acc; if (touched_new) touched_new[cov] = (uint8_t)((acc != 0.0) | (touched[cov] != 0)); }
-  if (i < k) {
-    const int p = Jpos[i];
-    const double xv = xk[i];
-    out[p] = xv;
-    if (touched_new) touched_new[p] = (uint8_t)((xv != 0.0) | (touched[p] != 0));  // k_touch_mark, folded in
-  }
-}
-// FTRAN tail after a column-group split (k_tall_part): alpha_slack = a_S - sum_g part[g], alpha[Jpos[t]] = x[t]
-__global__ void k_ftran_finish_parts(const double* __restrict__ part, int G, int64_t pld, int m, int k,
-                                     const double* __restrict__ xk, const double* __restrict__ rhs0,
-                                     const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                     double* __restrict__ out, const uint8_t* __restrict__ touched,
-                                     uint8_t* __restrict__ touched_new) {
-  pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) {
-    const int cov = rowcover[i];
-    if (cov >= 0) {
-      double tsum = 0.0;
-      for (int g = 0; g < G; ++g) tsum += part[(int64_t)g * pld + i];
-      const double v = rhs0[i] - tsum;
-      out[cov] = v;
-      if (touched_new) touched_new[cov] = (uint8_t)((v != 0.0) | (touched[cov] != 0));
-    }
-  }
-  if (i < k) {
-    const int p = Jpos[i];
-    const double xv = xk[i];
-    out[p] = xv;
-    if (touched_new) touched_new[p] = (uint8_t)((xv != 0.0) | (touched[p] != 0));
-  }
-}
-// core C = D[R,:] (k x k, column-major) from the column cache
-__global__ void k_extract_core(const double* __restrict__ Bcols, int64_t ldb, int k, const int32_t* __restrict__ Rp,
-                               const int32_t* __restrict__ Jslot, double* __restrict__ C, int64_t ld) {
-  pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int t = blockIdx.y;
-  if (i < k && t < k) C[(int64_t)t * ld + i] = Bcols[(int64_t)Jslot[t] * ldb + Rp[i]];
-}
-// BTRAN: right-hand side of the core solve, rhs_t = c[Jpos[t]] - sum_i Bcols[i, slot_t] cov_i; CTA (t, s) reduces a row
-// slice, k_gemv_t_fin adds the slices in order.
-__global__ void __launch_bounds__(256) k_core_rhs_part(const double* __restrict__ Bcols, int64_t ldb, int rows, int k,
-                                                        const int32_t* __restrict__ Jslot, const double* __restrict__ x,
-                                                        double* __restrict__ part) {
-  pdl_wait();
-  __shared__ double sm[32];
-  const int j = blockIdx.x, S = gridDim.y, sidx = blockIdx.y;
-  const int L = (rows + S - 1) / S;
-  const int r0 = sidx * L, r1 = min(rows, r0 + L);
-  const double* p = Bcols + (int64_t)Jslot[j] * ldb;
-  double acc = 0.0;
-  int i = r0 + threadIdx.x;
-  const int st = blockDim.x;
-  for (; i + 7 * st < r1; i += 8 * st) {  // 8 row pairs in flight per thread, added in row order
-    double a[8], b[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { a[u] = p[i + u * st]; b[u] = x[i + u * st]; }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc += a[u] * b[u];
-  }
-  for (; i < r1; i += st) acc += p[i] * x[i];
-  const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) part[(int64_t)sidx * k + j] = tot;
-}
-
-// ------------------------------------------------------------------------------------------------ sparse storage
-// Sparse A (CSR + CSC, u32 indices).  The basis-inverse machinery is shared with the dense engine: basis columns are
-// expanded into the dense column cache when they enter, so only three things read the sparse matrix — the column
-// load, the price-out and the set-up passes.
-// rhs.set(column) (solver.rs:672-675): dst is zero-filled by the caller; var < 0 comes from a candidate header.
-// Every shard of a sparse-storage engine holds the WHOLE matrix (12 nnz bytes: small next to HBM; the basis operations
-// need the basic columns wherever they price): n and lv are GLOBAL here.
-__global__ void k_load_col_csc(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                               int64_t n, int64_t lv_arg, const Cand* __restrict__ cand, double* __restrict__ dst,
-                               Cand* __restrict__ win_out) {
-  pdl_wait();
-  int64_t lv = lv_arg;
-  if (cand && win_out && blockIdx.x == 0 && threadIdx.x == 0) *win_out = *cand;
-  if (cand) {
-    if (cand->var < 0) return;
-    lv = cand->var;  // GLOBAL variable index
-  }
-  if (lv >= n) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) dst[lv - n] = 1.0;
-    return;
-  }
-  const int64_t b = ptr[lv], e = ptr[lv + 1];
-  for (int64_t t = b + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < e; t += (int64_t)gridDim.x * blockDim.x) dst[idx[t]] = val[t];
-}
-// Price-out over the CSC copy (calc_row_coeffs 685-692, update_primal_sq_norms 1117-1132, recalc_obj_coeffs 1216-1222,
-// column norms 297-299): gathers the DENSE multiplier vector w at each column's row indices — 12 bytes per stored entry.
-// Column lengths are power-law distributed (one column of a netlib-like LP can hold 10^5 entries), so the unit of work is
-// a SEGMENT of at most CSC_SEG consecutive entries of one column (table built once at creation): pass 1, one warp per
-// segment, rows ascending, fixed shuffle tree; pass 2 adds a column's segment sums in order.  Bit-reproducible, no atomics.
-// MODE 0: out[v] = sum_i A[i,v] w[i] (slack v: w[v-n]; basic v: 0)     MODE 1: out[v] = |a_v|^2 + 1
-constexpr int CSC_SEG = 1024;
-// Column-sharded engines price out only the segments [sg0, sg1) of their own column block.
-//
-// Latency, not bandwidth, bounds this kernel: a column of the config-4 LP holds ~100 entries, so a warp spends its time in
-// the dependent chain descriptor -> (row index, value) -> multiplier[row] -> shuffle tree, three global round trips per
-// segment (first version: five — segment column, its offset and end, the basic flag, then the entries — 89 us per launch
-// = 1.3 TB/s, profiles/r02_price_csc_full.md).  Here a segment is ONE 16-byte descriptor, the basic flag is left to
-// k_price_csc_fin, and a warp works on PR_CSC_U segments at once with the first two strides of each in flight together.
-// Per segment the sum is unchanged: lane-strided partial sums in ascending entry order, then the fixed shuffle tree.
-struct SegDesc {
-  int64_t begin;
-  int32_t len, col;
-};
-static_assert(sizeof(SegDesc) == 16, "SegDesc is one 16-byte load");
-constexpr int PR_CSC_U = 4;      // short segments (<= 64 entries) in flight per warp
-constexpr int PR_CSC_LONG = 64;  // a segment with more entries is "long": one per warp, eight strides in flight
-// Where the entries are: the column counts are power-law distributed, so on config 4 ~8 % of the segments (the full
-// 1024-entry pieces of the ~1 % longest columns) hold ~85 % of the entries, while ~90 % of the segments are short columns of a
-// few dozen entries.  Two work lists (built with the segment table): a LONG segment goes to one warp that keeps eight
-// strides (256 entries: values, row indices, then the gathers) in flight — bandwidth; SHORT ones are taken four at a time
-// with both strides of each issued together — latency.  Per segment the summation order is the same in both: lane-strided
-// partial sums in ascending entry order, then the fixed shuffle tree (bit-identical to the first version of the kernel).
-// STREAM: matrix entries are loaded with the evict-first policy (__ldcs: a matrix larger than L2 is streamed once per pivot) or
-// with the default policy (the 117 MB of config 4 can stay partly L2-resident between two price-outs; MLP_CSC_STREAM picks).
-template <int MODE, bool STREAM>
-__global__ void __launch_bounds__(256) k_price_csc_seg(const SegDesc* __restrict__ desc, const int32_t* __restrict__ idx,
-                                                       const double* __restrict__ val, const int32_t* __restrict__ long_ids,
-                                                       int nlong, const int32_t* __restrict__ short_ids, int nshort,
-                                                       const double* __restrict__ w, double* __restrict__ seg_sum) {
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int warps = (int)(((int64_t)gridDim.x * blockDim.x) >> 5);
-  const int wid = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  for (int i = wid; i < nlong; i += warps) {
-    const int sg = long_ids[i];
-    const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sg));
-    const int64_t b = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
-    const int len = d.z;
-    double acc = 0.0;
-    for (int o0 = lane; o0 < len; o0 += 256) {
-      double a[8];
-      int r[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int o = o0 + 32 * u;
-        const bool ok = o < len;
-        a[u] = ok ? (STREAM ? __ldcs(val + b + o) : __ldg(val + b + o)) : 0.0;
-        r[u] = (MODE == 0 && ok) ? (STREAM ? __ldcs(idx + b + o) : __ldg(idx + b + o)) : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (o0 + 32 * u < len) acc += (MODE == 0) ? a[u] * w[r[u]] : a[u] * a[u];
-    }
-    const double tot = warp_sum(acc);
-    if (lane == 0) seg_sum[sg] = tot;
-  }
-  for (int base = wid; base < nshort; base += warps * PR_CSC_U) {
-    int64_t b[PR_CSC_U];
-    int len[PR_CSC_U], sgq[PR_CSC_U];
-#pragma unroll
-    for (int q = 0; q < PR_CSC_U; ++q) {
-      const int i = base + q * warps;
-      b[q] = 0;
-      len[q] = 0;
-      sgq[q] = -1;
-      if (i < nshort) {
-        sgq[q] = short_ids[i];
-        const int4 d = __ldg(reinterpret_cast<const int4*>(desc + sgq[q]));
-        b[q] = ((int64_t)(unsigned)d.x) | ((int64_t)d.y << 32);
-        len[q] = d.z;
-      }
-    }
-    double a[PR_CSC_U][2];
-    int r[PR_CSC_U][2];
-#pragma unroll
-    for (int q = 0; q < PR_CSC_U; ++q)
-#pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int o = lane + 32 * it;
-        const bool ok = o < len[q];
-        a[q][it] = ok ? (STREAM ? __ldcs(val + b[q] + o) : __ldg(val + b[q] + o)) : 0.0;
-        r[q][it] = (MODE == 0 && ok) ? (STREAM ? __ldcs(idx + b[q] + o) : __ldg(idx + b[q] + o)) : 0;
-      }
-#pragma unroll
-    for (int q = 0; q < PR_CSC_U; ++q) {
-      double acc = 0.0;
-#pragma unroll
-      for (int it = 0; it < 2; ++it)
-        if (lane + 32 * it < len[q]) acc += (MODE == 0) ? a[q][it] * w[r[q][it]] : a[q][it] * a[q][it];
-      const double tot = warp_sum(acc);
-      if (lane == 0 && sgq[q] >= 0) seg_sum[sgq[q]] = tot;
-    }
-  }
-}
-template <int MODE>
-__global__ void __launch_bounds__(256) k_price_csc_fin(const int64_t* __restrict__ col_seg, const double* __restrict__ seg_sum,
-                                                       int64_t n, int64_t m, int64_t c0, const double* __restrict__ w,
-                                                       const uint8_t* __restrict__ vflag, double* __restrict__ out) {
-  pdl_wait();
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // LOCAL variable
-  if (v < n) {
-    double t = 0.0;
-    for (int64_t sg = col_seg[c0 + v]; sg < col_seg[c0 + v + 1]; ++sg) t += seg_sum[sg];
-    out[v] = (MODE == 1) ? t + 1.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : t);
-  } else if (v < n + m) {
-    out[v] = (MODE == 1) ? 2.0 : ((vflag[v] & MLP_BASIC) ? 0.0 : w[v - n]);
-  }
-}
-// rows of A x_N over the CSR copy (solver.rs:234-238): one warp per row
-// (a shard sums only the entries of its own column block [c0, c0 + n_loc); xnb is indexed by LOCAL variable)
-__global__ void __launch_bounds__(256) k_row_dot_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                     const double* __restrict__ val, int64_t m, int64_t c0, int64_t n_loc,
-                                                     const double* __restrict__ xnb, double* __restrict__ out) {
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (r >= m) return;
-  double acc = 0.0;
-  for (int64_t t = ptr[r] + lane; t < ptr[r + 1]; t += 32) {
-    const int64_t j = (int64_t)idx[t] - c0;
-    if (j >= 0 && j < n_loc) acc += val[t] * xnb[j];
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) out[r] = acc;
-}
-
-// The three places where the basis machinery touches the basic structural columns, read from the sparse matrix itself
-// instead of a dense m x k column cache (12 bytes per stored entry instead of 8 m k):
-//   corevar[t]  structural variable of core column t        corepos[v]  core column of variable v, or -1
-//   rowcore[i]  core row of constraint row i (i in R), or -1
-// FTRAN tail: alpha[cov_i] = a_i - sum_{j in row i, j in the core} A[i,j] x[corepos[j]]  (warp per CSR row)
-__global__ void __launch_bounds__(256) k_ftran_finish_csr(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                          const double* __restrict__ val, int m, int k,
-                                                          const double* __restrict__ xk, const double* __restrict__ rhs0,
-                                                          const int32_t* __restrict__ rowcover, const int32_t* __restrict__ Jpos,
-                                                          const int32_t* __restrict__ corepos, double* __restrict__ out) {
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gt < k) out[Jpos[gt]] = xk[gt];
-  const int64_t i = gt >> 5;
-  if (i >= m) return;
-  const int cov = rowcover[i];
-  if (cov < 0) return;
-  double acc = 0.0;
-  for (int64_t t = ptr[i] + lane; t < ptr[i + 1]; t += 32) {
-    const int c = corepos[idx[t]];
-    if (c >= 0) acc += val[t] * xk[c];
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) out[cov] = rhs0[i] - acc;
-}
-// BTRAN core right-hand side: x[t] = c[Jpos[t]] - sum_i A[i, corevar[t]] cov[i], over the segments of the core columns
-// (cseg_id[j] = global segment, cseg_first[t] = first entry of core column t in that list; built at each refactorization)
-__global__ void __launch_bounds__(256) k_core_rhs_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                      const double* __restrict__ val, const int32_t* __restrict__ seg_col,
-                                                      const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
-                                                      int ncseg, const double* __restrict__ cov, double* __restrict__ csum) {
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (j >= ncseg) return;
-  const int64_t sg = cseg_id[j];
-  const int v = seg_col[sg];
-  const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
-  double acc = 0.0;
-  for (int64_t q = b + lane; q < e; q += 32) acc += val[q] * cov[idx[q]];
-  acc = warp_sum(acc);
-  if (lane == 0) csum[j] = acc;
-}
-__global__ void k_core_rhs_fin(const double* __restrict__ csum, const int32_t* __restrict__ cseg_first, int k,
-                               const double* __restrict__ c, const int32_t* __restrict__ Jpos, double* __restrict__ x) {
-  pdl_wait();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= k) return;
-  double tsum = 0.0;
-  for (int j = cseg_first[t]; j < cseg_first[t + 1]; ++j) tsum += csum[j];
-  x[t] = c[Jpos[t]] - tsum;
-}
-// core C = D[R,:]: scatter the stored entries of each core column that fall into core rows (C zero-filled before)
-__global__ void __launch_bounds__(256) k_extract_core_seg(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
-                                                          const double* __restrict__ val, const int32_t* __restrict__ seg_col,
-                                                          const int64_t* __restrict__ seg_off, const int32_t* __restrict__ cseg_id,
-                                                          int ncseg, const int32_t* __restrict__ corepos,
-                                                          const int32_t* __restrict__ rowcore, double* __restrict__ C, int64_t ld) {
-  pdl_wait();
-  const int lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (j >= ncseg) return;
-  const int64_t sg = cseg_id[j];
-  const int v = seg_col[sg];
-  const int t = corepos[v];
-  const int64_t b = seg_off[sg], e = min(b + (int64_t)CSC_SEG, ptr[v + 1]);
-  for (int64_t q = b + lane; q < e; q += 32) {
-    const int r = rowcore[idx[q]];
-    if (r >= 0) C[(int64_t)t * ld + r] = val[q];
-  }
-}
-__global__ void k_set_corepos(int32_t* __restrict__ corepos, const int32_t* __restrict__ corevar, int k, int clear) {
-  pdl_wait();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < k) corepos[corevar[t]] = clear ? -1 : t;
-}
-
-// ------------------------------------------------------------------------------------------------ K1 pricing scan
-// choose_pivot, solver.rs:696-739: arg-max of d^2/gamma (or |d|) over eligible non-basic variables, strict '>' in
-// ascending position order => lowest position wins ties.  Writes this shard's candidate header.
-__global__ void __launch_bounds__(256) k_select_primal(const double* __restrict__ d, const double* __restrict__ gam,
-                                                        const uint8_t* __restrict__ vflag, const int32_t* __restrict__ vpos,
-                                                        int64_t nt, int64_t n, int64_t c0, int64_t ng, int use_se,
-                                                        double* __restrict__ red_f, long long* __restrict__ red_i,
-                                                        unsigned* counter, const double* __restrict__ xnb,
-                                                        const int* __restrict__ flags, Cand* out) {
-  pdl_wait();
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  KeyIdx best{-INFINITY, LLONG_MAX};
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned f = vflag[v];
-    if (f & MLP_BASIC) continue;
-    const double dv = d[v];
-    if (((f & MLP_AT_MIN) && dv > -EPS) || ((f & MLP_AT_MAX) && dv < EPS)) continue;  // 705-708
-    const double score = use_se ? dv * dv / gam[v] : fabs(dv);
-    const long long key2 = ((long long)vpos[v] << 32) | (long long)v;  // position decides ties
-    if (better_max(score, key2, best.key, best.idx)) { best.key = score; best.idx = key2; }
-  }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
-  if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
-    const double k = __ldcg(red_f + q);
-    const long long i = __ldcg(red_i + q);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
-  }
-  b = block_argmax(b, smk, smi);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    out->f[4] = flags[2] ? 2.0 : (double)flags[0];
-    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
-    else {
-      const long long v = b.idx & 0xffffffffLL;
-      out->key = b.key;
-      out->tie = (b.idx >> 32) << 32;
-      out->var = v < n ? c0 + v : ng + (v - n);
-      out->f[0] = d[v];
-      out->f[1] = xnb[v];
-    }
-  }
-}
-
-// low word of the winner's `tie` after absorbing a losing candidate of another shard: that candidate and its own ties
-// count towards the winner's when the keys agree exactly (low 16 bits) / within NEAR_TIE (next 16 bits)
-__host__ __device__ __forceinline__ long long merge_ties(long long wt, double wk, long long ct, double ck) {
-  long long e = wt & 0xffff, n = (wt >> 16) & 0xffff;
-  if (ck == wk) e += 1 + (ct & 0xffff);
-  if (ck >= wk * (1.0 - 1e-9)) n += 1 + ((ct >> 16) & 0xffff);
-  if (e > 65535) e = 65535;
-  if (n > 65535) n = 65535;
-  return (wt & ~0xffffffffLL) | (n << 16) | e;
-}
-// Arg-reduce of the gathered candidate headers ON THE DEVICE (larger key wins, ties go to the smaller `tie`: lowest
-// position, solver.rs:719) and copy of the winner's column into colq, so that the FTRAN of the entering column can be
-// queued behind the selection without a host round trip.  Every thread repeats the <= 8-way comparison.
-__global__ void __launch_bounds__(256) k_pick_winner(const char* __restrict__ recv, size_t xbytes, int world, int m,
-                                                      double* __restrict__ colq, Cand* __restrict__ win) {
-  pdl_wait();
-  int best = -1;
-  double err = 0.0;
-  for (int r = 0; r < world; ++r) {
-    const Cand* c = reinterpret_cast<const Cand*>(recv + (size_t)r * xbytes);
-    if (c->f[4] != 0.0) err = 1.0;
-    if (c->var < 0) continue;
-    if (best < 0) { best = r; continue; }
-    const Cand* b = reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
-    if (c->key > b->key || (c->key == b->key && c->tie < b->tie)) best = r;
-  }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) colq[i] = best < 0 ? 0.0 : reinterpret_cast<const double*>(recv + (size_t)best * xbytes + sizeof(Cand))[i];
-  if (i == 0) {
-    if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
-    else {
-      Cand w = *reinterpret_cast<const Cand*>(recv + (size_t)best * xbytes);
-      for (int r = 0; r < world; ++r) {  // ties of the winner across shards (dual ratio test)
-        const Cand* c = reinterpret_cast<const Cand*>(recv + (size_t)r * xbytes);
-        if (r != best && c->var >= 0) w.tie = merge_ties(w.tie, w.key, c->tie, c->key);
-      }
-      *win = w;
-    }
-    win->f[4] = err;
-  }
-}
-
-// The same exchange as ONE kernel over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC): every
-// rank stores its 64-byte candidate header into a mailbox slot of every peer and raises the slot's sequence flag
-// (system-scope fence in between); every rank then polls its OWN mailbox, arg-reduces the headers, and pulls the
-// winner's column (8 m bytes) straight out of the owner's memory.  Compared with the all-gather it moves one column
-// instead of `world` and has no collective launch latency.  Buffers and mailboxes are double-buffered by exchange
-// parity: a rank can be at most one exchange ahead of a peer, because finishing exchange s needs every peer's flag s.
-struct PeerTable { char* base[8]; };
-constexpr int P2P_SLOT = 128;  // 64 B header + flag, padded
-__global__ void __launch_bounds__(256) k_exchange_p2p(PeerTable pt, int rank, int world, unsigned long long seq, int parity,
-                                                       const Cand* __restrict__ mine, int m, size_t col_bytes, size_t box_off,
-                                                       double* __restrict__ colq, Cand* __restrict__ win) {
-  pdl_wait();
-  __shared__ Cand hdr[8];
-  __shared__ int s_best;
-  __shared__ int s_bad;
-  if (threadIdx.x == 0) s_bad = 0;
-  if (blockIdx.x == 0 && threadIdx.x < world) {  // publish into peer `threadIdx.x`
-    char* slot = pt.base[threadIdx.x] + box_off + ((size_t)parity * world + rank) * P2P_SLOT;
-    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(mine);
-    volatile unsigned long long* dst = reinterpret_cast<volatile unsigned long long*>(slot);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) dst[q] = src[q];
-    __threadfence_system();
-    dst[8] = seq;
-  }
-  __syncthreads();
-  if (threadIdx.x < world) {  // wait for peer `threadIdx.x`'s header in my own mailbox
-    const char* slot = pt.base[rank] + box_off + ((size_t)parity * world + threadIdx.x) * P2P_SLOT;
-    const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(slot);
-    const long long t0 = clock64();
-    bool ok = true;
-    while (src[8] != seq) {
-      if (clock64() - t0 > 120000000000LL) { ok = false; break; }  // ~60 s: a peer died; report instead of hanging forever
-      __nanosleep(64);
-    }
-    __threadfence_system();
-    unsigned long long* d = reinterpret_cast<unsigned long long*>(&hdr[threadIdx.x]);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) d[q] = src[q];
-    if (!ok) s_bad = 1;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int best = -1;
-    for (int r = 0; r < world; ++r) {
-      if (hdr[r].var < 0) continue;
-      if (best < 0 || hdr[r].key > hdr[best].key || (hdr[r].key == hdr[best].key && hdr[r].tie < hdr[best].tie)) best = r;
-    }
-    s_best = s_bad ? -1 : best;
-  }
-  __syncthreads();
-  const int best = s_best;
-  const double* src = best < 0 ? nullptr : reinterpret_cast<const double*>(pt.base[best] + (size_t)parity * col_bytes);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
-    colq[i] = best < 0 ? 0.0 : __ldcv(src + i);  // peer memory: never served from a stale cache line
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    double err = s_bad ? 2.0 : 0.0;
-    for (int r = 0; r < world; ++r) if (hdr[r].f[4] != 0.0 && err == 0.0) err = 1.0;
-    if (best < 0) { win->var = -1; win->key = -INFINITY; win->tie = LLONG_MAX; }
-    else {
-      Cand w = hdr[best];
-      for (int r = 0; r < world; ++r)
-        if (r != best && hdr[r].var >= 0) w.tie = merge_ties(w.tie, w.key, hdr[r].tie, hdr[r].key);
-      *win = w;
-    }
-    win->f[4] = err;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ K11 dual column
-// choose_entering_col_dual, solver.rs:919-1021
-__device__ __forceinline__ bool dual_eligible(double coeff, unsigned f, int leaving_diff_sign) {
-  bool entering_diff_sign;
-  if (coeff >= EPS) entering_diff_sign = !leaving_diff_sign;
-  else if (coeff <= -EPS) entering_diff_sign = leaving_diff_sign;
-  else return false;
-  return entering_diff_sign ? !(f & MLP_AT_MAX) : !(f & MLP_AT_MIN);
-}
-__device__ __forceinline__ double clamp_obj(double oc, unsigned f) {
-  if ((f & MLP_AT_MIN) && oc < 0.0) oc = 0.0;
-  if ((f & MLP_AT_MAX) && oc > 0.0) oc = 0.0;
-  return oc;
-}
-__global__ void __launch_bounds__(256) k_ratio_dual_1(const double* __restrict__ rc, const double* __restrict__ d,
-                                                       const uint8_t* __restrict__ vflag, int64_t nt, int lds,
-                                                       double* __restrict__ red_f, unsigned* counter, double* __restrict__ scal) {
-  pdl_wait();
-  __shared__ double sm[32];
-  double best = INFINITY;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned f = vflag[v];
-    if (f & MLP_BASIC) continue;
-    const double coeff = rc[v];
-    if (!dual_eligible(coeff, f, lds)) continue;
-    const double oc = clamp_obj(d[v], f);
-    const double cur = (fabs(oc) + EPS) / fabs(coeff);  // 970
-    if (cur < best) best = cur;
-  }
-  best = block_min(best, sm);
-  if (threadIdx.x == 0) red_f[blockIdx.x] = best;
-  if (!last_block(counter)) return;
-  double b = INFINITY;
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) b = fmin(b, __ldcg(red_f + q));
-  b = block_min(b, sm);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    scal[0] = b;
-  }
-}
-__global__ void k_min_small(const double* __restrict__ vals, int cnt, double* __restrict__ out) {
-  pdl_wait();
-  double b = INFINITY;
-  for (int q = 0; q < cnt; ++q) b = fmin(b, vals[q]);
-  *out = b;
-}
-// pass 2: exact ties in |coeff| go to the lowest GLOBAL variable index (the reference: first-touch order) and
-// are counted (candidate header `tie`, low word)
-__global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__ rc, const double* __restrict__ d,
-                                                       const uint8_t* __restrict__ vflag, const int32_t* __restrict__ vpos,
-                                                       const double* __restrict__ xnb, int64_t nt, int64_t n, int64_t c0,
-                                                       int64_t ng, int lds, const double* __restrict__ scal,
-                                                       double* __restrict__ red_f, long long* __restrict__ red_i,
-                                                       unsigned* counter, const int* __restrict__ flags, Cand* out,
-                                                       int scan_slacks) {
-  pdl_wait();
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  __shared__ long long smc[32];
-  const double max_step = scal[0];
-  KeyIdxC best{-INFINITY, LLONG_MAX, 0, 0};
-  // The slack variables are replicated on every shard: only ONE shard (rank 0) proposes and counts them, so that every
-  // variable is scanned exactly once across the shards and the tie counts add up to the single-shard ones.
-  const int64_t vend = scan_slacks ? nt : n;
-  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < vend; v += (int64_t)gridDim.x * blockDim.x) {
-    const unsigned f = vflag[v];
-    if (f & MLP_BASIC) continue;
-    const double coeff = rc[v];
-    if (!dual_eligible(coeff, f, lds)) continue;
-    const double oc = clamp_obj(d[v], f);
-    const double cur = fabs(oc) / fabs(coeff);  // 993
-    const long long g = v < n ? c0 + v : ng + (v - n);
-    if (cur <= max_step) kic_merge(best, fabs(coeff), g, 1, 1);
-  }
-  best = block_argmax_c(best, smk, smi, smc);
-  if (threadIdx.x == 0) {
-    red_f[blockIdx.x] = best.key;
-    red_i[blockIdx.x] = best.idx;
-    red_i[RED_CNT_OFF + blockIdx.x] = ((long long)best.ex << 32) | (unsigned)best.nr;
-  }
-  if (!last_block(counter)) return;
-  KeyIdxC b{-INFINITY, LLONG_MAX, 0, 0};
-  for (int q = threadIdx.x; q < (int)gridDim.x; q += blockDim.x) {
-    const double k = __ldcg(red_f + q);
-    const long long i = __ldcg(red_i + q);
-    const long long c = __ldcg(red_i + RED_CNT_OFF + q);
-    kic_merge(b, k, i, (int)(c >> 32), (int)(c & 0xffffffffLL));
-  }
-  b = block_argmax_c(b, smk, smi, smc);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    out->f[4] = flags[2] ? 2.0 : (double)flags[0];
-    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
-    else {
-      const long long g = b.idx;
-      const long long v = g >= ng ? n + (g - ng) : g - c0;
-      out->key = b.key;
-      out->tie = (g << 32) | pack_ties(b.ex, b.nr);
-      out->var = g;
-      out->f[0] = rc[v];
-      out->f[1] = d[v];
-      out->f[2] = xnb[v];
-      out->f[3] = (double)vpos[v];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ pivot updates
-// Row half of Solver::pivot: basic values (solver.rs:1049-1055), dual steepest-edge norms (update_dual_sq_norms
-// 1163-1173) and the new eta column (push_eta_matrix 1274-1284).  Replicated on every shard.
-__global__ void __launch_bounds__(256) k_pivot_rows(const double* __restrict__ alpha, const double* __restrict__ tau,
-                                                     double* __restrict__ xB, double* __restrict__ w, int m, int row,
-                                                     double entering_new_val, double entering_diff, double coeff, int has_elem,
-                                                     int dse, const double* __restrict__ scal, double* __restrict__ eta_col,
-                                                     int* __restrict__ flags, uint8_t* __restrict__ touched,
-                                                     const uint8_t* __restrict__ touched_new) {
-  pdl_wait();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m) return;
-  if (eta_col) touched[r] = touched_new[r];  // the pushed eta stores every listed position of col_coeffs (solver.rs:1274-1284)
-  const double a = alpha[r];
-  if (!has_elem) {  // bound flip, solver.rs:1035-1037
-    if (a != 0.0) xB[r] -= entering_diff * a;
-    return;
-  }
-  if (r == row) xB[r] = entering_new_val;
-  else if (a != 0.0) xB[r] -= entering_diff * a;
-  if (dse) {
-    const double pivot_sq_norm = scal[1];  // |rho|^2, solver.rs:1160
-    const double pcs = coeff * coeff;
-    if (r == row) {
-      w[r] = pivot_sq_norm / pcs;
-      if (!isfinite(w[r])) flags[0] = 1;
-    } else if (a != 0.0) {
-      const double nw = w[r] + (-2.0 * a * tau[r] / coeff + pivot_sq_norm * a * a / pcs);  // 1168-1169
-      w[r] = nw;
-      if (!isfinite(nw)) flags[0] = 1;
-    }
-  }
-  if (eta_col) eta_col[r] = (r == row) ? 1.0 - 1.0 / coeff : a / coeff;  // 1276-1280
-}
-__global__ void k_flip_var(double* xnb, uint8_t* vflag, const double* lo, const double* hi, int64_t q, int64_t ql, double new_val) {
-  pdl_wait();
-  xnb[ql] = new_val;
-  unsigned f = vflag[ql] & MLP_FIXED;
-  if (new_val == lo[q]) f |= MLP_AT_MIN;
-  if (new_val == hi[q]) f |= MLP_AT_MAX;
-  vflag[ql] = (uint8_t)f;  // solver.rs:1038-1040
-}
-
-// The variable half of Solver::pivot and the NEXT pricing scan in one pass over this shard's variables (SURVEY K1
-// "fused update+select"): per variable — finish the N^T v price-out (sum of the chunk partials in chunk order, as
-// k_price_finish), update reduced cost and primal steepest-edge norm (k_pivot_vars), apply the basis swap to the two
-// variables concerned (k_pivot_swap), then score the variable for choose_pivot (k_select_primal) with its new state.
-// Block partial arg-max -> last block finishes and leaves the candidate header for the exchange step.
-struct UpdSel {
-  // price-out finish (pse only; sparse storage has helper already)
-  const double* partial; const int32_t* count_ptr; int64_t lda; const double* slack_vals; double* helper; int finish;
-  // pivot
-  int64_t q, ql, lvl, lv; int col, row; double pivot_obj, coeff, leaving_new_val; int pse;
-};
-__global__ void __launch_bounds__(256) k_update_select(UpdSel a, double* __restrict__ d, double* __restrict__ gam,
-                                                        const double* __restrict__ rc, double* __restrict__ xnb,
-                                                        uint8_t* __restrict__ vflag, int32_t* __restrict__ vpos,
-                                                        int32_t* __restrict__ bvar, double* __restrict__ loB,
-                                                        double* __restrict__ hiB, const double* __restrict__ lo,
-                                                        const double* __restrict__ hi, int64_t nt, int64_t n, int64_t m,
-                                                        int64_t c0, int64_t ng, const double* __restrict__ scal,
-                                                        int* __restrict__ flags, double* __restrict__ red_f,
-                                                        long long* __restrict__ red_i, unsigned* counter, DevRes* res, Cand* out) {
-  pdl_wait();
-  __shared__ double smk[32];
-  __shared__ long long smi[32];
-  KeyIdx best{-INFINITY, LLONG_MAX};
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < nt) {
-    unsigned f = vflag[v];
-    double h = 0.0;
-    if (a.pse) {
-      if (a.finish) {
-        if (v < n) {
-          const int C = price_chunks_for(*a.count_ptr);
-          for (int c = 0; c < C; ++c) h += a.partial[(int64_t)c * a.lda + v];
-        } else h = a.slack_vals[v - n];
-        if (f & MLP_BASIC) h = 0.0;
-        a.helper[v] = h;
-      } else h = a.helper[v];
-    }
-    double dv = d[v], gv = gam[v];
-    if (v == a.lvl) {  // the leaving variable takes the non-basic slot (solver.rs:1066-1071, 1076, 1142)
-      xnb[v] = a.leaving_new_val;
-      f = 0;
-      if (a.leaving_new_val == lo[a.lv]) f |= MLP_AT_MIN;
-      if (a.leaving_new_val == hi[a.lv]) f |= MLP_AT_MAX;
-      vflag[v] = (uint8_t)f;
-      vpos[v] = a.col;
-      dv = -a.pivot_obj;
-      d[v] = dv;
-      if (a.pse) {
-        gv = (scal[2] + 1.0) / (a.coeff * a.coeff);
-        gam[v] = gv;
-        if (!isfinite(gv)) flags[0] = 1;
-      }
-    } else if (v == a.ql) {  // the entering variable becomes basic (1088-1091)
-      f = MLP_BASIC;
-      vflag[v] = MLP_BASIC;
-      vpos[v] = a.row;
-    } else if (!(f & MLP_BASIC)) {
-      const double c = rc[v];
-      if (c != 0.0) {
-        dv -= a.pivot_obj * c;  // 1073-1080
-        d[v] = dv;
-        if (a.pse) {
-          const double psn = scal[2] + 1.0;  // 1136
-          gv = gv + (-2.0 * c * h / a.coeff + psn * c * c / (a.coeff * a.coeff));  // 1144-1146
-          gam[v] = gv;
-          if (!isfinite(gv)) flags[0] = 1;
-        }
-      }
-    }
-    if (v == 0) {  // row-side bookkeeping, identical on every shard (1057-1058, 1088)
-      loB[a.row] = lo[a.q];
-      hiB[a.row] = hi[a.q];
-      res->i[0] = bvar[a.row];  // the device's idea of the leaving variable, cross-checked by the host
-      bvar[a.row] = (int32_t)a.q;
-    }
-    // choose_pivot's scan (696-739) on the updated state
-    if (!(f & MLP_BASIC) && !(((f & MLP_AT_MIN) && dv > -EPS) || ((f & MLP_AT_MAX) && dv < EPS))) {
-      best.key = a.pse ? dv * dv / gv : fabs(dv);
-      best.idx = ((long long)vpos[v] << 32) | (long long)v;
-    }
-  }
-  best = block_argmax(best, smk, smi);
-  if (threadIdx.x == 0) { red_f[blockIdx.x] = best.key; red_i[blockIdx.x] = best.idx; }
-  if (!last_block(counter)) return;
-  KeyIdx b{-INFINITY, LLONG_MAX};
-  for (int qd = threadIdx.x; qd < (int)gridDim.x; qd += blockDim.x) {
-    const double k = __ldcg(red_f + qd);
-    const long long i = __ldcg(red_i + qd);
-    if (better_max(k, i, b.key, b.idx)) { b.key = k; b.idx = i; }
-  }
-  b = block_argmax(b, smk, smi);
-  if (threadIdx.x == 0) {
-    *counter = 0;
-    const int nf = *((volatile int*)flags);
-    res->flags[0] = nf;
-    res->flags[1] = flags[1];
-    out->f[4] = flags[2] ? 2.0 : (double)nf;
-    if (b.idx == LLONG_MAX) { out->var = -1; out->key = -INFINITY; out->tie = LLONG_MAX; }
-    else {
-      const long long vv = b.idx & 0xffffffffLL;
-      out->key = b.key;
-      out->tie = (b.idx >> 32) << 32;
-      out->var = vv < n ? c0 + vv : ng + (vv - n);
-      out->f[0] = __ldcg(d + vv);
-      out->f[1] = __ldcg(xnb + vv);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ init kernels
-// partial of A x_N over this shard's columns (solver.rs:234-238). One CTA per row.
-__global__ void __launch_bounds__(256) k_row_dot(const double* __restrict__ A, int64_t lda, int64_t n,
-                                                  const double* __restrict__ xnb, double* __restrict__ out) {
-  pdl_wait();
-  __shared__ double sm[32];
-  const int r = blockIdx.x;
-  const double* row = A + (int64_t)r * lda;
-  double acc = 0.0;
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) acc += row[j] * xnb[j];
-  const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) out[r] = tot;
-}
-// basic_var_vals = rhs - sum over shards (in rank order) of the partial products
-__global__ void k_init_basic_vals(const double* __restrict__ parts, int world, int m, const double* __restrict__ rhs,
-                                  double* __restrict__ xB) {
-  pdl_wait();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= m) return;
-  double tot = 0.0;
-  for (int g = 0; g < world; ++g) tot += parts[(int64_t)g * m + r];
-  xB[r] = rhs[r] - tot;
-}
-// d_N = c_N - N^T y (recalc_obj_coeffs, solver.rs:1216-1222)
-__global__ void k_recalc_d(const double* __restrict__ cobj, const double* __restrict__ rc, const uint8_t* __restrict__ vflag,
-                           int64_t nt, int64_t n, int64_t c0, int64_t ng, double* __restrict__ d) {
-  pdl_wait();
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nt || (vflag[v] & MLP_BASIC)) return;
-  const int64_t g = v < n ? c0 + v : ng + (v - n);
-  d[v] = cobj[g] - rc[v];
-}
-// objective from scratch (solver.rs:1224-1230) in three parts: basic rows, non-basic slacks (both replicated),
-// non-basic structurals of this shard.  Single CTA, deterministic.
-__global__ void __launch_bounds__(1024) k_recalc_obj(const double* __restrict__ cobj, const int32_t* __restrict__ bvar,
-                                                      const double* __restrict__ xB, int m, const double* __restrict__ xnb,
-                                                      const uint8_t* __restrict__ vflag, int64_t n, int64_t c0, int64_t ng,
-                                                      double* __restrict__ out3) {
-  pdl_wait();
-  __shared__ double sm[32];
-  double a = 0.0, b = 0.0, c = 0.0;
-  for (int r = threadIdx.x; r < m; r += blockDim.x) a += cobj[bvar[r]] * xB[r];
-  for (int64_t i = threadIdx.x; i < m; i += blockDim.x)
-    if (!(vflag[n + i] & MLP_BASIC)) b += cobj[ng + i] * xnb[n + i];
-  for (int64_t v = threadIdx.x; v < n; v += blockDim.x)
-    if (!(vflag[v] & MLP_BASIC)) c += cobj[c0 + v] * xnb[v];
-  const double ta = block_sum(a, sm);
-  const double tb = block_sum(b, sm);
-  const double tc = block_sum(c, sm);
-  if (threadIdx.x == 0) { out3[0] = ta; out3[1] = tb; out3[2] = tc; }
-}
-__global__ void k_gather_cB(const double* __restrict__ cobj, const int32_t* __restrict__ bvar, int m, double* __restrict__ out) {
-  pdl_wait();
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < m) out[r] = cobj[bvar[r]];
-}
-
-// ------------------------------------------------------------------------------------------------ incremental API (row f2)
-// Solver::add_constraint (solver.rs:549-634) pieces.  A cut may carry coefficients g_i on slack variables
-// (add_gomory_cut, 440-460); slack columns stay unit columns here, so s_i = rhs_i - a_i x is substituted:
-// row' = c - A^T g, rhs' = rhs - g . rhs_old (the same constraint; see DESIGN.md §8 for what that changes).
-__global__ void k_row_combine(double* __restrict__ row, const double* __restrict__ partial, const int32_t* __restrict__ count_ptr,
-                              int64_t lda, int64_t n) {
-  pdl_wait();
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int C = price_chunks_for(*count_ptr);
-  double t = 0.0;
-  for (int c = 0; c < C; ++c) t += partial[(int64_t)c * lda + j];
-  row[j] -= t;
-}
-// out[0] = base - sum_i a_i b_i (single CTA, deterministic); used for rhs' and for the new basic value rhs - a . x
-__global__ void __launch_bounds__(1024) k_sub_dot(const double* __restrict__ a, const double* __restrict__ b, int64_t cnt, double base,
-                                                   const double* __restrict__ base_ptr, double* __restrict__ out) {
-  pdl_wait();
-  __shared__ double sm[32];
-  double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) acc += a[i] * b[i];
-  const double tot = block_sum(acc, sm);
-  if (threadIdx.x == 0) out[0] = (base_ptr ? *base_ptr : base) - tot;
-}
-// current value of every structural variable (Solver::get_value, 371-376) as a dense vector
-__global__ void k_struct_values(const double* __restrict__ xnb, const double* __restrict__ xB, const uint8_t* __restrict__ vflag,
-                                const int32_t* __restrict__ vpos, int64_t n, double* __restrict__ out) {
-  pdl_wait();
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < n) out[j] = (vflag[j] & MLP_BASIC) ? xB[vpos[j]] : xnb[j];
-}
-// state of the appended row and of its slack variable (563-571, 591)
-__global__ void k_new_row_state(int64_t r, int64_t lv, int64_t gv, double smin, double smax, const double* __restrict__ val,
-                                const double* __restrict__ rhs_new, double* lo, double* hi, double* cobj, double* d, double* gam,
-                                double* xnb, uint8_t* vflag, int32_t* vpos, int32_t* bvar, double* xB, double* loB, double* hiB,
-                                double* w, double* rhs, int32_t* rowcover) {
-  pdl_wait();
-  lo[gv] = smin; hi[gv] = smax; cobj[gv] = 0.0;
-  d[lv] = 0.0; gam[lv] = 0.0; xnb[lv] = 0.0;
-  vflag[lv] = MLP_BASIC; vpos[lv] = (int32_t)r;
-  bvar[r] = (int32_t)gv; xB[r] = *val; loB[r] = smin; hiB[r] = smax; w[r] = 1.0; rhs[r] = *rhs_new;
-  rowcover[r] = (int32_t)r;
-}
-// the cached basis columns get their entry of the new row
-__global__ void k_bcols_new_row(const double* __restrict__ rowA, const int32_t* __restrict__ slots, const int32_t* __restrict__ vars,
-                                int cnt, int64_t ldb, int64_t r, double* __restrict__ Bcols) {
-  pdl_wait();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cnt) Bcols[(int64_t)slots[t] * ldb + r] = rowA[vars[t]];
-}
-// primal_edge_sq_norms[c] += coeff^2 over the new tableau row (618-622)
-__global__ void k_add_sq(double* __restrict__ gam, const double* __restrict__ rc, const uint8_t* __restrict__ vflag, int64_t nt) {
-  pdl_wait();
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v < nt && !(vflag[v] & MLP_BASIC)) gam[v] += rc[v] * rc[v];
-}
-__global__ void k_copy1(double* dst, const double* src) {
-  pdl_wait(); *dst = *src; }
-__global__ void k_set_var_state(uint8_t* vflag, int64_t lv, unsigned f) {
-  pdl_wait(); vflag[lv] = (uint8_t)f; }
+#include "price_kernels.cuh"
+#include "engine_kernels.cuh"
 
 // ================================================================================================ host side
 // Two lanes (streams).  API calls keep sequential semantics through two marks: s0_mark is recorded on lane 0 at the end of
@@ -1876,606 +657,7 @@ static mlp_status btran(mlp_engine* e, Lane& ln, double* c, int unit_row, double
   return MLP_OK;
 }
 
-// Column cache / LU arenas.  First allocation is generous (~1 GB of basis columns): cudaFree/cudaMalloc of the big
-// arenas costs tens of milliseconds, so capacity grows by doubling and rarely; the cache content survives growth.
-static mlp_status ensure_lu_capacity(mlp_engine* e, int64_t k, bool exact = false) {
-  if (k <= e->kcap && e->Bcols) return MLP_OK;
-  int64_t cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, std::max<int64_t>(64, std::min<int64_t>(1024, (1ll << 30) / (8 * e->mld)))));
-  // sparse storage keeps no column cache: the arenas are kcap^2 (factors, inverse) — start at 4096 columns (0.27 GB) so that the
-  // first thousands of pivots meet no growth (each growth is a re-allocation AND a true factorization: 5 - 20 ms on config 4)
-  if (e->sparse) cap = std::max<int64_t>(e->kcap, std::min<int64_t>(e->m, 4096));
-  while (cap < k) cap *= 2;  // may exceed m: slots of columns that left since the last refactor stay occupied
-  if (exact) cap = k;        // clone: same leading dimensions as the source
-  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
-  PoolScope pool(e->use_pool ? e->stream : nullptr);
-  double* nb = nullptr;
-  ST(dev_alloc(&nb, e->sparse ? 1 : (size_t)e->mld * cap));  // sparse storage reads the basic columns from the matrix itself
-  if (!e->sparse && e->Bcols && e->kcap > 0) {
-    CU(cudaMemcpyAsync(nb, e->Bcols, (size_t)e->mld * e->kcap * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
-  }
-  for (int64_t s = cap - 1; s >= e->kcap; --s) e->h_free_slots.push_back((int32_t)s);
-  dev_free(e->Jpos); dev_free(e->Jslot); dev_free(e->Rp); dev_free(e->Bcols); dev_free(e->LUc); dev_free(e->Cinv);
-  dev_free(e->lu_aff); dev_free(e->lu_perm); dev_free(e->lu_rcnt);
-  ST(dev_alloc(&e->lu_aff, 192)); ST(dev_alloc(&e->lu_perm, cap)); ST(dev_alloc(&e->lu_rcnt, cap));
-  if (e->sparse) {
-    if (e->corevar_k > 0) {  // un-mark with the old list before it is freed
-      LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
-      CU(cudaStreamSynchronize(e->stream));
-      e->corevar_k = 0;
-    }
-    dev_free(e->corevar); dev_free(e->cseg_first);
-    ST(dev_alloc(&e->corevar, cap)); ST(dev_alloc(&e->cseg_first, cap + 1));
-    dev_free(e->rf_map); dev_free(e->rf_W); dev_free(e->rf_T); dev_free(e->rf_Ep);
-    ST(dev_alloc(&e->rf_map, 3 * (size_t)cap + 2 * RF_CAP));
-    ST(dev_alloc(&e->rf_W, (size_t)RF_CAP * cap)); ST(dev_alloc(&e->rf_T, (size_t)RF_CAP * cap)); ST(dev_alloc(&e->rf_Ep, (size_t)RF_CAP * cap));
-    e->inv_valid = false;  // C^-1 does not survive the re-allocation: the next refactorization is a true one
-  }
-  e->Bcols = nb;
-  e->kcap = cap;
-  ST(dev_alloc(&e->Jpos, cap)); ST(dev_alloc(&e->Jslot, cap)); ST(dev_alloc(&e->Rp, cap));
-  ST(dev_alloc(&e->LUc, (size_t)cap * cap)); ST(dev_alloc(&e->Cinv, (size_t)cap * cap));
-  for (int l = 0; l < 2; ++l) {
-    Lane& ln = e->lane[l];
-    dev_free(ln.xk); dev_free(ln.xk2); dev_free(ln.gt_part_k);
-    ST(dev_alloc(&ln.xk, cap)); ST(dev_alloc(&ln.xk2, cap)); ST(dev_alloc(&ln.gt_part_k, (size_t)GT_MAXSPLIT * cap));
-  }
-  return MLP_OK;
-}
-static mlp_status ensure_eta_capacity(mlp_engine* e, int64_t K, bool exact = false) {
-  if (K <= e->Kcap && e->E) return MLP_OK;
-  int64_t cap = std::max<int64_t>(e->Kcap, std::max<int64_t>(96, std::min<int64_t>(2080, (2ll << 30) / (8 * e->mld))));
-  while (cap < K) cap *= 2;
-  if (exact) cap = K;
-  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
-  PoolScope pool(e->use_pool ? e->stream : nullptr);
-  dev_free(e->E); dev_free(e->Ginv); dev_free(e->gK); dev_free(e->etaR); dev_free(e->etaPrev); dev_free(e->etaHead);
-  e->Kcap = cap;
-  ST(dev_alloc(&e->E, (size_t)e->mld * cap)); ST(dev_alloc(&e->Ginv, (size_t)cap * cap)); ST(dev_alloc(&e->gK, cap));
-  ST(dev_alloc(&e->etaR, cap)); ST(dev_alloc(&e->etaPrev, cap)); ST(dev_alloc(&e->etaHead, cap));
-  for (int l = 0; l < 2; ++l) {
-    Lane& ln = e->lane[l];
-    dev_free(ln.tK); dev_free(ln.tK2); dev_free(ln.gt_part_K);
-    ST(dev_alloc(&ln.tK, cap)); ST(dev_alloc(&ln.tK2, cap)); ST(dev_alloc(&ln.gt_part_K, (size_t)GT_MAXSPLIT * cap));
-  }
-  return MLP_OK;
-}
-
-// Compact row-major copy of the k basic structural columns (core column ids), built on the device from the CSC copy with the
-// same segmented counting transpose as the CSC copy itself (sparse_build.cuh; input "rows" = the core columns in core
-// order, so every row of the copy lists its entries in ascending core column).  jvar: the core columns' variables, already
-// uploaded to e->corevar.
-constexpr int DCSR_CHUNKS = 128;
-static mlp_status build_core_rows(mlp_engine* e, const std::vector<int32_t>& jvar) {
-  const int64_t m = e->m, k = (int64_t)jvar.size();
-  PoolScope pool(e->use_pool ? e->stream : nullptr);
-  if (!e->dcsr_ptr) {
-    ST(dev_alloc(&e->dcsr_ptr, (size_t)e->mld + 1));
-    ST(dev_alloc(&e->dcsr_hist, (size_t)DCSR_CHUNKS * e->mld));
-    ST(dev_alloc(&e->dcsr_cnt, (size_t)e->mld));
-  }
-  if (k == 0) {
-    CU(cudaMemsetAsync(e->dcsr_ptr, 0, (size_t)(m + 1) * sizeof(int64_t), e->stream));
-    return MLP_OK;
-  }
-  int64_t nz = 0;
-  for (int32_t v : jvar) nz += e->h_csc_ptr[(size_t)v + 1] - e->h_csc_ptr[(size_t)v];
-  if (nz > e->dcsr_cap) {
-    CU(cudaStreamSynchronize(e->lane[1].st));
-    dev_free(e->dcsr_idx); dev_free(e->dcsr_val);
-    e->dcsr_cap = std::max<int64_t>(4 * nz, 1 << 22);  // 12 bytes per entry: grow rarely
-    ST(dev_alloc(&e->dcsr_idx, (size_t)e->dcsr_cap)); ST(dev_alloc(&e->dcsr_val, (size_t)e->dcsr_cap));
-  }
-  const int ncseg = (int)e->ncseg;                                   // the core's segments (e->cseg_id), in core-column order
-  const int spc = (ncseg + DCSR_CHUNKS - 1) / DCSR_CHUNKS;          // segments per chunk
-  const int chunks = (ncseg + spc - 1) / spc;
-  CU(cudaMemsetAsync(e->dcsr_hist, 0, (size_t)chunks * m * sizeof(int32_t), e->stream));
-  LAUNCH(e, k_d_hist, cdiv((int64_t)ncseg * 32, 256), 256, 0, (const int4*)e->seg_desc, e->cseg_id, ncseg, e->csc_idx, m, spc, e->dcsr_hist);
-  // per constraint row: scan over the chunks + row counts (k_t_colscan's segment output is not needed: lane scratch)
-  LAUNCH(e, k_t_colscan, cdiv(m, 256), 256, 0, e->dcsr_hist, m, chunks, e->dcsr_cnt, (int64_t*)e->lane[0].wm, CSC_SEG);
-  LAUNCH(e, k_scan_excl, 1, 1024, 0, e->dcsr_cnt, m, e->dcsr_ptr);
-  LAUNCH(e, k_d_fill, chunks, 256, 0, (const int4*)e->seg_desc, e->cseg_id, ncseg, e->csc_idx, e->csc_val, m, spc, e->corepos, e->dcsr_hist,
-         e->dcsr_ptr, e->dcsr_idx, e->dcsr_val);
-  return MLP_OK;
-}
-
-static void refac_stage(mlp_engine* e, const char* name) {
-  if (!e->refac_trace) return;
-  if (e->refac_trace == 1) for (int l = 0; l < 2; ++l) cudaStreamSynchronize(e->lane[l].st);  // 2: host-side times only, no extra syncs
-  const auto now = std::chrono::steady_clock::now();
-  if (name) {
-    const double ms = std::chrono::duration<double, std::milli>(now - e->refac_t).count();
-    if (e->refac_trace == 2 && ms > 0.5)
-      fprintf(stderr, "[refactor event] #%lld since-lu %lld k %lld K %lld: %.3f ms in '%s'\n", (long long)e->cnt.refactors,
-              (long long)e->pivots_since_lu, (long long)e->k, (long long)e->K, ms, name);
-    bool found = false;
-    for (auto& st : e->refac_stage) if (st.first == name) { st.second += ms; found = true; break; }
-    if (!found) e->refac_stage.emplace_back(name, ms);
-  }
-  e->refac_t = std::chrono::steady_clock::now();
-}
-static void refac_report(mlp_engine* e) {
-  if (!e->refac_trace || e->cnt.refactors == 0) return;
-  double tot = 0.0;
-  for (auto& st : e->refac_stage) tot += st.second;
-  fprintf(stderr, "[refactor trace] %lld refactorizations (%lld of them product-form refreshes), mean k %.0f, %.3f ms each\n",
-          (long long)e->cnt.refactors, (long long)e->cnt.refreshes, e->refac_k_sum / e->cnt.refactors, tot / e->cnt.refactors);
-  fprintf(stderr, "[refactor trace] host blocked in %lld per-pivot device waits: %.1f ms in total (%.1f us each) over %lld basis changes, %lld launches\n",
-          (long long)e->waits, e->wait_ms, e->waits ? 1e3 * e->wait_ms / e->waits : 0.0, (long long)e->pivot_seq, (long long)e->cnt.kernel_launches);
-  fprintf(stderr, "[refactor trace] accuracy probe (normwise backward error of sampled columns of C^-1): worst accepted refresh %.3g, "
-                  "worst after a true factorization %.3g, tolerance %.3g, rejected refreshes %lld\n", e->rf_worst, e->rf_worst_true, e->rf_tol,
-          (long long)e->cnt.refresh_rejects);
-  for (auto& st : e->refac_stage) fprintf(stderr, "[refactor trace]   %-28s %9.3f ms each  %5.1f %%\n", st.first, st.second / e->cnt.refactors, 100.0 * st.second / tot);
-}
-
-// Product-form refresh (refresh_inverse.cuh): C_new^-1 from C_old^-1 and the eta file, written into the LUc buffer, which
-// then becomes Cinv.  jpos / R: the NEW core's positions and rows.  Runs before anything of the old factor state (index maps,
-// compact core rows, eta file) is touched; both lanes are drained.
-// Pinned staging: every index array of a refactorization goes through ONE pinned buffer (a cudaMemcpyAsync from pageable memory
-// first waits for the stream and then copies synchronously: eight of them serialised the host with the device).
-static mlp_status stage_begin(mlp_engine* e, size_t ints_needed) {
-  e->stg_cur ^= 1;
-  const int c = e->stg_cur;
-  if (!e->stg_ev[c]) CU(cudaEventCreateWithFlags(&e->stg_ev[c], cudaEventDisableTiming));
-  else CU(cudaEventSynchronize(e->stg_ev[c]));  // the copies that last used this buffer (two refactorizations ago) are long done
-  if (ints_needed > e->stg_cap[c]) {
-    if (e->stg_h[c]) cudaFreeHost(e->stg_h[c]);
-    e->stg_h[c] = nullptr;
-    e->stg_cap[c] = std::max<size_t>(2 * ints_needed, (size_t)1 << 16);
-    CU(cudaHostAlloc((void**)&e->stg_h[c], e->stg_cap[c] * sizeof(int32_t), cudaHostAllocDefault));
-  }
-  e->stg_off = 0;
-  return MLP_OK;
-}
-static mlp_status stage_put(mlp_engine* e, void* dst_dev, const int32_t* src, size_t n) {
-  if (n == 0) return MLP_OK;
-  const int c = e->stg_cur;
-  if (e->stg_off + n > e->stg_cap[c]) { set_err("refactor: staging buffer too small"); return MLP_INVALID; }
-  int32_t* h = e->stg_h[c] + e->stg_off;
-  std::memcpy(h, src, n * sizeof(int32_t));
-  e->stg_off += n;
-  CU(cudaMemcpyAsync(dst_dev, h, n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-  e->cnt.h2d_bytes += (int64_t)(n * sizeof(int32_t));
-  return MLP_OK;
-}
-static mlp_status stage_end(mlp_engine* e) {
-  CU(cudaEventRecord(e->stg_ev[e->stg_cur], e->stream));
-  return MLP_OK;
-}
-
-// dst[idx[i]] = val[i]
-__global__ void k_patch_i32(int32_t* __restrict__ dst, const int32_t* __restrict__ idx, const int32_t* __restrict__ val, int n) {
-  pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[idx[i]] = val[i];
-}
-// rowcore[Rp[c]] = c
-__global__ void k_set_rowcore(int32_t* __restrict__ rowcore, const int32_t* __restrict__ Rp, int k) {
-  pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < k) rowcore[Rp[c]] = c;
-}
-
-// The index sets of the new basis derived from those of the factorized one and the list of basis changes since
-// (sparse storage, every change recorded): O(k + K log k) instead of three passes over all m positions / rows.
-//   jpos   core columns' positions in order_simple's order (ordering.rs:4-21: ascending entry count, ascending position within a count)
-//   R      core rows, ascending
-//   prow / pval   rows whose rowcover entry changes and the new values (device patch)
-//   gone   rows that left the core (rowcore <- -1)
-// e->h_rowcover_f is updated in place.
-static mlp_status incremental_sets(mlp_engine* e, std::vector<int32_t>& jpos, std::vector<int32_t>& R, std::vector<int32_t>& prow,
-                                   std::vector<int32_t>& pval, std::vector<int32_t>& gone) {
-  const int64_t ng = e->ng;
-  std::vector<int32_t> P;       // distinct changed positions
-  std::vector<int64_t> oldv;    // variable the factorized basis held there
-  for (size_t j = 0; j < e->h_eta_pos.size(); ++j) {
-    const int32_t p = e->h_eta_pos[j];
-    if (std::find(P.begin(), P.end(), p) == P.end()) { P.push_back(p); oldv.push_back(e->h_eta_leave[j]); }
-  }
-  std::vector<int32_t>& rc = e->h_rowcover_f;
-  std::vector<int32_t> T;  // slack rows involved
-  e->h_rc_old_rows.clear();
-  e->h_rc_old_vals.clear();
-  auto touch = [&](int32_t i) {
-    if (std::find(T.begin(), T.end(), i) != T.end()) return;
-    T.push_back(i);
-    e->h_rc_old_rows.push_back(i);
-    e->h_rc_old_vals.push_back(rc[(size_t)i]);  // the factorized basis' value: the refresh needs it
-  };
-  for (size_t q = 0; q < P.size(); ++q) if (oldv[q] >= ng) touch((int32_t)(oldv[q] - ng));
-  for (size_t q = 0; q < P.size(); ++q) { const int64_t nv = e->h_bvar[(size_t)P[q]]; if (nv >= ng) touch((int32_t)(nv - ng)); }
-  for (size_t q = 0; q < P.size(); ++q) if (oldv[q] >= ng) rc[(size_t)(oldv[q] - ng)] = -1;
-  for (size_t q = 0; q < P.size(); ++q) { const int64_t nv = e->h_bvar[(size_t)P[q]]; if (nv >= ng) rc[(size_t)(nv - ng)] = P[q]; }
-  auto key_less = [&](int32_t pa, int32_t pb) {  // order_simple's key of the column at a position
-    const int64_t va = e->h_bvar[(size_t)pa], vb = e->h_bvar[(size_t)pb];
-    const int64_t ca = e->h_csc_ptr[(size_t)va + 1] - e->h_csc_ptr[(size_t)va], cb = e->h_csc_ptr[(size_t)vb + 1] - e->h_csc_ptr[(size_t)vb];
-    return ca != cb ? ca < cb : pa < pb;
-  };
-  jpos.clear();
-  jpos.reserve(e->h_Jpos_f.size() + P.size());
-  std::vector<int32_t> Ps(P);
-  std::sort(Ps.begin(), Ps.end());
-  for (int32_t p : e->h_Jpos_f)
-    if (!std::binary_search(Ps.begin(), Ps.end(), p)) jpos.push_back(p);  // unchanged columns keep their relative order
-  for (size_t q = 0; q < P.size(); ++q) {
-    if (e->h_bvar[(size_t)P[q]] >= ng) continue;
-    jpos.insert(std::lower_bound(jpos.begin(), jpos.end(), P[q], key_less), P[q]);
-  }
-  R = e->h_R_sorted;
-  prow.clear(); pval.clear(); gone.clear();
-  for (int32_t i : T) {
-    prow.push_back(i);
-    pval.push_back(rc[(size_t)i]);
-    auto it = std::lower_bound(R.begin(), R.end(), i);
-    const bool in_old = it != R.end() && *it == i;
-    const bool in_new = rc[(size_t)i] < 0;
-    if (in_old && !in_new) { R.erase(it); gone.push_back(i); }
-    else if (!in_old && in_new) R.insert(it, i);
-  }
-  return MLP_OK;
-}
-
-// k_rf_probe on the current C^-1 against the compact rows of the current basic columns; one read-back.  *err: the largest
-// normwise backward error over the sampled columns, *core_entries: entries of the core.
-static mlp_status probe_inverse(mlp_engine* e, int64_t k, double* err, int64_t* core_entries) {
-  unsigned long long* out = e->d_nnzcnt;
-  CU(cudaMemsetAsync(out, 0, (1 + 2 * RF_PROBE) * sizeof(unsigned long long), e->stream));
-  const int ncol = (int)std::min<int64_t>(RF_PROBE, k);
-  LAUNCH(e, k_rf_probe, cdiv(k, 256), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, e->Rp, (int)k, e->Cinv, e->kcap,
-         (int)((e->cnt.refactors * 2654435761ull) % (unsigned long long)k), (int)std::max<int64_t>(1, k / RF_PROBE), ncol, out);
-  unsigned long long h[1 + 2 * RF_PROBE];
-  ST(d2h(e, h, out, sizeof(h)));
-  *core_entries = (int64_t)h[0];
-  double worst = 0.0;
-  for (int q = 0; q < ncol; ++q) {
-    double num, den;
-    std::memcpy(&num, &h[1 + q], 8);
-    std::memcpy(&den, &h[1 + RF_PROBE + q], 8);
-    const double r = den > 0.0 ? num / den : num;
-    if (!(r <= worst)) worst = r;
-  }
-  *err = worst;
-  return MLP_OK;
-}
-static bool can_refresh(const mlp_engine* e) {
-  // the rank-K product costs 2 k^2 K flops: worth it while the eta file is short next to the core (a factorization is ~2 k^3)
-  return e->sparse && e->inv_valid && e->lu_every > 0 && e->k > 0 && e->K >= 1 && e->K <= std::min<int64_t>(e->Kcap, RF_CAP) &&
-         e->K <= std::max<int64_t>(RF_MAXK, e->k / 2) &&
-         (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_eta_pos.size() == e->K && (int64_t)e->h_pos_core.size() == e->m &&
-         e->rf_map != nullptr;
-}
-static mlp_status refresh_inverse(mlp_engine* e, const std::vector<int32_t>& jpos, const std::vector<int32_t>& R) {
-  const int k_old = (int)e->k, K = (int)e->K, k_new = (int)jpos.size();
-  const int64_t ld = e->kcap;
-  std::vector<int32_t> qpos, wrow;  // old slack positions whose row of B_old^-1 is needed, and the rows of those slacks
-  auto q_of = [&](int32_t p) -> int {
-    for (size_t q = 0; q < qpos.size(); ++q) if (qpos[q] == p) return (int)q;
-    return -1;
-  };
-  std::vector<int32_t> map((size_t)3 * k_new + 2 * (size_t)K + 8, 0);
-  int32_t *rowsrc = map.data(), *colsrc = rowsrc + k_new, *jposn = colsrc + k_new, *etasrc = jposn + k_new, *wr = etasrc + K;
-  for (int j = 0; j < K; ++j) {
-    const int32_t p = e->h_eta_pos[(size_t)j];
-    if (e->h_pos_core[(size_t)p] >= 0) { etasrc[j] = e->h_pos_core[(size_t)p]; continue; }
-    int q = q_of(p);
-    if (q < 0) {  // the FIRST eta at a position tells which variable the factorized basis held there
-      const int64_t v = e->h_eta_leave[(size_t)j];
-      if (v < e->ng) { set_err("refresh: basis bookkeeping inconsistent (structural variable at a slack position)"); return MLP_INVALID; }
-      q = (int)qpos.size();
-      qpos.push_back(p);
-      wrow.push_back((int32_t)(v - e->ng));
-    }
-    etasrc[j] = -1 - q;
-  }
-  for (int t = 0; t < k_new; ++t) {
-    const int32_t p = jpos[(size_t)t];
-    jposn[t] = p;
-    if (e->h_pos_core[(size_t)p] >= 0) { rowsrc[t] = e->h_pos_core[(size_t)p]; continue; }
-    const int q = q_of(p);
-    if (q < 0) { set_err("refresh: basis bookkeeping inconsistent (new core column without an eta)"); return MLP_INVALID; }
-    rowsrc[t] = -1 - q;
-  }
-  for (int c = 0; c < k_new; ++c) {
-    const int32_t r = R[(size_t)c];
-    if (e->h_row_core[(size_t)r] >= 0) { colsrc[c] = e->h_row_core[(size_t)r]; continue; }
-    int32_t p = e->h_rowcover_f[(size_t)r];  // position of the row's slack in the FACTORIZED basis: incremental_sets may have
-    for (size_t q = 0; q < e->h_rc_old_rows.size(); ++q)  // moved h_rowcover_f on to the new basis already
-      if (e->h_rc_old_rows[q] == r) { p = e->h_rc_old_vals[q]; break; }
-    if (p < 0) { set_err("refresh: basis bookkeeping inconsistent (new core row without a basic slack)"); return MLP_INVALID; }
-    colsrc[c] = -1 - p;
-  }
-  const int nq = (int)wrow.size();
-  for (int q = 0; q < nq; ++q) wr[q] = wrow[(size_t)q];
-  ST(stage_put(e, e->rf_map, map.data(), (size_t)3 * k_new + K + nq));
-  const int32_t *d_rowsrc = e->rf_map, *d_colsrc = d_rowsrc + k_new, *d_jposn = d_colsrc + k_new, *d_etasrc = d_jposn + k_new,
-                *d_wrow = d_etasrc + K;
-  if (nq > 0)
-    LAUNCH(e, k_rf_w, dim3(cdiv(k_old, 256), (unsigned)nq), 256, 0, e->dcsr_ptr, e->dcsr_idx, e->dcsr_val, d_wrow, k_old, e->Cinv, ld, e->rf_W, ld);
-  LAUNCH(e, k_rf_t, cdiv(k_new, 32), 256, 0, e->Ginv, e->Kcap, K, d_etasrc, e->etaR, d_colsrc, k_new, e->Cinv, ld, e->rf_W, ld, e->rf_T);
-  double* Cn = e->LUc;
-  LAUNCH(e, k_rf_x0, dim3(cdiv(k_new, 256), (unsigned)std::min(k_new, 16384)), 256, 0, d_rowsrc, d_jposn, d_colsrc, k_new, e->Cinv, ld, e->rf_W, ld, Cn);
-  LAUNCH(e, k_rf_ep, dim3(cdiv(k_new, 256), (unsigned)K), 256, 0, e->E, e->mld, d_jposn, k_new, e->rf_Ep, ld);
-  for (int j0 = 0; j0 < K; j0 += GB_K)
-    LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(k_new, GB_T), cdiv(k_new, GB_T)), 256, 0, k_new, k_new, std::min(GB_K, K - j0),
-           e->rf_Ep + (size_t)j0 * ld, ld, e->rf_T + j0, (int64_t)RF_CAP, Cn, ld);
-  std::swap(e->Cinv, e->LUc);
-  e->cnt.refreshes += 1;
-  return MLP_OK;
-}
-
-// BasisSolver::reset (solver.rs:1286-1303) for B = [D | E_S], see DESIGN.md §4.  allow_refresh: the caller (mlp_pivot) has
-// pushed the eta of the pivot that triggers the refactorization, so the eta file describes the whole change of the basis
-// since the factors were made and may be folded into C^-1 instead of factorizing (refresh_inverse above).
-static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
-  const int64_t m = e->m, ng = e->ng;
-  refac_stage(e, allow_refresh || e->refac_in_pivot ? "pivot: read-back, enter" : nullptr);
-  e->refac_in_pivot = false;
-  std::vector<int32_t> jpos, jslot, jvar, rowcover, R, prow, pval, gone;
-  // Sparse storage, every basis change since the last refactorization on record: the new sets follow from the old ones.
-  const bool incremental = e->sparse && e->chg_complete && (int64_t)e->h_pos_core.size() == m && (int64_t)e->h_rowcover_f.size() == m &&
-                           (int64_t)e->h_Jpos_f.size() == e->k && (int64_t)e->h_R_sorted.size() == e->k;
-  if (incremental) {
-    ST(incremental_sets(e, jpos, R, prow, pval, gone));
-    for (int32_t p : jpos) { jvar.push_back((int32_t)e->h_bvar[(size_t)p]); jslot.push_back(e->h_slot_of_row[(size_t)p]); }
-  } else {
-    rowcover.assign((size_t)m, -1);
-    for (int64_t p = 0; p < m; ++p) {
-      const int64_t v = e->h_bvar[p];
-      if (v < ng) {
-        jpos.push_back((int32_t)p);
-        jvar.push_back((int32_t)v);
-        if (!e->sparse && e->h_slot_of_row[p] < 0) { set_err("refactor: basic structural column missing from the cache"); return MLP_INVALID; }
-        jslot.push_back(e->h_slot_of_row[p]);
-      } else rowcover[v - ng] = (int32_t)p;
-    }
-    for (int64_t i = 0; i < m; ++i) if (rowcover[i] < 0) R.push_back((int32_t)i);
-  }
-  const int64_t k = (int64_t)jpos.size();
-  if (!incremental && e->sparse && k > 1) {
-    // order_simple (ordering.rs:4-21): columns by ascending entry count, FIFO — i.e. ascending basis position — within a
-    // count.  (For a dense A every column has m entries and the order is the basis-position order built above.)
-    std::vector<int32_t> ord((size_t)k);
-    for (int64_t t = 0; t < k; ++t) ord[(size_t)t] = (int32_t)t;
-    auto cnt = [&](int32_t t) { return e->h_csc_ptr[(size_t)jvar[(size_t)t] + 1] - e->h_csc_ptr[(size_t)jvar[(size_t)t]]; };
-    std::stable_sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return cnt(a) < cnt(b); });
-    std::vector<int32_t> p2((size_t)k), v2((size_t)k), s2((size_t)k);
-    for (int64_t t = 0; t < k; ++t) { p2[(size_t)t] = jpos[(size_t)ord[(size_t)t]]; v2[(size_t)t] = jvar[(size_t)ord[(size_t)t]]; s2[(size_t)t] = jslot[(size_t)ord[(size_t)t]]; }
-    jpos.swap(p2); jvar.swap(v2); jslot.swap(s2);
-  }
-  if ((int64_t)R.size() != k) { set_err("refactor: basis bookkeeping inconsistent"); return MLP_INVALID; }
-  std::vector<int32_t> Rsorted(R);  // R itself is overwritten with the factors' row order after a true factorization
-  refac_stage(e, "host: index sets + column order");
-  for (int32_t sl : e->h_pending_free) e->h_free_slots.push_back(sl);
-  e->h_pending_free.clear();
-  for (int l = 0; l < 2; ++l) CU(cudaStreamSynchronize(e->lane[l].st));
-  e->spec_var = -1;
-  e->ftran_var = -1;
-  refac_stage(e, "drain both lanes");
-  {
-    size_t segs = 0;
-    if (e->sparse) for (int32_t v : jvar) segs += (size_t)(e->h_col_seg[(size_t)v + 1] - e->h_col_seg[(size_t)v]);
-    ST(stage_begin(e, 2 * (size_t)m + 10 * (size_t)k + segs + 2 * (size_t)e->K + 4 * RF_MAXK + 4 * prow.size() + 256));
-  }
-  bool refreshed = false;
-  int64_t rf_core_before = 0;
-  if (allow_refresh && k > 0 && k <= e->kcap && can_refresh(e)) {
-    ST(refresh_inverse(e, jpos, R));
-    refreshed = true;
-    refac_stage(e, "refresh: C^-1 from the eta file");
-  }
-  ST(ensure_lu_capacity(e, k));
-  // eta arena: the reference allows eta nnz up to lu nnz (solver.rs:1096-1097) ~ (k+1) dense columns
-  {
-    // The arena is dense, m doubles per eta, and bounded at 16 GB — a full arena just forces the next refactorization.  Dense
-    // A: lu nnz ~ m k and an eta has m entries, so the file holds up to ~k etas: reserve 2k + 32.  Sparse A: the file is
-    // short (lu nnz / nnz(alpha): tens to hundreds of etas) — reserving 2k + 32 columns would re-allocate gigabytes every
-    // time k doubles (measured: 0.8 s per growth with peer mappings in place); follow the file's own length instead.
-    const int64_t by_mem = std::max<int64_t>(1024, ((int64_t)16 << 30) / (8 * e->mld));
-    const int64_t want = e->sparse ? std::min<int64_t>(2 * k + 32, 4 * e->K + 128) : 2 * k + 32;
-    ST(ensure_eta_capacity(e, std::min<int64_t>(want, by_mem)));
-  }
-  refac_stage(e, "capacity (LU, eta arena)");
-  e->k = k;
-  e->K = 0;
-  CU(cudaMemsetAsync(e->d_res->flags + 1, 0, sizeof(int), e->stream));
-  CU(cudaMemsetAsync(e->etaLast, 0xff, (size_t)e->mld * sizeof(int32_t), e->stream));  // eta file is empty: no chains
-  CU(cudaMemsetAsync(e->touched, 0, (size_t)e->mld, e->stream));
-  // device maps by patches (the touched slack rows fit the scratch behind the refresh's maps) or in full
-  const bool patch_maps = incremental && prow.size() <= (size_t)RF_MAXK && e->rf_map != nullptr;
-  if (incremental) for (int32_t p : e->h_eta_pos) e->h_last_eta_of_row[(size_t)p] = -1;
-  else std::fill(e->h_last_eta_of_row.begin(), e->h_last_eta_of_row.end(), -1);
-  if (patch_maps) {
-    int32_t* d_patch = e->rf_map + 3 * e->kcap;  // 2 RF_MAXK entries; stream-ordered behind the refresh kernels that read this area
-    if (!prow.empty()) {  // rowcover: only the slack rows the basis changes touched
-      ST(stage_put(e, d_patch, prow.data(), prow.size()));
-      ST(stage_put(e, d_patch + RF_MAXK, pval.data(), pval.size()));
-      LAUNCH(e, k_patch_i32, cdiv((int64_t)prow.size(), 256), 256, 0, e->rowcover, (const int32_t*)d_patch, (const int32_t*)(d_patch + RF_MAXK), (int)prow.size());
-    }
-    if (!gone.empty()) {  // rowcore: rows that left the core (a subset of the touched rows); the rows of the new core are set below
-      std::vector<int32_t> minus((size_t)gone.size(), -1);
-      ST(stage_put(e, d_patch, gone.data(), gone.size()));
-      ST(stage_put(e, d_patch + RF_MAXK, minus.data(), minus.size()));
-      LAUNCH(e, k_patch_i32, cdiv((int64_t)gone.size(), 256), 256, 0, e->rowcore, (const int32_t*)d_patch, (const int32_t*)(d_patch + RF_MAXK), (int)gone.size());
-    }
-  } else if (incremental) {
-    ST(stage_put(e, e->rowcover, e->h_rowcover_f.data(), (size_t)m));
-  } else {
-    ST(stage_put(e, e->rowcover, rowcover.data(), (size_t)m));
-  }
-  if (e->sparse && !patch_maps) {  // also for an empty core: later refactorizations patch this map
-    std::vector<int32_t> rowcore((size_t)m, -1);
-    for (int64_t i = 0; i < k; ++i) rowcore[R[i]] = (int32_t)i;
-    ST(stage_put(e, e->rowcore, rowcore.data(), (size_t)m));
-  }
-  if (k > 0) {
-    ST(stage_put(e, e->Jpos, jpos.data(), (size_t)k));
-    ST(stage_put(e, e->Jslot, jslot.data(), (size_t)k));
-    ST(stage_put(e, e->Rp, R.data(), (size_t)k));
-    if (e->sparse) {
-      if (e->corevar_k > 0) LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
-      ST(stage_put(e, e->corevar, jvar.data(), (size_t)k));
-      LAUNCH(e, k_set_corepos, cdiv(k, 256), 256, 0, e->corepos, e->corevar, (int)k, 0);
-      e->corevar_k = k;
-      if (patch_maps) LAUNCH(e, k_set_rowcore, cdiv(k, 256), 256, 0, e->rowcore, (const int32_t*)e->Rp, (int)k);
-      // the core's segments
-      std::vector<int32_t> cid, cfirst((size_t)k + 1, 0);
-      for (int64_t t = 0; t < k; ++t) {
-        cfirst[t] = (int32_t)cid.size();
-        for (int64_t sg = e->h_col_seg[jvar[t]]; sg < e->h_col_seg[jvar[t] + 1]; ++sg) cid.push_back((int32_t)sg);
-      }
-      cfirst[k] = (int32_t)cid.size();
-      e->ncseg = (int64_t)cid.size();
-      if (e->ncseg > e->cseg_cap) {
-        PoolScope pool(e->use_pool ? e->stream : nullptr);
-        dev_free(e->cseg_id); dev_free(e->csum[0]); dev_free(e->csum[1]);
-        e->cseg_cap = std::max<int64_t>(4 * e->ncseg, 1 << 15);
-        ST(dev_alloc(&e->cseg_id, e->cseg_cap)); ST(dev_alloc(&e->csum[0], e->cseg_cap)); ST(dev_alloc(&e->csum[1], e->cseg_cap));
-      }
-      ST(stage_put(e, e->cseg_id, cid.data(), cid.size()));
-      ST(stage_put(e, e->cseg_first, cfirst.data(), cfirst.size()));
-    }
-  refac_stage(e, "uploads: index maps, core segments");
-    if (e->sparse) ST(build_core_rows(e, jvar));
-  refac_stage(e, "compact core rows (DCSR)");
-    if (refreshed) {
-      // C^-1 is already the new core's.  Probe it against the new core (max |C C^-1 - I| over sampled columns) and count the
-      // core's entries for the estimate of LUFactors::nnz below — one read-back; a failed probe falls through to the true
-      // factorization (LUc, the old inverse's buffer, is scratch again).
-      double r;
-      ST(probe_inverse(e, k, &r, &rf_core_before));
-      if (r <= e->rf_tol) e->rf_worst = std::max(e->rf_worst, r);
-      if (!(r <= e->rf_tol)) { refreshed = false; e->cnt.refresh_rejects += 1; e->cnt.refreshes -= 1; }
-  refac_stage(e, "refresh: accuracy probe + read back");
-    }
-    if (!refreshed) {
-    if (e->sparse) {
-      CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
-      LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
-             (int)e->ncseg, e->corepos, e->rowcore, e->LUc, e->kcap);
-      CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
-      LAUNCH(e, k_core_row_counts, cdiv(k, 256), 256, 0, e->LUc, e->kcap, (int)k, e->lu_rcnt, e->d_nnzcnt);
-    } else
-      LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
-  refac_stage(e, "extract core + row counts");
-    int* flags = e->d_res->flags;
-    for (int j0 = 0; j0 < (int)k;) {
-      const int rows = (int)k - j0;
-      // widest panel whose rows x nb block (+ row ids, permutation) fits in shared memory; else work in place in global memory
-      int nb = LU_NB, use_smem = 0;
-      const size_t per_row = e->sparse ? 12 : 8;  // row ids + permutation (+ row entry counts)
-      for (int cand = LU_NB; cand >= 4; cand /= 2)
-        if ((size_t)rows * cand * 8 + (size_t)rows * per_row <= e->smem_optin) { nb = cand; use_smem = 1; break; }
-      nb = std::min(nb, rows);
-      const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * per_row : 0;
-      const int pt = std::max(64, std::min(1024, (rows + 31) / 32 * 32));  // one row per thread
-      LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, e->sparse ? e->lu_rcnt : (int32_t*)nullptr, flags,
-             e->lu_aff, e->lu_aff + 64, e->lu_aff + 128, e->lu_perm, use_smem);
-      if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
-                              e->lu_aff + 128, flags);
-      const int rem = rows - nb;
-      if (rem > 0) LAUNCH(e, k_lu_trailing, dim3(cdiv(rem, LU_NC), cdiv(rem, 256)), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, flags);
-      j0 += nb;
-    }
-  refac_stage(e, "LU panels / swap-solve / trailing");
-    {  // (L U)^-1, one CTA per column
-      const size_t need = (size_t)k * sizeof(double);
-      const int use_smem = need <= e->smem_optin ? 1 : 0;
-      if (k >= e->inv_blocked_min) {
-        // blocked substitution on all columns at once (dense_block.cuh): X = I; forward through L, backward through U
-        const int nbk = cdiv(k, 32);
-        LAUNCH(e, k_set_identity, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Cinv, e->kcap, (int)k);
-        for (int b = 0; b < nbk; ++b) {  // L y = e: X stays lower triangular, only columns < (b+1)*32 are non-zero
-          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0), nc = std::min<int>((int)k, r0 + nb), below = (int)k - (r0 + nb);
-          LAUNCH(e, k_tri_block<true>, cdiv(nc, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, nc);
-          if (below > 0)
-            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(below, GB_T), cdiv(nc, GB_T)), 256, 0, below, nc, nb, e->LUc + (size_t)r0 * e->kcap + r0 + nb,
-                   e->kcap, e->Cinv + r0, e->kcap, e->Cinv + r0 + nb, e->kcap);
-        }
-        for (int b = nbk - 1; b >= 0; --b) {  // U x = y over all k columns
-          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0);
-          LAUNCH(e, k_tri_block<false>, cdiv(k, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, (int)k);
-          if (r0 > 0)
-            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(r0, GB_T), cdiv(k, GB_T)), 256, 0, r0, (int)k, nb, e->LUc + (size_t)r0 * e->kcap, e->kcap,
-                   e->Cinv + r0, e->kcap, e->Cinv, e->kcap);
-        }
-      } else if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 2048) LAUNCH(e, k_core_inverse_pf<8>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 4096) LAUNCH(e, k_core_inverse_pf<16>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
-    }
-  refac_stage(e, "explicit inverse");
-    if (e->sparse) {
-      LAUNCH(e, k_count_offdiag, dim3(cdiv(k, 256), cdiv(k, 64)), 256, 0, e->LUc, e->kcap, (int)k, e->d_nnzcnt + 1);
-      CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
-    }
-    ST(fetch_res(e, e->lane[0]));
-    if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
-    // the factorization permuted the core's rows (Rp): column c of C^-1 belongs to row Rp[c] — the next refresh needs that order
-    if (e->sparse) ST(d2h(e, R.data(), e->Rp, (size_t)k * sizeof(int32_t)));
-    if (e->sparse && e->refac_trace) {  // calibration of the refresh probe: the same measure on a freshly factorized inverse
-      double r;
-      int64_t ce;
-      ST(probe_inverse(e, k, &r, &ce));
-      e->rf_worst_true = std::max(e->rf_worst_true, r);
-    }
-    }
-  refac_stage(e, "count off-diagonal + read back");
-  } else {
-    if (e->sparse) ST(build_core_rows(e, jvar));  // empty
-    if (e->sparse && e->corevar_k > 0) {
-      LAUNCH(e, k_set_corepos, cdiv(e->corevar_k, 256), 256, 0, e->corepos, e->corevar, (int)e->corevar_k, 1);
-      e->corevar_k = 0;
-    }
-    CU(cudaStreamSynchronize(e->stream));
-  }
-  // LUFactors::nnz (lu.rs:52-54): lower.nondiag + upper.nondiag + m.  The entries of the k structural basic columns in
-  // slack-covered rows go to U unchanged; the core contributes the off-diagonal entries of its factors, FILL-IN INCLUDED
-  // (counted on the device; exact zeros are not stored, lu.rs:253-255).  Dense A: no zeros, k(k-1) + (m-k)k + m in closed
-  // form.  The refactor rule (solver.rs:1096-1097) is the reference's, applied to the factors the engine really has: with
-  // the same column order and pivot rule (ties aside) their size tracks the reference's.
-  if (e->sparse) {
-    int64_t nz = 0;
-    for (int32_t v : jvar) nz += e->h_csc_ptr[(size_t)v + 1] - e->h_csc_ptr[(size_t)v];
-    if (refreshed) {
-      // no factors to count: the part outside the core is exact, the core's L\U is taken to fill as it did at the last true
-      // factorization (off-diagonal entries of the factors per entry of the core)
-      e->lu_nnz = (nz - rf_core_before) + (int64_t)((double)rf_core_before * e->fill_true) + m;
-    } else {
-      const int64_t core_before = k > 0 ? e->h_res->i[4] : 0, core_offdiag = k > 0 ? e->h_res->i[5] : 0;
-      e->lu_nnz = (nz - core_before) + core_offdiag + m;
-      e->fill_true = core_before > 0 ? (double)core_offdiag / (double)core_before : 1.0;
-      e->pivots_since_lu = 0;
-    }
-  } else e->lu_nnz = k * (k - 1) + (m - k) * k + m;
-  if (e->sparse) {  // the sets of the factorized basis, for the next refresh / the next incremental set-up
-    if (incremental) {
-      for (int32_t p : e->h_Jpos_f) e->h_pos_core[(size_t)p] = -1;
-      for (int32_t r : e->h_R_f) e->h_row_core[(size_t)r] = -1;
-    } else {
-      e->h_pos_core.assign((size_t)m, -1);
-      e->h_row_core.assign((size_t)m, -1);
-      e->h_rowcover_f.swap(rowcover);
-    }
-    for (int64_t t = 0; t < k; ++t) { e->h_pos_core[(size_t)jpos[(size_t)t]] = (int32_t)t; e->h_row_core[(size_t)R[(size_t)t]] = (int32_t)t; }
-    e->h_Jpos_f.swap(jpos);
-    e->h_R_f.swap(R);          // the factors' row order (permuted by a true factorization)
-    e->h_R_sorted.swap(Rsorted);
-    e->h_eta_pos.clear();
-    e->h_eta_leave.clear();
-    e->h_rc_old_rows.clear();
-    e->h_rc_old_vals.clear();
-    e->chg_complete = true;
-    e->inv_valid = true;
-  }
-  ST(stage_end(e));
-  e->cnt.refactors += 1;
-  e->cnt.k_structural = k;
-  e->refac_k_sum += (double)k;
-  refac_stage(e, "host: lu nnz");
-  return MLP_OK;
-}
+#include "refactor_host.cuh"
 
 // The exchange step: every shard's candidate header + candidate column are all-gathered, the winner is chosen with the
 // reference's tie rule on the host, and its column becomes colq.  world == 1: no collective, same code path.
