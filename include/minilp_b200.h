@@ -181,6 +181,11 @@ typedef struct mlp_dual_entering {
   int64_t ties, near_ties; /* as in mlp_leaving, for pass 2 at 982-1002 (the engine keeps the lowest variable index) */
 } mlp_dual_entering;
 mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out);
+/* The first half of one iteration of restore_feasibility (solver.rs:529-531) with ONE host round trip:
+ * choose_pivot_row_dual -> calc_row_coeffs(row) -> choose_entering_col_dual queued back to back, the chosen row handed from
+ * kernel to kernel in device memory; *row as mlp_select_row_dual, *out as mlp_ratio_dual (with leaving_new_val = the violated
+ * bound, 908-915).  row->row < 0: no infeasible row, *out is meaningless.  Same kernels and results as the three calls. */
+mlp_status mlp_dual_select_ratio(mlp_engine* e, mlp_dual_row* row, mlp_dual_entering* out);
 
 /* PivotInfo / PivotElem (solver.rs:1245-1261) plus the refactor decision of solver.rs:1096-1103,
  * which the host takes from the running eta nnz and lu_nnz. */

@@ -98,6 +98,7 @@ SIGNATURES = {
     "mlp_calc_row_coeffs": (i32, [vp, i64]),
     "mlp_select_row_dual": (i32, [vp, C.POINTER(DualRow)]),
     "mlp_ratio_dual": (i32, [vp, i64, f64, C.POINTER(DualEntering)]),
+    "mlp_dual_select_ratio": (i32, [vp, C.POINTER(DualRow), C.POINTER(DualEntering)]),
     "mlp_pivot": (i32, [vp, C.POINTER(PivotInfo), C.POINTER(PivotResult)]),
     "mlp_recalc_obj_coeffs": (i32, [vp, pd]),
     "mlp_recalc_basic_vals": (i32, [vp]),

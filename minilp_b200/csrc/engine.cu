@@ -1500,24 +1500,30 @@ mlp_status mlp_ratio_primal(mlp_engine* e, int32_t sign, double max_step0, mlp_l
   return MLP_OK;
 }
 
-mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
-  if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
-  CU(cudaSetDevice(e->device));
+// row_dev (optional): the row is taken from device memory — the record k_select_row_dual left in d_res — so that the host
+// can queue this BTRAN without having read the selection back (mlp_dual_select_ratio)
+static mlp_status btran_unit_impl(mlp_engine* e, int64_t row, const long long* row_dev) {
   Lane& l1 = e->lane[1];
   ST(begin1(e));
   // c = e_row and, with etas, u = row `row` of E (solver.rs:1326-1330 for a unit vector) in one launch
   if (e->merge_small && e->K > 0 && e->K <= FE_MAXK) {  // short eta file: ... and s = (I+G)^-T u as well
     LAUNCHS(e, l1.st, k_unit_eta_t, cdiv(std::max<int64_t>(e->m, 32 * e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, e->Ginv, e->Kcap,
-            (int)e->K, l1.tK2);
-    ST(btran(e, l1, e->work_mb, (int)row, e->rho, true, true));
+            (int)e->K, l1.tK2, row_dev);
+    ST(btran(e, l1, e->work_mb, 0, e->rho, true, true));
   } else {
-    LAUNCHS(e, l1.st, k_unit_and_gather, cdiv(std::max<int64_t>(e->m, e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, (int)e->K, l1.tK);
-    ST(btran(e, l1, e->work_mb, (int)row, e->rho, true));
+    LAUNCHS(e, l1.st, k_unit_and_gather, cdiv(std::max<int64_t>(e->m, e->K), 256), 256, 0, e->work_mb, e->m, row, e->E, e->mld, (int)e->K, l1.tK,
+            row_dev);
+    ST(btran(e, l1, e->work_mb, 0, e->rho, true));
   }
   // inv_basis_row_coeffs as a sparse list + |rho|^2 (solver.rs:683, 1160)
   compact(e, l1, e->rho, e->list_idx, e->list_val, e->icnt, e->scal + 1);
   ST(mark1(e));
   return MLP_OK;
+}
+mlp_status mlp_btran_unit(mlp_engine* e, int64_t row) {
+  if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  return btran_unit_impl(e, row, nullptr);
 }
 
 mlp_status mlp_price_row(mlp_engine* e) {
@@ -1533,15 +1539,19 @@ mlp_status mlp_calc_row_coeffs(mlp_engine* e, int64_t row) {
   return mlp_price_row(e);
 }
 
-mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
-  if (!e || !e->initialized) return MLP_INVALID;
-  CU(cudaSetDevice(e->device));
+static mlp_status select_row_dual_launch(mlp_engine* e) {
   const int grid = std::min(cdiv(e->m, 256), 1024);
   Lane& l0 = e->lane[0];
   ST(begin0(e));
   LAUNCH(e, k_select_row_dual, grid, 256, 0, e->xB, e->loB, e->hiB, e->w, (int)e->m, e->enable_dse, l0.red_f, l0.red_i,
          l0.red_counter, e->d_res);
-  ST(mark0(e));
+  return mark0(e);
+}
+mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
+  if (!e || !e->initialized) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  Lane& l0 = e->lane[0];
+  ST(select_row_dual_launch(e));
   ST(fetch_res(e, l0));
   out->row = e->h_res->i[0];
   out->val = e->h_res->f[0];
@@ -1552,24 +1562,20 @@ mlp_status mlp_select_row_dual(mlp_engine* e, mlp_dual_row* out) {
   return MLP_OK;
 }
 
-mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out) {
-  if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
-  CU(cudaSetDevice(e->device));
-  // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925)
+// choose_entering_col_dual (solver.rs:919-1021).  row_rec (optional): the leaving row's record in device memory (k_select_row_dual);
+// leaving_diff_sign is then formed on the device and `lds` is ignored.
+static mlp_status ratio_dual_impl(mlp_engine* e, int lds, const DevRes* row_rec, mlp_dual_entering* out) {
   Lane& l0 = e->lane[0];
   ST(begin0(e));
   e->sel_valid = false;  // the candidate buffer is reused for the dual ratio test
-  double bv = e->dual_row_val;  // basic_var_vals[row] as choose_pivot_row_dual saw it; x_B has not changed since
-  if (e->dual_row_host != row) ST(d2h(e, &bv, e->xB + row, sizeof(double)));
-  const int lds = leaving_new_val > bv ? 1 : 0;
   const int grid = std::min(cdiv(e->nt, 256), 1024);
-  LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, l0.red_f, l0.red_counter, e->scal);
+  LAUNCH(e, k_ratio_dual_1, grid, 256, 0, e->rc, e->d, e->vflag, e->nt, lds, l0.red_f, l0.red_counter, e->scal, row_rec);
   if (e->world > 1) {  // Harris pass 1 is a min over ALL variables: all-gather the shard minima
     ST(e->comm->allgather(e->scal, e->xred, sizeof(double), e->stream));
     LAUNCH(e, k_min_small, 1, 1, 0, e->xred, e->world, e->scal);
   }
   LAUNCH(e, k_ratio_dual_2, grid, 256, 0, e->rc, e->d, e->vflag, e->vpos, e->xnb, e->nt, e->n, e->c0, e->ng, lds, e->scal,
-         l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend, e->rank == 0 ? 1 : 0);
+         l0.red_f, l0.red_i, l0.red_counter, e->d_res->flags, (Cand*)e->xsend, e->rank == 0 ? 1 : 0, row_rec);
   Cand w;
   w.var = -1;
   ST(exchange_candidates(e, &w, true));
@@ -1583,6 +1589,40 @@ mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, ml
   out->near_ties = (w.tie >> 16) & 0xffff;
   if (out->ties > 0) e->cnt.ratio_ties += 1;
   if (out->near_ties > 0) e->cnt.ratio_near_ties += 1;
+  return MLP_OK;
+}
+mlp_status mlp_ratio_dual(mlp_engine* e, int64_t row, double leaving_new_val, mlp_dual_entering* out) {
+  if (!e || !e->initialized || row < 0 || row >= e->m) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  // leaving_diff_sign = leaving_new_val > basic_var_vals[row] (solver.rs:925)
+  double bv = e->dual_row_val;  // basic_var_vals[row] as choose_pivot_row_dual saw it; x_B has not changed since
+  if (e->dual_row_host != row) ST(d2h(e, &bv, e->xB + row, sizeof(double)));
+  return ratio_dual_impl(e, leaving_new_val > bv ? 1 : 0, nullptr, out);
+}
+
+// One host round trip for the first half of a dual iteration (solver.rs:529-531): choose_pivot_row_dual, calc_row_coeffs of
+// the chosen row and choose_entering_col_dual are queued back to back — the row travels from kernel to kernel in device memory
+// (k_select_row_dual's record: row, basic value, bounds) — and the host waits once, for the row's record and the winner's header
+// together.  Same kernels, same arithmetic as mlp_select_row_dual + mlp_calc_row_coeffs + mlp_ratio_dual.  No infeasible row
+// (row < 0): the queued BTRAN / price-out / ratio test run on a zero vector and find nothing; the caller stops on row < 0.
+mlp_status mlp_dual_select_ratio(mlp_engine* e, mlp_dual_row* row_out, mlp_dual_entering* out) {
+  if (!e || !e->initialized || !row_out || !out) return MLP_INVALID;
+  CU(cudaSetDevice(e->device));
+  Lane& l0 = e->lane[0];
+  ST(select_row_dual_launch(e));
+  CU(cudaMemcpyAsync(l0.h_res, l0.d_res, sizeof(DevRes), cudaMemcpyDeviceToHost, l0.st));  // read after the one wait below
+  ST(mark0(e));
+  e->cnt.d2h_bytes += (int64_t)sizeof(DevRes);
+  ST(btran_unit_impl(e, -1, (const long long*)&e->d_res->i[0]));
+  ST(mlp_price_row(e));
+  e->dual_row_host = -1;
+  ST(ratio_dual_impl(e, 0, e->d_res, out));  // waits for the winner's header: everything queued before it on lane 0 is done
+  row_out->row = e->h_res->i[0];
+  row_out->val = e->h_res->f[0];
+  row_out->min = e->h_res->f[1];
+  row_out->max = e->h_res->f[2];
+  e->dual_row_host = row_out->row;
+  e->dual_row_val = row_out->val;
   return MLP_OK;
 }
 

@@ -537,9 +537,11 @@ __device__ __forceinline__ double clamp_obj(double oc, unsigned f) {
 }
 __global__ void __launch_bounds__(256) k_ratio_dual_1(const double* __restrict__ rc, const double* __restrict__ d,
                                                        const uint8_t* __restrict__ vflag, int64_t nt, int lds,
-                                                       double* __restrict__ red_f, unsigned* counter, double* __restrict__ scal) {
+                                                       double* __restrict__ red_f, unsigned* counter, double* __restrict__ scal,
+                                                       const DevRes* __restrict__ dr) {
   pdl_wait();
   __shared__ double sm[32];
+  if (dr) lds = dr->f[0] < dr->f[1] ? 1 : 0;  // the row's record left by k_select_row_dual: leaving_new_val > basic value (solver.rs:908-915, 925)
   double best = INFINITY;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nt; v += (int64_t)gridDim.x * blockDim.x) {
     const unsigned f = vflag[v];
@@ -575,8 +577,9 @@ __global__ void __launch_bounds__(256) k_ratio_dual_2(const double* __restrict__
                                                        int64_t ng, int lds, const double* __restrict__ scal,
                                                        double* __restrict__ red_f, long long* __restrict__ red_i,
                                                        unsigned* counter, const int* __restrict__ flags, Cand* out,
-                                                       int scan_slacks) {
+                                                       int scan_slacks, const DevRes* __restrict__ dr) {
   pdl_wait();
+  if (dr) lds = dr->f[0] < dr->f[1] ? 1 : 0;  // as in k_ratio_dual_1
   __shared__ double smk[32];
   __shared__ long long smi[32];
   __shared__ long long smc[32];

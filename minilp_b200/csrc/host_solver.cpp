@@ -8,6 +8,7 @@
 
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -54,6 +55,9 @@ struct mlp_solver {
   // of a coalesced m x K pass, while a refactorization is O(k) sequential pivot steps plus O(k^3) work, so the balance
   // point lies elsewhere.  Only the rounding of later pivots depends on it.
   double refactor_factor = 1.0;
+  // the first half of a dual iteration as one engine call / one host round trip (mlp_dual_select_ratio); MLP_FUSED_DUAL=0: the
+  // three calls of the reference's control flow
+  bool fused_dual = [] { const char* v = getenv("MLP_FUSED_DUAL"); return !(v && atoi(v) == 0); }();
   bool artificial_obj = false;  // solver.rs:261: while the artificial objective is in place d must not be recomputed from c
   bool initialized = false;
 };
@@ -166,15 +170,24 @@ static mlp_status primal_iteration(mlp_solver* s, int* moved) {
 // One iteration of restore_feasibility() (solver.rs:529-533).
 static mlp_status dual_iteration(mlp_solver* s, int* moved) {
   mlp_dual_row dr;
-  ST(mlp_select_row_dual(s->eng, &dr));
-  if (dr.row < 0) { *moved = 0; return MLP_OK; }
-  double leaving_new_val;  // 908-915
-  if (dr.val < dr.min) leaving_new_val = dr.min;
-  else if (dr.val > dr.max) leaving_new_val = dr.max;
-  else return MLP_INVALID;  // unreachable!() in the reference
-  ST(mlp_calc_row_coeffs(s->eng, dr.row));  // 530
   mlp_dual_entering de;
-  ST(mlp_ratio_dual(s->eng, dr.row, leaving_new_val, &de));  // 531
+  double leaving_new_val;  // 908-915
+  if (s->fused_dual) {
+    // choose_pivot_row_dual -> calc_row_coeffs -> choose_entering_col_dual queued back to back on the device: one round trip
+    ST(mlp_dual_select_ratio(s->eng, &dr, &de));
+    if (dr.row < 0) { *moved = 0; return MLP_OK; }
+    if (dr.val < dr.min) leaving_new_val = dr.min;
+    else if (dr.val > dr.max) leaving_new_val = dr.max;
+    else return MLP_INVALID;  // unreachable!() in the reference
+  } else {
+    ST(mlp_select_row_dual(s->eng, &dr));
+    if (dr.row < 0) { *moved = 0; return MLP_OK; }
+    if (dr.val < dr.min) leaving_new_val = dr.min;
+    else if (dr.val > dr.max) leaving_new_val = dr.max;
+    else return MLP_INVALID;  // unreachable!() in the reference
+    ST(mlp_calc_row_coeffs(s->eng, dr.row));  // 530
+    ST(mlp_ratio_dual(s->eng, dr.row, leaving_new_val, &de));  // 531
+  }
   if (de.var < 0) return MLP_INFEASIBLE;                      // 1019
   note_ties(s, de.ties, de.near_ties);
   const double entering_diff = (dr.val - leaving_new_val) / de.coeff;  // 1005

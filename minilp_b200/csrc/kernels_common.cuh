@@ -491,15 +491,17 @@ __global__ void __launch_bounds__(256) k_eta_apply(const double* __restrict__ E,
 // s = (I+G)^-T u with u = row r of E read in place (k_unit_and_gather + k_mv_t<true>; one warp per column, same order).
 __global__ void __launch_bounds__(256) k_unit_eta_t(double* __restrict__ c, int64_t cnt, int64_t at, const double* __restrict__ E,
                                                      int64_t lde, const double* __restrict__ Ginv, int64_t Kld, int K,
-                                                     double* __restrict__ s) {
+                                                     double* __restrict__ s, const long long* __restrict__ at_dev) {
   pdl_wait();
+  if (at_dev) at = *at_dev;  // the row left in device memory by k_select_row_dual (< 0: none)
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) c[t] = (t == at) ? 1.0 : 0.0;
   const int lane = threadIdx.x & 31, j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= K) return;
   const double* col = Ginv + (int64_t)j * Kld;
   double acc = 0.0;
-  for (int i = j + lane; i < K; i += 32) acc += col[i] * E[(int64_t)i * lde + at];
+  if (at >= 0)
+    for (int i = j + lane; i < K; i += 32) acc += col[i] * E[(int64_t)i * lde + at];
   acc = warp_sum(acc);
   if (lane == 0) s[j] = acc;
 }
@@ -625,12 +627,14 @@ __global__ void k_gather_row(const double* __restrict__ M, int64_t ld, int row, 
   if (t < cnt) dst[t] = M[(int64_t)t * ld + row];
 }
 // c = e_at (cnt entries) and dst[j] = M[at + j ld] for j < ncols, in one launch (BTRAN of a unit vector with an eta file)
+// at_dev (optional): the row is read from device memory (left there by k_select_row_dual; < 0: no row — c = 0, nothing gathered)
 __global__ void k_unit_and_gather(double* __restrict__ c, int64_t cnt, int64_t at, const double* __restrict__ M, int64_t ld,
-                                  int ncols, double* __restrict__ dst) {
+                                  int ncols, double* __restrict__ dst, const long long* __restrict__ at_dev) {
   pdl_wait();
+  if (at_dev) at = *at_dev;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < cnt) c[t] = (t == at) ? 1.0 : 0.0;
-  if (t < ncols) dst[t] = M[t * ld + at];
+  if (t < ncols) dst[t] = at >= 0 ? M[t * ld + at] : 0.0;
 }
 __global__ void k_fill(double* p, int64_t cnt, double v) {
   pdl_wait();
