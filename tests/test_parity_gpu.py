@@ -228,3 +228,27 @@ def test_price_dense_bench_hook_runs():
     h = s.engine.download(10)[:512]
     assert close(h, 0.5 * lp.a.sum(axis=0), 1e-12)
     s.close()
+
+
+@pytest.mark.parametrize("storage,kind", [("dense", 1), ("dense", 3), ("sparse", None)])
+def test_one_round_trip_dual_iteration_is_bit_identical(storage, kind, monkeypatch):
+    """mlp_dual_select_ratio queues choose_pivot_row_dual -> calc_row_coeffs -> choose_entering_col_dual (solver.rs:529-531) back
+    to back with the chosen row kept in device memory; MLP_FUSED_DUAL=0 makes the host loop issue the reference's three calls.
+    Same kernels, same arithmetic: the two solves must agree in every bit of every pivot record and of the end state."""
+    def solve(flag):
+        monkeypatch.setenv("MLP_FUSED_DUAL", flag)
+        if storage == "dense":
+            s = mb.Solver.from_dense(mb.synth_dense(kind, 120, 160, 5))
+        else:
+            from minilp_b200 import mps, synth
+            from test_sparse_gpu import solver_from_problem
+            text, d = synth.netlib_like(300, 300, 6.0, 1)
+            s = solver_from_problem(mps.MpsFile.parse(text, d).problem, "sparse")
+        assert s.run()
+        out = (s.trace().copy(), s.cur_obj_val, s.values().copy(), s.basic_var_vals().copy())
+        s.close()
+        return out
+    a, b = solve("1"), solve("0")
+    assert a[0].shape == b[0].shape and a[0].shape[0] > 20
+    assert np.array_equal(a[0], b[0])
+    assert a[1] == b[1] and np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
