@@ -461,9 +461,9 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
       ST(stage_put(e, e->cseg_id, cid.data(), cid.size()));
       ST(stage_put(e, e->cseg_first, cfirst.data(), cfirst.size()));
     }
-  refac_stage(e, "uploads: index maps, core segments");
+    refac_stage(e, "uploads: index maps, core segments");
     if (e->sparse) ST(build_core_rows(e, jvar));
-  refac_stage(e, "compact core rows (DCSR)");
+    refac_stage(e, "compact core rows (DCSR)");
     if (refreshed) {
       // C^-1 is already the new core's.  Probe it against the new core (max |C C^-1 - I| over sampled columns) and count the
       // core's entries for the estimate of LUFactors::nnz below — one read-back; a failed probe falls through to the true
@@ -472,83 +472,83 @@ static mlp_status refactor_impl(mlp_engine* e, bool allow_refresh = false) {
       ST(probe_inverse(e, k, &r, &rf_core_before));
       if (r <= e->rf_tol) e->rf_worst = std::max(e->rf_worst, r);
       if (!(r <= e->rf_tol)) { refreshed = false; e->cnt.refresh_rejects += 1; e->cnt.refreshes -= 1; }
-  refac_stage(e, "refresh: accuracy probe + read back");
+    refac_stage(e, "refresh: accuracy probe + read back");
     }
     if (!refreshed) {
-    if (e->sparse) {
-      CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
-      LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
-             (int)e->ncseg, e->corepos, e->rowcore, e->LUc, e->kcap);
-      CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
-      LAUNCH(e, k_core_row_counts, cdiv(k, 256), 256, 0, e->LUc, e->kcap, (int)k, e->lu_rcnt, e->d_nnzcnt);
-    } else
-      LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
-  refac_stage(e, "extract core + row counts");
-    int* flags = e->d_res->flags;
-    for (int j0 = 0; j0 < (int)k;) {
-      const int rows = (int)k - j0;
-      // widest panel whose rows x nb block (+ row ids, permutation) fits in shared memory; else work in place in global memory
-      int nb = LU_NB, use_smem = 0;
-      const size_t per_row = e->sparse ? 12 : 8;  // row ids + permutation (+ row entry counts)
-      for (int cand = LU_NB; cand >= 4; cand /= 2)
-        if ((size_t)rows * cand * 8 + (size_t)rows * per_row <= e->smem_optin) { nb = cand; use_smem = 1; break; }
-      nb = std::min(nb, rows);
-      const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * per_row : 0;
-      const int pt = std::max(64, std::min(1024, (rows + 31) / 32 * 32));  // one row per thread
-      LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, e->sparse ? e->lu_rcnt : (int32_t*)nullptr, flags,
-             e->lu_aff, e->lu_aff + 64, e->lu_aff + 128, e->lu_perm, use_smem);
-      if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
-                              e->lu_aff + 128, flags);
-      const int rem = rows - nb;
-      if (rem > 0) LAUNCH(e, k_lu_trailing, dim3(cdiv(rem, LU_NC), cdiv(rem, 256)), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, flags);
-      j0 += nb;
+      if (e->sparse) {
+        CU(cudaMemsetAsync(e->LUc, 0, (size_t)e->kcap * k * sizeof(double), e->stream));
+        LAUNCH(e, k_extract_core_seg, cdiv(e->ncseg, 8), 256, 0, e->csc_ptr, e->csc_idx, e->csc_val, e->seg_col, e->seg_off, e->cseg_id,
+               (int)e->ncseg, e->corepos, e->rowcore, e->LUc, e->kcap);
+        CU(cudaMemsetAsync(e->d_nnzcnt, 0, 2 * sizeof(unsigned long long), e->stream));
+        LAUNCH(e, k_core_row_counts, cdiv(k, 256), 256, 0, e->LUc, e->kcap, (int)k, e->lu_rcnt, e->d_nnzcnt);
+      } else
+        LAUNCH(e, k_extract_core, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Bcols, e->mld, (int)k, e->Rp, e->Jslot, e->LUc, e->kcap);
+      refac_stage(e, "extract core + row counts");
+      int* flags = e->d_res->flags;
+      for (int j0 = 0; j0 < (int)k;) {
+        const int rows = (int)k - j0;
+        // widest panel whose rows x nb block (+ row ids, permutation) fits in shared memory; else work in place in global memory
+        int nb = LU_NB, use_smem = 0;
+        const size_t per_row = e->sparse ? 12 : 8;  // row ids + permutation (+ row entry counts)
+        for (int cand = LU_NB; cand >= 4; cand /= 2)
+          if ((size_t)rows * cand * 8 + (size_t)rows * per_row <= e->smem_optin) { nb = cand; use_smem = 1; break; }
+        nb = std::min(nb, rows);
+        const size_t smem = use_smem ? (size_t)rows * nb * 8 + (size_t)rows * per_row : 0;
+        const int pt = std::max(64, std::min(1024, (rows + 31) / 32 * 32));  // one row per thread
+        LAUNCH(e, k_lu_panel, 1, pt, smem, e->LUc, e->kcap, (int)k, j0, nb, e->Rp, e->sparse ? e->lu_rcnt : (int32_t*)nullptr, flags,
+               e->lu_aff, e->lu_aff + 64, e->lu_aff + 128, e->lu_perm, use_smem);
+        if ((int)k > nb) LAUNCH(e, k_lu_swap_solve, cdiv(k - nb, 8), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, e->lu_aff, e->lu_aff + 64,
+                                e->lu_aff + 128, flags);
+        const int rem = rows - nb;
+        if (rem > 0) LAUNCH(e, k_lu_trailing, dim3(cdiv(rem, LU_NC), cdiv(rem, 256)), 256, 0, e->LUc, e->kcap, (int)k, j0, nb, flags);
+        j0 += nb;
+      }
+      refac_stage(e, "LU panels / swap-solve / trailing");
+      {  // (L U)^-1, one CTA per column
+        const size_t need = (size_t)k * sizeof(double);
+        const int use_smem = need <= e->smem_optin ? 1 : 0;
+        if (k >= e->inv_blocked_min) {
+          // blocked substitution on all columns at once (dense_block.cuh): X = I; forward through L, backward through U
+          const int nbk = cdiv(k, 32);
+          LAUNCH(e, k_set_identity, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Cinv, e->kcap, (int)k);
+          for (int b = 0; b < nbk; ++b) {  // L y = e: X stays lower triangular, only columns < (b+1)*32 are non-zero
+            const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0), nc = std::min<int>((int)k, r0 + nb), below = (int)k - (r0 + nb);
+            LAUNCH(e, k_tri_block<true>, cdiv(nc, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, nc);
+            if (below > 0)
+              LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(below, GB_T), cdiv(nc, GB_T)), 256, 0, below, nc, nb, e->LUc + (size_t)r0 * e->kcap + r0 + nb,
+                     e->kcap, e->Cinv + r0, e->kcap, e->Cinv + r0 + nb, e->kcap);
+          }
+          for (int b = nbk - 1; b >= 0; --b) {  // U x = y over all k columns
+            const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0);
+            LAUNCH(e, k_tri_block<false>, cdiv(k, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, (int)k);
+            if (r0 > 0)
+              LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(r0, GB_T), cdiv(k, GB_T)), 256, 0, r0, (int)k, nb, e->LUc + (size_t)r0 * e->kcap, e->kcap,
+                     e->Cinv + r0, e->kcap, e->Cinv, e->kcap);
+          }
+        } else if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+        else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+        else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+        else if (k <= 2048) LAUNCH(e, k_core_inverse_pf<8>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+        else if (k <= 4096) LAUNCH(e, k_core_inverse_pf<16>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
+        else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
+      }
+      refac_stage(e, "explicit inverse");
+      if (e->sparse) {
+        LAUNCH(e, k_count_offdiag, dim3(cdiv(k, 256), cdiv(k, 64)), 256, 0, e->LUc, e->kcap, (int)k, e->d_nnzcnt + 1);
+        CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
+      }
+      ST(fetch_res(e, e->lane[0]));
+      if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
+      // the factorization permuted the core's rows (Rp): column c of C^-1 belongs to row Rp[c] — the next refresh needs that order
+      if (e->sparse) ST(d2h(e, R.data(), e->Rp, (size_t)k * sizeof(int32_t)));
+      if (e->sparse && e->refac_trace) {  // calibration of the refresh probe: the same measure on a freshly factorized inverse
+        double r;
+        int64_t ce;
+        ST(probe_inverse(e, k, &r, &ce));
+        e->rf_worst_true = std::max(e->rf_worst_true, r);
+      }
     }
-  refac_stage(e, "LU panels / swap-solve / trailing");
-    {  // (L U)^-1, one CTA per column
-      const size_t need = (size_t)k * sizeof(double);
-      const int use_smem = need <= e->smem_optin ? 1 : 0;
-      if (k >= e->inv_blocked_min) {
-        // blocked substitution on all columns at once (dense_block.cuh): X = I; forward through L, backward through U
-        const int nbk = cdiv(k, 32);
-        LAUNCH(e, k_set_identity, dim3(cdiv(k, 256), (unsigned)k), 256, 0, e->Cinv, e->kcap, (int)k);
-        for (int b = 0; b < nbk; ++b) {  // L y = e: X stays lower triangular, only columns < (b+1)*32 are non-zero
-          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0), nc = std::min<int>((int)k, r0 + nb), below = (int)k - (r0 + nb);
-          LAUNCH(e, k_tri_block<true>, cdiv(nc, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, nc);
-          if (below > 0)
-            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(below, GB_T), cdiv(nc, GB_T)), 256, 0, below, nc, nb, e->LUc + (size_t)r0 * e->kcap + r0 + nb,
-                   e->kcap, e->Cinv + r0, e->kcap, e->Cinv + r0 + nb, e->kcap);
-        }
-        for (int b = nbk - 1; b >= 0; --b) {  // U x = y over all k columns
-          const int r0 = b * 32, nb = std::min<int>(32, (int)k - r0);
-          LAUNCH(e, k_tri_block<false>, cdiv(k, 128), 128, 0, e->LUc, e->kcap, r0, nb, e->Cinv, e->kcap, (int)k);
-          if (r0 > 0)
-            LAUNCH(e, k_gemm_sub<true>, dim3(cdiv(r0, GB_T), cdiv(k, GB_T)), 256, 0, r0, (int)k, nb, e->LUc + (size_t)r0 * e->kcap, e->kcap,
-                   e->Cinv + r0, e->kcap, e->Cinv, e->kcap);
-        }
-      } else if (k <= 256) LAUNCH(e, k_core_inverse_pf<1>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 512) LAUNCH(e, k_core_inverse_pf<2>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 1024) LAUNCH(e, k_core_inverse_pf<4>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 2048) LAUNCH(e, k_core_inverse_pf<8>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else if (k <= 4096) LAUNCH(e, k_core_inverse_pf<16>, (unsigned)k, 256, need, e->LUc, e->kcap, (int)k, e->Cinv, flags);
-      else LAUNCH(e, k_core_inverse, (unsigned)k, 256, use_smem ? need : 0, e->LUc, e->kcap, (int)k, e->Cinv, flags, use_smem);
-    }
-  refac_stage(e, "explicit inverse");
-    if (e->sparse) {
-      LAUNCH(e, k_count_offdiag, dim3(cdiv(k, 256), cdiv(k, 64)), 256, 0, e->LUc, e->kcap, (int)k, e->d_nnzcnt + 1);
-      CU(cudaMemcpyAsync(&e->d_res->i[4], e->d_nnzcnt, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, e->stream));
-    }
-    ST(fetch_res(e, e->lane[0]));
-    if (e->h_res->flags[1]) { set_err("singular basis"); return MLP_SINGULAR; }
-    // the factorization permuted the core's rows (Rp): column c of C^-1 belongs to row Rp[c] — the next refresh needs that order
-    if (e->sparse) ST(d2h(e, R.data(), e->Rp, (size_t)k * sizeof(int32_t)));
-    if (e->sparse && e->refac_trace) {  // calibration of the refresh probe: the same measure on a freshly factorized inverse
-      double r;
-      int64_t ce;
-      ST(probe_inverse(e, k, &r, &ce));
-      e->rf_worst_true = std::max(e->rf_worst_true, r);
-    }
-    }
-  refac_stage(e, "count off-diagonal + read back");
+    refac_stage(e, "count off-diagonal + read back");
   } else {
     if (e->sparse) ST(build_core_rows(e, jvar));  // empty
     if (e->sparse && e->corevar_k > 0) {
