@@ -4,8 +4,8 @@
 // The reference refactorizes from scratch whenever the eta file has grown as large as the factors (solver.rs:1096-1103 ->
 // BasisSolver::reset 1286-1303 -> lu_factorize lu.rs:118-304): on netlib-like LPs every ~16 pivots.  A factorization is k
 // dependent column steps plus O(k^3) work for the explicit inverse this engine solves with — 60 % of the step on config 4
-// (profiles/r02d_*).  But between two refactorizations the basis changes in K <= 128 positions only, and the engine already
-// holds everything that describes the change:
+// (profiles/r02d_*).  But between two refactorizations the basis changes in K positions only (tens on config 4's first thousands
+// of pivots, up to RF_CAP handled here), and the engine already holds everything that describes the change:
 //
 //   B_new^-1 = E_K^-1 ... E_1^-1 B_old^-1                                  (solver.rs:1305-1319, the product form)
 //   B_old^-1 [pos of core column t, row r in R_old]            =  C_old^-1[t, c(r)]
@@ -17,7 +17,8 @@
 // is a gather of the old one (plus <= K new rows, one sparse row-times-matrix product each, and unit columns) minus a rank-K
 // product: O(k^2 K) throughput-bound work on all SMs instead of O(k) latency-bound steps + O(k^3).  It is the same
 // arithmetic a longer eta file would do at every solve, done once; rounding accumulates like an eta file of that length,
-// which is why a true factorization still happens every `lu_every` pivots (MLP_TUNE_LU_EVERY).  C^-1 is an engine-internal
+// which is why every refresh is probed against the new core (k_rf_probe; above the tolerance it is redone as a true
+// factorization) and why MLP_TUNE_LU_EVERY can bound the pivots between true factorizations.  C^-1 is an engine-internal
 // quantity (the reference solves with L and U), so the rank-K product may contract a*b+c.
 #pragma once
 
